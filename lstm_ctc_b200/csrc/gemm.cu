@@ -1,0 +1,334 @@
+// gemm.cu -- bf16 x bf16 -> fp32 GEMM on tcgen05 tensor cores fed by TMA (K1/K1b/K1c in DESIGN.md).
+//
+// Replaces the per-time-step sgemm inside tf.contrib.rnn.LSTMCell (nnet/bilstm.py:129-136 under
+// dynamic_rnn :171-188) by ONE contraction hoisted over all frames, plus the LSTM projection,
+// tf.nn.xw_plus_b (nnet/bilstm.py:249, nnet/moe.py:42,59) and the dgrad/wgrad GEMMs that
+// tf.gradients (nnet/graph.py:190-191) would emit.
+//
+// Structure (persistent, warp-specialised, one CTA per SM):
+//   warp 0      : TMA producer   -- cp.async.bulk.tensor 128B-swizzled boxes into a STAGES-deep smem ring
+//   warp 1      : MMA issuer     -- one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM,
+//                                    tcgen05.commit frees smem slots / publishes the accumulator
+//   warps 2..5  : epilogue       -- tcgen05.ld TMEM->regs, +bias, (+C), smem-transposed coalesced stores
+//   TMEM        : 2 accumulator stages x BN fp32 columns, so the epilogue of tile i overlaps the MMAs of tile i+1
+// Operand layouts: A and B can each be K-major or MN-major (canonical SWIZZLE_128B layouts), which
+// gives forward (X*W), dgrad (dG*W^T) and wgrad (X^T*dG) from row-major tensors without transposes.
+#include "ptx.cuh"
+#include "tma_host.h"
+#include "lstm_ctc_b200.h"
+
+namespace lcb {
+
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;          // 64 bf16 = 128 B = one swizzle row
+constexpr int GEMM_THREADS = 192;
+
+template <int BN> struct GemmCfg {
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;         // 16 KB
+    static constexpr int B_BYTES = BN * GEMM_BK * 2;              // 16/32 KB
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;             // per-warp transpose staging
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;
+};
+
+template <int BN, bool A_MN, bool B_MN, bool C_BF16>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         void* __restrict__ Cptr, int ldc, const float* __restrict__ bias, int accumulate,
+                         int M, int N, int K)
+{
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* tiles = smem;
+    float* epi = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
+    uint64_t* full_bar = bars;                    // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+    const int tiles_n = (N + BN - 1) / BN;
+    const int ntiles = tiles_m * tiles_n;
+    const int nkb = (K + GEMM_BK - 1) / GEMM_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * GEMM_BM;
+                const int n0 = (tile % tiles_n) * BN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    if (!mbar_wait(&empty_bar[stage], phase ^ 1)) { ok = false; break; }
+                    unsigned char* sa = tiles + stage * Cfg::STAGE_BYTES;
+                    unsigned char* sb = sa + Cfg::A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    const int k0 = kb * GEMM_BK;
+                    if constexpr (!A_MN) {
+                        tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);
+                    } else {
+#pragma unroll
+                        for (int bx = 0; bx < GEMM_BM / 64; ++bx) tma_load_2d(sa + bx * 8192, &tmA, &full_bar[stage], m0 + bx * 64, k0);
+                    }
+                    if constexpr (!B_MN) {
+                        tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+                    } else {
+#pragma unroll
+                        for (int bx = 0; bx < BN / 64; ++bx) tma_load_2d(sb + bx * 8192, &tmB, &full_bar[stage], n0 + bx * 64, k0);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16_f32(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
+                if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1)) { ok = false; break; }
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    if (!mbar_wait(&full_bar[stage], phase)) { ok = false; break; }
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        // K-major: advance 16 elements = 32 B inside the 128 B swizzle row.
+                        // MN-major: advance 16 k-rows = 2048 B.
+                        const uint64_t adesc = A_MN ? make_smem_desc_sw128(sa + k * 2048, 8192, 1024)
+                                                    : make_smem_desc_sw128(sa + k * 32, 16, 1024);
+                        const uint64_t bdesc = B_MN ? make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
+                                                    : make_smem_desc_sw128(sb + k * 32, 16, 1024);
+                        umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);           // smem slot reusable once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);                 // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue (warps 2..5) =================
+        const int q = warp & 3;                               // TMEM lane quarter this warp may access
+        float* st = epi + (warp - 2) * (32 * 33);
+        int acc = 0; uint32_t acc_phase = 0;
+        bool ok = true;
+        for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
+            const int m0 = (tile / tiles_n) * GEMM_BM;
+            const int n0 = (tile % tiles_n) * BN;
+            if (!mbar_wait(&tfull_bar[acc], acc_phase)) { ok = false; break; }
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(t_addr + ch * 32, r);
+                tmem_ld_wait();
+                const int col = n0 + ch * 32 + lane;
+                if (n0 + ch * 32 >= N) continue;              // warp-uniform
+#pragma unroll
+                for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(r[j]);
+                __syncwarp();
+                const float bv = (bias != nullptr && col < N) ? bias[col] : 0.f;
+#pragma unroll 4
+                for (int rr = 0; rr < 32; ++rr) {
+                    const int row = m0 + q * 32 + rr;
+                    if (row < M && col < N) {
+                        float v = st[rr * 33 + lane] + bv;
+                        if constexpr (C_BF16) {
+                            reinterpret_cast<__nv_bfloat16*>(Cptr)[(size_t)row * ldc + col] = __float2bfloat16(v);
+                        } else {
+                            float* cp = reinterpret_cast<float*>(Cptr) + (size_t)row * ldc + col;
+                            if (accumulate) v += *cp;
+                            *cp = v;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
+}
+
+// ------------------------------------------------------------------------------------------
+// plain CUDA-core checker (tests only)
+__global__ void gemm_simt_check_kernel(int M, int N, int K, const __nv_bfloat16* A, long long a_sm, long long a_sk,
+                                       const __nv_bfloat16* B, long long b_sn, long long b_sk, void* C, int ldc,
+                                       int c_bf16, const float* bias, int accumulate)
+{
+    __shared__ float As[16][17], Bs[16][17];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
+    float acc = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        int ka = k0 + tx, kb = k0 + ty;
+        As[ty][tx] = (row < M && ka < K) ? __bfloat162float(A[(long long)row * a_sm + (long long)ka * a_sk]) : 0.f;
+        int bcol = blockIdx.x * 16 + tx;
+        Bs[ty][tx] = (bcol < N && kb < K) ? __bfloat162float(B[(long long)bcol * b_sn + (long long)kb * b_sk]) : 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc += As[ty][k] * Bs[k][tx];
+        __syncthreads();
+    }
+    if (row < M && col < N) {
+        if (bias) acc += bias[col];
+        if (c_bf16) reinterpret_cast<__nv_bfloat16*>(C)[(size_t)row * ldc + col] = __float2bfloat16(acc);
+        else {
+            float* cp = reinterpret_cast<float*>(C) + (size_t)row * ldc + col;
+            *cp = accumulate ? *cp + acc : acc;
+        }
+    }
+}
+
+template <int BN, bool A_MN, bool B_MN, bool C_BF16>
+static int launch_gemm(int M, int N, int K, const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc,
+                       const float* bias, int accumulate, cudaStream_t st)
+{
+    using Cfg = GemmCfg<BN>;
+    auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN, C_BF16>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) return LCB_ERR_CUDA;
+        attr_done = true;
+    }
+    const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
+    int nsm = 148;
+    int grid = tiles < nsm ? tiles : nsm;
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, C, ldc, bias, accumulate, M, N, K);
+    return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
+}
+
+template <int BN, bool C_BF16>
+static int dispatch_layout(int a_layout, int b_layout, int M, int N, int K, const CUtensorMap& ta, const CUtensorMap& tb,
+                           void* C, int ldc, const float* bias, int accumulate, cudaStream_t st)
+{
+    if (!a_layout && !b_layout) return launch_gemm<BN, false, false, C_BF16>(M, N, K, ta, tb, C, ldc, bias, accumulate, st);
+    if (!a_layout && b_layout) return launch_gemm<BN, false, true, C_BF16>(M, N, K, ta, tb, C, ldc, bias, accumulate, st);
+    if (a_layout && !b_layout) return launch_gemm<BN, true, false, C_BF16>(M, N, K, ta, tb, C, ldc, bias, accumulate, st);
+    return launch_gemm<BN, true, true, C_BF16>(M, N, K, ta, tb, C, ldc, bias, accumulate, st);
+}
+
+}  // namespace lcb
+
+using namespace lcb;
+
+static int gemm_check_args(int M, int N, int K, const void* A, int lda, int a_layout, const void* B, int ldb,
+                           int b_layout, void* C, int ldc, int c_dtype, int accumulate)
+{
+    if (!A || !B || !C) return LCB_ERR_NULL_POINTER;
+    if (M <= 0 || N <= 0 || K <= 0) return LCB_ERR_BAD_SHAPE;
+    if ((a_layout | b_layout | c_dtype) & ~1) return LCB_ERR_BAD_SHAPE;
+    if (lda < (a_layout ? M : K) || ldb < (b_layout ? N : K) || ldc < N) return LCB_ERR_BAD_SHAPE;
+    if (accumulate && c_dtype != 0) return LCB_ERR_UNSUPPORTED;
+    return LCB_OK;
+}
+
+extern "C" int lcb_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_layout, const void* B, int ldb,
+                             int b_layout, void* C, int ldc, int c_dtype, const float* bias, int accumulate, void* stream)
+{
+    int rc = gemm_check_args(M, N, K, A, lda, a_layout, B, ldb, b_layout, C, ldc, c_dtype, accumulate);
+    if (rc != LCB_OK) return rc;
+    if ((lda & 7) || (ldb & 7) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) return LCB_ERR_MISALIGNED;
+    cudaStream_t st = (cudaStream_t)stream;
+    // tile width: 256 when that still fills the machine, else 128 for more CTAs
+    const int t256 = ((M + 127) / 128) * ((N + 255) / 256);
+    const bool bn256 = (N > 128) && (t256 >= 120 || N >= 1024);
+    const int BN = bn256 ? 256 : 128;
+    CUtensorMap ta, tb;
+    bool ok;
+    if (!a_layout) ok = make_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM, GEMM_BK);
+    else ok = make_tmap_2d_bf16(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK, 64);
+    if (!ok) return LCB_ERR_CUDA;
+    if (!b_layout) ok = make_tmap_2d_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)BN, GEMM_BK);
+    else ok = make_tmap_2d_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, GEMM_BK, 64);
+    if (!ok) return LCB_ERR_CUDA;
+    if (bn256) {
+        return c_dtype ? dispatch_layout<256, true>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, st)
+                       : dispatch_layout<256, false>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, st);
+    }
+    return c_dtype ? dispatch_layout<128, true>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, st)
+                   : dispatch_layout<128, false>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, st);
+}
+
+extern "C" int lcb_gemm_bf16_simt_check(int M, int N, int K, const void* A, int lda, int a_layout, const void* B, int ldb,
+                                        int b_layout, void* C, int ldc, int c_dtype, const float* bias, int accumulate,
+                                        void* stream)
+{
+    int rc = gemm_check_args(M, N, K, A, lda, a_layout, B, ldb, b_layout, C, ldc, c_dtype, accumulate);
+    if (rc != LCB_OK) return rc;
+    dim3 blk(16, 16), grd((N + 15) / 16, (M + 15) / 16);
+    long long a_sm = a_layout ? 1 : lda, a_sk = a_layout ? lda : 1;
+    long long b_sn = b_layout ? 1 : ldb, b_sk = b_layout ? ldb : 1;
+    gemm_simt_check_kernel<<<grd, blk, 0, (cudaStream_t)stream>>>(M, N, K, (const __nv_bfloat16*)A, a_sm, a_sk,
+                                                                  (const __nv_bfloat16*)B, b_sn, b_sk, C, ldc, c_dtype, bias, accumulate);
+    return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
+}
+
+extern "C" int lcb_version(void) { return 100; }
+
+extern "C" const char* lcb_status_string(int s)
+{
+    switch (s) {
+        case LCB_OK: return "ok";
+        case LCB_ERR_NULL_POINTER: return "null pointer argument";
+        case LCB_ERR_BAD_SHAPE: return "invalid shape / size argument";
+        case LCB_ERR_UNSUPPORTED: return "unsupported configuration";
+        case LCB_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
+        case LCB_ERR_CUDA: return "CUDA runtime error";
+        case LCB_ERR_INVALID_LABEL: return "InvalidArgument: label not in [0, num_classes-1)";
+        case LCB_ERR_MISALIGNED: return "misaligned pointer or leading dimension";
+        case LCB_ERR_DEVICE_TIMEOUT: return "device-side barrier timeout";
+        default: return "unknown status";
+    }
+}
+
+extern "C" int lcb_device_error(int reset)
+{
+    int h = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return LCB_ERR_CUDA;
+    if (cudaMemcpyFromSymbol(&h, lcb::g_dev_error, sizeof(int)) != cudaSuccess) return LCB_ERR_CUDA;
+    if (reset && h != 0) {
+        int z = 0;
+        cudaMemcpyToSymbol(lcb::g_dev_error, &z, sizeof(int));
+    }
+    return h;
+}

@@ -1,0 +1,63 @@
+"""GPU parity: tcgen05 GEMM (lcb_gemm_bf16) vs fp32 torch matmul of the same bf16 operands and vs
+the on-device CUDA-core checker.  Tolerance: fp32 accumulation of exact bf16 products -- only the
+summation order differs: |err| <= 2e-3 * sqrt(K)-scaled bound, checked as rtol 2e-3 on O(sqrt(K)) values."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(A, B, a_layout, b_layout, bias):
+    a = A.float() if a_layout == 0 else A.float().t()
+    b = B.float().t() if b_layout == 0 else B.float()
+    c = a @ b
+    if bias is not None:
+        c = c + bias
+    return c
+
+
+@pytest.mark.parametrize("a_layout,b_layout", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (300, 200, 136), (1000, 1288, 520), (64, 72, 1024)])
+def test_gemm_layouts(cuda_dev, a_layout, b_layout, M, N, K):
+    from lstm_ctc_b200.gemm import gemm
+    torch.manual_seed(M + N + K)
+    pad = lambda n: (n + 7) // 8 * 8
+    A = torch.randn((M, pad(K)) if a_layout == 0 else (K, pad(M)), device=cuda_dev).bfloat16()
+    B = torch.randn((N, pad(K)) if b_layout == 0 else (K, pad(N)), device=cuda_dev).bfloat16()
+    Av = A[:, :K] if a_layout == 0 else A[:, :M]
+    Bv = B[:, :K] if b_layout == 0 else B[:, :N]
+    bias = torch.randn(N, device=cuda_dev)
+    C = gemm(Av, Bv, a_layout, b_layout, bias=bias)
+    Cc = gemm(Av, Bv, a_layout, b_layout, bias=bias, check=True)
+    R = _ref(Av, Bv, a_layout, b_layout, bias)
+    torch.cuda.synchronize()
+    scale = K ** 0.5
+    assert (Cc - R).abs().max() < 2e-3 * scale
+    assert (C - R).abs().max() < 2e-3 * scale, ((C - R).abs().max().item(), a_layout, b_layout)
+
+
+def test_gemm_accumulate_and_bf16_out(cuda_dev):
+    from lstm_ctc_b200.gemm import gemm
+    torch.manual_seed(0)
+    A = torch.randn(512, 256, device=cuda_dev).bfloat16()
+    B = torch.randn(384, 256, device=cuda_dev).bfloat16()
+    C0 = torch.randn(512, 384, device=cuda_dev)
+    C = C0.clone()
+    gemm(A, B, out=C, accumulate=True)
+    R = C0 + A.float() @ B.float().t()
+    assert (C - R).abs().max() < 0.05
+    Cb = gemm(A, B, out_dtype=torch.bfloat16)
+    assert (Cb.float() - A.float() @ B.float().t()).abs().max() < 0.3
+
+
+def test_gemm_projection_shape(cuda_dev):
+    """The hoisted input projection at C1 scale: [B*T, Din] x [Din, 8H]."""
+    from lstm_ctc_b200.gemm import gemm
+    torch.manual_seed(1)
+    X = torch.randn(16 * 700, 640, device=cuda_dev).bfloat16()
+    W = (torch.randn(2560, 640, device=cuda_dev) * 0.05).bfloat16()
+    C = gemm(X, W)
+    R = X.float() @ W.float().t()
+    assert (C - R).abs().max() < 2e-2
+    from lstm_ctc_b200 import _lib
+    assert _lib.lib().lcb_device_error(0) == 0
