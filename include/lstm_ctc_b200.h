@@ -58,7 +58,7 @@ int lcb_ctc_loss_grad_f32(const float* logits, const int64_t* labels, int Lmax, 
  * Synchronises `stream`. */
 int lcb_ctc_status(const void* workspace, void* stream);
 
-/* ---- bf16 GEMM, fp32 accumulate (tcgen05 + TMA) ----------------------------------------
+/* ---- 16-bit GEMM, fp32 accumulate (tcgen05 + TMA) ---------------------------------------
  * replaces: the matmul inside tf.contrib.rnn.LSTMCell hoisted over all frames
  *           (nnet/bilstm.py:129-136,171-188), the LSTM projection, tf.nn.xw_plus_b
  *           (nnet/bilstm.py:249, nnet/moe.py:42,59) and their tf.gradients counterparts
@@ -66,20 +66,71 @@ int lcb_ctc_status(const void* workspace, void* stream);
  * C[M,N] (+)= op(A)[M,K] * op(B)[K,N] + bias[N]
  *   a_layout 0: A stored row-major [M,K] (ld = lda)      1: A stored row-major [K,M]
  *   b_layout 0: B stored row-major [N,K] (ld = ldb)      1: B stored row-major [K,N]
- *   c_dtype  0: C fp32                                    1: C bf16
- * A, B bf16; lda/ldb multiples of 8 elements, base pointers 16-byte aligned.
+ *   dtype codes: 0 = fp32 (C only), 1 = bf16, 2 = fp16.  A and B must share one 16-bit type (the
+ *   hardware rejects mixed kind::f16 operands): forward GEMMs are fp16 x fp16, gradient GEMMs bf16 x bf16.
+ * lda/ldb multiples of 8 elements, A/B base pointers 16-byte aligned.
  * accumulate != 0 adds into the existing fp32 C (c_dtype must be 0). */
+int lcb_gemm16(int M, int N, int K,
+               const void* A, int lda, int a_layout, int a_dtype,
+               const void* B, int ldb, int b_layout, int b_dtype,
+               void* C, int ldc, int c_dtype,
+               const float* bias, int accumulate, void* stream);
+/* bf16 x bf16 shorthand of the above. */
 int lcb_gemm_bf16(int M, int N, int K,
                   const void* A, int lda, int a_layout,
                   const void* B, int ldb, int b_layout,
                   void* C, int ldc, int c_dtype,
                   const float* bias, int accumulate, void* stream);
-/* Same contract on plain CUDA cores -- a slow on-device CHECKER for tests, not a product path. */
+/* Same contracts on plain CUDA cores -- slow on-device CHECKERS for tests, not a product path. */
+int lcb_gemm16_simt_check(int M, int N, int K,
+                          const void* A, int lda, int a_layout, int a_dtype,
+                          const void* B, int ldb, int b_layout, int b_dtype,
+                          void* C, int ldc, int c_dtype,
+                          const float* bias, int accumulate, void* stream);
 int lcb_gemm_bf16_simt_check(int M, int N, int K,
                              const void* A, int lda, int a_layout,
                              const void* B, int ldb, int b_layout,
                              void* C, int ldc, int c_dtype,
                              const float* bias, int accumulate, void* stream);
+
+/* ---- LSTM recurrence, both directions of one BiLSTM layer (cluster-persistent, DSMEM) ----
+ * replaces: tf.nn.dynamic_rnn(DropoutWrapper(LSTMCell(num_units, num_proj, use_peepholes,
+ *           forget_bias=5.0)), sequence_length=...) for "fd{i}" AND "bd{i}"  nnet/bilstm.py:127-188
+ *           and tf.reverse_sequence                                          nnet/bilstm.py:112,190,203
+ * Hp = hidden size padded to a multiple of 64 (<= 512).  Packed gate column = 4*unit + gate,
+ * gates (i,j,f,o); direction d owns columns [d*4Hp, (d+1)*4Hp).  Time-major rows n = t*B + b.
+ *   G     [T*B, 8Hp] f32   x_t*W_x + bias (from lcb_gemm_bf16)
+ *   Wfold [8Hp, Hp]  fp16 (fwd) / bf16 (bwd)  rows = packed gate columns of both directions,
+ *                          cols = unit: (W_proj*W_h)^T
+ *   peep  [2,3,Hp]   f32   (w_f, w_i, w_o) per direction, or NULL (use_peepholes = False)
+ *   lens  [B] int32        sequence_length
+ *   Mout  [T*B, 2Hp] fp16  m_t = o*tanh(c) per direction; rows with t >= lens[b] are 0 (dynamic_rnn
+ *                          zero output); h = Mout * W_proj is a bulk lcb_gemm_bf16 afterwards
+ *   acts  [6, T*B, 2Hp] f32 saved (i, tanh j, f, o, c, tanh c) for BPTT, or NULL for inference
+ *   cfin, mfin [B,2,Hp] f32 final states (both or neither) -- `encoder` of nnet/bilstm.py:206-208 */
+int lcb_lstm_rec_config(int Hp, int* units_per_cta_div32, int* cluster_size);
+int lcb_lstm_rec_fwd(const float* G, const void* Wfold, const float* peep, const int32_t* lens,
+                     void* Mout, float* acts, float* cfin, float* mfin,
+                     int T, int B, int Hp, float forget_bias, void* stream);
+/* BPTT of the above (replaces tf.gradients through the while_loop, nnet/graph.py:190-191).
+ *   dM    [T*B, 2Hp] f32   d loss / d m_t arriving from the output projection
+ *   dG    [T*B, 8Hp] bf16  d loss / d z_t (packed columns; 0 where t >= lens[b])
+ *   dbias [2*4Hp] f32 +=,  dpeep [2,3,Hp] f32 += (NULL iff peep NULL) */
+int lcb_lstm_rec_bwd(const float* dM, const float* acts, const void* Wfold, const float* peep,
+                     const int32_t* lens, void* dG, float* dbias, float* dpeep,
+                     int T, int B, int Hp, void* stream);
+
+/* ---- HBM-bound helpers -----------------------------------------------------------------
+ * lcb_pack_input: pipeline tensor nnet_input [B,T,D] f32 (nnet/pipeline.py:35-61) -> time-major
+ *                 fp16 [T,B,Dp] (pad columns zero, saturating); replaces the batch-major walk of dynamic_rnn.
+ * lcb_cast_f32_16 (dst_dtype 1 bf16 / 2 fp16) / lcb_split_f32_bf16: operand casts (x = hi + lo split
+ *                 for fp32-accurate weight folds).
+ * lcb_colsum: out[c] += sum_r src[r,c] (bias gradients). */
+int lcb_pack_input(const float* nnet_input, void* x0, int B, int T, int D, int Dp, void* stream);
+int lcb_cast_f32_16(const float* src, void* dst, int dst_dtype, size_t n, void* stream);
+int lcb_split_f32_bf16(const float* src, void* hi, void* lo, size_t n, void* stream);
+int lcb_f16_to_bf16(const void* src, void* dst, size_t n, void* stream);   /* n even */
+int lcb_colsum(const void* src, int src_dtype, int rows, int cols, int ld, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,380 @@
+"""Stacked BiLSTM encoder on the sm_100a kernels -- host-side mirror of
+`create_logits_blstm` (/root/reference/nnet/bilstm.py:25-273) up to the encoder output.
+
+What runs where (all compute is in liblstm_ctc_b200.so; torch only owns memory and streams):
+  lcb_pack_input      [B,T,D] f32 -> time-major bf16                       (pipeline.py:35-61 layout)
+  lcb_gemm_bf16       G = X*W_x + b for BOTH directions, all frames         (LSTMCell matmul, hoisted)
+  lcb_lstm_rec_fwd    masked recurrence, both directions concurrently       (dynamic_rnn + LSTMCell)
+  lcb_gemm_bf16       h = m*W_proj written straight into its half of [N,2P] (num_proj + tf.concat)
+and the mirrored sequence for the backward pass (lcb_lstm_rec_bwd + dgrad/wgrad GEMMs).
+
+Parameters live in DEVICE layout (packed gate columns 4*unit+gate, hidden size padded to 64) inside one
+flat fp32 buffer; `to_tf_dict` / `from_tf_dict` convert to/from the reference's TF variable names and
+shapes (fd{i}/frnn{i}/kernel, .../bias, .../w_{f,i,o}_diag, .../projection/kernel; bilstm.py:125-165).
+"""
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib
+from .gemm import gemm
+
+F32 = torch.float32
+BF16 = torch.bfloat16      # gradient operands (range-safe without loss scaling)
+F16 = torch.float16        # forward operands (|m| < 1, CMVN'd features, small weights: 8x finer than bf16)
+
+
+def _ceil(x, m):
+    return (x + m - 1) // m * m
+
+
+class ModelConfig:
+    """The nnet_config keys consumed by create_logits_blstm (bilstm.py:39-99)."""
+
+    def __init__(self, nnet_config: dict):
+        c = nnet_config
+        ctx = 1 + int(c.get("left_context") or 0) + int(c.get("right_context") or 0)
+        self.input_dim = int(c["input_dim"]) * ctx                       # bilstm.py:48
+        self.num_layers = int(c["num_layers"])
+        self.H = int(c["num_neurons"])
+        if c.get("num_projects") is None:
+            raise TypeError("num_projects is required (2 * None at bilstm.py:199)")
+        self.P = int(c["num_projects"])
+        self.V = int(c["num_targets"])
+        self.use_peepholes = bool(c.get("use_peepholes") or False)
+        self.K = int(c.get("num_experts") or 0)
+        self.tau = float(c["moe_temp"]) if c.get("moe_temp") is not None else 10.0
+        if c.get("dropout_rate") is None:
+            raise TypeError("dropout_rate (a keep-probability) is required ('%f' % None at bilstm.py:79)")
+        self.keep_prob = float(c["dropout_rate"])
+        is_training = c.get("is_training")
+        self.is_training = True if is_training is None else bool(is_training)
+        if not self.is_training:
+            self.keep_prob = 1.0                                          # bilstm.py:98-99
+        self.uniform_label_sm = c.get("uniform_label_sm")
+        self.prior_label_sm = c.get("prior_label_sm")
+        self.prior_label_path = c.get("prior_label_path")
+        self.forget_bias = 5.0                                            # bilstm.py:133,154
+        # device layout
+        self.Hp = _ceil(self.H, 64)
+        if self.Hp > 512:
+            raise _lib.LcbError(-3, "num_neurons > 512 does not fit the cluster-resident recurrence")
+        if self.P % 8:
+            raise _lib.LcbError(-3, "num_projects must be a multiple of 8")
+        self.Dp0 = _ceil(self.input_dim, 8)
+        self.residual0 = (self.input_dim == 2 * self.P)                   # bilstm.py:199-200
+
+    def din(self, i):
+        return self.input_dim if i == 0 else 2 * self.P
+
+    def dinp(self, i):
+        return self.Dp0 if i == 0 else 2 * self.P
+
+
+class ParamSpec:
+    def __init__(self, name, shape, decay):
+        self.name, self.shape, self.decay = name, tuple(shape), decay
+        self.numel = 1
+        for s in shape:
+            self.numel *= s
+        self.offset = 0
+
+
+class ParamStore:
+    """One flat fp32 buffer for weights and one for gradients (bucket = contiguous slice).
+    Order = gradient completion order of the backward pass (output layer first, layer 0 last) so
+    data-parallel all-reduce can start on finished slices while BPTT of lower layers still runs."""
+
+    def __init__(self, specs: List[ParamSpec], device):
+        off = 0
+        for s in specs:
+            s.offset = off
+            off += _ceil(s.numel, 64)          # 256-byte aligned slices
+        self.specs = {s.name: s for s in specs}
+        self.order = [s.name for s in specs]
+        self.total = off
+        self.flat = torch.zeros(off, dtype=F32, device=device)
+        self.gflat = torch.zeros(off, dtype=F32, device=device)
+
+    def w(self, name):
+        s = self.specs[name]
+        return self.flat[s.offset:s.offset + s.numel].view(s.shape)
+
+    def g(self, name):
+        s = self.specs[name]
+        return self.gflat[s.offset:s.offset + s.numel].view(s.shape)
+
+    def nodecay_ranges(self):
+        return [(s.offset, s.offset + s.numel) for s in (self.specs[n] for n in self.order) if not s.decay]
+
+
+def _cast16(src, dtype, dst=None):
+    L = _lib.lib()
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=dtype, device=src.device)
+    assert dst.dtype == dtype
+    _lib.check(L.lcb_cast_f32_16(_lib.ptr(src), _lib.ptr(dst), 1 if dtype == BF16 else 2, src.numel(), _lib.stream_ptr()),
+               "lcb_cast_f32_16")
+    return dst
+
+
+def _to_bf16(src, dst):
+    """fp16 activation -> bf16 scratch copy (same shape, both contiguous) for the wgrad GEMMs."""
+    assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
+    _lib.check(_lib.lib().lcb_f16_to_bf16(_lib.ptr(src), _lib.ptr(dst), src.numel(), _lib.stream_ptr()), "lcb_f16_to_bf16")
+    return dst
+
+
+def _split_bf16(src):
+    L = _lib.lib()
+    hi = torch.empty(src.shape, dtype=BF16, device=src.device)
+    lo = torch.empty(src.shape, dtype=BF16, device=src.device)
+    _lib.check(L.lcb_split_f32_bf16(_lib.ptr(src), _lib.ptr(hi), _lib.ptr(lo), src.numel(), _lib.stream_ptr()),
+               "lcb_split_f32_bf16")
+    return hi, lo
+
+
+class BLSTMEncoder:
+    """Weights + forward/backward of the L-layer BiLSTM stack."""
+
+    def __init__(self, cfg: ModelConfig, device, extra_specs: Optional[List[ParamSpec]] = None):
+        self.cfg = cfg
+        self.device = device
+        c = cfg
+        specs = list(extra_specs or [])                     # output layer first (its grads finish first)
+        for i in reversed(range(c.num_layers)):
+            specs += [ParamSpec("L%d/WpT" % i, (2, c.P, c.Hp), True),
+                      ParamSpec("L%d/Wh" % i, (8 * c.Hp, c.P), True),
+                      ParamSpec("L%d/peep" % i, (2, 3, c.Hp), True),
+                      ParamSpec("L%d/bias" % i, (8 * c.Hp,), False),
+                      ParamSpec("L%d/Wx" % i, (8 * c.Hp, c.dinp(i)), True)]
+        self.params = ParamStore(specs, device)
+        self._bf = {}            # bf16 operand copies, refreshed by refresh_operands()
+        self._ws = {}            # activation workspaces keyed by (T, B)
+        self._stale = True
+        mt = _lib.ctypes.c_int()
+        nc = _lib.ctypes.c_int()
+        _lib.check(_lib.lib().lcb_lstm_rec_config(c.Hp, _lib.ctypes.byref(mt), _lib.ctypes.byref(nc)), "lcb_lstm_rec_config")
+        self.rec_mt, self.rec_nc = mt.value, nc.value
+
+    # ------------------------------------------------------------------ TF <-> device layout
+    def _tf_names(self, i, d):
+        return "%s%d/%s%d" % ("fd" if d == 0 else "bd", i, "frnn" if d == 0 else "brnn", i)
+
+    def from_tf_dict(self, tf: Dict[str, torch.Tensor]):
+        """Load reference-layout variables (kernel [Din+P,4H] with gate blocks i,j,f,o; bias [4H];
+        w_*_diag [H]; projection/kernel [H,P])."""
+        c = self.cfg
+        H, Hp, P = c.H, c.Hp, c.P
+        ps = self.params
+        for i in range(c.num_layers):
+            din = c.din(i)
+            Wx, Wh, bias, peep, WpT = ps.w("L%d/Wx" % i), ps.w("L%d/Wh" % i), ps.w("L%d/bias" % i), ps.w("L%d/peep" % i), ps.w("L%d/WpT" % i)
+            Wx.zero_(); Wh.zero_(); bias.zero_(); peep.zero_(); WpT.zero_()
+            for d in range(2):
+                pre = self._tf_names(i, d)
+                k = tf[pre + "/kernel"].to(device=self.device, dtype=F32)          # [din+P, 4H]
+                assert k.shape == (din + P, 4 * H), (k.shape, din, P, H)
+                # packed row r = d*4Hp + 4*u + gate  <-  TF column gate*H + u
+                kk = k.view(din + P, 4, H).permute(2, 1, 0)                          # [H(u), 4(gate), din+P]
+                rows = Wx[d * 4 * Hp:(d + 1) * 4 * Hp].view(Hp, 4, -1)
+                rows[:H, :, :din] = kk[:, :, :din]
+                rowsh = Wh[d * 4 * Hp:(d + 1) * 4 * Hp].view(Hp, 4, P)
+                rowsh[:H] = kk[:, :, din:]
+                b = tf[pre + "/bias"].to(device=self.device, dtype=F32).view(4, H).t()   # [H, 4]
+                bias[d * 4 * Hp:(d + 1) * 4 * Hp].view(Hp, 4)[:H] = b
+                if c.use_peepholes:
+                    peep[d, 0, :H] = tf[pre + "/w_f_diag"].to(self.device, F32)
+                    peep[d, 1, :H] = tf[pre + "/w_i_diag"].to(self.device, F32)
+                    peep[d, 2, :H] = tf[pre + "/w_o_diag"].to(self.device, F32)
+                WpT[d, :, :H] = tf[pre + "/projection/kernel"].to(self.device, F32).t()  # [P, H]
+        self._stale = True
+
+    def to_tf_dict(self, grads=False) -> Dict[str, torch.Tensor]:
+        c = self.cfg
+        H, Hp, P = c.H, c.Hp, c.P
+        get = self.params.g if grads else self.params.w
+        out = {}
+        for i in range(c.num_layers):
+            din = c.din(i)
+            Wx, Wh, bias, peep, WpT = get("L%d/Wx" % i), get("L%d/Wh" % i), get("L%d/bias" % i), get("L%d/peep" % i), get("L%d/WpT" % i)
+            for d in range(2):
+                pre = self._tf_names(i, d)
+                rx = Wx[d * 4 * Hp:(d + 1) * 4 * Hp].view(Hp, 4, -1)[:H, :, :din]     # [H,4,din]
+                rh = Wh[d * 4 * Hp:(d + 1) * 4 * Hp].view(Hp, 4, P)[:H]               # [H,4,P]
+                k = torch.cat([rx, rh], 2).permute(2, 1, 0).reshape(din + P, 4 * H)
+                out[pre + "/kernel"] = k.clone()
+                out[pre + "/bias"] = bias[d * 4 * Hp:(d + 1) * 4 * Hp].view(Hp, 4)[:H].t().reshape(4 * H).clone()
+                if c.use_peepholes:
+                    out[pre + "/w_f_diag"] = peep[d, 0, :H].clone()
+                    out[pre + "/w_i_diag"] = peep[d, 1, :H].clone()
+                    out[pre + "/w_o_diag"] = peep[d, 2, :H].clone()
+                out[pre + "/projection/kernel"] = WpT[d, :, :H].t().clone()
+        return out
+
+    # ------------------------------------------------------------------ operand refresh (once per update)
+    def mark_stale(self):
+        self._stale = True
+
+    def refresh_operands(self):
+        """bf16 GEMM operands + folded recurrent weights W' = W_proj * W_h (fp32-accurate via a
+        3-term split-bf16 product on the tensor cores)."""
+        if not self._stale:
+            return
+        c = self.cfg
+        ps = self.params
+        for i in range(c.num_layers):
+            self._bf[("Wx16", i)] = _cast16(ps.w("L%d/Wx" % i), F16, self._bf.get(("Wx16", i)))
+            self._bf[("Wx", i)] = _cast16(ps.w("L%d/Wx" % i), BF16, self._bf.get(("Wx", i)))
+            self._bf[("WpT16", i)] = _cast16(ps.w("L%d/WpT" % i), F16, self._bf.get(("WpT16", i)))
+            Wh_hi, Wh_lo = _split_bf16(ps.w("L%d/Wh" % i))
+            Wp_hi, Wp_lo = _split_bf16(ps.w("L%d/WpT" % i))
+            fold = self._bf.get(("fold32", i))
+            if fold is None:
+                fold = torch.empty(8 * c.Hp, c.Hp, dtype=F32, device=self.device)
+            for d in range(2):
+                rows = slice(d * 4 * c.Hp, (d + 1) * 4 * c.Hp)
+                # W'^T[g,h] = sum_p Wh[g,p] * WpT[p,h]
+                gemm(Wh_hi[rows], Wp_hi[d], 0, 1, out=fold[rows])
+                gemm(Wh_hi[rows], Wp_lo[d], 0, 1, out=fold[rows], accumulate=True)
+                gemm(Wh_lo[rows], Wp_hi[d], 0, 1, out=fold[rows], accumulate=True)
+            self._bf[("Wh", i)] = Wh_hi
+            self._bf[("WpT", i)] = Wp_hi
+            self._bf[("fold32", i)] = fold
+            self._bf[("fold16", i)] = _cast16(fold, F16, self._bf.get(("fold16", i)))   # forward recurrence
+            self._bf[("fold", i)] = _cast16(fold, BF16, self._bf.get(("fold", i)))       # BPTT (bf16 dz operand)
+        self._stale = False
+
+    # ------------------------------------------------------------------ workspaces
+    def _workspace(self, T, B, training):
+        key = (T, B, training)
+        ws = self._ws.get(key)
+        if ws is None:
+            c = self.cfg
+            N = T * B
+            dev = self.device
+            ws = {"X0": torch.empty(N, c.Dp0, dtype=F16, device=dev),
+                  "G": torch.empty(N, 8 * c.Hp, dtype=F32, device=dev),
+                  "M": [torch.empty(N, 2 * c.Hp, dtype=F16, device=dev) for _ in range(c.num_layers)],
+                  "Hout": [torch.empty(N, 2 * c.P, dtype=F16, device=dev) for _ in range(c.num_layers)],
+                  "cfin": torch.zeros(B, 2, c.Hp, dtype=F32, device=dev),
+                  "mfin": torch.zeros(B, 2, c.Hp, dtype=F32, device=dev)}
+            if training:
+                ws["acts"] = [torch.empty(6, N, 2 * c.Hp, dtype=F32, device=dev) for _ in range(c.num_layers)]
+                ws["dM"] = torch.empty(N, 2 * c.Hp, dtype=F32, device=dev)
+                ws["dG"] = torch.empty(N, 8 * c.Hp, dtype=BF16, device=dev)
+                ws["dX"] = [torch.empty(N, 2 * c.P, dtype=BF16, device=dev) for _ in range(2)]
+                ws["dfold"] = torch.empty(4 * c.Hp, c.Hp, dtype=F32, device=dev)
+                ws["Xbf"] = torch.empty(N * max(c.Dp0, 2 * c.P), dtype=BF16, device=dev)     # bf16 copies for wgrad
+                ws["Mbf"] = torch.empty(N, 2 * c.Hp, dtype=BF16, device=dev)
+            self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, nnet_input, seq_len, training=True):
+        """nnet_input [B,T,D] f32 cuda (zero padded), seq_len [B] int32 cuda.
+        Returns the encoder output [T*B, 2P] fp16 (time-major rows n = t*B + b)."""
+        L = _lib.lib()
+        c = self.cfg
+        assert nnet_input.is_cuda and nnet_input.dtype == F32 and nnet_input.dim() == 3
+        B, T, D = nnet_input.shape
+        assert D == c.input_dim, (D, c.input_dim)
+        if c.residual0:
+            raise NotImplementedError("layer-0 residual (input_dim == 2*num_projects, bilstm.py:199-200)")
+        if c.keep_prob < 1.0 and training:
+            raise NotImplementedError("output dropout inside the stack (keep_prob < 1)")
+        self.refresh_operands()
+        ws = self._workspace(T, B, training)
+        st = _lib.stream_ptr()
+        nnet_input = nnet_input.contiguous()
+        seq_len = seq_len.to(device=self.device, dtype=torch.int32).contiguous()
+        _lib.check(L.lcb_pack_input(_lib.ptr(nnet_input), _lib.ptr(ws["X0"]), B, T, D, c.Dp0, st), "lcb_pack_input")
+        X = ws["X0"]
+        for i in range(c.num_layers):
+            gemm(X, self._bf[("Wx16", i)], 0, 0, out=ws["G"], bias=self.params.w("L%d/bias" % i))
+            peep = self.params.w("L%d/peep" % i) if c.use_peepholes else None
+            acts = ws["acts"][i] if training else None
+            last = (i == c.num_layers - 1)
+            _lib.check(L.lcb_lstm_rec_fwd(_lib.ptr(ws["G"]), _lib.ptr(self._bf[("fold16", i)]), _lib.ptr(peep), _lib.ptr(seq_len),
+                                          _lib.ptr(ws["M"][i]), _lib.ptr(acts),
+                                          _lib.ptr(ws["cfin"]) if last else None, _lib.ptr(ws["mfin"]) if last else None,
+                                          T, B, c.Hp, c.forget_bias, st), "lcb_lstm_rec_fwd")
+            Hout = ws["Hout"][i]
+            for d in range(2):
+                gemm(ws["M"][i][:, d * c.Hp:(d + 1) * c.Hp], self._bf[("WpT16", i)][d], 0, 0, out=Hout[:, d * c.P:(d + 1) * c.P])
+            X = Hout
+        self._last = (T, B, seq_len, training)
+        return X
+
+    def encoder_state(self):
+        """`encoder` of bilstm.py:206-208: concat(c_fw, h_fw, c_bw, h_bw) of the LAST layer, [B, 2(H+P)]."""
+        T, B, _, training = self._last
+        ws = self._workspace(T, B, training)
+        c = self.cfg
+        i = c.num_layers - 1
+        out = []
+        for d in range(2):
+            h = gemm(ws["mfin"][:, d].contiguous().to(F16), self._bf[("WpT16", i)][d], 0, 0)
+            out += [ws["cfin"][:, d, :c.H], h]
+        return torch.cat(out, 1)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, dXtop, bucket_ready=None):
+        """dXtop [T*B, 2P] bf16 = d loss / d encoder output.  Accumulates parameter gradients into
+        params.gflat (which the caller zeroed).  bucket_ready(name_list) is called as soon as the
+        gradients of a layer are final (data-parallel all-reduce hook)."""
+        L = _lib.lib()
+        c = self.cfg
+        T, B, seq_len, training = self._last
+        assert training
+        ws = self._workspace(T, B, True)
+        st = _lib.stream_ptr()
+        N = T * B
+        ps = self.params
+        dH = dXtop
+        for i in reversed(range(c.num_layers)):
+            X16 = ws["X0"] if i == 0 else ws["Hout"][i - 1]
+            X = _to_bf16(X16, ws["Xbf"][:X16.numel()].view(X16.shape))
+            M = _to_bf16(ws["M"][i], ws["Mbf"])
+            dM, dG = ws["dM"], ws["dG"]
+            gWpT, gWh, gWx = ps.g("L%d/WpT" % i), ps.g("L%d/Wh" % i), ps.g("L%d/Wx" % i)
+            for d in range(2):
+                dHd = dH[:, d * c.P:(d + 1) * c.P]
+                Md = M[:, d * c.Hp:(d + 1) * c.Hp]
+                # dM = dH * W_p^T
+                gemm(dHd, self._bf[("WpT", i)][d], 0, 1, out=dM[:, d * c.Hp:(d + 1) * c.Hp])
+                # dW_p^T[p,h] = sum_n dH[n,p] * M[n,h]
+                gemm(dHd, Md, 1, 1, out=gWpT[d])
+            peep = ps.w("L%d/peep" % i) if c.use_peepholes else None
+            gpeep = ps.g("L%d/peep" % i) if c.use_peepholes else None
+            _lib.check(L.lcb_lstm_rec_bwd(_lib.ptr(dM), _lib.ptr(ws["acts"][i]), _lib.ptr(self._bf[("fold", i)]), _lib.ptr(peep),
+                                          _lib.ptr(seq_len), _lib.ptr(dG), _lib.ptr(ps.g("L%d/bias" % i)), _lib.ptr(gpeep),
+                                          T, B, c.Hp, st), "lcb_lstm_rec_bwd")
+            for d in range(2):
+                dGd = dG[:, d * 4 * c.Hp:(d + 1) * 4 * c.Hp]
+                Md = M[:, d * c.Hp:(d + 1) * c.Hp]
+                dfold = ws["dfold"]
+                if T > 1:
+                    # dW'^T[g,h] = sum_n dz_n[g] * m_prev(n)[h]; prev = t-1 (fwd) / t+1 (bwd): a row shift of B
+                    if d == 0:
+                        gemm(dGd[B:], Md[:N - B], 1, 1, out=dfold)
+                    else:
+                        gemm(dGd[:N - B], Md[B:], 1, 1, out=dfold)
+                    df_hi, df_lo = _split_bf16(dfold)
+                    rows = slice(d * 4 * c.Hp, (d + 1) * 4 * c.Hp)
+                    # dW_h[g,p] = sum_h dW'^T[g,h] * WpT[p,h]
+                    gemm(df_hi, self._bf[("WpT", i)][d], 0, 0, out=gWh[rows])
+                    gemm(df_lo, self._bf[("WpT", i)][d], 0, 0, out=gWh[rows], accumulate=True)
+                    # dW_p^T[p,h] += sum_g Wh[g,p] * dW'^T[g,h]
+                    gemm(self._bf[("Wh", i)][rows], df_hi, 1, 1, out=gWpT[d], accumulate=True)
+                    gemm(self._bf[("Wh", i)][rows], df_lo, 1, 1, out=gWpT[d], accumulate=True)
+            # dW_x[g,k] = sum_n dz_n[g] * x_n[k]   (both directions at once)
+            gemm(dG, X, 1, 1, out=gWx)
+            if i > 0:
+                dXn = ws["dX"][i & 1]
+                gemm(dG, self._bf[("Wx", i)], 0, 1, out=dXn)        # dX = dG * W_x
+                dH = dXn
+            if bucket_ready is not None:
+                bucket_ready(["L%d/WpT" % i, "L%d/Wh" % i, "L%d/peep" % i, "L%d/bias" % i, "L%d/Wx" % i])
+        return None

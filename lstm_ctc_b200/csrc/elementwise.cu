@@ -1,0 +1,139 @@
+// elementwise.cu -- small HBM-bound helper kernels of the hot path (casts, packing, reductions).
+// They replace TF's implicit layout ops on the path: the [B,T,D] batch-major pipeline tensor
+// (nnet/pipeline.py:35-61) is re-laid time-major once, weights are re-cast to bf16 once per step.
+#include <cuda_fp16.h>
+#include "ptx.cuh"
+#include "lstm_ctc_b200.h"
+
+namespace lcb {
+
+__device__ __forceinline__ float sat_f16(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    __half2 v = __floats2half2_rn(sat_f16(lo), sat_f16(hi));
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// F16 = false: bf16 destination; true: fp16 destination (saturating)
+template <bool F16>
+__global__ void cast_f32_16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, size_t n) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+    for (; i + 3 < n; i += stride) {
+        const float4 v = *reinterpret_cast<const float4*>(src + i);
+        if constexpr (F16) *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w));
+        else *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+    if (i < n) for (size_t k = i; k < n && k < i + 4; ++k) {
+        if constexpr (F16) { __half h = __float2half_rn(sat_f16(src[k])); dst[k] = *reinterpret_cast<uint16_t*>(&h); }
+        else { __nv_bfloat16 h = __float2bfloat16(src[k]); dst[k] = *reinterpret_cast<uint16_t*>(&h); }
+    }
+}
+
+// fp16 -> bf16 (wgrad pairs bf16 gradients with a bf16 copy of the fp16 forward activations:
+// tcgen05 kind::f16 needs A and B in the same 16-bit format)
+__global__ void f16_to_bf16_kernel(const __half2* __restrict__ src, __nv_bfloat162* __restrict__ dst, size_t n2) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+        const float2 v = __half22float2(src[i]);
+        dst[i] = __floats2bfloat162_rn(v.x, v.y);
+    }
+}
+
+// hi = bf16(x), lo = bf16(x - hi): x ~= hi + lo to ~16 mantissa bits (split-bf16 GEMMs for weight folding)
+__global__ void split_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
+                                      __nv_bfloat16* __restrict__ lo, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float x = src[i];
+        const __nv_bfloat16 h = __float2bfloat16(x);
+        hi[i] = h;
+        lo[i] = __float2bfloat16(x - __bfloat162float(h));
+    }
+}
+
+// nnet_input [B,T,D] f32 (zero padded, batch-major)  ->  X0 [T,B,Dp] fp16 (time-major, Dp >= D, pad = 0)
+__global__ void pack_input_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, int T, int D, int Dp) {
+    const size_t total = (size_t)T * B * Dp;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int d = (int)(i % Dp);
+        const size_t tb = i / Dp;
+        const int b = (int)(tb % B), t = (int)(tb / B);
+        out[i] = (d < D) ? __float2half_rn(sat_f16(x[((size_t)b * T + t) * D + d])) : __float2half_rn(0.f);
+    }
+}
+
+// column sums of a row-major matrix: out[c] (+)= sum_r src[r, c]   (bias gradients)
+template <typename TIn>
+__global__ void colsum_kernel(const TIn* __restrict__ src, int rows, int cols, int ld, float* __restrict__ out, int accumulate) {
+    __shared__ float sm[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    float acc = 0.f;
+    const int r0 = blockIdx.y * 8 + threadIdx.y;
+    if (c < cols)
+        for (int r = r0; r < rows; r += gridDim.y * 8) {
+            if constexpr (sizeof(TIn) == 2) acc += __bfloat162float(src[(size_t)r * ld + c]);
+            else acc += src[(size_t)r * ld + c];
+        }
+    sm[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += sm[k][threadIdx.x];
+        atomicAdd(out + c, s);
+    }
+    (void)accumulate;
+}
+
+static inline int grid_for(size_t n, int per_thread, int threads) {
+    size_t b = (n + (size_t)per_thread * threads - 1) / ((size_t)per_thread * threads);
+    if (b < 1) b = 1;
+    if (b > 148 * 16) b = 148 * 16;
+    return (int)b;
+}
+
+}  // namespace lcb
+
+using namespace lcb;
+
+// dst_dtype 1: bf16, 2: fp16 (saturating)
+extern "C" int lcb_cast_f32_16(const float* src, void* dst, int dst_dtype, size_t n, void* stream) {
+    if (!src || !dst) return LCB_ERR_NULL_POINTER;
+    if (dst_dtype != 1 && dst_dtype != 2) return LCB_ERR_BAD_SHAPE;
+    if (((uintptr_t)src & 15) || ((uintptr_t)dst & 7)) return LCB_ERR_MISALIGNED;
+    if (n == 0) return LCB_OK;
+    if (dst_dtype == 2) cast_f32_16_kernel<true><<<grid_for(n, 4, 256), 256, 0, (cudaStream_t)stream>>>(src, (uint16_t*)dst, n);
+    else cast_f32_16_kernel<false><<<grid_for(n, 4, 256), 256, 0, (cudaStream_t)stream>>>(src, (uint16_t*)dst, n);
+    return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
+}
+
+extern "C" int lcb_f16_to_bf16(const void* src, void* dst, size_t n, void* stream) {
+    if (!src || !dst) return LCB_ERR_NULL_POINTER;
+    if ((n & 1) || ((uintptr_t)src & 3) || ((uintptr_t)dst & 3)) return LCB_ERR_MISALIGNED;
+    if (n == 0) return LCB_OK;
+    f16_to_bf16_kernel<<<grid_for(n / 2, 1, 256), 256, 0, (cudaStream_t)stream>>>((const __half2*)src, (__nv_bfloat162*)dst, n / 2);
+    return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
+}
+
+extern "C" int lcb_split_f32_bf16(const float* src, void* hi, void* lo, size_t n, void* stream) {
+    if (!src || !hi || !lo) return LCB_ERR_NULL_POINTER;
+    if (n == 0) return LCB_OK;
+    split_f32_bf16_kernel<<<grid_for(n, 1, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
+    return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
+}
+
+extern "C" int lcb_pack_input(const float* nnet_input, void* x0, int B, int T, int D, int Dp, void* stream) {
+    if (!nnet_input || !x0) return LCB_ERR_NULL_POINTER;
+    if (B <= 0 || T <= 0 || D <= 0 || Dp < D) return LCB_ERR_BAD_SHAPE;
+    pack_input_kernel<<<grid_for((size_t)T * B * Dp, 1, 256), 256, 0, (cudaStream_t)stream>>>(nnet_input, (__half*)x0, B, T, D, Dp);
+    return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
+}
+
+// out[c] += sum_r src[r,c];  src_dtype 0: f32, 1: bf16.  `out` must be initialised by the caller.
+extern "C" int lcb_colsum(const void* src, int src_dtype, int rows, int cols, int ld, float* out, void* stream) {
+    if (!src || !out) return LCB_ERR_NULL_POINTER;
+    if (rows <= 0 || cols <= 0 || ld < cols) return LCB_ERR_BAD_SHAPE;
+    dim3 blk(32, 8);
+    int gy = (rows + 511) / 512; if (gy > 256) gy = 256; if (gy < 1) gy = 1;
+    dim3 grd((cols + 31) / 32, gy);
+    if (src_dtype) colsum_kernel<__nv_bfloat16><<<grd, blk, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, rows, cols, ld, out, 1);
+    else colsum_kernel<float><<<grd, blk, 0, (cudaStream_t)stream>>>((const float*)src, rows, cols, ld, out, 1);
+    return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
+}

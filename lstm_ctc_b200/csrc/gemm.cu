@@ -13,6 +13,7 @@
 //   TMEM        : 2 accumulator stages x BN fp32 columns, so the epilogue of tile i overlaps the MMAs of tile i+1
 // Operand layouts: A and B can each be K-major or MN-major (canonical SWIZZLE_128B layouts), which
 // gives forward (X*W), dgrad (dG*W^T) and wgrad (X^T*dG) from row-major tensors without transposes.
+#include <cuda_fp16.h>
 #include "ptx.cuh"
 #include "tma_host.h"
 #include "lstm_ctc_b200.h"
@@ -35,11 +36,11 @@ template <int BN> struct GemmCfg {
     static constexpr int TMEM_COLS = 2 * BN;
 };
 
-template <int BN, bool A_MN, bool B_MN, bool C_BF16>
+template <int BN, bool A_MN, bool B_MN, int CT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          void* __restrict__ Cptr, int ldc, const float* __restrict__ bias, int accumulate,
-                         int M, int N, int K)
+                         int M, int N, int K, uint32_t idesc)
 {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
@@ -108,7 +109,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16_f32(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             bool ok = true;
@@ -167,8 +167,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     const int row = m0 + q * 32 + rr;
                     if (row < M && col < N) {
                         float v = st[rr * 33 + lane] + bv;
-                        if constexpr (C_BF16) {
+                        if constexpr (CT == 1) {
                             reinterpret_cast<__nv_bfloat16*>(Cptr)[(size_t)row * ldc + col] = __float2bfloat16(v);
+                        } else if constexpr (CT == 2) {
+                            reinterpret_cast<__half*>(Cptr)[(size_t)row * ldc + col] = __float2half_rn(v);
                         } else {
                             float* cp = reinterpret_cast<float*>(Cptr) + (size_t)row * ldc + col;
                             if (accumulate) v += *cp;
@@ -191,9 +193,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
 // ------------------------------------------------------------------------------------------
 // plain CUDA-core checker (tests only)
-__global__ void gemm_simt_check_kernel(int M, int N, int K, const __nv_bfloat16* A, long long a_sm, long long a_sk,
-                                       const __nv_bfloat16* B, long long b_sn, long long b_sk, void* C, int ldc,
-                                       int c_bf16, const float* bias, int accumulate)
+__device__ __forceinline__ float ld16(const void* p, long long i, int dt) {
+    return dt == 2 ? __half2float(reinterpret_cast<const __half*>(p)[i]) : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+__global__ void gemm_simt_check_kernel(int M, int N, int K, const void* A, int a_dt, long long a_sm, long long a_sk,
+                                       const void* B, int b_dt, long long b_sn, long long b_sk, void* C, int ldc,
+                                       int c_dt, const float* bias, int accumulate)
 {
     __shared__ float As[16][17], Bs[16][17];
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -201,9 +206,9 @@ __global__ void gemm_simt_check_kernel(int M, int N, int K, const __nv_bfloat16*
     float acc = 0.f;
     for (int k0 = 0; k0 < K; k0 += 16) {
         int ka = k0 + tx, kb = k0 + ty;
-        As[ty][tx] = (row < M && ka < K) ? __bfloat162float(A[(long long)row * a_sm + (long long)ka * a_sk]) : 0.f;
+        As[ty][tx] = (row < M && ka < K) ? ld16(A, (long long)row * a_sm + (long long)ka * a_sk, a_dt) : 0.f;
         int bcol = blockIdx.x * 16 + tx;
-        Bs[ty][tx] = (bcol < N && kb < K) ? __bfloat162float(B[(long long)bcol * b_sn + (long long)kb * b_sk]) : 0.f;
+        Bs[ty][tx] = (bcol < N && kb < K) ? ld16(B, (long long)bcol * b_sn + (long long)kb * b_sk, b_dt) : 0.f;
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 16; ++k) acc += As[ty][k] * Bs[k][tx];
@@ -211,7 +216,8 @@ __global__ void gemm_simt_check_kernel(int M, int N, int K, const __nv_bfloat16*
     }
     if (row < M && col < N) {
         if (bias) acc += bias[col];
-        if (c_bf16) reinterpret_cast<__nv_bfloat16*>(C)[(size_t)row * ldc + col] = __float2bfloat16(acc);
+        if (c_dt == 1) reinterpret_cast<__nv_bfloat16*>(C)[(size_t)row * ldc + col] = __float2bfloat16(acc);
+        else if (c_dt == 2) reinterpret_cast<__half*>(C)[(size_t)row * ldc + col] = __float2half_rn(acc);
         else {
             float* cp = reinterpret_cast<float*>(C) + (size_t)row * ldc + col;
             *cp = accumulate ? *cp + acc : acc;
@@ -219,12 +225,13 @@ __global__ void gemm_simt_check_kernel(int M, int N, int K, const __nv_bfloat16*
     }
 }
 
-template <int BN, bool A_MN, bool B_MN, bool C_BF16>
+template <int BN, bool A_MN, bool B_MN, int CT>
 static int launch_gemm(int M, int N, int K, const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc,
-                       const float* bias, int accumulate, cudaStream_t st)
+                       const float* bias, int accumulate, uint32_t fmt_bits, cudaStream_t st)
 {
     using Cfg = GemmCfg<BN>;
-    auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN, C_BF16>;
+    auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN, CT>;
+    const uint32_t idesc = (make_idesc_bf16_f32(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0) & ~((7u << 7) | (7u << 10))) | fmt_bits;
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) return LCB_ERR_CUDA;
@@ -233,39 +240,50 @@ static int launch_gemm(int M, int N, int K, const CUtensorMap& ta, const CUtenso
     const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
     int nsm = 148;
     int grid = tiles < nsm ? tiles : nsm;
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, C, ldc, bias, accumulate, M, N, K);
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, C, ldc, bias, accumulate, M, N, K, idesc);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }
 
-template <int BN, bool C_BF16>
+template <int BN, int CT>
 static int dispatch_layout(int a_layout, int b_layout, int M, int N, int K, const CUtensorMap& ta, const CUtensorMap& tb,
-                           void* C, int ldc, const float* bias, int accumulate, cudaStream_t st)
+                           void* C, int ldc, const float* bias, int accumulate, uint32_t fmt, cudaStream_t st)
 {
-    if (!a_layout && !b_layout) return launch_gemm<BN, false, false, C_BF16>(M, N, K, ta, tb, C, ldc, bias, accumulate, st);
-    if (!a_layout && b_layout) return launch_gemm<BN, false, true, C_BF16>(M, N, K, ta, tb, C, ldc, bias, accumulate, st);
-    if (a_layout && !b_layout) return launch_gemm<BN, true, false, C_BF16>(M, N, K, ta, tb, C, ldc, bias, accumulate, st);
-    return launch_gemm<BN, true, true, C_BF16>(M, N, K, ta, tb, C, ldc, bias, accumulate, st);
+    if (!a_layout && !b_layout) return launch_gemm<BN, false, false, CT>(M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st);
+    if (!a_layout && b_layout) return launch_gemm<BN, false, true, CT>(M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st);
+    if (a_layout && !b_layout) return launch_gemm<BN, true, false, CT>(M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st);
+    return launch_gemm<BN, true, true, CT>(M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st);
+}
+template <int BN>
+static int dispatch_ct(int c_dtype, int a_layout, int b_layout, int M, int N, int K, const CUtensorMap& ta, const CUtensorMap& tb,
+                       void* C, int ldc, const float* bias, int accumulate, uint32_t fmt, cudaStream_t st)
+{
+    if (c_dtype == 0) return dispatch_layout<BN, 0>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st);
+    if (c_dtype == 1) return dispatch_layout<BN, 1>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st);
+    return dispatch_layout<BN, 2>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st);
 }
 
 }  // namespace lcb
 
 using namespace lcb;
 
-static int gemm_check_args(int M, int N, int K, const void* A, int lda, int a_layout, const void* B, int ldb,
-                           int b_layout, void* C, int ldc, int c_dtype, int accumulate)
+static int gemm_check_args(int M, int N, int K, const void* A, int lda, int a_layout, int a_dtype, const void* B, int ldb,
+                           int b_layout, int b_dtype, void* C, int ldc, int c_dtype, int accumulate)
 {
     if (!A || !B || !C) return LCB_ERR_NULL_POINTER;
     if (M <= 0 || N <= 0 || K <= 0) return LCB_ERR_BAD_SHAPE;
-    if ((a_layout | b_layout | c_dtype) & ~1) return LCB_ERR_BAD_SHAPE;
+    if ((a_layout | b_layout) & ~1) return LCB_ERR_BAD_SHAPE;
+    if (a_dtype < 1 || a_dtype > 2 || b_dtype < 1 || b_dtype > 2 || c_dtype < 0 || c_dtype > 2) return LCB_ERR_BAD_SHAPE;
     if (lda < (a_layout ? M : K) || ldb < (b_layout ? N : K) || ldc < N) return LCB_ERR_BAD_SHAPE;
     if (accumulate && c_dtype != 0) return LCB_ERR_UNSUPPORTED;
+    if (a_dtype != b_dtype) return LCB_ERR_UNSUPPORTED;      // tcgen05 kind::f16: mixed f16 x bf16 is an illegal instruction
     return LCB_OK;
 }
 
-extern "C" int lcb_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_layout, const void* B, int ldb,
-                             int b_layout, void* C, int ldc, int c_dtype, const float* bias, int accumulate, void* stream)
+extern "C" int lcb_gemm16(int M, int N, int K, const void* A, int lda, int a_layout, int a_dtype,
+                          const void* B, int ldb, int b_layout, int b_dtype,
+                          void* C, int ldc, int c_dtype, const float* bias, int accumulate, void* stream)
 {
-    int rc = gemm_check_args(M, N, K, A, lda, a_layout, B, ldb, b_layout, C, ldc, c_dtype, accumulate);
+    int rc = gemm_check_args(M, N, K, A, lda, a_layout, a_dtype, B, ldb, b_layout, b_dtype, C, ldc, c_dtype, accumulate);
     if (rc != LCB_OK) return rc;
     if ((lda & 7) || (ldb & 7) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) return LCB_ERR_MISALIGNED;
     cudaStream_t st = (cudaStream_t)stream;
@@ -281,26 +299,37 @@ extern "C" int lcb_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_
     if (!b_layout) ok = make_tmap_2d_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)BN, GEMM_BK);
     else ok = make_tmap_2d_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, GEMM_BK, 64);
     if (!ok) return LCB_ERR_CUDA;
-    if (bn256) {
-        return c_dtype ? dispatch_layout<256, true>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, st)
-                       : dispatch_layout<256, false>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, st);
-    }
-    return c_dtype ? dispatch_layout<128, true>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, st)
-                   : dispatch_layout<128, false>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, st);
+    // instruction-descriptor operand formats: 0 = F16, 1 = BF16 (a: bits 7-9, b: bits 10-12)
+    const uint32_t fmt = ((a_dtype == 1 ? 1u : 0u) << 7) | ((b_dtype == 1 ? 1u : 0u) << 10);
+    if (bn256) return dispatch_ct<256>(c_dtype, a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st);
+    return dispatch_ct<128>(c_dtype, a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st);
+}
+
+extern "C" int lcb_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_layout, const void* B, int ldb,
+                             int b_layout, void* C, int ldc, int c_dtype, const float* bias, int accumulate, void* stream)
+{
+    return lcb_gemm16(M, N, K, A, lda, a_layout, 1, B, ldb, b_layout, 1, C, ldc, c_dtype, bias, accumulate, stream);
+}
+
+extern "C" int lcb_gemm16_simt_check(int M, int N, int K, const void* A, int lda, int a_layout, int a_dtype,
+                                     const void* B, int ldb, int b_layout, int b_dtype,
+                                     void* C, int ldc, int c_dtype, const float* bias, int accumulate, void* stream)
+{
+    int rc = gemm_check_args(M, N, K, A, lda, a_layout, a_dtype, B, ldb, b_layout, b_dtype, C, ldc, c_dtype, accumulate);
+    if (rc != LCB_OK) return rc;
+    dim3 blk(16, 16), grd((N + 15) / 16, (M + 15) / 16);
+    long long a_sm = a_layout ? 1 : lda, a_sk = a_layout ? lda : 1;
+    long long b_sn = b_layout ? 1 : ldb, b_sk = b_layout ? ldb : 1;
+    gemm_simt_check_kernel<<<grd, blk, 0, (cudaStream_t)stream>>>(M, N, K, A, a_dtype, a_sm, a_sk, B, b_dtype, b_sn, b_sk,
+                                                                  C, ldc, c_dtype, bias, accumulate);
+    return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }
 
 extern "C" int lcb_gemm_bf16_simt_check(int M, int N, int K, const void* A, int lda, int a_layout, const void* B, int ldb,
                                         int b_layout, void* C, int ldc, int c_dtype, const float* bias, int accumulate,
                                         void* stream)
 {
-    int rc = gemm_check_args(M, N, K, A, lda, a_layout, B, ldb, b_layout, C, ldc, c_dtype, accumulate);
-    if (rc != LCB_OK) return rc;
-    dim3 blk(16, 16), grd((N + 15) / 16, (M + 15) / 16);
-    long long a_sm = a_layout ? 1 : lda, a_sk = a_layout ? lda : 1;
-    long long b_sn = b_layout ? 1 : ldb, b_sk = b_layout ? ldb : 1;
-    gemm_simt_check_kernel<<<grd, blk, 0, (cudaStream_t)stream>>>(M, N, K, (const __nv_bfloat16*)A, a_sm, a_sk,
-                                                                  (const __nv_bfloat16*)B, b_sn, b_sk, C, ldc, c_dtype, bias, accumulate);
-    return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
+    return lcb_gemm16_simt_check(M, N, K, A, lda, a_layout, 1, B, ldb, b_layout, 1, C, ldc, c_dtype, bias, accumulate, stream);
 }
 
 extern "C" int lcb_version(void) { return 100; }

@@ -2,3 +2,5 @@
 // word and the inline-PTX helpers are shared without relocatable device code).
 #include "gemm.cu"
 #include "ctc.cu"
+#include "lstm_rec.cu"
+#include "elementwise.cu"

@@ -1,0 +1,611 @@
+// lstm_rec.cu -- persistent thread-block-cluster kernels for the LSTM recurrence (K2) and its BPTT (K2b).
+//
+// Replaces tf.nn.dynamic_rnn over DropoutWrapper(LSTMCell(num_units=H, num_proj=P, use_peepholes,
+// forget_bias=5.0)) for BOTH directions of one BiLSTM layer (nnet/bilstm.py:127-137,148-158,171-188),
+// the three tf.reverse_sequence copies per layer (bilstm.py:112,190,203) and the autodiff'd while-loop
+// that tf.gradients builds for it (nnet/graph.py:190-191).
+//
+// Formulation.  TF's cell is z = [x_t, h_{t-1}] * kernel + bias, h = m * W_proj.  The x-part is hoisted
+// into one GEMM over all frames (G = X * W_x + bias, gemm.cu); the recurrent part is folded,
+//     h_{t-1} * W_h = m_{t-1} * (W_proj * W_h) = m_{t-1} * W',        W' : [H, 4H]
+// so that one time step costs ONE on-chip exchange (of m_t) instead of two; h = M * W_proj is again a
+// bulk GEMM after the loop.  Gate columns are packed unit-major: col = 4*unit + gate, gates (i,j,f,o).
+//
+// Mapping.  One cluster of NC CTAs per (direction, group of BG=16 utterances); both directions and all
+// utterance groups run concurrently in one launch.  CTA c keeps the rows of W'^T for its 32*MT units
+// (128*MT gate rows x H, bf16, 128B-swizzled K-major) resident in shared memory for the whole
+// sequence.  Per step: one elected thread issues tcgen05.mma  D[128 gate rows, 16 utts] = W'^T_slice *
+// m_{t-1}^T  into TMEM (weights are the M operand, the tiny batch is N); 4*MT warps read TMEM, add the
+// TMA-prefetched G tile, apply gates / peepholes / cell update / length mask in registers (the cell
+// state never leaves registers), write m_t + saved activations to HBM, and scatter m_t (bf16) into the
+// operand buffer of every CTA of the cluster through DSMEM; one barrier.cluster per step.
+// The backward direction is the same scan in descending absolute time under the mask t < len[b]
+// (state stays at its zero initial value until t = len[b]-1), so no reversed copies are ever made.
+//
+// BPTT runs the mirrored scan: dz_t is formed in registers, staged locally as the MMA B operand,
+// partial dm_{t-1} = W'_slice * dz_t^T (same smem weights read through an MN-major descriptor) is
+// reduce-scattered across the cluster through DSMEM (double-buffered), one barrier.cluster per step.
+#include <cuda_fp16.h>
+#include "ptx.cuh"
+#include "tma_host.h"
+#include "lstm_ctc_b200.h"
+
+namespace lcb {
+
+constexpr int REC_GROW = 136;     // padded fp32 row of a staged G tile (bank-conflict-free transposed reads)
+
+struct RecFwdParams {
+    const float* G;               // [T*B][8Hp] fp32  x_t * W_x + bias, packed gate columns
+    const float* peep;            // [2][3][Hp]  (w_f, w_i, w_o) or nullptr
+    const int* lens;              // [B]
+    __half* Mout;                 // [T*B][2Hp]   m_t, fp16 (0 where t >= len)
+    float* acts;                  // [6][T*B][2Hp] ig, jt, fg, og, c, tanh(c)   (nullptr: inference)
+    float* cfin;                  // [B][2][Hp] final cell state   (nullable)
+    float* mfin;                  // [B][2][Hp] final m (pre-projection output) (nullable)
+    int T, B, Hp, NC;
+    float forget_bias;
+};
+
+struct RecBwdParams {
+    const float* dM;              // [T*B][2Hp]  d loss / d m_t from the output projection
+    const float* acts;            // [6][T*B][2Hp]
+    const float* peep;            // [2][3][Hp] or nullptr
+    const int* lens;              // [B]
+    __nv_bfloat16* dG;            // [T*B][8Hp]  d loss / d z_t  (0 where t >= len)
+    float* dbias;                 // [2][4Hp]   += (packed column order)
+    float* dpeep;                 // [2][3][Hp] += (nullable)
+    int T, B, Hp, NC;
+};
+
+__device__ __forceinline__ unsigned char* align_1024(unsigned char* p) {
+    return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+}
+
+template <int MT> struct RecFwdCfg {
+    static constexpr int NCW = 4 * MT;
+    static constexpr int SG = (MT == 1) ? 4 : 2;
+    static constexpr int THREADS = 32 * (NCW + 1);
+    static size_t smem_bytes(int KB, int BG) {
+        return 1024 + (size_t)MT * KB * 16384 + (size_t)2 * KB * BG * 128 + (size_t)SG * MT * BG * REC_GROW * 4 +
+               (size_t)NCW * BG * 16 + 256;
+    }
+};
+
+// =================================================================================================
+// forward
+// =================================================================================================
+template <int MT, int BG>
+__global__ void __launch_bounds__(32 * (4 * MT + 1), 1)
+lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const RecFwdParams p)
+{
+    static_assert(BG == 16, "batch group of 16 utterances");
+    using Cfg = RecFwdCfg<MT>;
+    constexpr int NCW = Cfg::NCW;
+    constexpr int SG = Cfg::SG;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = align_1024(smem_raw);
+    const int Hp = p.Hp, KB = Hp >> 6, NC = p.NC, T = p.T, B = p.B;
+    unsigned char* Wsm = smem;
+    unsigned char* Bsm = Wsm + (size_t)MT * KB * 16384;
+    float* Gsm = reinterpret_cast<float*>(Bsm + (size_t)2 * KB * BG * 128);
+    unsigned char* Msm = reinterpret_cast<unsigned char*>(Gsm + (size_t)SG * MT * BG * REC_GROW);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Msm + NCW * BG * 16);
+    uint64_t* mbar_w = bars;
+    uint64_t* mbar_mma = bars + 1;
+    uint64_t* mbar_g = bars + 2;                       // [SG]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + SG);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta = cluster_ctarank();
+    const int cid = (int)cluster_id_x();
+    const int dir = cid & 1, bg = cid >> 1;
+    const int b0 = bg * BG;
+    const size_t ld2 = (size_t)2 * Hp;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmW);
+        mbar_init(mbar_w, 1);
+        mbar_init(mbar_mma, 1);
+        for (int s = 0; s < SG; ++s) mbar_init(&mbar_g[s], 1);
+        fence_mbar_init();
+    }
+    if (warp == NCW) tmem_alloc<32>(tmem_slot);
+    {   // zero both operand buffers (m_{-1} = 0)
+        uint4* bz = reinterpret_cast<uint4*>(Bsm);
+        const int n16 = 2 * KB * BG * 128 / 16;
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) bz[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async_all();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int nvalid = (B - b0) < BG ? (B - b0) : BG;          // utterances of this group that exist
+    auto issue_g = [&](int s) {      // control lane 0 only: one 512-byte bulk copy per (M tile, utterance)
+        const int t = dir ? (T - 1 - s) : s;
+        const int stage = s % SG;
+        mbar_arrive_expect_tx(&mbar_g[stage], (uint32_t)(MT * nvalid * 512));
+        for (int mt = 0; mt < MT; ++mt)
+            for (int b = 0; b < nvalid; ++b)
+                bulk_load_1d(Gsm + ((size_t)(stage * MT + mt) * BG + b) * REC_GROW,
+                             p.G + ((size_t)t * B + b0 + b) * 8 * Hp + (size_t)dir * 4 * Hp + ((int)cta * MT + mt) * 128,
+                             512, &mbar_g[stage]);
+    };
+
+    if (warp == NCW && lane == 0) {
+        mbar_arrive_expect_tx(mbar_w, (uint32_t)(MT * KB * 16384));
+        for (int mt = 0; mt < MT; ++mt)
+            for (int kb = 0; kb < KB; ++kb)
+                tma_load_2d(Wsm + (size_t)(mt * KB + kb) * 16384, &tmW, mbar_w, kb * 64,
+                            dir * 4 * Hp + ((int)cta * MT + mt) * 128);
+        for (int s = 0; s < SG && s < T; ++s) issue_g(s);
+    }
+    cluster_sync_all();          // every CTA of the cluster is resident and initialised
+
+    bool ok = true;
+    if (warp == NCW) {
+        // ============================ control warp: MMA issue + G prefetch ============================
+        // forward operands are fp16 (|m| < 1, small weights): a_format = b_format = F16 (0)
+        constexpr uint32_t idesc = make_idesc_bf16_f32(128, BG, 0, 0) & ~((7u << 7) | (7u << 10));
+        const uint32_t w_addr = smem_u32(Wsm), b_addr = smem_u32(Bsm);
+        for (int s = 0; s < T; ++s) {
+            if (lane == 0 && ok) {
+                if (s == 0) ok = mbar_wait(mbar_w, 0);
+                tc_fence_after();
+                const uint32_t bbuf = b_addr + (uint32_t)((s & 1) * KB * BG * 128);
+                for (int mt = 0; mt < MT; ++mt)
+                    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ad = make_smem_desc_sw128(w_addr + (uint32_t)((mt * KB + kb) * 16384 + k * 32), 16, 1024);
+                            const uint64_t bd = make_smem_desc_sw128(bbuf + (uint32_t)(kb * BG * 128 + k * 32), 16, 1024);
+                            umma_f16_ss(tmem_base + mt * BG, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                        }
+                umma_commit(mbar_mma);
+            }
+            __syncwarp();
+            cluster_arrive_release();
+            cluster_wait_acquire();
+            if (lane == 0 && s + SG < T) issue_g(s + SG);      // stage s%SG is free again
+        }
+    } else {
+        // ============================ compute warps ============================
+        const int q = warp & 3, mt = warp >> 2;
+        const int up = lane >> 2, g = lane & 3;
+        const int unit0 = ((int)cta * MT + mt) * 32 + q * 8;   // first of the 8 units of this warp
+        const int unit = unit0 + up;
+        float wf = 0.f, wi = 0.f, wo = 0.f;
+        if (p.peep) {
+            wf = p.peep[(size_t)(dir * 3 + 0) * Hp + unit];
+            wi = p.peep[(size_t)(dir * 3 + 1) * Hp + unit];
+            wo = p.peep[(size_t)(dir * 3 + 2) * Hp + unit];
+        }
+        int len_j[4];
+        float c_reg[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int b = b0 + g + 4 * j;
+            len_j[j] = (b < B) ? p.lens[b] : 0;
+            c_reg[j] = 0.f;
+        }
+        const size_t plane = (size_t)T * B * ld2;
+        unsigned char* mst = Msm + warp * (BG * 16);
+        // DSMEM chunk address pieces (warp-uniform): 8 units = one 16-byte chunk of the K-major operand
+        const int kbw = unit0 >> 6, c16 = (unit0 & 63) >> 3;
+        const int brow = lane & 15, bhalf = lane >> 4;
+        const uint32_t chunk_off = (uint32_t)(kbw * (BG * 128) + (brow >> 3) * 1024 + (brow & 7) * 128 + ((c16 ^ (brow & 7)) << 4));
+        const uint32_t b_addr = smem_u32(Bsm);
+
+        for (int s = 0; s < T; ++s) {
+            const int t = dir ? (T - 1 - s) : s;
+            const int stage = s % SG;
+            if (ok) ok = mbar_wait(&mbar_g[stage], (uint32_t)((s / SG) & 1));
+            if (ok) ok = mbar_wait(mbar_mma, (uint32_t)(s & 1));
+            tc_fence_after();
+            uint32_t acc[16];
+            tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + mt * BG, acc);
+            tmem_ld_wait();
+            float* gt = Gsm + (size_t)(stage * MT + mt) * BG * REC_GROW;
+#pragma unroll
+            for (int b = 0; b < BG; ++b) gt[b * REC_GROW + q * 32 + lane] += __uint_as_float(acc[b]);   // z = G + m W'
+            __syncwarp();
+            uint16_t mb16[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int bl = g + 4 * j;
+                const int b = b0 + bl;
+                float4 z4 = *reinterpret_cast<const float4*>(&gt[bl * REC_GROW + q * 32 + 4 * up]);   // (i, j, f, o)
+                if (b >= B) z4 = make_float4(0.f, 0.f, 0.f, 0.f);                                   // padding utterance
+                const float cp = c_reg[j];
+                const float ig = sigmoidf_fast(z4.x + wi * cp);
+                const float fg = sigmoidf_fast(z4.z + p.forget_bias + wf * cp);
+                const float jt = tanhf_fast(z4.y);
+                const float cn = fg * cp + ig * jt;
+                const float og = sigmoidf_fast(z4.w + wo * cn);
+                const float tc = tanhf_fast(cn);
+                const float mn = og * tc;
+                const bool live = t < len_j[j];
+                if (live) c_reg[j] = cn;
+                const float mo = live ? mn : 0.f;
+                const __half mbf = __float2half_rn(mo);
+                mb16[j] = *reinterpret_cast<const uint16_t*>(&mbf);
+                if (b < B) {
+                    const size_t idx = ((size_t)t * B + b) * ld2 + (size_t)dir * Hp + unit;
+                    p.Mout[idx] = mbf;
+                    if (p.acts) {
+                        p.acts[idx] = ig;
+                        p.acts[plane + idx] = jt;
+                        p.acts[2 * plane + idx] = fg;
+                        p.acts[3 * plane + idx] = og;
+                        p.acts[4 * plane + idx] = cn;
+                        p.acts[5 * plane + idx] = tc;
+                    }
+                    // final state = state at the last live step in this direction's own order
+                    const bool last = dir ? (t == 0 && live) : (t == len_j[j] - 1);
+                    if (last && p.cfin) {
+                        p.cfin[((size_t)b * 2 + dir) * Hp + unit] = cn;
+                        p.mfin[((size_t)b * 2 + dir) * Hp + unit] = mn;
+                    }
+                }
+            }
+            if (s + 1 < T) {
+                // stage the warp's [16 utts][8 units] bf16 block, then 16-byte DSMEM stores to every CTA
+                uint16_t* ms16 = reinterpret_cast<uint16_t*>(mst);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ms16[(g + 4 * j) * 8 + up] = mb16[j];
+                __syncwarp();
+                const uint4 chunk = *reinterpret_cast<const uint4*>(mst + brow * 16);
+                const uint32_t dst_local = b_addr + (uint32_t)(((s + 1) & 1) * KB * BG * 128) + chunk_off;
+                for (int dst = bhalf; dst < NC; dst += 2)
+                    st_cluster_v4(mapa_shared(dst_local, (uint32_t)dst), chunk.x, chunk.y, chunk.z, chunk.w);
+                fence_proxy_async_all();
+            }
+            tc_fence_before();
+            cluster_arrive_release();
+            cluster_wait_acquire();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == NCW) { tc_fence_after(); tmem_dealloc<32>(tmem_base); }
+}
+
+// =================================================================================================
+// backward (BPTT)
+// =================================================================================================
+template <int MT> struct RecBwdCfg {
+    static constexpr int NCW = 4 * MT;
+    static constexpr int THREADS = 32 * (NCW + 1);
+    static size_t smem_bytes(int KB, int BG, int NC) {
+        return 1024 + (size_t)MT * KB * 16384 + 16384 /* slack read by the partial last M tile */ +
+               (size_t)2 * MT * BG * 128 + (size_t)2 * NC * 32 * MT * BG * 4 + 256;
+    }
+};
+
+template <int MT, int BG>
+__global__ void __launch_bounds__(32 * (4 * MT + 1), 1)
+lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const RecBwdParams p)
+{
+    static_assert(BG == 16, "batch group of 16 utterances");
+    using Cfg = RecBwdCfg<MT>;
+    constexpr int NCW = Cfg::NCW;
+    constexpr int UC = 32 * MT;                        // units per CTA
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = align_1024(smem_raw);
+    const int Hp = p.Hp, KB = Hp >> 6, NC = p.NC, T = p.T, B = p.B;
+    const int MB = (Hp + 127) >> 7;                    // M tiles of 128 units
+    unsigned char* Wsm = smem;
+    unsigned char* Bp = Wsm + (size_t)MT * KB * 16384 + 16384;
+    float* red = reinterpret_cast<float*>(Bp + (size_t)2 * MT * BG * 128);       // [2][NC][UC][BG]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + (size_t)2 * NC * UC * BG);
+    uint64_t* mbar_w = bars;
+    uint64_t* mbar_mma = bars + 1;
+    uint64_t* mbar_dz = bars + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta = cluster_ctarank();
+    const int cid = (int)cluster_id_x();
+    const int dir = cid & 1, bg = cid >> 1;
+    const int b0 = bg * BG;
+    const size_t ld2 = (size_t)2 * Hp, ld8 = (size_t)8 * Hp;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmW);
+        mbar_init(mbar_w, 1);
+        mbar_init(mbar_mma, 1);
+        mbar_init(mbar_dz, NCW * 32);
+        fence_mbar_init();
+    }
+    if (warp == NCW) tmem_alloc<64>(tmem_slot);
+    {   // the slack region behind the weights is read (and ignored) by the partial last M tile: keep it finite
+        uint4* z = reinterpret_cast<uint4*>(Wsm + (size_t)MT * KB * 16384);
+        for (int i = threadIdx.x; i < 16384 / 16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async_all();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == NCW && lane == 0) {
+        mbar_arrive_expect_tx(mbar_w, (uint32_t)(MT * KB * 16384));
+        for (int mt = 0; mt < MT; ++mt)
+            for (int kb = 0; kb < KB; ++kb)
+                tma_load_2d(Wsm + (size_t)(mt * KB + kb) * 16384, &tmW, mbar_w, kb * 64,
+                            dir * 4 * Hp + ((int)cta * MT + mt) * 128);
+    }
+    cluster_sync_all();
+
+    bool ok = true;
+    if (warp == NCW) {
+        // ============================ control warp ============================
+        constexpr uint32_t idesc = make_idesc_bf16_f32(128, BG, 1 /*A MN-major*/, 0);
+        const uint32_t w_addr = smem_u32(Wsm), bp_addr = smem_u32(Bp);
+        for (int s = 0; s < T; ++s) {
+            if (lane == 0 && ok) {
+                if (s == 0) ok = mbar_wait(mbar_w, 0);
+                if (ok) ok = mbar_wait(mbar_dz, (uint32_t)(s & 1));
+                tc_fence_after();
+                if (s + 1 < T) {                      // the last step's dm_{-1} is never used
+                    for (int jt = 0; jt < MB; ++jt)
+                        for (int kk = 0; kk < 8 * MT; ++kk) {
+                            const int mtp = kk >> 3, r0 = (kk & 7) * 16;
+                            // A' = W'_slice viewed [units (M, contiguous), gate rows (K)]: MN-major, 64-unit blocks 16 KB apart
+                            const uint64_t ad = make_smem_desc_sw128(w_addr + (uint32_t)((mtp * KB + 2 * jt) * 16384 + r0 * 128), 16384, 1024);
+                            const uint64_t bd = make_smem_desc_sw128(bp_addr + (uint32_t)((kk >> 2) * (BG * 128) + (kk & 3) * 32), 16, 1024);
+                            umma_f16_ss(tmem_base + jt * BG, ad, bd, idesc, kk ? 1u : 0u);
+                        }
+                }
+                umma_commit(mbar_mma);
+            }
+            __syncwarp();
+            cluster_arrive_release();
+            cluster_wait_acquire();
+        }
+    } else {
+        // ============================ compute warps ============================
+        const int q = warp & 3, mt = warp >> 2;
+        const int up = lane >> 2, g = lane & 3;
+        const int ul = mt * 32 + q * 8 + up;               // local unit
+        const int unit = (int)cta * UC + ul;
+        float wf = 0.f, wi = 0.f, wo = 0.f;
+        if (p.peep) {
+            wf = p.peep[(size_t)(dir * 3 + 0) * Hp + unit];
+            wi = p.peep[(size_t)(dir * 3 + 1) * Hp + unit];
+            wo = p.peep[(size_t)(dir * 3 + 2) * Hp + unit];
+        }
+        int len_j[4];
+        float dcc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int b = b0 + 4 * g + j;
+            len_j[j] = (b < B) ? p.lens[b] : 0;
+            dcc[j] = 0.f;
+        }
+        float db[4] = {0.f, 0.f, 0.f, 0.f};
+        float dpf = 0.f, dpi = 0.f, dpo = 0.f;
+        const size_t plane = (size_t)T * B * ld2;
+
+        struct Pre { float ig[4], jt[4], fg[4], og[4], c[4], tc[4], cp[4], dmo[4]; };
+        auto load_pre = [&](int s, Pre& r) {
+            const int t = dir ? s : (T - 1 - s);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int b = b0 + 4 * g + j;
+                const bool live = (s < T) && (t < len_j[j]);
+                if (live) {
+                    const size_t idx = ((size_t)t * B + b) * ld2 + (size_t)dir * Hp + unit;
+                    r.ig[j] = __ldg(p.acts + idx);
+                    r.jt[j] = __ldg(p.acts + plane + idx);
+                    r.fg[j] = __ldg(p.acts + 2 * plane + idx);
+                    r.og[j] = __ldg(p.acts + 3 * plane + idx);
+                    r.c[j] = __ldg(p.acts + 4 * plane + idx);
+                    r.tc[j] = __ldg(p.acts + 5 * plane + idx);
+                    r.dmo[j] = __ldg(p.dM + idx);
+                    // previous step in the direction's own order: fwd t-1, bwd t+1 (zero initial state)
+                    const int tp = dir ? (t + 1) : (t - 1);
+                    const bool has_prev = dir ? (tp < len_j[j]) : (tp >= 0);
+                    r.cp[j] = has_prev ? __ldg(p.acts + 4 * plane + ((size_t)tp * B + b) * ld2 + (size_t)dir * Hp + unit) : 0.f;
+                } else {
+                    r.ig[j] = r.jt[j] = r.fg[j] = r.og[j] = r.c[j] = r.tc[j] = r.cp[j] = r.dmo[j] = 0.f;
+                }
+            }
+        };
+        Pre cur, nxt;
+        load_pre(0, cur);
+        const uint32_t red_addr = smem_u32(red);
+
+        for (int s = 0; s < T; ++s) {
+            const int t = dir ? s : (T - 1 - s);
+            load_pre(s + 1, nxt);                                  // latency hidden behind this step
+            // ---- phase A: dm_rec from the reduce buffer of the previous step, then dz_t ----
+            float dmr[4] = {0.f, 0.f, 0.f, 0.f};
+            if (s > 0) {
+                const float* rb = red + (size_t)((s - 1) & 1) * NC * UC * BG + (size_t)ul * BG + 4 * g;
+                for (int src = 0; src < NC; ++src) {
+                    const float4 v = *reinterpret_cast<const float4*>(rb + (size_t)src * UC * BG);
+                    dmr[0] += v.x; dmr[1] += v.y; dmr[2] += v.z; dmr[3] += v.w;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int bl = 4 * g + j;
+                const int b = b0 + bl;
+                const bool live = t < len_j[j];
+                float dzi = 0.f, dzj = 0.f, dzf = 0.f, dzo = 0.f;
+                if (live) {
+                    const float ig = cur.ig[j], jt = cur.jt[j], fg = cur.fg[j], og = cur.og[j], tc = cur.tc[j], cp = cur.cp[j];
+                    const float dm = cur.dmo[j] + dmr[j];
+                    dzo = dm * tc * og * (1.f - og);
+                    const float dc = dcc[j] + dm * og * (1.f - tc * tc) + dzo * wo;
+                    dzf = dc * cp * fg * (1.f - fg);
+                    dzi = dc * jt * ig * (1.f - ig);
+                    dzj = dc * ig * (1.f - jt * jt);
+                    dcc[j] = dc * fg + dzi * wi + dzf * wf;
+                    dpi += dzi * cp; dpf += dzf * cp; dpo += dzo * cur.c[j];
+                    db[0] += dzi; db[1] += dzj; db[2] += dzf; db[3] += dzo;
+                } else {
+                    dcc[j] = 0.f;
+                }
+                const uint32_t lo = pack_bf16x2(dzi, dzj), hi = pack_bf16x2(dzf, dzo);
+                if (b < B) *reinterpret_cast<uint2*>(p.dG + ((size_t)t * B + b) * ld8 + (size_t)dir * 4 * Hp + 4 * unit) = make_uint2(lo, hi);
+                // local MMA B operand  dz_t [16 utts][128*MT gate rows], K-major 128B swizzle
+                const int kp = 4 * ul;
+                const uint32_t off = (uint32_t)((kp >> 6) * (BG * 128) + (bl >> 3) * 1024 + (bl & 7) * 128 +
+                                                ((((kp & 63) >> 3) ^ (bl & 7)) << 4) + ((kp & 7) >> 2) * 8);
+                *reinterpret_cast<uint2*>(Bp + off) = make_uint2(lo, hi);
+            }
+            fence_proxy_async_all();
+            mbar_arrive(mbar_dz);
+            // ---- phase B: partial dm_{t-1} tiles -> owners' reduce buffers (DSMEM) ----
+            if (ok) ok = mbar_wait(mbar_mma, (uint32_t)(s & 1));
+            tc_fence_after();
+            if (s + 1 < T) {
+                for (int jt = mt; jt < MB; jt += MT) {
+                    uint32_t acc[16];
+                    tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + jt * BG, acc);
+                    tmem_ld_wait();
+                    const int uu = jt * 128 + q * 32 + lane;          // unit this TMEM row belongs to
+                    if (uu < Hp) {
+                        const int owner = uu / UC, ulo = uu % UC;
+                        const uint32_t dst = mapa_shared(red_addr + (uint32_t)((((s & 1) * NC + (int)cta) * UC + ulo) * BG * 4), (uint32_t)owner);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) st_cluster_v4(dst + v * 16, acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            cluster_arrive_release();
+            cluster_wait_acquire();
+            cur = nxt;
+        }
+        // ---- parameter gradients held in registers: reduce the 4 lanes of a unit, then atomics ----
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) db[k] += __shfl_xor_sync(0xffffffffu, db[k], o);
+            dpf += __shfl_xor_sync(0xffffffffu, dpf, o);
+            dpi += __shfl_xor_sync(0xffffffffu, dpi, o);
+            dpo += __shfl_xor_sync(0xffffffffu, dpo, o);
+        }
+        if (g == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) atomicAdd(p.dbias + (size_t)dir * 4 * Hp + 4 * unit + k, db[k]);
+            if (p.dpeep) {
+                atomicAdd(p.dpeep + (size_t)(dir * 3 + 0) * Hp + unit, dpf);
+                atomicAdd(p.dpeep + (size_t)(dir * 3 + 1) * Hp + unit, dpi);
+                atomicAdd(p.dpeep + (size_t)(dir * 3 + 2) * Hp + unit, dpo);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == NCW) { tc_fence_after(); tmem_dealloc<64>(tmem_base); }
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+struct RecPlan { int MT, NC; };
+
+static bool rec_plan(int Hp, RecPlan& pl) {
+    if (Hp < 64 || (Hp & 63) || Hp > 512) return false;
+    const int KB = Hp / 64;
+    // MT = 2 (64 units per CTA) halves the cluster when the weight slice still fits in shared memory
+    {
+        const int nc = Hp / 64;
+        if (RecFwdCfg<2>::smem_bytes(KB, 16) <= 232448 && RecBwdCfg<2>::smem_bytes(KB, 16, nc) <= 232448) {
+            pl.MT = 2; pl.NC = nc; return true;
+        }
+    }
+    const int nc = Hp / 32;
+    if (nc <= 16 && RecFwdCfg<1>::smem_bytes(KB, 16) <= 232448 && RecBwdCfg<1>::smem_bytes(KB, 16, nc) <= 232448) {
+        pl.MT = 1; pl.NC = nc; return true;
+    }
+    return false;
+}
+
+template <typename K, typename... Args>
+static int launch_cluster(K kern, int grid, int threads, size_t smem, int nc, cudaStream_t st, Args... args) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return LCB_ERR_CUDA;
+    if (nc > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return LCB_ERR_CUDA;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3((unsigned)threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)nc;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
+    if (e != cudaSuccess) { cudaGetLastError(); return LCB_ERR_CUDA; }
+    return LCB_OK;
+}
+
+}  // namespace lcb
+
+using namespace lcb;
+
+extern "C" int lcb_lstm_rec_config(int Hp, int* mt_out, int* nc_out)
+{
+    RecPlan pl;
+    if (!rec_plan(Hp, pl)) return LCB_ERR_UNSUPPORTED;
+    if (mt_out) *mt_out = pl.MT;
+    if (nc_out) *nc_out = pl.NC;
+    return LCB_OK;
+}
+
+extern "C" int lcb_lstm_rec_fwd(const float* G, const void* Wfold, const float* peep, const int32_t* lens,
+                                void* Mout, float* acts, float* cfin, float* mfin,
+                                int T, int B, int Hp, float forget_bias, void* stream)
+{
+    if (!G || !Wfold || !lens || !Mout) return LCB_ERR_NULL_POINTER;
+    if (T <= 0 || B <= 0) return LCB_ERR_BAD_SHAPE;
+    if ((cfin == nullptr) != (mfin == nullptr)) return LCB_ERR_NULL_POINTER;
+    RecPlan pl;
+    if (!rec_plan(Hp, pl)) return LCB_ERR_UNSUPPORTED;
+    const int BG = 16, KB = Hp / 64;
+    CUtensorMap tmW;
+    if (((uintptr_t)G & 15) != 0) return LCB_ERR_MISALIGNED;
+    if (!make_tmap_2d_bf16(&tmW, Wfold, (uint64_t)8 * Hp, (uint64_t)Hp, (uint64_t)Hp, 128, 64)) return LCB_ERR_CUDA;
+    RecFwdParams p;
+    p.G = G; p.peep = peep; p.lens = lens; p.Mout = (__half*)Mout; p.acts = acts; p.cfin = cfin; p.mfin = mfin;
+    p.T = T; p.B = B; p.Hp = Hp; p.NC = pl.NC; p.forget_bias = forget_bias;
+    const int nbg = (B + BG - 1) / BG;
+    const int grid = 2 * nbg * pl.NC;
+    if (pl.MT == 1)
+        return launch_cluster(lstm_rec_fwd_kernel<1, 16>, grid, RecFwdCfg<1>::THREADS, RecFwdCfg<1>::smem_bytes(KB, BG), pl.NC,
+                              (cudaStream_t)stream, tmW, p);
+    return launch_cluster(lstm_rec_fwd_kernel<2, 16>, grid, RecFwdCfg<2>::THREADS, RecFwdCfg<2>::smem_bytes(KB, BG), pl.NC,
+                          (cudaStream_t)stream, tmW, p);
+}
+
+extern "C" int lcb_lstm_rec_bwd(const float* dM, const float* acts, const void* Wfold, const float* peep,
+                                const int32_t* lens, void* dG, float* dbias, float* dpeep,
+                                int T, int B, int Hp, void* stream)
+{
+    if (!dM || !acts || !Wfold || !lens || !dG || !dbias) return LCB_ERR_NULL_POINTER;
+    if (T <= 0 || B <= 0) return LCB_ERR_BAD_SHAPE;
+    if ((peep == nullptr) != (dpeep == nullptr)) return LCB_ERR_NULL_POINTER;
+    RecPlan pl;
+    if (!rec_plan(Hp, pl)) return LCB_ERR_UNSUPPORTED;
+    const int BG = 16, KB = Hp / 64;
+    CUtensorMap tmW;
+    if (!make_tmap_2d_bf16(&tmW, Wfold, (uint64_t)8 * Hp, (uint64_t)Hp, (uint64_t)Hp, 128, 64)) return LCB_ERR_CUDA;
+    RecBwdParams p;
+    p.dM = dM; p.acts = acts; p.peep = peep; p.lens = lens; p.dG = (__nv_bfloat16*)dG; p.dbias = dbias; p.dpeep = dpeep;
+    p.T = T; p.B = B; p.Hp = Hp; p.NC = pl.NC;
+    const int nbg = (B + BG - 1) / BG;
+    const int grid = 2 * nbg * pl.NC;
+    if (pl.MT == 1)
+        return launch_cluster(lstm_rec_bwd_kernel<1, 16>, grid, RecBwdCfg<1>::THREADS, RecBwdCfg<1>::smem_bytes(KB, BG, pl.NC), pl.NC,
+                              (cudaStream_t)stream, tmW, p);
+    return launch_cluster(lstm_rec_bwd_kernel<2, 16>, grid, RecBwdCfg<2>::THREADS, RecBwdCfg<2>::smem_bytes(KB, BG, pl.NC), pl.NC,
+                          (cudaStream_t)stream, tmW, p);
+}

@@ -52,6 +52,9 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+__device__ __forceinline__ void fence_proxy_async_all() {       // generic-proxy writes (incl. DSMEM) -> async proxy
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -94,6 +97,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster_acq(uint64_t* bar, uint32_
 #endif
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return true;
+    if (dev_has_error()) return false;          // somebody already timed out: drain fast
     uint64_t t0 = 0;
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {

@@ -38,17 +38,17 @@ inline bool make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t rows, u
     return r == CUDA_SUCCESS;
 }
 
-// 3-D bf16 tensor [d2, d1, d0] (d0 innermost) with byte strides s1 (dim1) and s2 (dim2).
-inline bool make_tmap_3d_bf16(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
-                              uint64_t s1_bytes, uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2,
-                              bool swizzle128) {
+// 3-D tensor [d2, d1, d0] (d0 innermost) with byte strides s1 (dim1) and s2 (dim2); fp32 or bf16.
+inline bool make_tmap_3d(CUtensorMap* m, bool is_f32, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                         uint64_t s1_bytes, uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2,
+                         bool swizzle128) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return false;
     cuuint64_t gdim[3] = {d0, d1, d2};
     cuuint64_t gstr[2] = {s1_bytes, s2_bytes};
     cuuint32_t box[3] = {b0, b1, b2};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+    CUresult r = enc(m, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;

@@ -1,7 +1,9 @@
-"""bf16 GEMM (tcgen05 + TMA) -- thin host wrapper over lcb_gemm_bf16."""
+"""16-bit GEMM (tcgen05 + TMA) -- thin host wrapper over lcb_gemm16."""
 import torch
 
 from . import _lib
+
+_DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 
 
 def _ld(t):
@@ -10,18 +12,18 @@ def _ld(t):
 
 
 def gemm(A, B, a_layout=0, b_layout=0, out=None, out_dtype=torch.float32, bias=None, accumulate=False, check=False):
-    """C[M,N] (+)= op(A) * op(B) + bias.
+    """C[M,N] (+)= op(A) * op(B) + bias.   A, B: bf16 or fp16 (may differ).
     a_layout 0: A is [M,K]; 1: A is [K,M].   b_layout 0: B is [N,K]; 1: B is [K,N]."""
     L = _lib.lib()
-    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.is_cuda and B.is_cuda
+    assert A.is_cuda and B.is_cuda and _DT.get(A.dtype, 0) and _DT.get(B.dtype, 0), (A.dtype, B.dtype)
     M, K = (A.shape[0], A.shape[1]) if a_layout == 0 else (A.shape[1], A.shape[0])
     N, K2 = (B.shape[0], B.shape[1]) if b_layout == 0 else (B.shape[1], B.shape[0])
     assert K == K2, (A.shape, B.shape, a_layout, b_layout)
     if out is None:
         out = torch.empty(M, N, dtype=out_dtype, device=A.device)
     assert out.shape[0] == M and out.shape[1] == N and out.stride(1) == 1
-    fn = L.lcb_gemm_bf16_simt_check if check else L.lcb_gemm_bf16
-    st = fn(M, N, K, _lib.ptr(A), _ld(A), a_layout, _lib.ptr(B), _ld(B), b_layout, _lib.ptr(out), out.stride(0),
-            1 if out.dtype == torch.bfloat16 else 0, _lib.ptr(bias), 1 if accumulate else 0, _lib.stream_ptr())
-    _lib.check(st, "lcb_gemm_bf16")
+    fn = L.lcb_gemm16_simt_check if check else L.lcb_gemm16
+    st = fn(M, N, K, _lib.ptr(A), _ld(A), a_layout, _DT[A.dtype], _lib.ptr(B), _ld(B), b_layout, _DT[B.dtype],
+            _lib.ptr(out), out.stride(0), _DT[out.dtype], _lib.ptr(bias), 1 if accumulate else 0, _lib.stream_ptr())
+    _lib.check(st, "lcb_gemm16")
     return out

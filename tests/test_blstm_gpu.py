@@ -1,0 +1,105 @@
+"""GPU parity: the BiLSTM stack (hoisted tcgen05 projections + cluster-persistent recurrence + BPTT)
+vs the fp64 oracle restatement of create_logits_blstm (oracle/model.py).
+
+Stated tolerance (fp16 forward operands, bf16 gradient operands, fp32 accumulate / cell state / master
+weights): activations within 1e-2 of max|h| (absolute) -- also after 200 recurrent steps -- and parameter
+gradients within 4e-2 normwise relative error per variable.  Length masking is exact:
+outputs at t >= seq_len[b] are exactly 0."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def make_case(H, P, D, L, B, T, peep, seed=0, full=False):
+    cfg = oracle.OracleConfig(input_dim=D, num_layers=L, num_neurons=H, num_projects=P, num_targets=8,
+                              use_peepholes=peep, num_experts=0)
+    params = oracle.init_params(cfg, seed=seed, bias_scale=0.1)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(B, T, D, generator=g, dtype=torch.float64)
+    lens = torch.full((B,), T, dtype=torch.int32) if full else torch.randint(max(1, T // 2), T + 1, (B,), generator=g).to(torch.int32)
+    lens[0] = T
+    for b in range(B):
+        x[b, lens[b]:] = 0
+    return cfg, params, x, lens
+
+
+def nnet_config(cfg):
+    return {"input_dim": cfg.input_dim, "left_context": 0, "right_context": 0, "num_layers": cfg.num_layers,
+            "num_neurons": cfg.num_neurons, "num_projects": cfg.num_projects, "num_targets": cfg.num_targets,
+            "use_peepholes": cfg.use_peepholes, "num_experts": cfg.num_experts, "dropout_rate": 1.0}
+
+
+def run_ours(cfg, params, x, lens, R=None):
+    from lstm_ctc_b200.blstm import BLSTMEncoder, ModelConfig
+    dev = torch.device("cuda:0")
+    enc = BLSTMEncoder(ModelConfig(nnet_config(cfg)), dev)
+    enc.from_tf_dict(params)
+    rt = enc.to_tf_dict()
+    for k, v in params.items():
+        if k.startswith(("fd", "bd")):
+            assert torch.equal(rt[k].cpu().double(), v.float().double()), k      # layout round trip is exact
+    B, T, D = x.shape
+    out = enc.forward(x.float().to(dev), lens.to(dev), training=True)
+    out_bt = out.float().view(T, B, -1).permute(1, 0, 2).contiguous()
+    grads = None
+    if R is not None:
+        enc.params.gflat.zero_()
+        dX = R.permute(1, 0, 2).contiguous().view(T * B, -1).to(dev).bfloat16().contiguous()
+        enc.last_R = dX
+        enc.backward(dX)
+        grads = {k: v.cpu().double() for k, v in enc.to_tf_dict(grads=True).items()}
+    torch.cuda.synchronize()
+    from lstm_ctc_b200 import _lib
+    assert _lib.lib().lcb_device_error(1) == 0
+    return out_bt.cpu().double(), grads, enc
+
+
+@pytest.mark.parametrize("H,P,D,L,B,T,peep", [
+    (64, 64, 24, 1, 5, 9, False),      # one-CTA cluster, ragged batch < 16
+    (128, 64, 40, 2, 16, 12, True),    # 2-CTA cluster, peepholes
+    (96, 48, 16, 2, 20, 7, True),      # H padded 96 -> 128, two utterance groups
+    (320, 320, 120, 2, 16, 10, True),  # WSJ recipe cell: 5-CTA cluster, 64 units / CTA
+    (512, 512, 120, 1, 8, 6, True),    # Libri-shape cell: 16-CTA (non-portable) cluster
+    (384, 128, 64, 1, 4, 5, False),    # 12-CTA cluster
+])
+def test_forward_backward_vs_oracle(cuda_dev, H, P, D, L, B, T, peep):
+    cfg, params, x, lens = make_case(H, P, D, L, B, T, peep)
+    p64 = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    ref, _ = oracle.blstm_forward(p64, cfg, x, lens)
+    g = torch.Generator().manual_seed(7)
+    R = torch.randn(ref.shape, generator=g, dtype=torch.float64).bfloat16().double()
+    (ref * R).sum().backward()
+    out, grads, _ = run_ours(cfg, params, x, lens, R)
+    scale = ref.abs().max().item()
+    err = (out - ref.detach()).abs().max().item()
+    assert err < 1e-2 * scale, ("activations", err, scale)
+    mask = torch.arange(T).unsqueeze(0) >= lens.unsqueeze(1)
+    assert out[mask].abs().max().item() == 0.0 if mask.any() else True      # exact length masking
+    worst = {}
+    for k, v in grads.items():
+        rg = p64[k].grad
+        rel = ((v - rg).norm() / (rg.norm() + 1e-12)).item()
+        worst[k] = rel
+    bad = {k: r for k, r in worst.items() if r > 4e-2}
+    assert not bad, bad
+
+
+def test_long_sequence_state_precision(cuda_dev):
+    """T=200: the fp32 cell state kept in registers must not drift (bf16 only touches m and the weights)."""
+    cfg, params, x, lens = make_case(128, 128, 40, 1, 16, 200, True, seed=3)
+    ref, _ = oracle.blstm_forward(params, cfg, x, lens)
+    out, _, _ = run_ours(cfg, params, x, lens)
+    assert (out - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
+
+
+def test_final_state_encoder(cuda_dev):
+    cfg, params, x, lens = make_case(64, 32, 16, 2, 6, 11, True, seed=5)
+    _, enc_ref = oracle.blstm_forward(params, cfg, x, lens)
+    _, _, enc = run_ours(cfg, params, x, lens)
+    e = enc.encoder_state().cpu().double()
+    assert e.shape == enc_ref.shape
+    assert (e - enc_ref).abs().max().item() < 3e-2 * enc_ref.abs().max().item()

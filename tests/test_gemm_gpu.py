@@ -61,3 +61,30 @@ def test_gemm_projection_shape(cuda_dev):
     assert (C - R).abs().max() < 2e-2
     from lstm_ctc_b200 import _lib
     assert _lib.lib().lcb_device_error(0) == 0
+
+
+@pytest.mark.parametrize("a_layout,b_layout", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_fp16_operands(cuda_dev, a_layout, b_layout):
+    """Forward GEMMs run fp16 x fp16 (same tensor throughput, 3 more mantissa bits than bf16)."""
+    from lstm_ctc_b200.gemm import gemm
+    torch.manual_seed(5)
+    M, N, K = 384, 264, 520
+    A = torch.randn((M, K) if a_layout == 0 else (K, M), device=cuda_dev).half()
+    B = torch.randn((N, K) if b_layout == 0 else (K, N), device=cuda_dev).half()
+    R = _ref(A, B, a_layout, b_layout, None)
+    C = gemm(A, B, a_layout, b_layout)
+    Cc = gemm(A, B, a_layout, b_layout, check=True)
+    Ch = gemm(A, B, a_layout, b_layout, out_dtype=torch.float16)
+    assert (Cc - R).abs().max() < 2e-3 * K ** 0.5
+    assert (C - R).abs().max() < 2e-3 * K ** 0.5, (C - R).abs().max().item()
+    assert (Ch.float() - R).abs().max() < 0.1
+
+
+def test_gemm_mixed_formats_rejected(cuda_dev):
+    """tcgen05 kind::f16 with A=bf16, B=fp16 is an illegal instruction on B200: the ABI refuses it."""
+    from lstm_ctc_b200 import _lib
+    from lstm_ctc_b200.gemm import gemm
+    A = torch.randn(128, 64, device=cuda_dev).bfloat16()
+    B = torch.randn(128, 64, device=cuda_dev).half()
+    with pytest.raises(_lib.LcbError):
+        gemm(A, B)
