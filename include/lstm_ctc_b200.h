@@ -132,6 +132,36 @@ int lcb_split_f32_bf16(const float* src, void* hi, void* lo, size_t n, void* str
 int lcb_f16_to_bf16(const void* src, void* dst, size_t n, void* stream);   /* n even */
 int lcb_colsum(const void* src, int src_dtype, int rows, int cols, int ld, float* out, void* stream);
 
+/* ---- output layer: mixture of tanh-bounded expert logits, or affine -------------------------
+ * lcb_output_fwd replaces create_moe (nnet/moe.py:29-72) / tf.nn.xw_plus_b (nnet/bilstm.py:249)
+ * and the reshape to [B,T,V] (nnet/bilstm.py:250).  One fused tcgen05 GEMM + mixture epilogue; the
+ * [N,K,V] expert tensor (moe.py:60) is never materialised.
+ *   X      [T*B, ldx] fp16 time-major encoder output (D2 = 2*num_projects columns used)
+ *   Wall   [K*V + K, D2] fp16: row v*K+k = column k*V+v of the reference's W (moe.py:50-58),
+ *          rows K*V.. = W_prior^T (moe.py:34-41).  K == 0 (affine): Wall = W^T [V, D2].
+ *   bias   [K*V + K] f32 in the same order (affine: [V])
+ *   logits [B,T,V] f32 batch-major.   tau = moe_temperature.   K <= 128.
+ * lcb_mos_bwd_dz: rows [n0, n0+R) of Z = X*Wall^T + bias (recomputed with lcb_gemm16, [R, ldz] f32)
+ *   and dlogits [B,T,V] f32 -> dZ [R, ldz] bf16 (same column order, pad columns zero); dX, dWall and
+ *   dbias then follow from lcb_gemm16 / lcb_colsum (tf.gradients, nnet/graph.py:190-191).
+ * lcb_pack_dlogits: [B,T,V] f32 -> time-major [T*B, ldo] bf16 (the affine layer's dZ). */
+int lcb_output_fwd(const void* X, int ldx, const void* Wall, const float* bias, float* logits,
+                   int T, int B, int D2, int V, int K, float tau, void* stream);
+int lcb_mos_bwd_dz(const float* Z, const float* dlogits, void* dZ, int n0, int R, int ldz,
+                   int T, int B, int V, int K, float tau, void* stream);
+int lcb_pack_dlogits(const float* dlogits, void* out, int T, int B, int V, int ldo, void* stream);
+
+/* ---- fused L2 + global-norm clip + optimizer on flat fp32 buffers ---------------------------
+ * replaces nnet/graph.py:183-200: g += l2*w outside the no-decay ranges (LSTM biases, :186),
+ * clip_by_global_norm (:190-192), and apply_gradients for opt = 0 sgd / 1 momentum / 2 adam
+ * (tf.train.* semantics, :37-48).  step >= 1 is the Adam time step.  nodecay_ranges_host: n_ranges
+ * [lo,hi) element ranges (HOST pointer, <= 24).  sumsq_scratch: device double.  gnorm_out: device
+ * float receiving the pre-clip global norm (nullable).  No host synchronisation. */
+int lcb_optimizer_step(float* w, float* g, float* s1, float* s2, long long n, int opt,
+                       float lr, long long step, float beta1, float beta2, float eps, float momentum,
+                       float l2, float clip_norm, const long long* nodecay_ranges_host, int n_ranges,
+                       double* sumsq_scratch, float* gnorm_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

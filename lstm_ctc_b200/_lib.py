@@ -75,6 +75,12 @@ _SIGS = {
                                       c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "lcb_split_f32_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "lcb_f16_to_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "lcb_output_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "lcb_mos_bwd_dz": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "lcb_pack_dlogits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "lcb_optimizer_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_float, ctypes.c_longlong,
+                                   c_float, c_float, c_float, c_float, c_float, c_float, ctypes.POINTER(ctypes.c_longlong), c_int,
+                                   c_void_p, c_void_p, c_void_p]),
     "lcb_colsum": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 

@@ -4,3 +4,5 @@
 #include "ctc.cu"
 #include "lstm_rec.cu"
 #include "elementwise.cu"
+#include "mos.cu"
+#include "optim.cu"

@@ -1,0 +1,326 @@
+// mos.cu -- output layer of the acoustic model (K3 / K3b in DESIGN.md).
+//
+// Forward replaces nnet/moe.py:29-72 (create_moe) or, for num_experts == 0, the affine layer of
+// nnet/bilstm.py:237-250, plus the reshape to [B,T,V] (bilstm.py:250):
+//     pi[n,k]  = softmax_k(x_n . Wp[:,k] + bp[k])
+//     y[n,v]   = sum_k pi[n,k] * tau * tanh(x_n . W[:, k*V+v] + b[k*V+v])
+// One fused tcgen05 GEMM per 128-row tile with the mixture applied in the epilogue: the [N,K,V]
+// expert tensor (moe.py:60) is never written anywhere.  Device weight layout is v-major
+// (row v*K+k of Wall = column k*V+v of the reference's W) so the K experts of one target are
+// adjacent accumulator columns and the sum over k is a running sum in one thread; the K prior rows
+// follow at row K*V.  Work per tile: pass 0 = prior logits (N = K rounded to 16) -> softmax -> smem,
+// then ceil(K*V/256) passes of 256 columns; passes alternate between two TMEM accumulators so the
+// tanh/mixture epilogue of one pass overlaps the MMAs of the next.  Rows are time-major
+// (n = t*B + b); the epilogue writes logits batch-major [B,T,V] as the CTC kernel and the reference API
+// expect them.
+//
+// Backward (recompute, row-chunked): z is recomputed by lcb_gemm16 for a chunk of rows that stays
+// L2-resident, mos_bwd_kernel turns (z, dy) into dz (bf16, same column order) with one warp per row,
+// and dX / dW / db come from the generic GEMM + column sums.
+#include <cuda_fp16.h>
+#include "ptx.cuh"
+#include "tma_host.h"
+#include "lstm_ctc_b200.h"
+
+namespace lcb {
+
+constexpr int OUT_BM = 128, OUT_BN = 256, OUT_BK = 64, OUT_STAGES = 3, OUT_THREADS = 192;
+constexpr int OUT_A_BYTES = OUT_BM * OUT_BK * 2, OUT_B_BYTES = OUT_BN * OUT_BK * 2;
+constexpr int OUT_STAGE_BYTES = OUT_A_BYTES + OUT_B_BYTES;
+
+struct OutFwdParams {
+    const float* bias;     // [KV + K]  (affine: [V])
+    float* logits;         // [B,T,V] batch-major
+    int N, D2, T, B, V, K; // K == 0: affine
+    int KV;                // K*V (affine: V)
+    int Kp16;              // K rounded up to 16 (MMA N of the prior pass)
+    int pis;               // row stride of pi in smem (odd)
+    float tau;
+};
+
+__global__ void __launch_bounds__(OUT_THREADS, 1)
+out_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmWp, const OutFwdParams p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* tiles = smem;
+    float* pi_s = reinterpret_cast<float*>(smem + OUT_STAGES * OUT_STAGE_BYTES);            // [128][pis]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pi_s + (size_t)OUT_BM * p.pis + 2);
+    bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bars) + 7) & ~(uintptr_t)7);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + OUT_STAGES;
+    uint64_t* tfull_bar = bars + 2 * OUT_STAGES;
+    uint64_t* tempty_bar = bars + 2 * OUT_STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * OUT_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (p.N + OUT_BM - 1) / OUT_BM;
+    const int nkb = (p.D2 + OUT_BK - 1) / OUT_BK;
+    const int nchunks = (p.KV + OUT_BN - 1) / OUT_BN;
+    const int npass = nchunks + (p.K > 0 ? 1 : 0);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmWp);
+        for (int s = 0; s < OUT_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0; bool ok = true;
+            for (int tile = blockIdx.x; tile < tiles_m && ok; tile += gridDim.x) {
+                const int m0 = tile * OUT_BM;
+                for (int ps = 0; ps < npass && ok; ++ps) {
+                    const bool prior = (p.K > 0 && ps == 0);
+                    const int n0 = prior ? p.KV : (ps - (p.K > 0 ? 1 : 0)) * OUT_BN;
+                    const uint32_t bbytes = prior ? (uint32_t)p.Kp16 * OUT_BK * 2 : (uint32_t)OUT_B_BYTES;
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        if (!mbar_wait(&empty_bar[stage], phase ^ 1)) { ok = false; break; }
+                        unsigned char* sa = tiles + stage * OUT_STAGE_BYTES;
+                        unsigned char* sb = sa + OUT_A_BYTES;
+                        mbar_arrive_expect_tx(&full_bar[stage], OUT_A_BYTES + bbytes);
+                        tma_load_2d(sa, &tmX, &full_bar[stage], kb * OUT_BK, m0);
+                        tma_load_2d(sb, prior ? &tmWp : &tmW, &full_bar[stage], kb * OUT_BK, n0);
+                        if (++stage == OUT_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // fp16 x fp16 -> f32, both K-major; N set per pass
+            const uint32_t idesc_base = make_idesc_bf16_f32(OUT_BM, 8, 0, 0) & ~((7u << 7) | (7u << 10) | (63u << 17));
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0; bool ok = true;
+            for (int tile = blockIdx.x; tile < tiles_m && ok; tile += gridDim.x) {
+                for (int ps = 0; ps < npass && ok; ++ps) {
+                    const bool prior = (p.K > 0 && ps == 0);
+                    const uint32_t nmma = prior ? (uint32_t)p.Kp16 : (uint32_t)OUT_BN;
+                    const uint32_t idesc = idesc_base | ((nmma >> 3) << 17);
+                    if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1)) { ok = false; break; }
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * OUT_BN;
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        if (!mbar_wait(&full_bar[stage], phase)) { ok = false; break; }
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(tiles + stage * OUT_STAGE_BYTES);
+                        const uint32_t sb = sa + OUT_A_BYTES;
+#pragma unroll
+                        for (int k = 0; k < OUT_BK / 16; ++k)
+                            umma_f16_ss(d_tmem, make_smem_desc_sw128(sa + k * 32, 16, 1024), make_smem_desc_sw128(sb + k * 32, 16, 1024),
+                                        idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_commit(&empty_bar[stage]);
+                        if (++stage == OUT_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(&tfull_bar[acc]);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue: softmax over experts, tanh mixture, batch-major store =================
+        const int q = warp & 3;
+        const int rloc = q * 32 + lane;
+        float* pir = pi_s + (size_t)rloc * p.pis;
+        int acc = 0; uint32_t acc_phase = 0; bool ok = true;
+        const int K = p.K, V = p.V, KV = p.KV;
+        for (int tile = blockIdx.x; tile < tiles_m && ok; tile += gridDim.x) {
+            const int n = tile * OUT_BM + rloc;
+            const bool rowok = n < p.N;
+            const int t = rowok ? n / p.B : 0, b = rowok ? n % p.B : 0;
+            float* orow = p.logits + ((size_t)b * p.T + t) * V;
+            int kk = 0, vv = 0; float accv = 0.f;                 // running mixture state across passes
+            for (int ps = 0; ps < npass && ok; ++ps) {
+                const bool prior = (K > 0 && ps == 0);
+                if (!mbar_wait(&tfull_bar[acc], acc_phase)) { ok = false; break; }
+                tc_fence_after();
+                const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * OUT_BN;
+                if (prior) {
+                    // pass A: max; pass B: exp, sum -> smem; then normalise
+                    float mx = -INFINITY;
+                    for (int c0 = 0; c0 < K; c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld_32x32b_x32(t_addr + c0, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (c0 + j < K) mx = fmaxf(mx, __uint_as_float(r[j]) + p.bias[KV + c0 + j]);
+                    }
+                    float sum = 0.f;
+                    for (int c0 = 0; c0 < K; c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld_32x32b_x32(t_addr + c0, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (c0 + j < K) {
+                            const float e = __expf(__uint_as_float(r[j]) + p.bias[KV + c0 + j] - mx);
+                            pir[c0 + j] = e; sum += e;
+                        }
+                    }
+                    const float inv = 1.f / sum;
+                    for (int k = 0; k < K; ++k) pir[k] *= inv;
+                } else {
+                    const int c_base = (ps - (K > 0 ? 1 : 0)) * OUT_BN;
+                    for (int c0 = 0; c0 < OUT_BN && c_base + c0 < KV; c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld_32x32b_x32(t_addr + c0, r);
+                        tmem_ld_wait();
+                        if (K > 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int col = c_base + c0 + j;
+                                if (col < KV) {
+                                    accv += pir[kk] * tanhf_fast(__uint_as_float(r[j]) + __ldg(p.bias + col));
+                                    if (++kk == K) {
+                                        if (rowok) orow[vv] = p.tau * accv;
+                                        ++vv; kk = 0; accv = 0.f;
+                                    }
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int col = c_base + c0 + j;
+                                if (col < KV && rowok) orow[col] = __uint_as_float(r[j]) + __ldg(p.bias + col);
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward elementwise: one warp per row.
+//   Z   [R, ldz] f32   recomputed x.Wall^T + bias for rows [n0, n0+R) (v-major expert cols, then K prior cols)
+//   dY  [B,T,V]  f32   d loss / d logits (batch-major, from the CTC kernel)
+//   dZ  [R, ldz] bf16  d loss / d z  (same column order; pad columns zeroed)
+__global__ void __launch_bounds__(256)
+mos_bwd_kernel(const float* __restrict__ Z, const float* __restrict__ dY, __nv_bfloat16* __restrict__ dZ,
+               int n0, int R, int ldz, int T, int B, int V, int K, float tau)
+{
+    extern __shared__ float sm[];                     // per warp: dpi[K], pi[K]
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* dpi = sm + (size_t)w * 2 * K;
+    float* pi = dpi + K;
+    const int KV = K * V;
+    for (int r = blockIdx.x * 8 + w; r < R; r += gridDim.x * 8) {
+        const int n = n0 + r;
+        const int t = n / B, b = n % B;
+        const float* z = Z + (size_t)r * ldz;
+        const float* dy = dY + ((size_t)b * T + t) * V;
+        __nv_bfloat16* dz = dZ + (size_t)r * ldz;
+        for (int k = lane; k < K; k += 32) dpi[k] = 0.f;
+        // prior softmax
+        float mx = -INFINITY;
+        for (int k = lane; k < K; k += 32) mx = fmaxf(mx, z[KV + k]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float s = 0.f;
+        for (int k = lane; k < K; k += 32) { const float e = __expf(z[KV + k] - mx); pi[k] = e; s += e; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        __syncwarp();
+        const float inv = 1.f / s;
+        for (int k = lane; k < K; k += 32) pi[k] *= inv;
+        __syncwarp();
+        // expert columns: dz = dy * pi * tau * (1 - tanh^2);  dpi[k] += dy * tau * tanh
+        for (int c = lane; c < KV; c += 32) {
+            const int v = c / K, k = c - v * K;
+            const float th = tanhf_fast(z[c]);
+            const float g = dy[v] * tau;
+            atomicAdd(&dpi[k], g * th);
+            dz[c] = __float2bfloat16(g * pi[k] * (1.f - th * th));
+        }
+        __syncwarp();
+        // softmax backward: dlogit_k = pi_k * (dpi_k - sum_j pi_j dpi_j)
+        float dot = 0.f;
+        for (int k = lane; k < K; k += 32) dot += pi[k] * dpi[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        for (int k = lane; k < K; k += 32) dz[KV + k] = __float2bfloat16(pi[k] * (dpi[k] - dot));
+        for (int c = KV + K + lane; c < ldz; c += 32) dz[c] = __float2bfloat16(0.f);
+        __syncwarp();
+    }
+}
+
+// dlogits [B,T,V] f32 batch-major -> [N, ldo] bf16 time-major (pad columns zero): the affine layer's dZ
+__global__ void pack_dlogits_kernel(const float* __restrict__ dY, __nv_bfloat16* __restrict__ out, int T, int B, int V, int ldo) {
+    const size_t total = (size_t)T * B * ldo;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % ldo);
+        const size_t n = i / ldo;
+        const int b = (int)(n % B), t = (int)(n / B);
+        out[i] = __float2bfloat16(c < V ? dY[((size_t)b * T + t) * V + c] : 0.f);
+    }
+}
+
+}  // namespace lcb
+
+using namespace lcb;
+
+extern "C" int lcb_output_fwd(const void* X, int ldx, const void* Wall, const float* bias, float* logits,
+                              int T, int B, int D2, int V, int K, float tau, void* stream)
+{
+    if (!X || !Wall || !bias || !logits) return LCB_ERR_NULL_POINTER;
+    if (T <= 0 || B <= 0 || D2 <= 0 || V <= 0 || K < 0) return LCB_ERR_BAD_SHAPE;
+    if (K > 128) return LCB_ERR_UNSUPPORTED;
+    if ((ldx & 7) || (D2 & 7) || ((uintptr_t)X & 15) || ((uintptr_t)Wall & 15)) return LCB_ERR_MISALIGNED;
+    OutFwdParams p;
+    p.bias = bias; p.logits = logits; p.N = T * B; p.D2 = D2; p.T = T; p.B = B; p.V = V; p.K = K;
+    p.KV = (K > 0 ? K : 1) * V;
+    p.Kp16 = K > 0 ? ((K + 15) & ~15) : 16;
+    p.pis = (K | 1) + 2 * (K > 0 ? 0 : 0);
+    p.tau = tau;
+    const int rows = p.KV + K;
+    CUtensorMap tx, tw, twp;
+    if (!make_tmap_2d_bf16(&tx, X, (uint64_t)p.N, (uint64_t)D2, (uint64_t)ldx, OUT_BM, OUT_BK)) return LCB_ERR_CUDA;
+    if (!make_tmap_2d_bf16(&tw, Wall, (uint64_t)rows, (uint64_t)D2, (uint64_t)D2, OUT_BN, OUT_BK)) return LCB_ERR_CUDA;
+    if (!make_tmap_2d_bf16(&twp, Wall, (uint64_t)rows, (uint64_t)D2, (uint64_t)D2, (uint32_t)p.Kp16, OUT_BK)) return LCB_ERR_CUDA;
+    const size_t smem = 1024 + (size_t)OUT_STAGES * OUT_STAGE_BYTES + (size_t)OUT_BM * p.pis * 4 + 512;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        if (cudaFuncSetAttribute(out_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return LCB_ERR_CUDA;
+        smem_set = smem;
+    }
+    const int tiles_m = (p.N + OUT_BM - 1) / OUT_BM;
+    const int grid = tiles_m < 148 ? tiles_m : 148;
+    out_fwd_kernel<<<grid, OUT_THREADS, smem, (cudaStream_t)stream>>>(tx, tw, twp, p);
+    return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
+}
+
+extern "C" int lcb_mos_bwd_dz(const float* Z, const float* dlogits, void* dZ, int n0, int R, int ldz,
+                              int T, int B, int V, int K, float tau, void* stream)
+{
+    if (!Z || !dlogits || !dZ) return LCB_ERR_NULL_POINTER;
+    if (R <= 0 || K <= 0 || V <= 0 || ldz < K * V + K) return LCB_ERR_BAD_SHAPE;
+    int grid = (R + 7) / 8; if (grid > 148 * 8) grid = 148 * 8;
+    const size_t smem = (size_t)8 * 2 * K * sizeof(float);
+    mos_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(Z, dlogits, (__nv_bfloat16*)dZ, n0, R, ldz, T, B, V, K, tau);
+    return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
+}
+
+extern "C" int lcb_pack_dlogits(const float* dlogits, void* out, int T, int B, int V, int ldo, void* stream)
+{
+    if (!dlogits || !out) return LCB_ERR_NULL_POINTER;
+    if (T <= 0 || B <= 0 || V <= 0 || ldo < V) return LCB_ERR_BAD_SHAPE;
+    const size_t total = (size_t)T * B * ldo;
+    size_t blocks = (total + 255) / 256; if (blocks > 148 * 16) blocks = 148 * 16;
+    pack_dlogits_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(dlogits, (__nv_bfloat16*)out, T, B, V, ldo);
+    return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
+}

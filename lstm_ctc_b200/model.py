@@ -1,0 +1,260 @@
+"""BiLSTM + mixture/affine output + CTC on the sm_100a kernels: the executable behind the graph
+dicts of graph.py.  Mirrors the maths of create_logits_blstm (/root/reference/nnet/bilstm.py:25-273),
+create_moe (/root/reference/nnet/moe.py:29-72) and the loss/optimizer wiring of
+/root/reference/nnet/graph.py:51-209.  Every FLOP runs in liblstm_ctc_b200.so."""
+import ctypes
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from .blstm import BF16, F16, F32, BLSTMEncoder, ModelConfig, ParamSpec, _cast16, _ceil, _to_bf16
+from .ctc import ctc_loss_grad
+from .gemm import gemm
+
+OPT_CODES = {"sgd": 0, "momentum": 1, "adam": 2}
+
+
+def _glorot(shape, gen):
+    fan_in, fan_out = (shape[0], shape[1]) if len(shape) == 2 else (shape[0], shape[0])
+    lim = math.sqrt(6.0 / (fan_in + fan_out))
+    return (torch.rand(shape, generator=gen, dtype=torch.float32) * 2 - 1) * lim
+
+
+def _trunc_normal(shape, std, gen):
+    x = torch.randn(shape, generator=gen, dtype=torch.float32)
+    for _ in range(8):
+        bad = x.abs() > 2
+        if not bad.any():
+            break
+        x[bad] = torch.randn(int(bad.sum()), generator=gen, dtype=torch.float32)
+    return x.clamp_(-2, 2) * std
+
+
+def random_tf_variables(cfg: ModelConfig, seed=None) -> Dict[str, torch.Tensor]:
+    """TF default initialisers in the reference's variable layout (what nnet-init.py:73 produces):
+    glorot-uniform LSTM kernels / peepholes / projection, zero biases, truncated-normal output layer
+    (moe.py:33-58, bilstm.py:239-248)."""
+    g = torch.Generator()
+    if seed is None:
+        g.seed()
+    else:
+        g.manual_seed(int(seed))
+    tf = {}
+    for i in range(cfg.num_layers):
+        din = cfg.din(i)
+        for d, c in (("fd", "frnn"), ("bd", "brnn")):
+            pre = "%s%d/%s%d" % (d, i, c, i)
+            tf[pre + "/kernel"] = _glorot((din + cfg.P, 4 * cfg.H), g)
+            tf[pre + "/bias"] = torch.zeros(4 * cfg.H)
+            if cfg.use_peepholes:
+                for w in ("w_f_diag", "w_i_diag", "w_o_diag"):
+                    tf[pre + "/" + w] = _glorot((cfg.H,), g)
+            tf[pre + "/projection/kernel"] = _glorot((cfg.H, cfg.P), g)
+    od = 2 * cfg.P
+    if cfg.K > 0:
+        std = 1.0 / math.sqrt(od)
+        tf["Variable"] = _trunc_normal((od, cfg.K), std, g)
+        tf["Variable_1"] = torch.zeros(cfg.K)
+        tf["Variable_2"] = _trunc_normal((od, cfg.K * cfg.V), std, g)
+        tf["Variable_3"] = torch.zeros(cfg.K * cfg.V)
+    else:
+        tf["Variable"] = _trunc_normal((od, cfg.V), 1.0 / math.sqrt(cfg.H), g)
+        tf["Variable_1"] = torch.zeros(cfg.V)
+    return tf
+
+
+class AcousticModel:
+    """Weights, activations and the forward / loss / backward / update sequence for one GPU."""
+
+    MOS_BWD_ROWS = 16384          # row chunk of the recompute backward (dz chunk stays L2 resident)
+
+    def __init__(self, nnet_config: dict, device=None, seed=None, init=True):
+        self.cfg = c = ModelConfig(nnet_config)
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if (c.uniform_label_sm or 0) > 0 or ((c.prior_label_sm or 0) > 0 and c.prior_label_path):
+            raise NotImplementedError("label-smoothing regulariser (bilstm.py:254-269); both recipes set weight 0")
+        self.rows_out = (c.K * c.V + c.K) if c.K > 0 else c.V
+        self.ldz = _ceil(self.rows_out, 8)
+        # output-layer variables are the unnamed tf.Variable's: L2-decayed, biases included (graph.py:186)
+        specs = [ParamSpec("out/Wall", (self.rows_out, 2 * c.P), True), ParamSpec("out/ball", (self.rows_out,), True)]
+        self.enc = BLSTMEncoder(c, self.device, extra_specs=specs)
+        self.params = self.enc.params
+        self._out16 = None
+        self._outbf = None
+        self._out_stale = True
+        self._ows = {}
+        self.opt_state = None
+        self.global_step = 0
+        self._nodecay = self.params.nodecay_ranges()
+        self._sumsq = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._gnorm = torch.zeros(1, dtype=F32, device=self.device)
+        if init:
+            self.from_tf_dict(random_tf_variables(c, seed))
+
+    # ------------------------------------------------------------------ variables
+    def from_tf_dict(self, tf: Dict[str, torch.Tensor]):
+        c = self.cfg
+        self.enc.from_tf_dict(tf)
+        Wall, ball = self.params.w("out/Wall"), self.params.w("out/ball")
+        dev = self.device
+        if c.K > 0:
+            K, V = c.K, c.V
+            Wp, bp = tf["Variable"].to(dev, F32), tf["Variable_1"].to(dev, F32)
+            W, b = tf["Variable_2"].to(dev, F32), tf["Variable_3"].to(dev, F32)
+            assert W.shape == (2 * c.P, K * V) and Wp.shape == (2 * c.P, K)
+            # row v*K+k  <-  reference column k*V+v (moe.py:60 reshapes [.., K, V])
+            Wall[:K * V] = W.t().reshape(K, V, 2 * c.P).permute(1, 0, 2).reshape(K * V, 2 * c.P)
+            Wall[K * V:] = Wp.t()
+            ball[:K * V] = b.view(K, V).t().reshape(K * V)
+            ball[K * V:] = bp
+        else:
+            Wall.copy_(tf["Variable"].to(dev, F32).t())
+            ball.copy_(tf["Variable_1"].to(dev, F32))
+        self.mark_stale()
+
+    def to_tf_dict(self, grads=False) -> Dict[str, torch.Tensor]:
+        c = self.cfg
+        out = self.enc.to_tf_dict(grads)
+        get = self.params.g if grads else self.params.w
+        Wall, ball = get("out/Wall"), get("out/ball")
+        if c.K > 0:
+            K, V = c.K, c.V
+            out["Variable"] = Wall[K * V:].t().clone()
+            out["Variable_1"] = ball[K * V:].clone()
+            out["Variable_2"] = Wall[:K * V].reshape(V, K, 2 * c.P).permute(1, 0, 2).reshape(K * V, 2 * c.P).t().clone()
+            out["Variable_3"] = ball[:K * V].view(V, K).t().reshape(K * V).clone()
+        else:
+            out["Variable"] = Wall.t().clone()
+            out["Variable_1"] = ball.clone()
+        return out
+
+    def mark_stale(self):
+        self.enc.mark_stale()
+        self._out_stale = True
+
+    def _refresh(self):
+        if self._out_stale:
+            self._out16 = _cast16(self.params.w("out/Wall"), F16, self._out16)
+            self._outbf = _cast16(self.params.w("out/Wall"), BF16, self._outbf)
+            self._out_stale = False
+
+    def num_params(self):
+        return sum(int(v.numel()) for v in self.to_tf_dict().values())
+
+    # ------------------------------------------------------------------ forward
+    def _out_ws(self, T, B):
+        key = (T, B)
+        ws = self._ows.get(key)
+        if ws is None:
+            c = self.cfg
+            N = T * B
+            R = min(self.MOS_BWD_ROWS, N)
+            ws = {"logits": torch.empty(B, T, c.V, dtype=F32, device=self.device),
+                  "Xbf": torch.empty(N, 2 * c.P, dtype=BF16, device=self.device),
+                  "dXtop": torch.empty(N, 2 * c.P, dtype=BF16, device=self.device),
+                  "dZ": torch.empty(R if c.K > 0 else N, self.ldz, dtype=BF16, device=self.device)}
+            if c.K > 0:
+                ws["Z"] = torch.empty(R, self.ldz, dtype=F32, device=self.device)
+            self._ows[key] = ws
+        return ws
+
+    def forward_logits(self, nnet_input, seq_len, training=True):
+        """create_logits_blstm: returns logits [B,T,V] f32 (batch-major).  Rows past seq_len hold the
+        output layer applied to a zero encoder row (bias-only / MoE(0)), like the reference."""
+        L = _lib.lib()
+        c = self.cfg
+        self._refresh()
+        X = self.enc.forward(nnet_input, seq_len, training)
+        B, T = nnet_input.shape[0], nnet_input.shape[1]
+        ws = self._out_ws(T, B)
+        _lib.check(L.lcb_output_fwd(_lib.ptr(X), X.stride(0), _lib.ptr(self._out16), _lib.ptr(self.params.w("out/ball")),
+                                    _lib.ptr(ws["logits"]), T, B, 2 * c.P, c.V, c.K, c.tau, _lib.stream_ptr()), "lcb_output_fwd")
+        self._top = (X, T, B)
+        return ws["logits"]
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, dlogits, bucket_ready=None):
+        """dlogits [B,T,V] f32 -> all parameter gradients (accumulated into params.gflat)."""
+        L = _lib.lib()
+        c = self.cfg
+        X16, T, B = self._top
+        N = T * B
+        ws = self._out_ws(T, B)
+        st = _lib.stream_ptr()
+        Xbf = _to_bf16(X16, ws["Xbf"])
+        gW, gb = self.params.g("out/Wall"), self.params.g("out/ball")
+        dXtop = ws["dXtop"]
+        ro = self.rows_out
+        if c.K == 0:
+            dZ = ws["dZ"]
+            _lib.check(L.lcb_pack_dlogits(_lib.ptr(dlogits), _lib.ptr(dZ), T, B, c.V, self.ldz, st), "lcb_pack_dlogits")
+            gemm(dZ[:, :ro], self._outbf, 0, 1, out=dXtop)                       # dX = dZ * W^T
+            gemm(dZ[:, :ro], Xbf, 1, 1, out=gW)                                   # dW^T = dZ^T * X
+            _lib.check(L.lcb_colsum(_lib.ptr(dZ), 1, N, ro, self.ldz, _lib.ptr(gb), st), "lcb_colsum")
+        else:
+            R = ws["Z"].shape[0]
+            for ci, n0 in enumerate(range(0, N, R)):
+                r = min(R, N - n0)
+                Z, dZ = ws["Z"][:r], ws["dZ"][:r]
+                gemm(X16[n0:n0 + r], self._out16, 0, 0, out=Z[:, :ro], bias=self.params.w("out/ball"))   # recompute z
+                _lib.check(L.lcb_mos_bwd_dz(_lib.ptr(Z), _lib.ptr(dlogits), _lib.ptr(dZ), n0, r, self.ldz, T, B, c.V, c.K,
+                                            c.tau, st), "lcb_mos_bwd_dz")
+                gemm(dZ[:, :ro], self._outbf, 0, 1, out=dXtop[n0:n0 + r])
+                gemm(dZ[:, :ro], Xbf[n0:n0 + r], 1, 1, out=gW, accumulate=(ci > 0))
+                _lib.check(L.lcb_colsum(_lib.ptr(dZ), 1, r, ro, self.ldz, _lib.ptr(gb), st), "lcb_colsum")
+        if bucket_ready is not None:
+            bucket_ready(["out/Wall", "out/ball"])
+        self.enc.backward(dXtop, bucket_ready)
+
+    # ------------------------------------------------------------------ loss
+    def ctc(self, logits, labels, seq_len, check_labels=True):
+        """tf.nn.ctc_loss(..., ignore_longer_outputs_than_inputs=True) + its gradient (graph.py:109-114)."""
+        return ctc_loss_grad(logits, labels, seq_len, check_labels=check_labels)
+
+    def loss_and_grad(self, nnet_input, seq_len, labels, bucket_ready=None, check_labels=True):
+        """Forward + CTC + backward for one minibatch.  Returns (sum of per-utt CTC losses as a device
+        scalar, per-utt losses).  Gradients are left in params.gflat (un-clipped, no L2 yet)."""
+        self.params.gflat.zero_()
+        logits = self.forward_logits(nnet_input, seq_len, training=True)
+        loss, dlogits = self.ctc(logits, labels, seq_len, check_labels)
+        self.backward(dlogits, bucket_ready)
+        return loss.sum(), loss
+
+    # ------------------------------------------------------------------ update
+    def optimizer_step(self, optimizer, learn_rate, clip_norm=5.0, l2_decay_weight=1e-5, momentum=0.9,
+                       beta1=0.9, beta2=0.999, eps=1e-8):
+        """L2 + clip_by_global_norm + apply_gradients (graph.py:183-200) on the flat buffers."""
+        L = _lib.lib()
+        opt = OPT_CODES[optimizer]
+        ps = self.params
+        if self.opt_state is None or self.opt_state[0] != opt:
+            s1 = torch.zeros_like(ps.flat) if opt >= 1 else None
+            s2 = torch.zeros_like(ps.flat) if opt == 2 else None
+            self.opt_state = (opt, s1, s2)
+            self.opt_t = 0
+        self.opt_t += 1
+        _, s1, s2 = self.opt_state
+        nr = len(self._nodecay)
+        arr = (ctypes.c_longlong * (2 * max(nr, 1)))()
+        for k, (lo, hi) in enumerate(self._nodecay):
+            arr[2 * k], arr[2 * k + 1] = lo, hi
+        _lib.check(L.lcb_optimizer_step(_lib.ptr(ps.flat), _lib.ptr(ps.gflat), _lib.ptr(s1), _lib.ptr(s2), ps.total, opt,
+                                        float(learn_rate), self.opt_t, beta1, beta2, eps, momentum, float(l2_decay_weight),
+                                        float(clip_norm), arr, nr, _lib.ptr(self._sumsq), _lib.ptr(self._gnorm),
+                                        _lib.stream_ptr()), "lcb_optimizer_step")
+        self.global_step += 1
+        self.mark_stale()
+
+    def last_grad_norm(self):
+        return float(self._gnorm.item())
+
+    # ------------------------------------------------------------------ checkpoint (trainable variables only)
+    def state_dict(self):
+        """Reference checkpoints hold tf.trainable_variables() only (nnet-train.py:83-84,95): no optimizer
+        slots, no global_step."""
+        return {k: v.cpu() for k, v in self.to_tf_dict().items()}
+
+    def load_state_dict(self, sd):
+        self.from_tf_dict(sd)

@@ -1,0 +1,134 @@
+"""GPU parity of the whole hot path (BiLSTM -> mixture/affine output -> CTC -> gradients -> L2/clip/optimizer)
+vs the fp64 oracle (oracle/model.py), same synthetic inputs and weights.
+
+Stated tolerances: logits within 1e-2 * max|logit| (fp16 operands / fp32 accumulate); summed CTC loss within
+2e-3 relative; per-variable gradients within 5e-2 normwise relative; the optimizer kernel itself (fp32 maths on
+given gradients) within 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def make_batch(cfg, B, T, Lmax, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, T, cfg.input_dim, generator=g, dtype=torch.float64)
+    lens = torch.randint(max(2, int(0.7 * T)), T + 1, (B,), generator=g).to(torch.int32)
+    lens[0] = T
+    labels = -torch.ones(B, Lmax, dtype=torch.int64)
+    for b in range(B):
+        x[b, lens[b]:] = 0
+        n = int(torch.randint(1, min(Lmax, int(lens[b]) // 2) + 1, (1,), generator=g))
+        labels[b, :n] = torch.randint(0, cfg.num_targets - 1, (n,), generator=g)
+    return x, lens, labels
+
+
+def nnet_config(cfg):
+    return {"nnet_type": "blstm", "input_dim": cfg.input_dim, "left_context": 0, "right_context": 0,
+            "num_layers": cfg.num_layers, "num_neurons": cfg.num_neurons, "num_projects": cfg.num_projects,
+            "num_targets": cfg.num_targets, "use_peepholes": cfg.use_peepholes, "num_experts": cfg.num_experts,
+            "moe_temp": cfg.moe_temp, "dropout_rate": 1.0}
+
+
+CASES = {
+    "affine": dict(input_dim=40, num_layers=2, num_neurons=128, num_projects=64, num_targets=20, use_peepholes=True, num_experts=0),
+    "mos_k4": dict(input_dim=24, num_layers=1, num_neurons=64, num_projects=64, num_targets=13, use_peepholes=False, num_experts=4),
+    "mos_k8_v72": dict(input_dim=40, num_layers=2, num_neurons=128, num_projects=128, num_targets=72, use_peepholes=True, num_experts=8),
+    "mos_k5_odd": dict(input_dim=16, num_layers=1, num_neurons=64, num_projects=32, num_targets=31, use_peepholes=True, num_experts=5),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_logits_loss_grads_vs_oracle(cuda_dev, name):
+    from lstm_ctc_b200.model import AcousticModel
+    cfg = oracle.OracleConfig(**CASES[name])
+    params = oracle.init_params(cfg, seed=11, bias_scale=0.1)
+    x, lens, labels = make_batch(cfg, B=6, T=30, Lmax=8, seed=12)
+    p64 = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    ctc, total, ref_logits = oracle.training_loss(p64, cfg, x, lens, labels, l2_decay_weight=0.0)
+    ctc.backward()
+
+    m = AcousticModel(nnet_config(cfg), cuda_dev, init=False)
+    m.from_tf_dict(params)
+    rt = m.to_tf_dict()
+    for k, v in params.items():
+        assert torch.equal(rt[k].cpu().double(), v.float().double()), k                  # exact layout round trip
+    loss_sum, loss = m.loss_and_grad(x.float().to(cuda_dev), lens.to(cuda_dev), labels.to(cuda_dev))
+    logits = m._out_ws(30, 6)["logits"].cpu().double()
+    scale = ref_logits.abs().max().item()
+    mask = (torch.arange(30).unsqueeze(0) < lens.unsqueeze(1))
+    err = (logits - ref_logits.detach())[mask].abs().max().item()
+    assert err < 1e-2 * scale, ("logits", err, scale)
+    assert abs(loss_sum.item() - ctc.item()) < 2e-3 * abs(ctc.item()), (loss_sum.item(), ctc.item())
+    grads = {k: v.cpu().double() for k, v in m.to_tf_dict(grads=True).items()}
+    bad = {}
+    for k, v in grads.items():
+        rg = p64[k].grad
+        rel = ((v - rg).norm() / (rg.norm() + 1e-12)).item()
+        if rel > 5e-2:
+            bad[k] = rel
+    assert not bad, bad
+    from lstm_ctc_b200 import _lib
+    assert _lib.lib().lcb_device_error(1) == 0
+
+
+@pytest.mark.parametrize("opt", ["sgd", "momentum", "adam"])
+def test_optimizer_kernel_vs_oracle(cuda_dev, opt):
+    """L2 (skipping 'bias' variables) + clip_by_global_norm + update, 3 consecutive steps, on a tiny model's
+    flat buffers with injected gradients."""
+    from lstm_ctc_b200.model import AcousticModel
+    cfg = oracle.OracleConfig(input_dim=8, num_layers=1, num_neurons=64, num_projects=8, num_targets=5, use_peepholes=True, num_experts=2)
+    params = oracle.init_params(cfg, seed=3, bias_scale=0.1)
+    m = AcousticModel(nnet_config(cfg), cuda_dev, init=False)
+    m.from_tf_dict(params)
+    p = {k: v.clone().float().double() for k, v in params.items()}
+    state = {}
+    g = torch.Generator().manual_seed(0)
+    for step in range(3):
+        grads = {k: torch.randn(v.shape, generator=g, dtype=torch.float64) * (3.0 if step == 1 else 0.01) for k, v in p.items()}
+        # inject: write the TF-layout gradients into the device-layout flat gradient buffer
+        m.params.gflat.zero_()
+        shadow = AcousticModel(nnet_config(cfg), cuda_dev, init=False)
+        shadow.from_tf_dict(grads)
+        m.params.gflat.copy_(shadow.params.flat)
+        full = {k: grads[k] + (1e-3 * p[k] if "bias" not in k else 0) for k in p}
+        clipped, gn = oracle.clip_by_global_norm(full, 5.0)
+        if opt == "adam":
+            p = oracle.adam_step(p, clipped, state, 1e-2)
+        elif opt == "momentum":
+            p = oracle.momentum_step(p, clipped, state, 1e-2)
+        else:
+            p = oracle.sgd_step(p, clipped, state, 1e-2)
+        m.optimizer_step(opt, 1e-2, clip_norm=5.0, l2_decay_weight=1e-3)
+        assert abs(m.last_grad_norm() - gn) < 1e-4 * gn
+        ours = m.to_tf_dict()
+        for k in p:
+            assert (ours[k].cpu().double() - p[k]).abs().max().item() < 2e-5, (opt, step, k)
+
+
+def test_training_steps_track_oracle(cuda_dev):
+    """Three SGD steps on the same batch: loss sequence and final weights follow the fp64 oracle."""
+    from lstm_ctc_b200.model import AcousticModel
+    cfg = oracle.OracleConfig(**CASES["mos_k4"])
+    params = oracle.init_params(cfg, seed=21, bias_scale=0.05)
+    x, lens, labels = make_batch(cfg, B=4, T=20, Lmax=5, seed=22)
+    m = AcousticModel(nnet_config(cfg), cuda_dev, init=False)
+    m.from_tf_dict(params)
+    p = {k: v.clone() for k, v in params.items()}
+    for step in range(3):
+        pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+        ctc, total, _ = oracle.training_loss(pr, cfg, x, lens, labels, l2_decay_weight=1e-5)
+        total.backward()
+        clipped, _ = oracle.clip_by_global_norm({k: v.grad for k, v in pr.items()}, 5.0)
+        p = oracle.sgd_step({k: v.detach() for k, v in pr.items()}, clipped, {}, 1e-3)
+        loss_sum, _ = m.loss_and_grad(x.float().to(cuda_dev), lens.to(cuda_dev), labels.to(cuda_dev))
+        m.optimizer_step("sgd", 1e-3, clip_norm=5.0, l2_decay_weight=1e-5)
+        assert abs(loss_sum.item() - ctc.item()) < 3e-3 * abs(ctc.item()), (step, loss_sum.item(), ctc.item())
+    ours = m.to_tf_dict()
+    for k in p:
+        d_ref = (p[k] - params[k]).norm().item()
+        d_err = (ours[k].cpu().double() - p[k]).norm().item()
+        assert d_err < 0.1 * d_ref + 1e-7, (k, d_err, d_ref)
