@@ -40,6 +40,8 @@ const char* lcb_status_string(int status);
 /* device-side error word (barrier time-outs etc.); returns 0 if clean.  reset!=0 clears it.
  * Synchronises the device. */
 int lcb_device_error(int reset);
+/* number of kernels this library has launched in this process; reset != 0 zeroes the counter. */
+long long lcb_launch_count(int reset);
 
 /* ---- CTC loss + gradient ---------------------------------------------------------------
  * replaces: tf.nn.ctc_loss(labels, inputs, sequence_length,
@@ -130,6 +132,11 @@ int lcb_pack_input(const float* nnet_input, void* x0, int B, int T, int D, int D
 int lcb_cast_f32_16(const float* src, void* dst, int dst_dtype, size_t n, void* stream);
 int lcb_split_f32_bf16(const float* src, void* hi, void* lo, size_t n, void* stream);
 int lcb_f16_to_bf16(const void* src, void* dst, size_t n, void* stream);   /* n even */
+/* in-place inverted dropout on a 16-bit tensor (dtype 1 bf16 / 2 fp16): DropoutWrapper(output_keep_prob)
+ * on the LSTM layer outputs (nnet/bilstm.py:128,137); the same call on the gradient is its backward.
+ * lcb_dropout_mask writes the 0/1 mask of (seed, index) as bytes. */
+int lcb_dropout16(void* x, int dtype, size_t n, float keep_prob, unsigned long long seed, void* stream);
+int lcb_dropout_mask(unsigned char* mask, size_t n, float keep_prob, unsigned long long seed, void* stream);
 int lcb_colsum(const void* src, int src_dtype, int rows, int cols, int ld, float* out, void* stream);
 
 /* ---- output layer: mixture of tanh-bounded expert logits, or affine -------------------------
@@ -141,14 +148,19 @@ int lcb_colsum(const void* src, int src_dtype, int rows, int cols, int ld, float
  *          rows K*V.. = W_prior^T (moe.py:34-41).  K == 0 (affine): Wall = W^T [V, D2].
  *   bias   [K*V + K] f32 in the same order (affine: [V])
  *   logits [B,T,V] f32 batch-major.   tau = moe_temperature.   K <= 128.
+ *   keep_prob / seed: dropout on the mixture weights (moe.py:46) and on tau*tanh (moe.py:61), keep_prob = 1
+ *   disables it.  Masks are a pure function of (seed, n, column): lcb_mos_bwd_dz regenerates them, and
+ *   lcb_dropout_mask exports them (mixture weights: seed, index n*K+k; expert logits:
+ *   seed ^ 0xD1B54A32D192ED03, index n*K*V + v*K+k).
  * lcb_mos_bwd_dz: rows [n0, n0+R) of Z = X*Wall^T + bias (recomputed with lcb_gemm16, [R, ldz] f32)
  *   and dlogits [B,T,V] f32 -> dZ [R, ldz] bf16 (same column order, pad columns zero); dX, dWall and
  *   dbias then follow from lcb_gemm16 / lcb_colsum (tf.gradients, nnet/graph.py:190-191).
  * lcb_pack_dlogits: [B,T,V] f32 -> time-major [T*B, ldo] bf16 (the affine layer's dZ). */
 int lcb_output_fwd(const void* X, int ldx, const void* Wall, const float* bias, float* logits,
-                   int T, int B, int D2, int V, int K, float tau, void* stream);
+                   int T, int B, int D2, int V, int K, float tau, float keep_prob, unsigned long long seed,
+                   void* stream);
 int lcb_mos_bwd_dz(const float* Z, const float* dlogits, void* dZ, int n0, int R, int ldz,
-                   int T, int B, int V, int K, float tau, void* stream);
+                   int T, int B, int V, int K, float tau, float keep_prob, unsigned long long seed, void* stream);
 int lcb_pack_dlogits(const float* dlogits, void* out, int T, int B, int V, int ldo, void* stream);
 
 /* ---- fused L2 + global-norm clip + optimizer on flat fp32 buffers ---------------------------
@@ -161,6 +173,16 @@ int lcb_optimizer_step(float* w, float* g, float* s1, float* s2, long long n, in
                        float lr, long long step, float beta1, float beta2, float eps, float momentum,
                        float l2, float clip_norm, const long long* nodecay_ranges_host, int n_ranges,
                        double* sumsq_scratch, float* gnorm_out, void* stream);
+
+/* ---- validation / inference tails ---------------------------------------------------------------
+ * lcb_greedy_decode replaces tf.nn.ctc_greedy_decoder(merge_repeated=True) (nnet/graph.py:138-142):
+ *   out [B,T] int32 receives the collapsed label sequence of each utterance, out_len [B] its length.
+ * lcb_posterior replaces tf.nn.softmax(smooth_factor*logits) (nnet/graph.py:236) and the numpy.log /
+ *   class-prior subtraction of bin/nnet-forward.py:87-91 (log_prior nullable, [V]). */
+int lcb_greedy_decode(const float* logits, const int32_t* seq_len, int32_t* out, int32_t* out_len,
+                      int B, int T, int V, void* stream);
+int lcb_posterior(const float* logits, float* out, long long rows, int V, float smooth_factor,
+                  int apply_log, const float* log_prior, void* stream);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,7 @@ _SIGS = {
     "lcb_version": (c_int, []),
     "lcb_status_string": (ctypes.c_char_p, [c_int]),
     "lcb_device_error": (c_int, [c_int]),
+    "lcb_launch_count": (ctypes.c_longlong, [c_int]),
     "lcb_ctc_workspace_bytes": (c_size_t, [c_int] * 4),
     "lcb_ctc_loss_grad_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                       c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -75,12 +76,18 @@ _SIGS = {
                                       c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "lcb_split_f32_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "lcb_f16_to_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
-    "lcb_output_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
-    "lcb_mos_bwd_dz": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "lcb_output_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                               c_float, ctypes.c_ulonglong, c_void_p]),
+    "lcb_mos_bwd_dz": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                               c_float, ctypes.c_ulonglong, c_void_p]),
+    "lcb_dropout16": (c_int, [c_void_p, c_int, c_size_t, c_float, ctypes.c_ulonglong, c_void_p]),
+    "lcb_dropout_mask": (c_int, [c_void_p, c_size_t, c_float, ctypes.c_ulonglong, c_void_p]),
     "lcb_pack_dlogits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "lcb_optimizer_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_float, ctypes.c_longlong,
                                    c_float, c_float, c_float, c_float, c_float, c_float, ctypes.POINTER(ctypes.c_longlong), c_int,
                                    c_void_p, c_void_p, c_void_p]),
+    "lcb_greedy_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "lcb_posterior": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_float, c_int, c_void_p, c_void_p]),
     "lcb_colsum": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 

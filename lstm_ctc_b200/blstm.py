@@ -153,10 +153,21 @@ class BLSTMEncoder:
         self._bf = {}            # bf16 operand copies, refreshed by refresh_operands()
         self._ws = {}            # activation workspaces keyed by (T, B)
         self._stale = True
+        self.seed_base = 777           # reference default --seed (nnet-train.py:141-142)
+        self.step_id = 0
         mt = _lib.ctypes.c_int()
         nc = _lib.ctypes.c_int()
         _lib.check(_lib.lib().lcb_lstm_rec_config(c.Hp, _lib.ctypes.byref(mt), _lib.ctypes.byref(nc)), "lcb_lstm_rec_config")
         self.rec_mt, self.rec_nc = mt.value, nc.value
+
+    def dropout_seed(self, layer):
+        """One mask stream per (training step, layer); layer 255 = mixture output layer."""
+        return ((self.seed_base & 0xffffffff) << 32) ^ ((self.step_id & 0xffffff) << 8) ^ (layer & 0xff)
+
+    def _dropout(self, x, layer):
+        dt = 2 if x.dtype == F16 else 1
+        _lib.check(_lib.lib().lcb_dropout16(_lib.ptr(x), dt, x.numel(), self.cfg.keep_prob, self.dropout_seed(layer),
+                                            _lib.stream_ptr()), "lcb_dropout16")
 
     # ------------------------------------------------------------------ TF <-> device layout
     def _tf_names(self, i, d):
@@ -282,8 +293,7 @@ class BLSTMEncoder:
         assert D == c.input_dim, (D, c.input_dim)
         if c.residual0:
             raise NotImplementedError("layer-0 residual (input_dim == 2*num_projects, bilstm.py:199-200)")
-        if c.keep_prob < 1.0 and training:
-            raise NotImplementedError("output dropout inside the stack (keep_prob < 1)")
+        self.step_id += 1 if training else 0
         self.refresh_operands()
         ws = self._workspace(T, B, training)
         st = _lib.stream_ptr()
@@ -303,6 +313,8 @@ class BLSTMEncoder:
             Hout = ws["Hout"][i]
             for d in range(2):
                 gemm(ws["M"][i][:, d * c.Hp:(d + 1) * c.Hp], self._bf[("WpT16", i)][d], 0, 0, out=Hout[:, d * c.P:(d + 1) * c.P])
+            if training and c.keep_prob < 1.0:
+                self._dropout(Hout, i)              # DropoutWrapper(output_keep_prob), bilstm.py:128,137
             X = Hout
         self._last = (T, B, seq_len, training)
         return X
@@ -334,6 +346,8 @@ class BLSTMEncoder:
         ps = self.params
         dH = dXtop
         for i in reversed(range(c.num_layers)):
+            if c.keep_prob < 1.0:
+                self._dropout(dH, i)                # same (seed, index) mask as the forward pass, on the gradient
             X16 = ws["X0"] if i == 0 else ws["Hout"][i - 1]
             X = _to_bf16(X16, ws["Xbf"][:X16.numel()].view(X16.shape))
             M = _to_bf16(ws["M"][i], ws["Mbf"])

@@ -571,7 +571,7 @@ extern "C" int lcb_ctc_loss_grad_f32(const float* logits, const int64_t* labels,
     double* alpha = (double*)(ws + p.off_alpha);
 
     cudaMemsetAsync(status, 0, 16, st);
-    ctc_prep_kernel<<<(B + 3) / 4, 128, 0, st>>>(labels, Lmax, seq_len, B, T, V, meta, lab, p.LABP, status);
+    g_launches += 3; ctc_prep_kernel<<<(B + 3) / 4, 128, 0, st>>>(labels, Lmax, seq_len, B, T, V, meta, lab, p.LABP, status);
     if ((V & 3) == 0 && ((uintptr_t)logits & 15) == 0 && ((uintptr_t)grad & 15) == 0)
         dispatch_softmax<4>(logits, grad, B, T, V, meta, lab, p.LABP, lpb, lpl, p.LPP, st);
     else if ((V & 1) == 0 && ((uintptr_t)logits & 7) == 0 && ((uintptr_t)grad & 7) == 0)

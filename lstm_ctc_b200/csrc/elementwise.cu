@@ -37,6 +37,25 @@ __global__ void f16_to_bf16_kernel(const __half2* __restrict__ src, __nv_bfloat1
     }
 }
 
+// in-place inverted dropout on a 16-bit tensor: x[i] = keep(seed, i) ? x[i] / keep_prob : 0
+// (DropoutWrapper(output_keep_prob) on the LSTM layer outputs, nnet/bilstm.py:128,137; the same call on the
+// bf16 gradient with the same seed is its backward)
+template <bool F16>
+__global__ void dropout16_kernel(uint16_t* __restrict__ x, size_t n, float inv_keep, uint32_t thr, uint64_t seed) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float v;
+        if constexpr (F16) v = __half2float(reinterpret_cast<__half*>(x)[i]);
+        else v = __bfloat162float(reinterpret_cast<__nv_bfloat16*>(x)[i]);
+        v = rng_keep(seed, i, thr) ? v * inv_keep : 0.f;
+        if constexpr (F16) reinterpret_cast<__half*>(x)[i] = __float2half_rn(sat_f16(v));
+        else reinterpret_cast<__nv_bfloat16*>(x)[i] = __float2bfloat16(v);
+    }
+}
+__global__ void dropout_mask_kernel(uint8_t* __restrict__ m, size_t n, uint32_t thr, uint64_t seed) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        m[i] = rng_keep(seed, i, thr) ? 1 : 0;
+}
+
 // hi = bf16(x), lo = bf16(x - hi): x ~= hi + lo to ~16 mantissa bits (split-bf16 GEMMs for weight folding)
 __global__ void split_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
                                       __nv_bfloat16* __restrict__ lo, size_t n) {
@@ -99,6 +118,7 @@ extern "C" int lcb_cast_f32_16(const float* src, void* dst, int dst_dtype, size_
     if (dst_dtype != 1 && dst_dtype != 2) return LCB_ERR_BAD_SHAPE;
     if (((uintptr_t)src & 15) || ((uintptr_t)dst & 7)) return LCB_ERR_MISALIGNED;
     if (n == 0) return LCB_OK;
+    g_launches += 1;
     if (dst_dtype == 2) cast_f32_16_kernel<true><<<grid_for(n, 4, 256), 256, 0, (cudaStream_t)stream>>>(src, (uint16_t*)dst, n);
     else cast_f32_16_kernel<false><<<grid_for(n, 4, 256), 256, 0, (cudaStream_t)stream>>>(src, (uint16_t*)dst, n);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
@@ -108,13 +128,34 @@ extern "C" int lcb_f16_to_bf16(const void* src, void* dst, size_t n, void* strea
     if (!src || !dst) return LCB_ERR_NULL_POINTER;
     if ((n & 1) || ((uintptr_t)src & 3) || ((uintptr_t)dst & 3)) return LCB_ERR_MISALIGNED;
     if (n == 0) return LCB_OK;
+    g_launches += 1;
     f16_to_bf16_kernel<<<grid_for(n / 2, 1, 256), 256, 0, (cudaStream_t)stream>>>((const __half2*)src, (__nv_bfloat162*)dst, n / 2);
+    return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
+}
+
+extern "C" int lcb_dropout16(void* x, int dtype, size_t n, float keep_prob, unsigned long long seed, void* stream) {
+    if (!x) return LCB_ERR_NULL_POINTER;
+    if ((dtype != 1 && dtype != 2) || !(keep_prob > 0.f) || keep_prob > 1.f) return LCB_ERR_BAD_SHAPE;
+    if (n == 0 || keep_prob == 1.f) return LCB_OK;
+    g_launches += 1;
+    if (dtype == 2) dropout16_kernel<true><<<grid_for(n, 2, 256), 256, 0, (cudaStream_t)stream>>>((uint16_t*)x, n, 1.f / keep_prob, keep_threshold(keep_prob), seed);
+    else dropout16_kernel<false><<<grid_for(n, 2, 256), 256, 0, (cudaStream_t)stream>>>((uint16_t*)x, n, 1.f / keep_prob, keep_threshold(keep_prob), seed);
+    return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
+}
+
+// the 0/1 mask lcb_dropout16 / the mixture kernels use for (seed, element index) -- for tests
+extern "C" int lcb_dropout_mask(unsigned char* mask, size_t n, float keep_prob, unsigned long long seed, void* stream) {
+    if (!mask) return LCB_ERR_NULL_POINTER;
+    if (n == 0) return LCB_OK;
+    g_launches += 1;
+    dropout_mask_kernel<<<grid_for(n, 2, 256), 256, 0, (cudaStream_t)stream>>>(mask, n, keep_threshold(keep_prob), seed);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }
 
 extern "C" int lcb_split_f32_bf16(const float* src, void* hi, void* lo, size_t n, void* stream) {
     if (!src || !hi || !lo) return LCB_ERR_NULL_POINTER;
     if (n == 0) return LCB_OK;
+    g_launches += 1;
     split_f32_bf16_kernel<<<grid_for(n, 1, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }
@@ -122,6 +163,7 @@ extern "C" int lcb_split_f32_bf16(const float* src, void* hi, void* lo, size_t n
 extern "C" int lcb_pack_input(const float* nnet_input, void* x0, int B, int T, int D, int Dp, void* stream) {
     if (!nnet_input || !x0) return LCB_ERR_NULL_POINTER;
     if (B <= 0 || T <= 0 || D <= 0 || Dp < D) return LCB_ERR_BAD_SHAPE;
+    g_launches += 1;
     pack_input_kernel<<<grid_for((size_t)T * B * Dp, 1, 256), 256, 0, (cudaStream_t)stream>>>(nnet_input, (__half*)x0, B, T, D, Dp);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }
@@ -133,6 +175,7 @@ extern "C" int lcb_colsum(const void* src, int src_dtype, int rows, int cols, in
     dim3 blk(32, 8);
     int gy = (rows + 511) / 512; if (gy > 256) gy = 256; if (gy < 1) gy = 1;
     dim3 grd((cols + 31) / 32, gy);
+    g_launches += 1;
     if (src_dtype) colsum_kernel<__nv_bfloat16><<<grd, blk, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, rows, cols, ld, out, 1);
     else colsum_kernel<float><<<grd, blk, 0, (cudaStream_t)stream>>>((const float*)src, rows, cols, ld, out, 1);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;

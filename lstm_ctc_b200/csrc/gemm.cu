@@ -240,7 +240,7 @@ static int launch_gemm(int M, int N, int K, const CUtensorMap& ta, const CUtenso
     const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
     int nsm = 148;
     int grid = tiles < nsm ? tiles : nsm;
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, C, ldc, bias, accumulate, M, N, K, idesc);
+    g_launches += 1; kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, C, ldc, bias, accumulate, M, N, K, idesc);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }
 
@@ -320,7 +320,7 @@ extern "C" int lcb_gemm16_simt_check(int M, int N, int K, const void* A, int lda
     dim3 blk(16, 16), grd((N + 15) / 16, (M + 15) / 16);
     long long a_sm = a_layout ? 1 : lda, a_sk = a_layout ? lda : 1;
     long long b_sn = b_layout ? 1 : ldb, b_sk = b_layout ? ldb : 1;
-    gemm_simt_check_kernel<<<grd, blk, 0, (cudaStream_t)stream>>>(M, N, K, A, a_dtype, a_sm, a_sk, B, b_dtype, b_sn, b_sk,
+    g_launches += 1; gemm_simt_check_kernel<<<grd, blk, 0, (cudaStream_t)stream>>>(M, N, K, A, a_dtype, a_sm, a_sk, B, b_dtype, b_sn, b_sk,
                                                                   C, ldc, c_dtype, bias, accumulate);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }
@@ -333,6 +333,14 @@ extern "C" int lcb_gemm_bf16_simt_check(int M, int N, int K, const void* A, int 
 }
 
 extern "C" int lcb_version(void) { return 100; }
+
+// kernels launched by this library so far in this process (reset != 0 zeroes the counter afterwards)
+extern "C" long long lcb_launch_count(int reset)
+{
+    const long long v = lcb::g_launches;
+    if (reset) lcb::g_launches = 0;
+    return v;
+}
 
 extern "C" const char* lcb_status_string(int s)
 {

@@ -6,3 +6,4 @@
 #include "elementwise.cu"
 #include "mos.cu"
 #include "optim.cu"
+#include "decode.cu"

@@ -543,7 +543,7 @@ static int launch_cluster(K kern, int grid, int threads, size_t smem, int nc, cu
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
+    g_launches += 1; cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
     if (e != cudaSuccess) { cudaGetLastError(); return LCB_ERR_CUDA; }
     return LCB_OK;
 }

@@ -36,6 +36,9 @@ struct OutFwdParams {
     int Kp16;              // K rounded up to 16 (MMA N of the prior pass)
     int pis;               // row stride of pi in smem (odd)
     float tau;
+    float inv_keep;        // 1 / keep_prob (1 when dropout is off)
+    uint32_t thr;          // keep threshold (0xffffffff: dropout off)
+    unsigned long long seed_pi, seed_d;   // mask streams: mixture weights [N,K] (moe.py:46), expert logits [N,K*V] (moe.py:61)
 };
 
 __global__ void __launch_bounds__(OUT_THREADS, 1)
@@ -165,7 +168,9 @@ out_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                         }
                     }
                     const float inv = 1.f / sum;
-                    for (int k = 0; k < K; ++k) pir[k] *= inv;
+                    // y_prior = dropout(softmax(...))  (moe.py:45-46): fold mask and 1/keep into the stored weights
+                    for (int k = 0; k < K; ++k)
+                        pir[k] = rng_keep(p.seed_pi, (uint64_t)n * K + k, p.thr) ? pir[k] * inv * p.inv_keep : 0.f;
                 } else {
                     const int c_base = (ps - (K > 0 ? 1 : 0)) * OUT_BN;
                     for (int c0 = 0; c0 < OUT_BN && c_base + c0 < KV; c0 += 32) {
@@ -177,9 +182,10 @@ out_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                             for (int j = 0; j < 32; ++j) {
                                 const int col = c_base + c0 + j;
                                 if (col < KV) {
-                                    accv += pir[kk] * tanhf_fast(__uint_as_float(r[j]) + __ldg(p.bias + col));
+                                    if (rng_keep(p.seed_d, (uint64_t)n * KV + col, p.thr))      // dropout on tau*tanh (moe.py:61)
+                                        accv += pir[kk] * tanhf_fast(__uint_as_float(r[j]) + __ldg(p.bias + col));
                                     if (++kk == K) {
-                                        if (rowok) orow[vv] = p.tau * accv;
+                                        if (rowok) orow[vv] = p.tau * p.inv_keep * accv;
                                         ++vv; kk = 0; accv = 0.f;
                                     }
                                 }
@@ -212,7 +218,8 @@ out_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 //   dZ  [R, ldz] bf16  d loss / d z  (same column order; pad columns zeroed)
 __global__ void __launch_bounds__(256)
 mos_bwd_kernel(const float* __restrict__ Z, const float* __restrict__ dY, __nv_bfloat16* __restrict__ dZ,
-               int n0, int R, int ldz, int T, int B, int V, int K, float tau)
+               int n0, int R, int ldz, int T, int B, int V, int K, float tau,
+               float inv_keep, uint32_t thr, unsigned long long seed_pi, unsigned long long seed_d)
 {
     extern __shared__ float sm[];                     // per warp: dpi[K], pi[K]
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -240,12 +247,15 @@ mos_bwd_kernel(const float* __restrict__ Z, const float* __restrict__ dY, __nv_b
         for (int k = lane; k < K; k += 32) pi[k] *= inv;
         __syncwarp();
         // expert columns: dz = dy * pi * tau * (1 - tanh^2);  dpi[k] += dy * tau * tanh
+        // forward: y_v = sum_k pi'_k * tau * th_k * m2/keep,  pi'_k = pi_k * m1/keep
         for (int c = lane; c < KV; c += 32) {
             const int v = c / K, k = c - v * K;
             const float th = tanhf_fast(z[c]);
-            const float g = dy[v] * tau;
-            atomicAdd(&dpi[k], g * th);
-            dz[c] = __float2bfloat16(g * pi[k] * (1.f - th * th));
+            const float m2 = rng_keep(seed_d, (uint64_t)n * KV + c, thr) ? inv_keep : 0.f;
+            const float m1 = rng_keep(seed_pi, (uint64_t)n * K + k, thr) ? inv_keep : 0.f;
+            const float g = dy[v] * tau * m2;
+            atomicAdd(&dpi[k], g * th * m1);                       // d loss / d pi_k
+            dz[c] = __float2bfloat16(g * pi[k] * m1 * (1.f - th * th));
         }
         __syncwarp();
         // softmax backward: dlogit_k = pi_k * (dpi_k - sum_j pi_j dpi_j)
@@ -275,10 +285,12 @@ __global__ void pack_dlogits_kernel(const float* __restrict__ dY, __nv_bfloat16*
 using namespace lcb;
 
 extern "C" int lcb_output_fwd(const void* X, int ldx, const void* Wall, const float* bias, float* logits,
-                              int T, int B, int D2, int V, int K, float tau, void* stream)
+                              int T, int B, int D2, int V, int K, float tau, float keep_prob, unsigned long long seed,
+                              void* stream)
 {
     if (!X || !Wall || !bias || !logits) return LCB_ERR_NULL_POINTER;
     if (T <= 0 || B <= 0 || D2 <= 0 || V <= 0 || K < 0) return LCB_ERR_BAD_SHAPE;
+    if (!(keep_prob > 0.f) || keep_prob > 1.f) return LCB_ERR_BAD_SHAPE;
     if (K > 128) return LCB_ERR_UNSUPPORTED;
     if ((ldx & 7) || (D2 & 7) || ((uintptr_t)X & 15) || ((uintptr_t)Wall & 15)) return LCB_ERR_MISALIGNED;
     OutFwdParams p;
@@ -287,6 +299,9 @@ extern "C" int lcb_output_fwd(const void* X, int ldx, const void* Wall, const fl
     p.Kp16 = K > 0 ? ((K + 15) & ~15) : 16;
     p.pis = (K | 1) + 2 * (K > 0 ? 0 : 0);
     p.tau = tau;
+    p.inv_keep = 1.f / keep_prob;
+    p.thr = keep_threshold(keep_prob);
+    p.seed_pi = seed; p.seed_d = seed ^ 0xD1B54A32D192ED03ull;
     const int rows = p.KV + K;
     CUtensorMap tx, tw, twp;
     if (!make_tmap_2d_bf16(&tx, X, (uint64_t)p.N, (uint64_t)D2, (uint64_t)ldx, OUT_BM, OUT_BK)) return LCB_ERR_CUDA;
@@ -300,18 +315,20 @@ extern "C" int lcb_output_fwd(const void* X, int ldx, const void* Wall, const fl
     }
     const int tiles_m = (p.N + OUT_BM - 1) / OUT_BM;
     const int grid = tiles_m < 148 ? tiles_m : 148;
-    out_fwd_kernel<<<grid, OUT_THREADS, smem, (cudaStream_t)stream>>>(tx, tw, twp, p);
+    g_launches += 1; out_fwd_kernel<<<grid, OUT_THREADS, smem, (cudaStream_t)stream>>>(tx, tw, twp, p);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }
 
 extern "C" int lcb_mos_bwd_dz(const float* Z, const float* dlogits, void* dZ, int n0, int R, int ldz,
-                              int T, int B, int V, int K, float tau, void* stream)
+                              int T, int B, int V, int K, float tau, float keep_prob, unsigned long long seed, void* stream)
 {
+    if (!(keep_prob > 0.f) || keep_prob > 1.f) return LCB_ERR_BAD_SHAPE;
     if (!Z || !dlogits || !dZ) return LCB_ERR_NULL_POINTER;
     if (R <= 0 || K <= 0 || V <= 0 || ldz < K * V + K) return LCB_ERR_BAD_SHAPE;
     int grid = (R + 7) / 8; if (grid > 148 * 8) grid = 148 * 8;
     const size_t smem = (size_t)8 * 2 * K * sizeof(float);
-    mos_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(Z, dlogits, (__nv_bfloat16*)dZ, n0, R, ldz, T, B, V, K, tau);
+    g_launches += 1; mos_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(Z, dlogits, (__nv_bfloat16*)dZ, n0, R, ldz, T, B, V, K, tau,
+                                                            1.f / keep_prob, keep_threshold(keep_prob), seed, seed ^ 0xD1B54A32D192ED03ull);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }
 
@@ -321,6 +338,6 @@ extern "C" int lcb_pack_dlogits(const float* dlogits, void* out, int T, int B, i
     if (T <= 0 || B <= 0 || V <= 0 || ldo < V) return LCB_ERR_BAD_SHAPE;
     const size_t total = (size_t)T * B * ldo;
     size_t blocks = (total + 255) / 256; if (blocks > 148 * 16) blocks = 148 * 16;
-    pack_dlogits_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(dlogits, (__nv_bfloat16*)out, T, B, V, ldo);
+    g_launches += 1; pack_dlogits_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(dlogits, (__nv_bfloat16*)out, T, B, V, ldo);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }

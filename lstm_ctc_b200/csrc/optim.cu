@@ -87,7 +87,7 @@ extern "C" int lcb_optimizer_step(float* w, float* g, float* s1, float* s2, long
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
     cudaMemsetAsync(sumsq_scratch, 0, sizeof(double), st);
-    l2_sumsq_kernel<<<(int)blocks, 256, 0, st>>>(w, g, n, l2, nd, sumsq_scratch);
+    g_launches += 2; l2_sumsq_kernel<<<(int)blocks, 256, 0, st>>>(w, g, n, l2, nd, sumsq_scratch);
     // tf.train.AdamOptimizer: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
     const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
     apply_update_kernel<<<(int)blocks, 256, 0, st>>>(w, g, s1, s2, n, opt, lr, (float)lr_t, beta1, beta2, eps, momentum,

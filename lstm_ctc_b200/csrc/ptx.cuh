@@ -8,6 +8,9 @@
 
 namespace lcb {
 
+// host-side count of kernels launched by this library (bench.py reports it as gpu_launches)
+static long long g_launches = 0;
+
 // ----------------------------------------------------------------------------------------
 // device-side error word: a kernel that times out on a barrier records a code here and bails
 // out instead of hanging the GPU.  Host reads it through lcb_device_error().
@@ -289,6 +292,26 @@ __device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint32_t a, uint32_
 }
 __device__ __forceinline__ void st_cluster_b32(uint32_t addr, uint32_t a) {
     asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
+}
+
+// ----------------------------------------------------------------------------------------
+// counter-based dropout RNG: keep(seed, idx) is a pure function, so the backward pass regenerates the
+// forward mask instead of storing it (TF's DropoutWrapper / tf.nn.dropout streams cannot be matched
+// bit-for-bit anyway; parity tests export this mask and feed it to the oracle).
+// ----------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t rng_u32(uint64_t seed, uint64_t idx) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (uint32_t)(z >> 32);
+}
+__host__ __device__ __forceinline__ uint32_t keep_threshold(float keep) {      // P(u32 < thr) = keep
+    double t = (double)keep * 4294967296.0;
+    return t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
+}
+__host__ __device__ __forceinline__ bool rng_keep(uint64_t seed, uint64_t idx, uint32_t thr) {
+    return thr == 0xffffffffu || rng_u32(seed, idx) < thr;
 }
 
 // ----------------------------------------------------------------------------------------

@@ -1,0 +1,228 @@
+"""Graph-construction / loss API of the hot path -- host-side mirror of /root/reference/nnet/graph.py.
+
+Same entry points, argument meaning and returned dict keys as the reference:
+  get_create_logits, get_optimizer,
+  create_graph_for_validation_ctc(pipeline, nnet_config)                     (graph.py:51-162)
+  create_graph_for_training_ctc(pipeline, nnet_config, learn_rate, clip_norm, optimizer, l2_decay_weight)  (:165-209)
+  create_graph_for_inference(pipeline, nnet_config, smooth_factor)            (:212-241)
+The returned values are `Node` handles; `Session.run(nodes)` pulls ONE minibatch from the pipeline and
+executes the step on the sm_100a kernels (the equivalent of one sess.run of the reference, funcs.py:40-41).
+"""
+import sys
+
+import numpy as np
+import torch
+
+from . import _lib
+from .model import AcousticModel
+from .pipeline import OutOfRangeError, PipelineTensor  # noqa: F401
+from . import dist as _dist
+
+
+class Node:
+    def __init__(self, name, graph):
+        self.name, self.graph = name, graph
+
+    def __repr__(self):
+        return "<node %s>" % self.name
+
+
+_default_model = [None]
+
+
+def trainable_variables():
+    """Handle on the variables of the most recently built graph (tf.trainable_variables())."""
+    return _default_model[0]
+
+
+class Saver:
+    """tf.train.Saver(tf.trainable_variables()): trainable variables ONLY, in the reference's TF names
+    (no optimizer slots, no global_step -- nnet-train.py:83-84,95)."""
+
+    def __init__(self, var_list=None):
+        self.model = var_list if var_list is not None else _default_model[0]
+
+    def save(self, sess, path):
+        torch.save(self.model.state_dict(), path)
+        return path
+
+    def restore(self, sess, path):
+        self.model.load_state_dict(torch.load(path, map_location="cpu"))
+
+
+def get_create_logits(string):
+    """graph.py:24-34.  Only 'blstm' is functional in the reference (the other two builders are stale)."""
+    if not string:
+        return None
+    if string == "blstm":
+        from .bilstm import create_logits_blstm
+        return create_logits_blstm
+    return None
+
+
+def get_optimizer(string, learning_rate, momentum=0.9):
+    """graph.py:37-48: 'adam' | 'sgd' | 'momentum' -> (name, hyper-parameters) consumed by lcb_optimizer_step."""
+    if string in ("adam", "sgd", "momentum"):
+        return {"name": string, "learning_rate": learning_rate, "momentum": momentum}
+    return None
+
+
+def _edit_distance(a, b):
+    n, m = len(a), len(b)
+    d = list(range(m + 1))
+    for i in range(1, n + 1):
+        prev, d[0] = d[0], i
+        for j in range(1, m + 1):
+            cur = d[j]
+            d[j] = min(d[j] + 1, d[j - 1] + 1, prev + (a[i - 1] != b[j - 1]))
+            prev = cur
+    return d[m]
+
+
+class _Graph:
+    def __init__(self, pipeline, nnet_config, mode, seed=None):
+        self.mode = mode
+        self.source = pipeline["nnet_input"].source
+        self.nnet_config = dict(nnet_config)
+        nnet_type = nnet_config.get("nnet_type")
+        if get_create_logits(nnet_type) is None:
+            raise ValueError("unsupported nnet_type: %s" % nnet_type)
+        self.model = AcousticModel(self.nnet_config, seed=seed)
+        _default_model[0] = self.model
+        self.train_cfg = None
+        self.smooth_factor = 1.0
+        self.reducer = _dist.GradientAllReducer(self.model.params)
+        self.reducer.broadcast_weights()
+        self._scal = torch.zeros(2, dtype=torch.float64, device=self.model.device)
+
+    # one sess.run ----------------------------------------------------------------
+    def step(self, wanted):
+        batch = self.source.next()                                   # may raise OutOfRangeError
+        m = self.model
+        dev = m.device
+        if self.mode == "infer":
+            return self._infer(batch, wanted)
+        x = batch["nnet_input"].to(dev, non_blocking=True)
+        lens = batch["sequence_length"].to(dev, non_blocking=True)
+        y = batch["nnet_target"].to(dev, non_blocking=True)
+        size = int((batch["nnet_target"] != -1).sum())                # graph.py:105-106
+        out = {"size": size, "sequence_length": batch["sequence_length"].numpy(), "summary": None,
+               "raw_target": batch["nnet_target"].numpy()}
+        if "train" in wanted:
+            tc = self.train_cfg
+            self.reducer.begin_step()
+            loss_sum, _ = m.loss_and_grad(x, lens, y, bucket_ready=self.reducer.bucket_ready)
+            self.reducer.finish()
+            m.optimizer_step(tc["optimizer"], tc["learn_rate"], tc["clip_norm"], tc["l2_decay_weight"])
+            out["train"] = None
+            logits = m._out_ws(x.shape[1], x.shape[0])["logits"]
+        else:
+            logits = m.forward_logits(x, lens, training=False)
+            loss, _ = m.ctc(logits, y, lens)
+            loss_sum = loss.sum()
+        if self.reducer.world > 1:
+            self._scal[0] = loss_sum.double()
+            self._scal[1] = float(size)
+            self.reducer.all_reduce_scalars(self._scal)
+            vals = self._scal.tolist()
+            out["eval_loss"], out["size"] = vals[0], int(round(vals[1]))
+        else:
+            out["eval_loss"] = float(loss_sum.item())                 # D2H read of the step's result
+        out["loss"] = out["eval_loss"]                                # reg losses are 0 in both recipes (graph.py:120-136)
+        out["global_step"] = m.global_step
+        if "logits" in wanted:
+            out["logits"] = logits.cpu().numpy()
+        if "eval" in wanted:
+            out["eval"] = self._greedy_edit_distance(logits, batch)
+        return out
+
+    def _greedy_edit_distance(self, logits, batch):
+        """ctc_greedy_decoder(merge_repeated=True) + edit_distance(normalize=False), summed (graph.py:138-150)."""
+        from .decode import greedy_decode
+        seqs = greedy_decode(logits, batch["sequence_length"].to(logits.device))
+        tot = 0.0
+        y = batch["nnet_target"].numpy()
+        for b, hyp in enumerate(seqs):
+            ref = [int(v) for v in y[b] if v != -1]
+            tot += _edit_distance(hyp, ref)
+        return tot
+
+    def _infer(self, batch, wanted):
+        m = self.model
+        x = batch["nnet_input"].to(m.device, non_blocking=True).unsqueeze(0)      # graph.py:227
+        T = x.shape[1]
+        lens = torch.tensor([batch["sequence_length"]], dtype=torch.int32, device=m.device)
+        logits = m.forward_logits(x, lens, training=False)[0]                       # squeeze, graph.py:234
+        out = {"filename": batch["filename"], "sequence_length": batch["sequence_length"]}
+        if "logits" in wanted:
+            out["logits"] = logits.cpu().numpy()
+        if "nnet_output" in wanted:
+            from .decode import softmax_rows
+            out["nnet_output"] = softmax_rows(logits, self.smooth_factor).cpu().numpy()   # graph.py:236
+        return out
+
+
+class Session:
+    """Stand-in for tf.Session: run(initializer) starts the pipeline; run(nodes) executes one step."""
+
+    def __init__(self, config=None):
+        pass
+
+    def run(self, fetches):
+        if callable(fetches):
+            fetches()
+            return None
+        if fetches is None:
+            return None
+        if isinstance(fetches, dict):
+            items = list(fetches.items())
+        elif isinstance(fetches, (list, tuple)):
+            items = list(enumerate(fetches))
+        else:
+            items = [(0, fetches)]
+        nodes = [n for _, n in items if isinstance(n, Node)]
+        if not nodes:
+            return None
+        g = nodes[0].graph
+        values = g.step({n.name for n in nodes})
+        res = {k: (values.get(n.name) if isinstance(n, Node) else None) for k, n in items}
+        if isinstance(fetches, dict):
+            return res
+        if isinstance(fetches, (list, tuple)):
+            return [res[i] for i in range(len(items))]
+        return res[0]
+
+
+def global_variables_initializer():
+    return None          # variables are initialised at graph construction (TF default initialisers)
+
+
+local_variables_initializer = global_variables_initializer
+
+_VALID_KEYS = ("nnet_input", "sequence_length", "logits", "raw_target", "nnet_target", "size", "eval_loss", "loss",
+               "eval", "global_step", "summary")
+
+
+def create_graph_for_validation_ctc(pipeline, nnet_config, seed=None):
+    g = _Graph(pipeline, nnet_config, "valid", seed)
+    return {k: Node(k, g) for k in _VALID_KEYS}
+
+
+def create_graph_for_training_ctc(pipeline, nnet_config, learn_rate, clip_norm=5.0, optimizer="sgd",
+                                  l2_decay_weight=1e-5, seed=None):
+    if get_optimizer(optimizer, learn_rate) is None:
+        raise ValueError("unsupported optimizer: %s" % optimizer)
+    g = _Graph(pipeline, nnet_config, "train", seed)
+    g.train_cfg = {"learn_rate": float(learn_rate), "clip_norm": float(clip_norm), "optimizer": optimizer,
+                   "l2_decay_weight": float(l2_decay_weight)}
+    graph = {k: Node(k, g) for k in _VALID_KEYS}
+    graph["lrate"] = float(learn_rate)
+    graph["train"] = Node("train", g)
+    return graph
+
+
+def create_graph_for_inference(pipeline, nnet_config, smooth_factor=1.0, seed=None):
+    cfg = dict(nnet_config)
+    g = _Graph(pipeline, cfg, "infer", seed)
+    g.smooth_factor = float(smooth_factor)
+    return {k: Node(k, g) for k in ("filename", "nnet_input", "sequence_length", "logits", "nnet_output")}

@@ -169,8 +169,11 @@ class AcousticModel:
         X = self.enc.forward(nnet_input, seq_len, training)
         B, T = nnet_input.shape[0], nnet_input.shape[1]
         ws = self._out_ws(T, B)
+        keep = c.keep_prob if training else 1.0
+        self._out_seed = self.enc.dropout_seed(255)
         _lib.check(L.lcb_output_fwd(_lib.ptr(X), X.stride(0), _lib.ptr(self._out16), _lib.ptr(self.params.w("out/ball")),
-                                    _lib.ptr(ws["logits"]), T, B, 2 * c.P, c.V, c.K, c.tau, _lib.stream_ptr()), "lcb_output_fwd")
+                                    _lib.ptr(ws["logits"]), T, B, 2 * c.P, c.V, c.K, c.tau, keep, self._out_seed,
+                                    _lib.stream_ptr()), "lcb_output_fwd")
         self._top = (X, T, B)
         return ws["logits"]
 
@@ -200,7 +203,7 @@ class AcousticModel:
                 Z, dZ = ws["Z"][:r], ws["dZ"][:r]
                 gemm(X16[n0:n0 + r], self._out16, 0, 0, out=Z[:, :ro], bias=self.params.w("out/ball"))   # recompute z
                 _lib.check(L.lcb_mos_bwd_dz(_lib.ptr(Z), _lib.ptr(dlogits), _lib.ptr(dZ), n0, r, self.ldz, T, B, c.V, c.K,
-                                            c.tau, st), "lcb_mos_bwd_dz")
+                                            c.tau, c.keep_prob, self._out_seed, st), "lcb_mos_bwd_dz")
                 gemm(dZ[:, :ro], self._outbf, 0, 1, out=dXtop[n0:n0 + r])
                 gemm(dZ[:, :ro], Xbf[n0:n0 + r], 1, 1, out=gW, accumulate=(ci > 0))
                 _lib.check(L.lcb_colsum(_lib.ptr(dZ), 1, r, ro, self.ldz, _lib.ptr(gb), st), "lcb_colsum")

@@ -132,3 +132,58 @@ def test_training_steps_track_oracle(cuda_dev):
         d_ref = (p[k] - params[k]).norm().item()
         d_err = (ours[k].cpu().double() - p[k]).norm().item()
         assert d_err < 0.1 * d_ref + 1e-7, (k, d_err, d_ref)
+
+
+def _mask(n, keep, seed, dev):
+    from lstm_ctc_b200 import _lib
+    m = torch.empty(n, dtype=torch.uint8, device=dev)
+    _lib.check(_lib.lib().lcb_dropout_mask(_lib.ptr(m), n, keep, seed, _lib.stream_ptr()), "mask")
+    return m.cpu().double()
+
+
+def test_dropout_parity_with_exported_masks(cuda_dev):
+    """keep_prob = 0.8 on LSTM layer outputs (bilstm.py:128,137), mixture weights (moe.py:46) and expert logits
+    (moe.py:61).  TF's RNG stream cannot be matched, so the kernels' counter-based masks are exported and fed to
+    the oracle: logits, loss and gradients must then agree at the usual tolerance."""
+    from lstm_ctc_b200.model import AcousticModel
+    cfg = oracle.OracleConfig(**CASES["mos_k4"])
+    cfg.num_layers = 2
+    params = oracle.init_params(cfg, seed=31, bias_scale=0.1)
+    B, T, keep = 5, 14, 0.8
+    x, lens, labels = make_batch(cfg, B=B, T=T, Lmax=4, seed=32)
+    nc = nnet_config(cfg); nc["dropout_rate"] = keep
+    m = AcousticModel(nc, cuda_dev, init=False)
+    m.from_tf_dict(params)
+    loss_sum, _ = m.loss_and_grad(x.float().to(cuda_dev), lens.to(cuda_dev), labels.to(cuda_dev))
+    P, K, V = cfg.num_projects, cfg.num_experts, cfg.num_targets
+    N = T * B
+    # export masks (absolute time order, time-major rows n = t*B + b) and convert to the oracle's conventions
+    masks = {}
+    for i in range(cfg.num_layers):
+        mk = _mask(N * 2 * P, keep, m.enc.dropout_seed(i), cuda_dev).view(T, B, 2 * P).permute(1, 0, 2)   # [B,T,2P]
+        masks[(i, "f")] = mk[:, :, :P].contiguous()
+        masks[(i, "b")] = oracle.model.reverse_sequence(mk[:, :, P:].contiguous(), lens)    # bwd cell runs in reversed time
+    seed = m._out_seed
+    mp = _mask(N * K, keep, seed, cuda_dev).view(T, B, K).permute(1, 0, 2).reshape(B * T, K, 1)
+    md = _mask(N * K * V, keep, seed ^ 0xD1B54A32D192ED03, cuda_dev).view(T, B, V, K).permute(1, 0, 3, 2).reshape(B * T, K, V)
+    p64 = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    enc, _ = oracle.blstm_forward(p64, cfg, x, lens, keep_prob=keep, masks=masks)
+    y = oracle.create_moe(enc.reshape(-1, 2 * P), p64["Variable"], p64["Variable_1"], p64["Variable_2"], p64["Variable_3"],
+                          V, K, cfg.moe_temp, keep_prob=keep, mask_prior=mp, mask_dec=md).reshape(B, T, V)
+    ctc = oracle.ctc_loss_sum(y, labels, lens)
+    ctc.backward()
+    logits = m._out_ws(T, B)["logits"].cpu().double()
+    live = (torch.arange(T).unsqueeze(0) < lens.unsqueeze(1))
+    assert (logits - y.detach())[live].abs().max().item() < 1e-2 * y.abs().max().item()
+    assert abs(loss_sum.item() - ctc.item()) < 2e-3 * abs(ctc.item())
+    grads = {k: v.cpu().double() for k, v in m.to_tf_dict(grads=True).items()}
+    bad = {k: ((v - p64[k].grad).norm() / (p64[k].grad.norm() + 1e-12)).item() for k, v in grads.items()}
+    bad = {k: r for k, r in bad.items() if r > 5e-2}
+    assert not bad, bad
+    # and: inference mode ignores dropout (bilstm.py:98-99)
+    nc2 = dict(nc); nc2["is_training"] = False
+    m2 = AcousticModel(nc2, cuda_dev, init=False)
+    m2.from_tf_dict(params)
+    lg2 = m2.forward_logits(x.float().to(cuda_dev), lens.to(cuda_dev), training=False).cpu().double()
+    ref2 = oracle.output_layer(params, cfg, oracle.blstm_forward(params, cfg, x, lens)[0])
+    assert (lg2 - ref2)[live].abs().max().item() < 1e-2 * ref2.abs().max().item()
