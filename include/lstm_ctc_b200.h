@@ -99,26 +99,32 @@ int lcb_gemm_bf16_simt_check(int M, int N, int K,
  * replaces: tf.nn.dynamic_rnn(DropoutWrapper(LSTMCell(num_units, num_proj, use_peepholes,
  *           forget_bias=5.0)), sequence_length=...) for "fd{i}" AND "bd{i}"  nnet/bilstm.py:127-188
  *           and tf.reverse_sequence                                          nnet/bilstm.py:112,190,203
- * Hp = hidden size padded to a multiple of 64 (<= 512).  Packed gate column = 4*unit + gate,
- * gates (i,j,f,o); direction d owns columns [d*4Hp, (d+1)*4Hp).  Time-major rows n = t*B + b.
- *   G     [T*B, 8Hp] f32   x_t*W_x + bias (from lcb_gemm_bf16)
- *   Wfold [8Hp, Hp]  fp16 (fwd) / bf16 (bwd)  rows = packed gate columns of both directions,
- *                          cols = unit: (W_proj*W_h)^T
- *   peep  [2,3,Hp]   f32   (w_f, w_i, w_o) per direction, or NULL (use_peepholes = False)
- *   lens  [B] int32        sequence_length
- *   Mout  [T*B, 2Hp] fp16  m_t = o*tanh(c) per direction; rows with t >= lens[b] are 0 (dynamic_rnn
- *                          zero output); h = Mout * W_proj is a bulk lcb_gemm_bf16 afterwards
- *   acts  [6, T*B, 2Hp] f32 saved (i, tanh j, f, o, c, tanh c) for BPTT, or NULL for inference
+ * Hp = hidden size padded to a multiple of 64 (<= 512).  Packed gate column of (unit, gate) =
+ * (unit/8)*32 + gate*8 + unit%8, gates (i,j,f,o); direction d owns columns [d*4Hp, (d+1)*4Hp).  Time-major rows n = t*B + b.
+ *   G      [T*B, 8Hp] f32   x_t*W_x + bias (from lcb_gemm16)
+ *   WfoldT [8Hp, Hp]  fp16  (W_proj*W_h)^T: rows = packed gate columns of both directions, cols = unit.
+ *                           Each CTA keeps its 128 rows resident in tensor memory for the whole sequence.
+ *   peep   [2,3,Hp]   f32   (w_f, w_i, w_o) per direction, or NULL (use_peepholes = False)
+ *   lens   [B] int32        sequence_length
+ *   Mout   [T*B, 2Hp] fp16  m_t = o*tanh(c) per direction; rows with t >= lens[b] are 0 (dynamic_rnn
+ *                           zero output); h = Mout * W_proj is a bulk lcb_gemm16 afterwards
+ *   gates  [T*B, 2Hp] 8 B   saved (i, tanh j, f, o) as 4 x fp16, and
+ *   cst    [T*B, 2Hp] f32   saved cell state, for BPTT -- both NULL for inference
  *   cfin, mfin [B,2,Hp] f32 final states (both or neither) -- `encoder` of nnet/bilstm.py:206-208 */
 int lcb_lstm_rec_config(int Hp, int* units_per_cta_div32, int* cluster_size);
-int lcb_lstm_rec_fwd(const float* G, const void* Wfold, const float* peep, const int32_t* lens,
-                     void* Mout, float* acts, float* cfin, float* mfin,
+/* clusters of the forward (which=0) / BPTT (which=1) kernel the device keeps resident at once (<0: error) */
+int lcb_lstm_rec_max_clusters(int Hp, int which);
+/* debug probe: the next lcb_lstm_rec_fwd launches write steps*16 clock64 samples of CTA 0 into buf (NULL: off). */
+int lcb_debug_rec_profile(long long* buf, int steps);
+int lcb_lstm_rec_fwd(const float* G, const void* WfoldT, const float* peep, const int32_t* lens,
+                     void* Mout, void* gates, float* cst, float* cfin, float* mfin,
                      int T, int B, int Hp, float forget_bias, void* stream);
 /* BPTT of the above (replaces tf.gradients through the while_loop, nnet/graph.py:190-191).
  *   dM    [T*B, 2Hp] f32   d loss / d m_t arriving from the output projection
+ *   Wfold [2*Hp, 4Hp] bf16 W' = W_proj*W_h per direction: rows = units, cols = packed gate columns
  *   dG    [T*B, 8Hp] bf16  d loss / d z_t (packed columns; 0 where t >= lens[b])
  *   dbias [2*4Hp] f32 +=,  dpeep [2,3,Hp] f32 += (NULL iff peep NULL) */
-int lcb_lstm_rec_bwd(const float* dM, const float* acts, const void* Wfold, const float* peep,
+int lcb_lstm_rec_bwd(const float* dM, const void* gates, const float* cst, const void* Wfold, const float* peep,
                      const int32_t* lens, void* dG, float* dbias, float* dpeep,
                      int T, int B, int Hp, void* stream);
 

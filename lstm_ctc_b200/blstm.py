@@ -8,7 +8,7 @@ What runs where (all compute is in liblstm_ctc_b200.so; torch only owns memory a
   lcb_gemm_bf16       h = m*W_proj written straight into its half of [N,2P] (num_proj + tf.concat)
 and the mirrored sequence for the backward pass (lcb_lstm_rec_bwd + dgrad/wgrad GEMMs).
 
-Parameters live in DEVICE layout (packed gate columns 4*unit+gate, hidden size padded to 64) inside one
+Parameters live in DEVICE layout (gate columns packed (unit/8)*32 + gate*8 + unit%8, hidden size padded to 64) inside one
 flat fp32 buffer; `to_tf_dict` / `from_tf_dict` convert to/from the reference's TF variable names and
 shapes (fd{i}/frnn{i}/kernel, .../bias, .../w_{f,i,o}_diag, .../projection/kernel; bilstm.py:125-165).
 """
@@ -187,14 +187,15 @@ class BLSTMEncoder:
                 pre = self._tf_names(i, d)
                 k = tf[pre + "/kernel"].to(device=self.device, dtype=F32)          # [din+P, 4H]
                 assert k.shape == (din + P, 4 * H), (k.shape, din, P, H)
-                # packed row r = d*4Hp + 4*u + gate  <-  TF column gate*H + u
-                kk = k.view(din + P, 4, H).permute(2, 1, 0)                          # [H(u), 4(gate), din+P]
-                rows = Wx[d * 4 * Hp:(d + 1) * 4 * Hp].view(Hp, 4, -1)
-                rows[:H, :, :din] = kk[:, :, :din]
-                rowsh = Wh[d * 4 * Hp:(d + 1) * 4 * Hp].view(Hp, 4, P)
-                rowsh[:H] = kk[:, :, din:]
-                b = tf[pre + "/bias"].to(device=self.device, dtype=F32).view(4, H).t()   # [H, 4]
-                bias[d * 4 * Hp:(d + 1) * 4 * Hp].view(Hp, 4)[:H] = b
+                # packed row of (unit u, gate) = d*4Hp + (u//8)*32 + gate*8 + u%8   <-  TF column gate*H + u
+                kk = torch.zeros(Hp, 4, din + P, dtype=F32, device=self.device)
+                kk[:H] = k.view(din + P, 4, H).permute(2, 1, 0)                      # [u, gate, din+P]
+                kk = kk.view(Hp // 8, 8, 4, din + P).permute(0, 2, 1, 3).reshape(4 * Hp, din + P)
+                Wx[d * 4 * Hp:(d + 1) * 4 * Hp, :din] = kk[:, :din]
+                Wh[d * 4 * Hp:(d + 1) * 4 * Hp] = kk[:, din:]
+                bb = torch.zeros(Hp, 4, dtype=F32, device=self.device)
+                bb[:H] = tf[pre + "/bias"].to(device=self.device, dtype=F32).view(4, H).t()
+                bias[d * 4 * Hp:(d + 1) * 4 * Hp] = bb.view(Hp // 8, 8, 4).permute(0, 2, 1).reshape(4 * Hp)
                 if c.use_peepholes:
                     peep[d, 0, :H] = tf[pre + "/w_f_diag"].to(self.device, F32)
                     peep[d, 1, :H] = tf[pre + "/w_i_diag"].to(self.device, F32)
@@ -212,11 +213,13 @@ class BLSTMEncoder:
             Wx, Wh, bias, peep, WpT = get("L%d/Wx" % i), get("L%d/Wh" % i), get("L%d/bias" % i), get("L%d/peep" % i), get("L%d/WpT" % i)
             for d in range(2):
                 pre = self._tf_names(i, d)
-                rx = Wx[d * 4 * Hp:(d + 1) * 4 * Hp].view(Hp, 4, -1)[:H, :, :din]     # [H,4,din]
-                rh = Wh[d * 4 * Hp:(d + 1) * 4 * Hp].view(Hp, 4, P)[:H]               # [H,4,P]
+                def unpack(m2):          # [4Hp, cols] packed rows -> [H, 4, cols]
+                    return m2.reshape(Hp // 8, 4, 8, -1).permute(0, 2, 1, 3).reshape(Hp, 4, -1)[:H]
+                rx = unpack(Wx[d * 4 * Hp:(d + 1) * 4 * Hp])[:, :, :din]                # [H,4,din]
+                rh = unpack(Wh[d * 4 * Hp:(d + 1) * 4 * Hp])                            # [H,4,P]
                 k = torch.cat([rx, rh], 2).permute(2, 1, 0).reshape(din + P, 4 * H)
                 out[pre + "/kernel"] = k.clone()
-                out[pre + "/bias"] = bias[d * 4 * Hp:(d + 1) * 4 * Hp].view(Hp, 4)[:H].t().reshape(4 * H).clone()
+                out[pre + "/bias"] = unpack(bias[d * 4 * Hp:(d + 1) * 4 * Hp].unsqueeze(1))[:, :, 0].t().reshape(4 * H).clone()
                 if c.use_peepholes:
                     out[pre + "/w_f_diag"] = peep[d, 0, :H].clone()
                     out[pre + "/w_i_diag"] = peep[d, 1, :H].clone()
@@ -253,8 +256,20 @@ class BLSTMEncoder:
             self._bf[("Wh", i)] = Wh_hi
             self._bf[("WpT", i)] = Wp_hi
             self._bf[("fold32", i)] = fold
-            self._bf[("fold16", i)] = _cast16(fold, F16, self._bf.get(("fold16", i)))   # forward recurrence
-            self._bf[("fold", i)] = _cast16(fold, BF16, self._bf.get(("fold", i)))       # BPTT (bf16 dz operand)
+            self._bf[("fold16", i)] = _cast16(fold, F16, self._bf.get(("fold16", i)))   # forward recurrence: (W')^T, fp16
+            # BPTT keeps W' itself ([units, packed gate cols], bf16) in tensor memory: same product, other orientation
+            foldb = self._bf.get(("foldb32", i))
+            if foldb is None:
+                foldb = torch.empty(2 * c.Hp, 4 * c.Hp, dtype=F32, device=self.device)
+            for d in range(2):
+                rows = slice(d * 4 * c.Hp, (d + 1) * 4 * c.Hp)
+                out = foldb[d * c.Hp:(d + 1) * c.Hp]
+                # W'[u,g] = sum_p WpT[p,u] * Wh[g,p]
+                gemm(Wp_hi[d], Wh_hi[rows], 1, 0, out=out)
+                gemm(Wp_lo[d], Wh_hi[rows], 1, 0, out=out, accumulate=True)
+                gemm(Wp_hi[d], Wh_lo[rows], 1, 0, out=out, accumulate=True)
+            self._bf[("foldb32", i)] = foldb
+            self._bf[("fold", i)] = _cast16(foldb, BF16, self._bf.get(("fold", i)))
         self._stale = False
 
     # ------------------------------------------------------------------ workspaces
@@ -272,7 +287,8 @@ class BLSTMEncoder:
                   "cfin": torch.zeros(B, 2, c.Hp, dtype=F32, device=dev),
                   "mfin": torch.zeros(B, 2, c.Hp, dtype=F32, device=dev)}
             if training:
-                ws["acts"] = [torch.empty(6, N, 2 * c.Hp, dtype=F32, device=dev) for _ in range(c.num_layers)]
+                ws["gates"] = [torch.empty(N, 2 * c.Hp, dtype=torch.int64, device=dev) for _ in range(c.num_layers)]   # 4 x fp16
+                ws["cst"] = [torch.empty(N, 2 * c.Hp, dtype=F32, device=dev) for _ in range(c.num_layers)]
                 ws["dM"] = torch.empty(N, 2 * c.Hp, dtype=F32, device=dev)
                 ws["dG"] = torch.empty(N, 8 * c.Hp, dtype=BF16, device=dev)
                 ws["dX"] = [torch.empty(N, 2 * c.P, dtype=BF16, device=dev) for _ in range(2)]
@@ -304,10 +320,11 @@ class BLSTMEncoder:
         for i in range(c.num_layers):
             gemm(X, self._bf[("Wx16", i)], 0, 0, out=ws["G"], bias=self.params.w("L%d/bias" % i))
             peep = self.params.w("L%d/peep" % i) if c.use_peepholes else None
-            acts = ws["acts"][i] if training else None
+            gates = ws["gates"][i] if training else None
+            cst = ws["cst"][i] if training else None
             last = (i == c.num_layers - 1)
             _lib.check(L.lcb_lstm_rec_fwd(_lib.ptr(ws["G"]), _lib.ptr(self._bf[("fold16", i)]), _lib.ptr(peep), _lib.ptr(seq_len),
-                                          _lib.ptr(ws["M"][i]), _lib.ptr(acts),
+                                          _lib.ptr(ws["M"][i]), _lib.ptr(gates), _lib.ptr(cst),
                                           _lib.ptr(ws["cfin"]) if last else None, _lib.ptr(ws["mfin"]) if last else None,
                                           T, B, c.Hp, c.forget_bias, st), "lcb_lstm_rec_fwd")
             Hout = ws["Hout"][i]
@@ -362,7 +379,8 @@ class BLSTMEncoder:
                 gemm(dHd, Md, 1, 1, out=gWpT[d])
             peep = ps.w("L%d/peep" % i) if c.use_peepholes else None
             gpeep = ps.g("L%d/peep" % i) if c.use_peepholes else None
-            _lib.check(L.lcb_lstm_rec_bwd(_lib.ptr(dM), _lib.ptr(ws["acts"][i]), _lib.ptr(self._bf[("fold", i)]), _lib.ptr(peep),
+            _lib.check(L.lcb_lstm_rec_bwd(_lib.ptr(dM), _lib.ptr(ws["gates"][i]), _lib.ptr(ws["cst"][i]),
+                                          _lib.ptr(self._bf[("fold", i)]), _lib.ptr(peep),
                                           _lib.ptr(seq_len), _lib.ptr(dG), _lib.ptr(ps.g("L%d/bias" % i)), _lib.ptr(gpeep),
                                           T, B, c.Hp, st), "lcb_lstm_rec_bwd")
             for d in range(2):

@@ -197,6 +197,42 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uin
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, descriptors given as (lo, hi) words: only `lo` (start address field) changes between k-steps, so the
+// issue loop is one integer add per operand instead of rebuilding 64-bit descriptors
+__device__ __forceinline__ void umma_f16_ss_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                 uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// TS form: A operand resident in TMEM (lane = row, two 16-bit K elements per 32-bit column), B from smem
+__device__ __forceinline__ void umma_f16_ts_lohi(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi,
+                                                 uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// registers -> TMEM: thread i of the warp writes 8 consecutive 32-bit columns of lane (quarter base + i)
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 16 lanes x 256 bit: thread t of the warp receives rows (t/4, t/4+8) of the 16-lane slab at [taddr],
+// columns 2*(t%4), 2*(t%4)+1:  r0,r1 = row t/4;  r2,r3 = row t/4 + 8
+__device__ __forceinline__ void tmem_ld_16x256b_x1(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
 // commit all prior async tcgen05 ops of this thread to an mbarrier (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -247,6 +283,21 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
     d |= (uint64_t)2 << 61;     // layout_type = SWIZZLE_128B
     return d;
 }
+// SWIZZLE_NONE ("interleave") K-major canonical layout: 8 rows x 16 bytes core matrices, each a contiguous
+// 128-byte block; LBO = byte distance between core matrices adjacent in K, SBO = adjacent in M/N
+__device__ __forceinline__ uint64_t make_smem_desc_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;     // descriptor version = 1 (Blackwell); layout_type = 0 (SWIZZLE_NONE)
+    return d;
+}
+// bulk DSMEM copy: own shared memory -> shared memory of another CTA of the cluster, complete_tx on ITS mbarrier
+__device__ __forceinline__ void bulk_copy_s2c(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes, uint32_t mbar_cluster_addr) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_cluster_addr), "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr) : "memory");
+}
 // instruction descriptor for kind::f16: bf16 x bf16 -> f32
 __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4)                       // c_format = F32
@@ -289,6 +340,12 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_
 }
 __device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint32_t a, uint32_t b) {
     asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+// asynchronous DSMEM store: lands in CTA-remote shared memory and performs complete_tx(16) on the mbarrier
+// (of the SAME destination CTA) when it does -- no release fence / barrier.cluster needed on the sender
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(mbar) : "memory");
 }
 __device__ __forceinline__ void st_cluster_b32(uint32_t addr, uint32_t a) {
     asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
