@@ -40,7 +40,7 @@ template <int BN, bool A_MN, bool B_MN, int CT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          void* __restrict__ Cptr, int ldc, const float* __restrict__ bias, int accumulate,
-                         int M, int N, int K, uint32_t idesc)
+                         int M, int N, int K, uint32_t idesc, int splits)
 {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
@@ -60,7 +60,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
     const int tiles_n = (N + BN - 1) / BN;
     const int ntiles = tiles_m * tiles_n;
-    const int nkb = (K + GEMM_BK - 1) / GEMM_BK;
+    const int nkb_all = (K + GEMM_BK - 1) / GEMM_BK;
+    // split-K: work item = (tile, K split); partial products are accumulated into fp32 C with red.global.add
+    const int kb_per = (nkb_all + splits - 1) / splits;
+    const int nwork = ntiles * splits;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -80,10 +83,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             bool ok = true;
-            for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
+            for (int work = blockIdx.x; work < nwork && ok; work += gridDim.x) {
+                const int tile = work % ntiles, split = work / ntiles;
                 const int m0 = (tile / tiles_n) * GEMM_BM;
                 const int n0 = (tile % tiles_n) * BN;
-                for (int kb = 0; kb < nkb; ++kb) {
+                const int kb0 = split * kb_per, kb1 = min(nkb_all, kb0 + kb_per);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     if (!mbar_wait(&empty_bar[stage], phase ^ 1)) { ok = false; break; }
                     unsigned char* sa = tiles + stage * Cfg::STAGE_BYTES;
                     unsigned char* sb = sa + Cfg::A_BYTES;
@@ -112,11 +117,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             bool ok = true;
-            for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
+            for (int work = blockIdx.x; work < nwork && ok; work += gridDim.x) {
+                const int split = work / ntiles;
+                const int kb0 = split * kb_per, kb1 = min(nkb_all, kb0 + kb_per);
                 if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1)) { ok = false; break; }
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < nkb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     if (!mbar_wait(&full_bar[stage], phase)) { ok = false; break; }
                     tc_fence_after();
                     const uint32_t sa = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
@@ -129,7 +136,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                                                     : make_smem_desc_sw128(sa + k * 32, 16, 1024);
                         const uint64_t bdesc = B_MN ? make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
                                                     : make_smem_desc_sw128(sb + k * 32, 16, 1024);
-                        umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);           // smem slot reusable once these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -145,9 +152,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         float* st = epi + (warp - 2) * (32 * 33);
         int acc = 0; uint32_t acc_phase = 0;
         bool ok = true;
-        for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
+        for (int work = blockIdx.x; work < nwork && ok; work += gridDim.x) {
+            const int tile = work % ntiles, split = work / ntiles;
             const int m0 = (tile / tiles_n) * GEMM_BM;
             const int n0 = (tile % tiles_n) * BN;
+            const bool empty_split = split * kb_per >= nkb_all;          // nothing was accumulated: contributes zero
             if (!mbar_wait(&tfull_bar[acc], acc_phase)) { ok = false; break; }
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -161,7 +170,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                 for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(r[j]);
                 __syncwarp();
-                const float bv = (bias != nullptr && col < N) ? bias[col] : 0.f;
+                const float bv = (bias != nullptr && col < N && split == 0) ? bias[col] : 0.f;
 #pragma unroll 4
                 for (int rr = 0; rr < 32; ++rr) {
                     const int row = m0 + q * 32 + rr;
@@ -173,8 +182,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             reinterpret_cast<__half*>(Cptr)[(size_t)row * ldc + col] = __float2half_rn(v);
                         } else {
                             float* cp = reinterpret_cast<float*>(Cptr) + (size_t)row * ldc + col;
-                            if (accumulate) v += *cp;
-                            *cp = v;
+                            if (splits > 1) { if (!empty_split) atomicAdd(cp, v); }
+                            else { if (accumulate) v += *cp; *cp = v; }
                         }
                     }
                 }
@@ -229,6 +238,18 @@ template <int BN, bool A_MN, bool B_MN, int CT>
 static int launch_gemm(int M, int N, int K, const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc,
                        const float* bias, int accumulate, uint32_t fmt_bits, cudaStream_t st)
 {
+    const int tiles0 = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
+    const int nkb0 = (K + GEMM_BK - 1) / GEMM_BK;
+    // split-K for reductions with few output tiles (wgrad: K = frames): fill ~all SMs, >= 16 k-blocks per split
+    int splits = 1;
+    if (CT == 0 && tiles0 <= 74 && nkb0 >= 64) {
+        splits = (148 + tiles0 - 1) / tiles0;
+        if (splits > nkb0 / 16) splits = nkb0 / 16;
+        if (splits < 1) splits = 1;
+    }
+    if (splits > 1 && !accumulate) {      // partial sums are added atomically: start from zero
+        if (cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st) != cudaSuccess) return LCB_ERR_CUDA;
+    }
     using Cfg = GemmCfg<BN>;
     auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN, CT>;
     const uint32_t idesc = (make_idesc_bf16_f32(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0) & ~((7u << 7) | (7u << 10))) | fmt_bits;
@@ -237,10 +258,10 @@ static int launch_gemm(int M, int N, int K, const CUtensorMap& ta, const CUtenso
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) return LCB_ERR_CUDA;
         attr_done = true;
     }
-    const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
+    const int tiles = tiles0 * splits;
     int nsm = 148;
     int grid = tiles < nsm ? tiles : nsm;
-    g_launches += 1; kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, C, ldc, bias, accumulate, M, N, K, idesc);
+    g_launches += 1; kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, C, ldc, bias, accumulate, M, N, K, idesc, splits);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }
 

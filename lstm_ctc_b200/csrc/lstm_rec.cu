@@ -376,7 +376,7 @@ lstm_rec_fwd_kernel(const RecFwdParams p)
 constexpr int BWD_NCW = 8;                    // compute warps per sub-group
 constexpr int BWD_BARS = 8;                   // mma[4] dz red[2] (+pad)
 template <int NSG> struct RecBwdCfg {
-    static constexpr int THREADS = 32 * NSG * (BWD_NCW + 4);     // + up to 4 MMA issuer warps (one per 128-unit M tile)
+    static constexpr int THREADS = 32 * (NSG * BWD_NCW + 4);     // + 4 MMA issuer warps (one per 128-unit M tile), shared by the sub-groups
     __host__ __device__ static size_t sg_bytes(int NC) {          // dz operand + reduce double buffer (bf16) + partial staging (bf16)
         size_t b = (size_t)2 * REC_BG * 128 + (size_t)2 * NC * 32 * REC_BG * 2 + (size_t)4 * 8 * 1024;
         return (b + 1023) & ~(size_t)1023;
@@ -385,7 +385,7 @@ template <int NSG> struct RecBwdCfg {
 };
 
 template <int NSG>
-__global__ void __launch_bounds__(32 * NSG * 12, 1)
+__global__ void __launch_bounds__(32 * (NSG * 8 + 4), 1)
 lstm_rec_bwd_kernel(const RecBwdParams p)
 {
     constexpr int BG = REC_BG, NCW = BWD_NCW;
@@ -397,7 +397,7 @@ lstm_rec_bwd_kernel(const RecBwdParams p)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int role, sg, rw;
     if (warp < NCW * NSG) { role = 0; sg = warp / NCW; rw = warp % NCW; }
-    else { role = 1; sg = (warp - NCW * NSG) / 4; rw = (warp - NCW * NSG) % 4; }
+    else { role = 1; sg = 0; rw = warp - NCW * NSG; }          // issuer warps serve every sub-group in turn
 
     unsigned char* sgbase = smem + (size_t)sg * Cfg::sg_bytes(NC);
     unsigned char* Bp = sgbase;                                                  // [2][16 x 128 B] operand dz_t (K' = 128 gate rows)
@@ -459,35 +459,45 @@ lstm_rec_bwd_kernel(const RecBwdParams p)
     cluster_sync_all();
     tc_fence_after();
 
+    long long* prof = (blockIdx.x == 0 && lane == 0 && sg == 0 && rw == 0) ? g_rec_prof : nullptr;
+    const int prof_steps = g_rec_prof_steps;
     bool ok = true;
-    if (!sg_active) {
-        // idle sub-group
-    } else if (role == 1) {
-        // ============================ MMA issuer warps: one 128-unit M tile each ============================
+    if (role == 1) {
+        // ============================ MMA issuer warps: one 128-unit M tile each, sub-groups in turn ============================
         constexpr uint32_t idesc = make_idesc_bf16_f32(128, BG, 0, 0);           // bf16 x bf16, A (TMEM) K-major
         const int jt = rw;
         if (lane == 0 && jt < MB) {
-            const uint64_t bb0 = make_smem_desc_sw128(smem_u32(Bp), 16, 1024);
-            const uint32_t b_lo0 = (uint32_t)bb0, b_hi = (uint32_t)(bb0 >> 32);
-            const uint32_t d_tmem = tmem_base + REC_TMEM_ACC + (sg * 4 + jt) * BG;
             const uint32_t a_tmem = tmem_base + jt * 64;
             for (int s = 0; s < T && ok; ++s) {
-                ok = mbar_wait(mbar_dz, (uint32_t)(s & 1));                      // dz_t staged by all compute threads
-                if (!ok) break;
-                // the reduce buffer the NEXT step's partials go to: its previous contents were consumed in phase A
-                // of this step (all compute threads arrived on mbar_dz after reading them)
-                if (jt == 0 && s + 2 < T) mbar_arrive_expect_tx(&mbar_red[(s + 1) & 1], red_bytes);
-                tc_fence_after();
-                if (s + 1 < T) {                      // the last step's dm_{-1} is never used
+                for (int g2 = 0; g2 < NSG && ok; ++g2) {
+                    if ((bg * NSG + g2) * BG >= B) continue;                      // idle sub-group
+                    uint64_t* bb = bars_all + (size_t)g2 * BWD_BARS;              // mma[4] dz red[2] of sub-group g2
+                    const uint64_t bb0 = make_smem_desc_sw128(smem_u32(smem + (size_t)g2 * Cfg::sg_bytes(NC)), 16, 1024);
+                    const uint32_t b_lo0 = (uint32_t)bb0, b_hi = (uint32_t)(bb0 >> 32);
+                    const uint32_t d_tmem = tmem_base + REC_TMEM_ACC + (g2 * 4 + jt) * BG;
+                    if (g2 == 0) { REC_PROBE(0); }
+                    ok = mbar_wait(&bb[4], (uint32_t)(s & 1));                    // dz_t staged by all compute threads
+                    if (!ok) break;
+                    if (g2 == 0) { REC_PROBE(1); }
+                    // the reduce buffer the NEXT step's partials go to: its previous contents were consumed in phase A
+                    // of this step (all compute threads arrived on mbar_dz after reading them)
+                    if (jt == 0 && s + 2 < T) mbar_arrive_expect_tx(&bb[5 + ((s + 1) & 1)], red_bytes);
+                    tc_fence_after();
+                    if (s + 1 < T) {                      // the last step's dm_{-1} is never used
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)
-                        umma_f16_ts_lohi(d_tmem, a_tmem + 8 * kk, b_lo0 + (uint32_t)((kk >> 2) * (BG * 128 / 16) + (kk & 3) * 2), b_hi,
-                                         idesc, kk ? 1u : 0u);
+                        for (int kk = 0; kk < 8; ++kk)
+                            umma_f16_ts_lohi(d_tmem, a_tmem + 8 * kk, b_lo0 + (uint32_t)((kk >> 2) * (BG * 128 / 16) + (kk & 3) * 2), b_hi,
+                                             idesc, kk ? 1u : 0u);
+                    }
+                    if (g2 == 0) { REC_PROBE(7); }
+                    umma_commit(&bb[jt]);
+                    if (g2 == 0) { REC_PROBE(2); }
                 }
-                umma_commit(&mbar_mma[jt]);
             }
         }
         __syncwarp();
+    } else if (!sg_active) {
+        // idle sub-group
     } else {
         // ============================ compute warps ============================
         const int cg = rw >> 2, q = rw & 3;
@@ -511,56 +521,99 @@ lstm_rec_bwd_kernel(const RecBwdParams p)
         float db[4] = {0.f, 0.f, 0.f, 0.f};
         float dpf = 0.f, dpi = 0.f, dpo = 0.f;
 
-        struct Pre { float ig[2], jt[2], fg[2], og[2], c[2], tc[2], cp[2], dmo[2]; };
-        auto load_pre = [&](int s, Pre& r) {
+        // raw prefetch of the next step's saved activations: loads only, no arithmetic, so they stay in flight
+        // behind the current step (the first version applied tanh inside and stalled ~2600 cycles per step).
+        // Row indices advance by a constant stride per step, so no 64-bit multiplies sit in the loop.
+        struct Pre { uint2 gp[2]; float c[2], cp[2], dmo[2]; };
+        const long long row_stride = (dir ? 1 : -1) * (long long)B * (long long)ld2;      // elements per time step, in scan order
+        long long idx_j[2];                                                                // element index of (t(s), b_j, dir, unit)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int b = b0 + cg * 8 + 2 * g + j;
+            idx_j[j] = ((long long)(dir ? 0 : T - 1) * B + (b < B ? b : 0)) * (long long)ld2 + (long long)dir * Hp + unit;
+        }
+        auto load_pre = [&](int s, Pre& r) {          // loads step s (idx_j must already point at step s)
             const int t = dir ? s : (T - 1 - s);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int b = b0 + cg * 8 + 2 * g + j;
                 const bool live = (s < T) && (t < len_j[j]);
+                r.gp[j] = make_uint2(0u, 0u); r.c[j] = 0.f; r.cp[j] = 0.f; r.dmo[j] = 0.f;
                 if (live) {
-                    const size_t idx = ((size_t)t * B + b) * ld2 + (size_t)dir * Hp + unit;
-                    const uint2 gp = __ldg(p.gates + idx);
-                    const float2 g01 = __half22float2(*reinterpret_cast<const __half2*>(&gp.x));
-                    const float2 g23 = __half22float2(*reinterpret_cast<const __half2*>(&gp.y));
-                    r.ig[j] = g01.x; r.jt[j] = g01.y; r.fg[j] = g23.x; r.og[j] = g23.y;
-                    r.c[j] = __ldg(p.cst + idx);
-                    r.tc[j] = tanhf_fast(r.c[j]);
-                    r.dmo[j] = __ldg(p.dM + idx);
-                    // previous step in the direction's own order: fwd t-1, bwd t+1 (zero initial state)
+                    r.gp[j] = __ldg(p.gates + idx_j[j]);
+                    r.c[j] = __ldg(p.cst + idx_j[j]);
+                    r.dmo[j] = __ldg(p.dM + idx_j[j]);
+                    // previous step in the direction's own order: fwd t-1, bwd t+1 (zero initial state) = the row one
+                    // stride AHEAD in scan order
                     const int tp = dir ? (t + 1) : (t - 1);
                     const bool has_prev = dir ? (tp < len_j[j]) : (tp >= 0);
-                    r.cp[j] = has_prev ? __ldg(p.cst + ((size_t)tp * B + b) * ld2 + (size_t)dir * Hp + unit) : 0.f;
-                } else {
-                    r.ig[j] = r.jt[j] = r.fg[j] = r.og[j] = r.c[j] = r.tc[j] = r.cp[j] = r.dmo[j] = 0.f;
+                    if (has_prev) r.cp[j] = __ldg(p.cst + idx_j[j] + row_stride);
                 }
             }
         };
         Pre cur, nxt;
         load_pre(0, cur);
         const uint32_t red_addr = smem_u32(red);
+        // per-thread constants of the dz staging: smem offsets of the local MMA B operand and global columns
+        uint32_t bp_off[2][4];
+        int gcol[4];
+#pragma unroll
+        for (int gate = 0; gate < 4; ++gate) {
+            gcol[gate] = dir * 4 * Hp + packed_col(unit, gate);
+            const int kp = packed_col(ul, gate);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int bl = cg * 8 + 2 * g + j;
+                bp_off[j][gate] = (uint32_t)((kp >> 6) * (BG * 128) + (bl >> 3) * 1024 + (bl & 7) * 128 +
+                                             ((((kp & 63) >> 3) ^ (bl & 7)) << 4) + (kp & 7) * 2);
+            }
+        }
+        long long grow_j[2];                          // element index of dG row (t(s), b_j)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int b = b0 + cg * 8 + 2 * g + j;
+            grow_j[j] = ((long long)(dir ? 0 : T - 1) * B + (b < B ? b : 0)) * (long long)ld8;
+        }
+        const long long grow_stride = (dir ? 1 : -1) * (long long)B * (long long)ld8;
 
         for (int s = 0; s < T; ++s) {
             const int t = dir ? s : (T - 1 - s);
+            REC_PROBE(8);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) idx_j[j] += row_stride;
             load_pre(s + 1, nxt);                                  // latency hidden behind this step
+            REC_PROBE(9);
             // ---- phase A: dm_rec from the reduce buffer of the previous step, then dz_t ----
             float dmr[2] = {0.f, 0.f};
             if (s > 0) {
                 if (ok) ok = mbar_wait_cluster_acq(&mbar_red[(s - 1) & 1], (uint32_t)(((s - 1) >> 1) & 1));
+                REC_PROBE(10);
                 const __nv_bfloat16* rb = red + (size_t)((s - 1) & 1) * NC * 32 * BG + (size_t)ul * BG + cg * 8 + 2 * g;
-                for (int src = 0; src < NC; ++src) {
-                    const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(rb + (size_t)src * 32 * BG));
-                    dmr[0] += v.x; dmr[1] += v.y;
+                float2 accv[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+                int src = 0;
+                for (; src + 4 <= NC; src += 4) {                  // 4 independent loads in flight
+                    __nv_bfloat162 v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const __nv_bfloat162*>(rb + (size_t)(src + k) * 32 * BG);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(v[k]); accv[k].x += f.x; accv[k].y += f.y; }
                 }
+                for (; src < NC; ++src) {
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(rb + (size_t)src * 32 * BG));
+                    accv[0].x += f.x; accv[0].y += f.y;
+                }
+                dmr[0] = (accv[0].x + accv[1].x) + (accv[2].x + accv[3].x);
+                dmr[1] = (accv[0].y + accv[1].y) + (accv[2].y + accv[3].y);
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int bl = cg * 8 + 2 * g + j;
-                const int b = b0 + bl;
+                const int b = b0 + cg * 8 + 2 * g + j;
                 const bool live = t < len_j[j];
                 float dzi = 0.f, dzj = 0.f, dzf = 0.f, dzo = 0.f;
                 if (live) {
-                    const float ig = cur.ig[j], jt = cur.jt[j], fg = cur.fg[j], og = cur.og[j], tc = cur.tc[j], cp = cur.cp[j];
+                    const float2 g01 = __half22float2(*reinterpret_cast<const __half2*>(&cur.gp[j].x));
+                    const float2 g23 = __half22float2(*reinterpret_cast<const __half2*>(&cur.gp[j].y));
+                    const float ig = g01.x, jt = g01.y, fg = g23.x, og = g23.y, cp = cur.cp[j];
+                    const float tc = tanhf_fast(cur.c[j]);
                     const float dm = cur.dmo[j] + dmr[j];
                     dzo = dm * tc * og * (1.f - og);
                     const float dc = dcc[j] + dm * og * (1.f - tc * tc) + dzo * wo;
@@ -575,36 +628,40 @@ lstm_rec_bwd_kernel(const RecBwdParams p)
                 }
                 const float dzg[4] = {dzi, dzj, dzf, dzo};
                 // gate columns are gate-major inside each 8-unit group: col(unit, gate) = packed_col(unit, gate)
-                __nv_bfloat16* dgrow = p.dG + ((size_t)t * B + b) * ld8 + (size_t)dir * 4 * Hp;
+                __nv_bfloat16* dgrow = p.dG + grow_j[j];
 #pragma unroll
                 for (int gate = 0; gate < 4; ++gate) {
                     const __nv_bfloat16 v = __float2bfloat16(dzg[gate]);
-                    if (b < B) dgrow[packed_col(unit, gate)] = v;
-                    // local MMA B operand  dz_t [16 utts][128 gate rows], K-major 128B swizzle
-                    const int kp = packed_col(ul, gate);
-                    const uint32_t off = (uint32_t)((kp >> 6) * (BG * 128) + (bl >> 3) * 1024 + (bl & 7) * 128 +
-                                                    ((((kp & 63) >> 3) ^ (bl & 7)) << 4) + (kp & 7) * 2);
-                    *reinterpret_cast<__nv_bfloat16*>(Bp + off) = v;
+                    *reinterpret_cast<__nv_bfloat16*>(Bp + bp_off[j][gate]) = v;      // local MMA B operand dz_t (K-major, 128B swizzle)
+                    if (b < B) dgrow[gcol[gate]] = v;
                 }
+                grow_j[j] += grow_stride;
             }
+            REC_PROBE(11);
             fence_proxy_async_smem();                  // locally staged dz_t -> visible to the tensor core
             mbar_arrive(mbar_dz);
+            REC_PROBE(12);
             // ---- phase B: partial dm_{t-1} tiles -> owners' reduce buffers (bulk DSMEM copies) ----
             if (s + 1 < T) {
-                for (int jt = cg; jt < MB; jt += 2) {
+                // this warp's tiles: jt = cg, cg + 2 (one at a time: the kernel is register-bound at 640 threads)
+#pragma unroll 1
+                for (int k = 0; k < 2; ++k) {
+                    const int jt = cg + 2 * k;
+                    if (jt >= MB) break;
                     if (ok) ok = mbar_wait(&mbar_mma[jt], (uint32_t)(s & 1));
+                    if (k == 0) { REC_PROBE(13); }
                     tc_fence_after();
-                    uint32_t acc[16];
-                    tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + (sg * 4 + jt) * BG, acc);
+                    uint32_t a[16];
+                    tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + (sg * 4 + jt) * BG, a);
                     tmem_ld_wait();
                     // the 32 rows of this (tile, quarter) are 32 consecutive units of ONE owner CTA: stage them as a
                     // [32][16] bf16 slice and ship it with a single 1 KB bulk DSMEM copy
-                    __nv_bfloat16* pw = pst + (size_t)((((s & 1) * 2 + ((jt >> 1) & 1)) * 8 + rw) * 512);
+                    __nv_bfloat16* pw = pst + (size_t)((((s & 1) * 2 + k) * 8 + rw) * 512);
                     uint4* ps = reinterpret_cast<uint4*>(pw + lane * 16);
-                    ps[0] = make_uint4(pack_bf16x2(__uint_as_float(acc[0]), __uint_as_float(acc[1])), pack_bf16x2(__uint_as_float(acc[2]), __uint_as_float(acc[3])),
-                                       pack_bf16x2(__uint_as_float(acc[4]), __uint_as_float(acc[5])), pack_bf16x2(__uint_as_float(acc[6]), __uint_as_float(acc[7])));
-                    ps[1] = make_uint4(pack_bf16x2(__uint_as_float(acc[8]), __uint_as_float(acc[9])), pack_bf16x2(__uint_as_float(acc[10]), __uint_as_float(acc[11])),
-                                       pack_bf16x2(__uint_as_float(acc[12]), __uint_as_float(acc[13])), pack_bf16x2(__uint_as_float(acc[14]), __uint_as_float(acc[15])));
+                    ps[0] = make_uint4(pack_bf16x2(__uint_as_float(a[0]), __uint_as_float(a[1])), pack_bf16x2(__uint_as_float(a[2]), __uint_as_float(a[3])),
+                                       pack_bf16x2(__uint_as_float(a[4]), __uint_as_float(a[5])), pack_bf16x2(__uint_as_float(a[6]), __uint_as_float(a[7])));
+                    ps[1] = make_uint4(pack_bf16x2(__uint_as_float(a[8]), __uint_as_float(a[9])), pack_bf16x2(__uint_as_float(a[10]), __uint_as_float(a[11])),
+                                       pack_bf16x2(__uint_as_float(a[12]), __uint_as_float(a[13])), pack_bf16x2(__uint_as_float(a[14]), __uint_as_float(a[15])));
                     __syncwarp();
                     const int u0 = jt * 128 + q * 32;
                     if (lane == 0 && u0 < Hp) {
@@ -613,10 +670,10 @@ lstm_rec_bwd_kernel(const RecBwdParams p)
                         bulk_copy_s2c(mapa_shared(red_addr + (uint32_t)((((s & 1) * NC + (int)cta) * 32) * BG * 2), owner),
                                       smem_u32(pw), 1024u, mapa_shared(smem_u32(&mbar_red[s & 1]), owner));
                     }
-                    __syncwarp();
                 }
             }
             tc_fence_before();
+            REC_PROBE(14);
             cur = nxt;
         }
         // ---- parameter gradients held in registers: reduce the 4 lanes of a unit, then atomics ----

@@ -88,3 +88,21 @@ def test_gemm_mixed_formats_rejected(cuda_dev):
     B = torch.randn(128, 64, device=cuda_dev).half()
     with pytest.raises(_lib.LcbError):
         gemm(A, B)
+
+
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_gemm_split_k_wgrad_shape(cuda_dev, accumulate):
+    """wgrad with few output tiles and a huge reduction (K = frames): the kernel splits K over CTAs and
+    accumulates partial tiles with fp32 red.add; also through a strided (column-slice) output view."""
+    from lstm_ctc_b200.gemm import gemm
+    torch.manual_seed(3)
+    K, M, N = 24000, 320, 200
+    A = (torch.randn(K, M, device=cuda_dev) * 0.1).bfloat16()
+    B = (torch.randn(K, N, device=cuda_dev) * 0.1).bfloat16()
+    Cfull = torch.randn(M, N + 56, device=cuda_dev)
+    C0 = Cfull.clone()
+    out = Cfull[:, 8:8 + N]
+    gemm(A, B, 1, 1, out=out, accumulate=accumulate)
+    R = A.float().t() @ B.float() + (C0[:, 8:8 + N] if accumulate else 0)
+    assert (out - R).abs().max() < 5e-3 * (K ** 0.5) * 0.01 + 1e-2
+    assert torch.equal(Cfull[:, :8], C0[:, :8]) and torch.equal(Cfull[:, 8 + N:], C0[:, 8 + N:])   # neighbours untouched
