@@ -114,7 +114,7 @@ def synth_batch(w, seed, device=None):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_reference(args, w):
+def run_reference(args, w, emit):
     """The reference's own CPU path: TF 1.8 cannot be installed offline, so (north_star fallback) the
     PyTorch-CPU transcription of the same ops in oracle/ is timed on the host cores, all threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -152,7 +152,7 @@ def run_reference(args, w):
             "config": {"workload": w["desc"], "sample": sample},
             "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def cpu_baseline_sample(w, budget_s=20.0):
@@ -185,6 +185,13 @@ def cpu_baseline_sample(w, budget_s=20.0):
 
 # ------------------------------------------------------------------------------------------------
 def main():
+    # the driver expects exactly ONE JSON line on stdout: route everything else (NCCL banners, warnings) to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=6)
@@ -197,7 +204,7 @@ def main():
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args, w)
+        run_reference(args, w, emit)
         return
     args.warmup = max(args.warmup, 3)
 
@@ -283,7 +290,9 @@ def main():
         out["kernels"] = kt["kernels"]
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_sample(w)
-    print(json.dumps(out))
+    emit(out)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def _peaks():

@@ -77,6 +77,9 @@ int lcb_gemm16(int M, int N, int K,
                const void* B, int ldb, int b_layout, int b_dtype,
                void* C, int ldc, int c_dtype,
                const float* bias, int accumulate, void* stream);
+/* caps the persistent grid of subsequent lcb_gemm16 launches (1..148 CTAs); returns the previous cap.  Used when a
+ * GEMM runs on a side stream next to a cluster kernel that owns part of the SMs. */
+int lcb_gemm_set_max_ctas(int n);
 /* bf16 x bf16 shorthand of the above. */
 int lcb_gemm_bf16(int M, int N, int K,
                   const void* A, int lda, int a_layout,

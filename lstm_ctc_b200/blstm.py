@@ -153,6 +153,8 @@ class BLSTMEncoder:
         self._bf = {}            # bf16 operand copies, refreshed by refresh_operands()
         self._ws = {}            # activation workspaces keyed by (T, B)
         self._stale = True
+        self.wstream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None   # wgrad side stream
+        self.overlap_wgrad = True
         self.seed_base = 777           # reference default --seed (nnet-train.py:141-142)
         self.step_id = 0
         mt = _lib.ctypes.c_int()
@@ -290,11 +292,13 @@ class BLSTMEncoder:
                 ws["gates"] = [torch.empty(N, 2 * c.Hp, dtype=torch.int64, device=dev) for _ in range(c.num_layers)]   # 4 x fp16
                 ws["cst"] = [torch.empty(N, 2 * c.Hp, dtype=F32, device=dev) for _ in range(c.num_layers)]
                 ws["dM"] = torch.empty(N, 2 * c.Hp, dtype=F32, device=dev)
-                ws["dG"] = torch.empty(N, 8 * c.Hp, dtype=BF16, device=dev)
+                # double-buffered by layer parity: the wgrad GEMMs of layer i run on a side stream while the main
+                # stream already produces layer i-1's tensors
+                ws["dG"] = [torch.empty(N, 8 * c.Hp, dtype=BF16, device=dev) for _ in range(2)]
                 ws["dX"] = [torch.empty(N, 2 * c.P, dtype=BF16, device=dev) for _ in range(2)]
-                ws["dfold"] = torch.empty(4 * c.Hp, c.Hp, dtype=F32, device=dev)
-                ws["Xbf"] = torch.empty(N * max(c.Dp0, 2 * c.P), dtype=BF16, device=dev)     # bf16 copies for wgrad
-                ws["Mbf"] = torch.empty(N, 2 * c.Hp, dtype=BF16, device=dev)
+                ws["dfold"] = [torch.empty(4 * c.Hp, c.Hp, dtype=F32, device=dev) for _ in range(2)]
+                ws["Xbf"] = [torch.empty(N * max(c.Dp0, 2 * c.P), dtype=BF16, device=dev) for _ in range(2)]   # bf16 copies for wgrad
+                ws["Mbf"] = [torch.empty(N, 2 * c.Hp, dtype=BF16, device=dev) for _ in range(2)]
             self._ws[key] = ws
         return ws
 
@@ -352,61 +356,90 @@ class BLSTMEncoder:
     def backward(self, dXtop, bucket_ready=None):
         """dXtop [T*B, 2P] bf16 = d loss / d encoder output.  Accumulates parameter gradients into
         params.gflat (which the caller zeroed).  bucket_ready(name_list) is called as soon as the
-        gradients of a layer are final (data-parallel all-reduce hook)."""
+        gradients of a layer are final (data-parallel all-reduce hook).
+
+        Stream structure: the serial chain (dM GEMM -> BPTT -> dX GEMM) stays on the current stream; the
+        weight-gradient GEMMs of layer i are enqueued on a side stream and execute on the SMs the next layer's
+        BPTT clusters leave free."""
         L = _lib.lib()
         c = self.cfg
         T, B, seq_len, training = self._last
         assert training
         ws = self._workspace(T, B, True)
-        st = _lib.stream_ptr()
         N = T * B
         ps = self.params
+        main = torch.cuda.current_stream()
+        side = self.wstream if (self.overlap_wgrad and self.wstream is not None) else main
+        overlap = side is not main
+        side_done = {}                       # layer -> event: its side-stream work (reads of set k, dH) has finished
         dH = dXtop
         for i in reversed(range(c.num_layers)):
+            k = i & 1
+            if overlap and (i + 2) in side_done:
+                main.wait_event(side_done[i + 2])             # buffer set k is free again
             if c.keep_prob < 1.0:
                 self._dropout(dH, i)                # same (seed, index) mask as the forward pass, on the gradient
             X16 = ws["X0"] if i == 0 else ws["Hout"][i - 1]
-            X = _to_bf16(X16, ws["Xbf"][:X16.numel()].view(X16.shape))
-            M = _to_bf16(ws["M"][i], ws["Mbf"])
-            dM, dG = ws["dM"], ws["dG"]
+            X = _to_bf16(X16, ws["Xbf"][k][:X16.numel()].view(X16.shape))
+            M = _to_bf16(ws["M"][i], ws["Mbf"][k])
+            dM, dG = ws["dM"], ws["dG"][k]
             gWpT, gWh, gWx = ps.g("L%d/WpT" % i), ps.g("L%d/Wh" % i), ps.g("L%d/Wx" % i)
             for d in range(2):
-                dHd = dH[:, d * c.P:(d + 1) * c.P]
-                Md = M[:, d * c.Hp:(d + 1) * c.Hp]
                 # dM = dH * W_p^T
-                gemm(dHd, self._bf[("WpT", i)][d], 0, 1, out=dM[:, d * c.Hp:(d + 1) * c.Hp])
-                # dW_p^T[p,h] = sum_n dH[n,p] * M[n,h]
-                gemm(dHd, Md, 1, 1, out=gWpT[d])
+                gemm(dH[:, d * c.P:(d + 1) * c.P], self._bf[("WpT", i)][d], 0, 1, out=dM[:, d * c.Hp:(d + 1) * c.Hp])
             peep = ps.w("L%d/peep" % i) if c.use_peepholes else None
             gpeep = ps.g("L%d/peep" % i) if c.use_peepholes else None
             _lib.check(L.lcb_lstm_rec_bwd(_lib.ptr(dM), _lib.ptr(ws["gates"][i]), _lib.ptr(ws["cst"][i]),
                                           _lib.ptr(self._bf[("fold", i)]), _lib.ptr(peep),
                                           _lib.ptr(seq_len), _lib.ptr(dG), _lib.ptr(ps.g("L%d/bias" % i)), _lib.ptr(gpeep),
-                                          T, B, c.Hp, st), "lcb_lstm_rec_bwd")
-            for d in range(2):
-                dGd = dG[:, d * 4 * c.Hp:(d + 1) * 4 * c.Hp]
-                Md = M[:, d * c.Hp:(d + 1) * c.Hp]
-                dfold = ws["dfold"]
-                if T > 1:
-                    # dW'^T[g,h] = sum_n dz_n[g] * m_prev(n)[h]; prev = t-1 (fwd) / t+1 (bwd): a row shift of B
-                    if d == 0:
-                        gemm(dGd[B:], Md[:N - B], 1, 1, out=dfold)
-                    else:
-                        gemm(dGd[:N - B], Md[B:], 1, 1, out=dfold)
-                    df_hi, df_lo = _split_bf16(dfold)
-                    rows = slice(d * 4 * c.Hp, (d + 1) * 4 * c.Hp)
-                    # dW_h[g,p] = sum_h dW'^T[g,h] * WpT[p,h]
-                    gemm(df_hi, self._bf[("WpT", i)][d], 0, 0, out=gWh[rows])
-                    gemm(df_lo, self._bf[("WpT", i)][d], 0, 0, out=gWh[rows], accumulate=True)
-                    # dW_p^T[p,h] += sum_g Wh[g,p] * dW'^T[g,h]
-                    gemm(self._bf[("Wh", i)][rows], df_hi, 1, 1, out=gWpT[d], accumulate=True)
-                    gemm(self._bf[("Wh", i)][rows], df_lo, 1, 1, out=gWpT[d], accumulate=True)
-            # dW_x[g,k] = sum_n dz_n[g] * x_n[k]   (both directions at once)
-            gemm(dG, X, 1, 1, out=gWx)
+                                          T, B, c.Hp, _lib.stream_ptr()), "lcb_lstm_rec_bwd")
+            ev_dg = None
+            if overlap:
+                ev_dg = torch.cuda.Event()
+                ev_dg.record(main)
+            dH_this = dH
             if i > 0:
-                dXn = ws["dX"][i & 1]
+                dXn = ws["dX"][k]
+                if overlap and (i + 1) in side_done:
+                    main.wait_event(side_done[i + 1])         # layer i+1's wgrad still reads this buffer as its dH
                 gemm(dG, self._bf[("Wx", i)], 0, 1, out=dXn)        # dX = dG * W_x
                 dH = dXn
-            if bucket_ready is not None:
-                bucket_ready(["L%d/WpT" % i, "L%d/Wh" % i, "L%d/peep" % i, "L%d/bias" % i, "L%d/Wx" % i])
+            # ---- weight gradients of layer i (side stream) ----
+            with torch.cuda.stream(side):
+                if overlap:
+                    side.wait_event(ev_dg)
+                    old_cap = L.lcb_gemm_set_max_ctas(80)      # the SMs not owned by the next layer's BPTT clusters
+                for d in range(2):
+                    dHd = dH_this[:, d * c.P:(d + 1) * c.P]
+                    Md = M[:, d * c.Hp:(d + 1) * c.Hp]
+                    dGd = dG[:, d * 4 * c.Hp:(d + 1) * 4 * c.Hp]
+                    # dW_p^T[p,h] = sum_n dH[n,p] * M[n,h]
+                    gemm(dHd, Md, 1, 1, out=gWpT[d])
+                    dfold = ws["dfold"][d]
+                    if T > 1:
+                        # dW'^T[g,h] = sum_n dz_n[g] * m_prev(n)[h]; prev = t-1 (fwd) / t+1 (bwd): a row shift of B
+                        if d == 0:
+                            gemm(dGd[B:], Md[:N - B], 1, 1, out=dfold)
+                        else:
+                            gemm(dGd[:N - B], Md[B:], 1, 1, out=dfold)
+                        df_hi, df_lo = _split_bf16(dfold)
+                        rows = slice(d * 4 * c.Hp, (d + 1) * 4 * c.Hp)
+                        # dW_h[g,p] = sum_h dW'^T[g,h] * WpT[p,h]
+                        gemm(df_hi, self._bf[("WpT", i)][d], 0, 0, out=gWh[rows])
+                        gemm(df_lo, self._bf[("WpT", i)][d], 0, 0, out=gWh[rows], accumulate=True)
+                        # dW_p^T[p,h] += sum_g Wh[g,p] * dW'^T[g,h]
+                        gemm(self._bf[("Wh", i)][rows], df_hi, 1, 1, out=gWpT[d], accumulate=True)
+                        gemm(self._bf[("Wh", i)][rows], df_lo, 1, 1, out=gWpT[d], accumulate=True)
+                # dW_x[g,k] = sum_n dz_n[g] * x_n[k]   (both directions at once)
+                gemm(dG, X, 1, 1, out=gWx)
+                if overlap:
+                    L.lcb_gemm_set_max_ctas(old_cap)
+                if bucket_ready is not None:
+                    bucket_ready(["L%d/WpT" % i, "L%d/Wh" % i, "L%d/peep" % i, "L%d/bias" % i, "L%d/Wx" % i])
+                if overlap:
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    side_done[i] = ev
+        if overlap:
+            main.wait_stream(side)
         return None

@@ -21,6 +21,10 @@
 namespace lcb {
 
 
+// upper bound on the persistent grid (host-side knob): GEMMs that are overlapped with a cluster kernel on another
+// stream are launched with only as many CTAs as there are free SMs, so no CTA sits waiting with its share of tiles
+static int g_gemm_max_ctas = 148;
+
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;          // 64 bf16 = 128 B = one swizzle row
 constexpr int GEMM_THREADS = 192;
@@ -259,7 +263,7 @@ static int launch_gemm(int M, int N, int K, const CUtensorMap& ta, const CUtenso
         attr_done = true;
     }
     const int tiles = tiles0 * splits;
-    int nsm = 148;
+    int nsm = g_gemm_max_ctas;
     int grid = tiles < nsm ? tiles : nsm;
     g_launches += 1; kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, C, ldc, bias, accumulate, M, N, K, idesc, splits);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
@@ -351,6 +355,13 @@ extern "C" int lcb_gemm_bf16_simt_check(int M, int N, int K, const void* A, int 
                                         void* stream)
 {
     return lcb_gemm16_simt_check(M, N, K, A, lda, a_layout, 1, B, ldb, b_layout, 1, C, ldc, c_dtype, bias, accumulate, stream);
+}
+
+extern "C" int lcb_gemm_set_max_ctas(int n)
+{
+    const int old = lcb::g_gemm_max_ctas;
+    lcb::g_gemm_max_ctas = (n < 1) ? 1 : (n > 148 ? 148 : n);
+    return old;
 }
 
 extern "C" int lcb_version(void) { return 100; }

@@ -8,6 +8,9 @@ here a `pipeline` is a dict of handles bound to one batch source that yields, pe
 as PINNED host tensors; the Session copies them to the device.  `dataset` is any re-iterable of utterance
 dicts {'nnet_input': [T,D] float32, 'nnet_target': [L] int, optional 'filename'}.  TFRecord decoding
 (nnet/tfrecord.py) is outside the hot path."""
+import queue
+import threading
+
 import numpy as np
 import torch
 
@@ -31,17 +34,43 @@ class _BatchSource:
         self.pin = torch.cuda.is_available()
 
     def initialize(self):
+        """(Re)start the epoch.  Batches are assembled into pinned memory by a background thread, two ahead
+        (the reference's tf.data pipeline prefetches on host threads as well, tfrecord.py:122-123)."""
         self._it = iter(self.dataset)
+        self._q = queue.Queue(maxsize=2)
+        self._thread = threading.Thread(target=self._producer, args=(self._it, self._q), daemon=True)
+        self._thread.start()
 
-    def _pinned(self, t):
-        return t.pin_memory() if self.pin else t
+    def _producer(self, it, q):
+        while True:
+            try:
+                item = self._assemble(it)
+            except OutOfRangeError:
+                q.put(None)
+                return
+            except Exception as e:          # surface data errors on the consumer side
+                q.put(e)
+                return
+            q.put(item)
 
     def next(self):
         if self._it is None:
             raise RuntimeError("pipeline not initialised: sess.run(pipeline_initializer) first")
+        item = self._q.get()
+        if item is None:
+            self._q.put(None)               # stay exhausted
+            raise OutOfRangeError()
+        if isinstance(item, Exception):
+            raise item
+        return item
+
+    def _pinned(self, t):
+        return t.pin_memory() if self.pin else t
+
+    def _assemble(self, it):
         if self.sequential:
             try:
-                utt = next(self._it)
+                utt = next(it)
             except StopIteration:
                 raise OutOfRangeError()
             x = torch.as_tensor(np.asarray(utt["nnet_input"], dtype=np.float32))
@@ -50,7 +79,7 @@ class _BatchSource:
         utts = []
         for _ in range(self.batch_size):
             try:
-                utts.append(next(self._it))
+                utts.append(next(it))
             except StopIteration:
                 break
         if not utts:
