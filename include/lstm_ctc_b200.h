@@ -147,6 +147,13 @@ int lcb_f16_to_bf16(const void* src, void* dst, size_t n, void* stream);   /* n 
 int lcb_dropout16(void* x, int dtype, size_t n, float keep_prob, unsigned long long seed, void* stream);
 int lcb_dropout_mask(unsigned char* mask, size_t n, float keep_prob, unsigned long long seed, void* stream);
 int lcb_colsum(const void* src, int src_dtype, int rows, int cols, int ld, float* out, void* stream);
+/* y += x on fp16 tensors, n even: the layer-0 residual  finput = finput + concat(fwd, bwd)  (nnet/bilstm.py:199-200). */
+int lcb_add_f16(void* y, const void* x, size_t n, void* stream);
+/* label-smoothing regulariser (nnet/bilstm.py:254-269) over `rows` rows of logits [rows,V]:
+ *   *loss_out += weight * sum p (log p - q),  dlogits (nullable) += its gradient;  q = log(1/V) when log_prior is
+ *   NULL (uniform_label_sm) else log_prior[V] (prior_label_sm, nnet/class_prior.py).  All rows, padding included. */
+int lcb_label_smooth(const float* logits, float* dlogits, long long rows, int V, float weight,
+                     const float* log_prior, float* loss_out, void* stream);
 
 /* ---- output layer: mixture of tanh-bounded expert logits, or affine -------------------------
  * lcb_output_fwd replaces create_moe (nnet/moe.py:29-72) / tf.nn.xw_plus_b (nnet/bilstm.py:249)

@@ -311,8 +311,6 @@ class BLSTMEncoder:
         assert nnet_input.is_cuda and nnet_input.dtype == F32 and nnet_input.dim() == 3
         B, T, D = nnet_input.shape
         assert D == c.input_dim, (D, c.input_dim)
-        if c.residual0:
-            raise NotImplementedError("layer-0 residual (input_dim == 2*num_projects, bilstm.py:199-200)")
         self.step_id += 1 if training else 0
         self.refresh_operands()
         ws = self._workspace(T, B, training)
@@ -336,6 +334,8 @@ class BLSTMEncoder:
                 gemm(ws["M"][i][:, d * c.Hp:(d + 1) * c.Hp], self._bf[("WpT16", i)][d], 0, 0, out=Hout[:, d * c.P:(d + 1) * c.P])
             if training and c.keep_prob < 1.0:
                 self._dropout(Hout, i)              # DropoutWrapper(output_keep_prob), bilstm.py:128,137
+            if i == 0 and c.residual0:              # finput = finput + concat(...)  iff input_dim == 2*num_projects (bilstm.py:199-200)
+                _lib.check(L.lcb_add_f16(_lib.ptr(Hout), _lib.ptr(ws["X0"]), Hout.numel(), st), "lcb_add_f16")
             X = Hout
         self._last = (T, B, seq_len, training)
         return X

@@ -56,6 +56,55 @@ __global__ void dropout_mask_kernel(uint8_t* __restrict__ m, size_t n, uint32_t 
         m[i] = rng_keep(seed, i, thr) ? 1 : 0;
 }
 
+// y += x on fp16 tensors (layer-0 residual: finput = finput + concat(fwd, bwd), nnet/bilstm.py:199-200)
+__global__ void add_f16_kernel(__half2* __restrict__ y, const __half2* __restrict__ x, size_t n2) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+        const float2 a = __half22float2(y[i]), b = __half22float2(x[i]);
+        y[i] = __floats2half2_rn(sat_f16(a.x + b.x), sat_f16(a.y + b.y));
+    }
+}
+
+// label-smoothing regulariser (nnet/bilstm.py:254-269): per row p = softmax(logits),
+//   loss += w * sum_v p_v (log p_v - q_v),   q = log(1/V) (uniform) or the given log prior;
+//   dlogits_v += w * p_v * ((log p_v - q_v) - sum_u p_u (log p_u - q_u)).   Over ALL B*T rows, padding included,
+// exactly as the reference sums it.  One warp per row.
+__global__ void __launch_bounds__(256)
+label_smooth_kernel(const float* __restrict__ logits, float* __restrict__ dlogits, long long rows, int V, float w,
+                    const float* __restrict__ log_prior, float* __restrict__ loss_out)
+{
+    const int lane = threadIdx.x & 31;
+    float local = 0.f;
+    const float qu = -logf((float)V);
+    for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * 8) {
+        const float* x = logits + (size_t)r * V;
+        float mx = -INFINITY;
+        for (int v = lane; v < V; v += 32) mx = fmaxf(mx, x[v]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float s = 0.f;
+        for (int v = lane; v < V; v += 32) s += __expf(x[v] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float lse = mx + logf(s);
+        float kl = 0.f;
+        for (int v = lane; v < V; v += 32) {
+            const float lp = x[v] - lse;
+            kl += __expf(lp) * (lp - (log_prior ? log_prior[v] : qu));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) kl += __shfl_xor_sync(0xffffffffu, kl, o);
+        if (dlogits) {
+            float* g = dlogits + (size_t)r * V;
+            for (int v = lane; v < V; v += 32) {
+                const float lp = x[v] - lse;
+                g[v] += w * __expf(lp) * ((lp - (log_prior ? log_prior[v] : qu)) - kl);
+            }
+        }
+        local += kl;
+    }
+    if (lane == 0 && loss_out) atomicAdd(loss_out, w * local);
+}
+
 // hi = bf16(x), lo = bf16(x - hi): x ~= hi + lo to ~16 mantissa bits (split-bf16 GEMMs for weight folding)
 __global__ void split_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
                                       __nv_bfloat16* __restrict__ lo, size_t n) {
@@ -149,6 +198,26 @@ extern "C" int lcb_dropout_mask(unsigned char* mask, size_t n, float keep_prob, 
     if (n == 0) return LCB_OK;
     g_launches += 1;
     dropout_mask_kernel<<<grid_for(n, 2, 256), 256, 0, (cudaStream_t)stream>>>(mask, n, keep_threshold(keep_prob), seed);
+    return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
+}
+
+extern "C" int lcb_add_f16(void* y, const void* x, size_t n, void* stream) {
+    if (!y || !x) return LCB_ERR_NULL_POINTER;
+    if ((n & 1) || ((uintptr_t)y & 3) || ((uintptr_t)x & 3)) return LCB_ERR_MISALIGNED;
+    if (n == 0) return LCB_OK;
+    g_launches += 1;
+    add_f16_kernel<<<grid_for(n / 2, 1, 256), 256, 0, (cudaStream_t)stream>>>((__half2*)y, (const __half2*)x, n / 2);
+    return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
+}
+
+// loss_out (device float, caller-initialised) += weight * sum_rows KL-term; dlogits (nullable) += its gradient
+extern "C" int lcb_label_smooth(const float* logits, float* dlogits, long long rows, int V, float weight,
+                                const float* log_prior, float* loss_out, void* stream) {
+    if (!logits) return LCB_ERR_NULL_POINTER;
+    if (rows <= 0 || V <= 0) return LCB_ERR_BAD_SHAPE;
+    long long blocks = (rows + 7) / 8; if (blocks > 148 * 8) blocks = 148 * 8;
+    g_launches += 1;
+    label_smooth_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(logits, dlogits, rows, V, weight, log_prior, loss_out);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }
 

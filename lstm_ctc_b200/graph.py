@@ -128,7 +128,8 @@ class _Graph:
             out["eval_loss"], out["size"] = vals[0], int(round(vals[1]))
         else:
             out["eval_loss"] = float(loss_sum.item())                 # D2H read of the step's result
-        out["loss"] = out["eval_loss"]                                # reg losses are 0 in both recipes (graph.py:120-136)
+        reg = m.reg_loss if "train" in wanted else m.label_smoothing(logits)
+        out["loss"] = out["eval_loss"] + (float(reg.item()) if reg is not None else 0.0)   # graph.py:120-136
         out["global_step"] = m.global_step
         if "logits" in wanted:
             out["logits"] = logits.cpu().numpy()

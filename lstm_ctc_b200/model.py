@@ -73,8 +73,14 @@ class AcousticModel:
     def __init__(self, nnet_config: dict, device=None, seed=None, init=True):
         self.cfg = c = ModelConfig(nnet_config)
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        if (c.uniform_label_sm or 0) > 0 or ((c.prior_label_sm or 0) > 0 and c.prior_label_path):
-            raise NotImplementedError("label-smoothing regulariser (bilstm.py:254-269); both recipes set weight 0")
+        # label-smoothing regulariser (bilstm.py:254-269): uniform wins over prior, like the reference's if/elif
+        self.sm_weight, self.sm_prior = 0.0, None
+        if (c.uniform_label_sm or 0) > 0:
+            self.sm_weight = float(c.uniform_label_sm)
+        elif (c.prior_label_sm or 0) > 0 and c.prior_label_path:
+            from .class_prior import get_class_prior
+            self.sm_weight = float(c.prior_label_sm)
+            self.sm_prior = torch.from_numpy(get_class_prior(c.prior_label_path)).to(self.device).contiguous()
         self.rows_out = (c.K * c.V + c.K) if c.K > 0 else c.V
         self.ldz = _ceil(self.rows_out, 8)
         # output-layer variables are the unnamed tf.Variable's: L2-decayed, biases included (graph.py:186)
@@ -86,6 +92,7 @@ class AcousticModel:
         self._out_stale = True
         self._ows = {}
         self.opt_state = None
+        self.reg_loss = None
         self.global_step = 0
         self._nodecay = self.params.nodecay_ranges()
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=self.device)
@@ -222,8 +229,20 @@ class AcousticModel:
         self.params.gflat.zero_()
         logits = self.forward_logits(nnet_input, seq_len, training=True)
         loss, dlogits = self.ctc(logits, labels, seq_len, check_labels)
+        self.reg_loss = self.label_smoothing(logits, dlogits)
         self.backward(dlogits, bucket_ready)
         return loss.sum(), loss
+
+    def label_smoothing(self, logits, dlogits=None):
+        """reg_loss of create_logits_blstm (bilstm.py:254-269), added to the training loss by graph.py:120-133.
+        Returns a device scalar (or None when the weight is 0); adds its gradient into dlogits."""
+        if self.sm_weight <= 0:
+            return None
+        out = torch.zeros(1, dtype=F32, device=self.device)
+        rows = logits.numel() // logits.shape[-1]
+        _lib.check(_lib.lib().lcb_label_smooth(_lib.ptr(logits), _lib.ptr(dlogits), rows, logits.shape[-1], self.sm_weight,
+                                               _lib.ptr(self.sm_prior), _lib.ptr(out), _lib.stream_ptr()), "lcb_label_smooth")
+        return out
 
     # ------------------------------------------------------------------ update
     def optimizer_step(self, optimizer, learn_rate, clip_norm=5.0, l2_decay_weight=1e-5, momentum=0.9,

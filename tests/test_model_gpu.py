@@ -187,3 +187,63 @@ def test_dropout_parity_with_exported_masks(cuda_dev):
     lg2 = m2.forward_logits(x.float().to(cuda_dev), lens.to(cuda_dev), training=False).cpu().double()
     ref2 = oracle.output_layer(params, cfg, oracle.blstm_forward(params, cfg, x, lens)[0])
     assert (lg2 - ref2)[live].abs().max().item() < 1e-2 * ref2.abs().max().item()
+
+
+@pytest.mark.parametrize("kind", ["uniform", "prior"])
+def test_label_smoothing_regulariser(cuda_dev, kind, tmp_path):
+    """reg_loss of bilstm.py:254-269 (KL to uniform / to the class prior, over ALL rows incl. padding) and its
+    contribution to the gradients, vs torch autograd on the oracle logits."""
+    from lstm_ctc_b200.model import AcousticModel
+    cfg = oracle.OracleConfig(**CASES["affine"])
+    params = oracle.init_params(cfg, seed=41, bias_scale=0.1)
+    B, T = 4, 18
+    x, lens, labels = make_batch(cfg, B=B, T=T, Lmax=5, seed=42)
+    nc = nnet_config(cfg)
+    w = 0.05
+    prior = None
+    if kind == "uniform":
+        nc["uniform_label_sm"] = w
+    else:
+        counts = np.arange(1, cfg.num_targets + 1, dtype=np.float64)
+        p = tmp_path / "label.counts"
+        p.write_text("[ " + " ".join(str(c) for c in counts) + " ]\n")
+        nc["prior_label_sm"] = w; nc["prior_label_path"] = str(p)
+        from lstm_ctc_b200 import get_class_prior
+        prior = torch.from_numpy(get_class_prior(str(p))).double()
+    m = AcousticModel(nc, cuda_dev, init=False)
+    m.from_tf_dict(params)
+    loss_sum, _ = m.loss_and_grad(x.float().to(cuda_dev), lens.to(cuda_dev), labels.to(cuda_dev))
+    p64 = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    ctc, _, logits = oracle.training_loss(p64, cfg, x, lens, labels, 0.0)
+    pr = torch.softmax(logits, -1)
+    q = torch.full((cfg.num_targets,), -np.log(cfg.num_targets), dtype=torch.float64) if prior is None else prior
+    reg = w * (pr * (torch.log(pr) - q)).sum()                     # bilstm.py:258-260 / :265-267
+    (ctc + reg).backward()
+    assert abs(m.reg_loss.item() - reg.item()) < 2e-2 * abs(reg.item()) + 1e-3, (m.reg_loss.item(), reg.item())
+    grads = {k: v.cpu().double() for k, v in m.to_tf_dict(grads=True).items()}
+    bad = {k: ((v - p64[k].grad).norm() / (p64[k].grad.norm() + 1e-12)).item() for k, v in grads.items()}
+    bad = {k: r for k, r in bad.items() if r > 5e-2}
+    assert not bad, bad
+
+
+def test_layer0_residual(cuda_dev):
+    """input_dim == 2*num_projects switches on finput = finput + concat(fwd, bwd) in layer 0 (bilstm.py:199-200)."""
+    from lstm_ctc_b200.model import AcousticModel
+    cfg = oracle.OracleConfig(input_dim=64, num_layers=2, num_neurons=64, num_projects=32, num_targets=9, use_peepholes=True, num_experts=0)
+    params = oracle.init_params(cfg, seed=51, bias_scale=0.1)
+    x, lens, labels = make_batch(cfg, B=3, T=12, Lmax=4, seed=52)
+    m = AcousticModel(nnet_config(cfg), cuda_dev, init=False)
+    assert m.cfg.residual0
+    m.from_tf_dict(params)
+    loss_sum, _ = m.loss_and_grad(x.float().to(cuda_dev), lens.to(cuda_dev), labels.to(cuda_dev))
+    p64 = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    ctc, _, ref_logits = oracle.training_loss(p64, cfg, x, lens, labels, 0.0)
+    ctc.backward()
+    logits = m._out_ws(12, 3)["logits"].cpu().double()
+    live = (torch.arange(12).unsqueeze(0) < lens.unsqueeze(1))
+    assert (logits - ref_logits.detach())[live].abs().max().item() < 1e-2 * ref_logits.abs().max().item()
+    assert abs(loss_sum.item() - ctc.item()) < 2e-3 * abs(ctc.item())
+    grads = {k: v.cpu().double() for k, v in m.to_tf_dict(grads=True).items()}
+    bad = {k: ((v - p64[k].grad).norm() / (p64[k].grad.norm() + 1e-12)).item() for k, v in grads.items()}
+    bad = {k: r for k, r in bad.items() if r > 5e-2}
+    assert not bad, bad
