@@ -119,9 +119,13 @@ int lcb_lstm_rec_config(int Hp, int* units_per_cta_div32, int* cluster_size);
 int lcb_lstm_rec_max_clusters(int Hp, int which);
 /* debug probe: the next lcb_lstm_rec_fwd launches write steps*16 clock64 samples of CTA 0 into buf (NULL: off). */
 int lcb_debug_rec_profile(long long* buf, int steps);
+/* workspace: device scratch of lcb_lstm_rec_workspace_bytes(B, Hp) bytes (16-byte aligned, caller-owned, one per
+ * concurrently running launch): the per-step exchange of m_t goes  shared memory -> bulk store -> this L2-resident
+ * scratch -> ONE multicast bulk load into all CTAs of the cluster.  NULL keeps the exchange on unicast DSMEM copies. */
+size_t lcb_lstm_rec_workspace_bytes(int B, int Hp);
 int lcb_lstm_rec_fwd(const float* G, const void* WfoldT, const float* peep, const int32_t* lens,
                      void* Mout, void* gates, float* cst, float* cfin, float* mfin,
-                     int T, int B, int Hp, float forget_bias, void* stream);
+                     int T, int B, int Hp, float forget_bias, void* workspace, size_t workspace_bytes, void* stream);
 /* BPTT of the above (replaces tf.gradients through the while_loop, nnet/graph.py:190-191).
  *   dM    [T*B, 2Hp] f32   d loss / d m_t arriving from the output projection
  *   Wfold [2*Hp, 4Hp] bf16 W' = W_proj*W_h per direction: rows = units, cols = packed gate columns
@@ -129,7 +133,7 @@ int lcb_lstm_rec_fwd(const float* G, const void* WfoldT, const float* peep, cons
  *   dbias [2*4Hp] f32 +=,  dpeep [2,3,Hp] f32 += (NULL iff peep NULL) */
 int lcb_lstm_rec_bwd(const float* dM, const void* gates, const float* cst, const void* Wfold, const float* peep,
                      const int32_t* lens, void* dG, float* dbias, float* dpeep,
-                     int T, int B, int Hp, void* stream);
+                     int T, int B, int Hp, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- HBM-bound helpers -----------------------------------------------------------------
  * lcb_pack_input: pipeline tensor nnet_input [B,T,D] f32 (nnet/pipeline.py:35-61) -> time-major

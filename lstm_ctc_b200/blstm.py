@@ -286,6 +286,7 @@ class BLSTMEncoder:
                   "G": torch.empty(N, 8 * c.Hp, dtype=F32, device=dev),
                   "M": [torch.empty(N, 2 * c.Hp, dtype=F16, device=dev) for _ in range(c.num_layers)],
                   "Hout": [torch.empty(N, 2 * c.P, dtype=F16, device=dev) for _ in range(c.num_layers)],
+                  "rec_ws": torch.zeros(max(16, _lib.lib().lcb_lstm_rec_workspace_bytes(B, c.Hp)), dtype=torch.uint8, device=dev),
                   "cfin": torch.zeros(B, 2, c.Hp, dtype=F32, device=dev),
                   "mfin": torch.zeros(B, 2, c.Hp, dtype=F32, device=dev)}
             if training:
@@ -328,7 +329,7 @@ class BLSTMEncoder:
             _lib.check(L.lcb_lstm_rec_fwd(_lib.ptr(ws["G"]), _lib.ptr(self._bf[("fold16", i)]), _lib.ptr(peep), _lib.ptr(seq_len),
                                           _lib.ptr(ws["M"][i]), _lib.ptr(gates), _lib.ptr(cst),
                                           _lib.ptr(ws["cfin"]) if last else None, _lib.ptr(ws["mfin"]) if last else None,
-                                          T, B, c.Hp, c.forget_bias, st), "lcb_lstm_rec_fwd")
+                                          T, B, c.Hp, c.forget_bias, _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(), st), "lcb_lstm_rec_fwd")
             Hout = ws["Hout"][i]
             for d in range(2):
                 gemm(ws["M"][i][:, d * c.Hp:(d + 1) * c.Hp], self._bf[("WpT16", i)][d], 0, 0, out=Hout[:, d * c.P:(d + 1) * c.P])
@@ -392,7 +393,7 @@ class BLSTMEncoder:
             _lib.check(L.lcb_lstm_rec_bwd(_lib.ptr(dM), _lib.ptr(ws["gates"][i]), _lib.ptr(ws["cst"][i]),
                                           _lib.ptr(self._bf[("fold", i)]), _lib.ptr(peep),
                                           _lib.ptr(seq_len), _lib.ptr(dG), _lib.ptr(ps.g("L%d/bias" % i)), _lib.ptr(gpeep),
-                                          T, B, c.Hp, _lib.stream_ptr()), "lcb_lstm_rec_bwd")
+                                          T, B, c.Hp, _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(), _lib.stream_ptr()), "lcb_lstm_rec_bwd")
             ev_dg = None
             if overlap:
                 ev_dg = torch.cuda.Event()

@@ -30,6 +30,8 @@
 // BPTT runs the mirrored scan with W' (bf16) resident in TMEM as [units, own gate rows]: dz_t is formed in
 // registers, staged locally as the MMA B operand, partial dm_{t-1} tiles are reduce-scattered to their owner
 // CTAs with st.async (double-buffered reduce buffer, mbarrier tx-counted).
+#include <cstring>
+#include <cstdlib>
 #include <cuda_fp16.h>
 #include "ptx.cuh"
 #include "tma_host.h"
@@ -60,6 +62,7 @@ struct RecFwdParams {
     float* mfin;                  // [B][2][Hp] final m (pre-projection output) (nullable)
     int T, B, Hp, NC;
     float forget_bias;
+    unsigned char* xch;           // v2: L2 exchange scratch [clusters][2][NC][slice] (nullptr: DSMEM copies)
 };
 
 struct RecBwdParams {
@@ -73,6 +76,7 @@ struct RecBwdParams {
     float* dbias;                 // [2][4Hp]   += (packed column order)
     float* dpeep;                 // [2][3][Hp] += (nullable)
     int T, B, Hp, NC;
+    unsigned char* xch;           // v3: L2 exchange scratch [clusters][2][NC][dz slice]
 };
 
 __device__ __forceinline__ unsigned char* align_1024(unsigned char* p) {
@@ -702,12 +706,998 @@ lstm_rec_bwd_kernel(const RecBwdParams p)
 }
 
 // =================================================================================================
+// v2 kernels: ONE group of BG utterances per cluster, in lockstep (MMA N = BG, BG = 16 or 32)
+//
+// Measured on the v1 kernels (profiles/r01_recprobe_*): a 128 x 16 x 16 tcgen05.mma costs ~36 cycles whatever N <= 64 is
+// (the 4 KB weight operand streams at ~128 B/clk), so two interleaved 16-utterance sub-groups pay the 32-MMA pass
+// (~1150 cycles) twice per step pair.  v2 issues it once for 32 utterances; the cluster then runs in lockstep and the
+// per-step chain is  commit->wake, tcgen05.ld, gate math (MUFU-bound: 5 ex2 + 2 rcp per cell with shared reciprocals),
+// slice barrier + 16 bulk DSMEM copies of 512*BG/8 bytes, ingress (BG KB per CTA at ~17 B/clk) overlapped with the
+// K-block-pipelined MMA issue.
+// =================================================================================================
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float clamp25(float x) { return fminf(fmaxf(x, -25.f), 25.f); }
+// (sigmoid(a), sigmoid(b), tanh(c)) with ONE reciprocal: 1/(1+e^-a) = (1+e^-b)(1+e^-2c) / prod, ...  Arguments are clamped
+// to +-25 (sigmoid(25) = 1 - 1.4e-11) so the product of the three denominators stays below 2^110.
+__device__ __forceinline__ void sig_sig_tanh(float a, float b, float c, float& sa, float& sb, float& tc) {
+    const float ea = 1.f + ex2_approx(-1.4426950408889634f * clamp25(a));
+    const float eb = 1.f + ex2_approx(-1.4426950408889634f * clamp25(b));
+    const float ec = 1.f + ex2_approx(-2.8853900817779268f * clamp25(c));
+    const float ab = ea * eb;
+    const float r = rcp_approx(ab * ec);
+    sa = r * eb * ec;
+    sb = r * ea * ec;
+    tc = 2.f * (r * ab) - 1.f;
+}
+__device__ __forceinline__ void sig_tanh(float a, float c, float& sa, float& tc) {
+    const float ea = 1.f + ex2_approx(-1.4426950408889634f * clamp25(a));
+    const float ec = 1.f + ex2_approx(-2.8853900817779268f * clamp25(c));
+    const float r = rcp_approx(ea * ec);
+    sa = r * ec;
+    tc = 2.f * (r * ea) - 1.f;
+}
+
+template <int BG> struct RecFwd2Cfg {
+    static constexpr int NUB = BG / 8;                     // utterance blocks of 8 (core-matrix rows of the MMA B operand)
+    static constexpr int NCW = 4 * NUB;                    // compute warps: (utterance block, TMEM lane quarter)
+    static constexpr int NIW = 2;                          // MMA issuer warps: one thread issues a 128xBGx16 MMA every ~65 cycles,
+                                                           // the tensor pipe retires one every ~36 -> two issuers keep it busy
+    static constexpr int THREADS = 32 * (NCW + NIW + 2);   // + loader warp + exchange warp
+    static constexpr int SLICE = 512 * NUB;                // bytes of one CTA's m_t slice: 32 units x BG utterances, fp16
+    static constexpr int BARS = 1 + 2 * REC_SG + 2 + 2 + 1; // mma g[SG] gfree[SG] op[2] slice[2] acc
+    __host__ __device__ static size_t op_bytes(int KB) { return (size_t)KB * 8 * NUB * 128; }    // one operand buffer (all K blocks)
+    __host__ __device__ static size_t g_bytes() { return (size_t)REC_SG * BG * REC_GROW * 4; }
+    static size_t smem_bytes(int KB) { return 1024 + 2 * op_bytes(KB) + g_bytes() + 2 * SLICE + BARS * 8 + 64; }
+};
+
+template <int BG>
+__global__ void __launch_bounds__(RecFwd2Cfg<BG>::THREADS, 1)
+lstm_rec_fwd2_kernel(const RecFwdParams p)
+{
+    using Cfg = RecFwd2Cfg<BG>;
+    constexpr int SG = REC_SG, NUB = Cfg::NUB, NCW = Cfg::NCW, NIW = Cfg::NIW, SLICE = Cfg::SLICE;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = align_1024(smem_raw);
+    const int Hp = p.Hp, KB = Hp >> 6, NC = p.NC, T = p.T, B = p.B;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int role = warp < NCW ? 0 : (warp < NCW + NIW ? 1 : warp - NCW - NIW + 2);   // 0 compute | 1 MMA issuers | 2 loader | 3 exchange
+    const int rw = role == 0 ? warp : warp - NCW;
+    const uint32_t OPB = (uint32_t)Cfg::op_bytes(KB);
+
+    // operand m_{t-1}: no-swizzle K-major core matrices (8 utterances x 8 units = 128 B), index (unit/8)*NUB + utt/8
+    unsigned char* Bsm = smem;                                                   // [2][KB*8][NUB][128 B]
+    float* Gsm = reinterpret_cast<float*>(Bsm + 2 * (size_t)OPB);               // [SG][BG][132]
+    unsigned char* Msm = reinterpret_cast<unsigned char*>(Gsm + (size_t)SG * BG * REC_GROW);   // [2 step parities][SLICE]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Msm + 2 * SLICE);
+    uint64_t* mbar_mma = bars;                         //      this step's accumulator is complete
+    uint64_t* mbar_g = bars + 1;                       // [SG] G tile landed (bulk-copy tx)
+    uint64_t* mbar_gfree = bars + 1 + SG;              // [SG] compute warps are done with the G stage
+    uint64_t* mbar_op = bars + 1 + 2 * SG;             // [2]  operand buffer: the slices of all NC CTAs have landed
+    uint64_t* mbar_slice = bars + 3 + 2 * SG;          // [2]  this CTA's m_t slice is staged for the exchange warp
+    uint64_t* mbar_acc = bars + 5 + 2 * SG;            //      the accumulator holds the next step's x-part (G tile): MMAs may accumulate
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::BARS);
+
+    const uint32_t cta = cluster_ctarank();
+    const int cid = (int)cluster_id_x();
+    const int dir = cid & 1, bg = cid >> 1;
+    const int b0 = bg * BG;                            // first utterance of this cluster's group
+    const size_t ld2 = (size_t)2 * Hp;
+
+    if (threadIdx.x == 0) {
+        mbar_init(mbar_mma, NIW);
+        mbar_init(mbar_acc, NCW);
+        for (int s = 0; s < SG; ++s) { mbar_init(&mbar_g[s], 1); mbar_init(&mbar_gfree[s], NCW); }
+        mbar_init(&mbar_op[0], 1); mbar_init(&mbar_op[1], 1);
+        mbar_init(&mbar_slice[0], NCW); mbar_init(&mbar_slice[1], NCW);
+        fence_mbar_init();
+    }
+    if (warp == NCW) tmem_alloc<512>(tmem_slot);
+    {   // m_{-1} = 0
+        uint4* bz = reinterpret_cast<uint4*>(Bsm);
+        const int n16 = (int)(2 * OPB / 16);
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) bz[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // ---- W'^T slice -> tensor memory: row r of the slice lives in TMEM lane r, 16 fp16 per 8 columns ----
+    if (role == 0) {
+        const int q = warp & 3;
+        const __half* wrow = p.Wt + ((size_t)dir * 4 * Hp + (size_t)cta * 128 + q * 32 + lane) * Hp;
+        for (int ch = warp >> 2; ch < Hp / 16; ch += NUB) {
+            const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(wrow + ch * 16));
+            const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(wrow + ch * 16 + 8));
+            const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            tmem_st_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + ch * 8, r);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    cluster_sync_all();          // weights resident; every CTA of the cluster is initialised before any multicast traffic
+    tc_fence_after();
+
+    long long* prof = (blockIdx.x == 0 && lane == 0 && (role == 1 || (role == 0 && rw == 0))) ? g_rec_prof : nullptr;
+    const int prof_steps = g_rec_prof_steps;
+    const int nvalid = (B - b0) < BG ? (B - b0) : BG;           // utterances of this group that exist
+
+    bool ok = true;
+    if (role == 2) {
+        // ============================ loader warp: G tile prefetch, one 512-byte bulk copy per lane ============================
+        for (int s = 0; s < T; ++s) {
+            const int stage = s % SG;
+            if (s >= SG) {              // wait until the compute warps drained this stage (step s - SG)
+                if (lane == 0 && ok) ok = mbar_wait(&mbar_gfree[stage], (uint32_t)(((s - SG) / SG) & 1));
+                ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+                if (!ok) break;
+            }
+            const int t = dir ? (T - 1 - s) : s;
+            if (lane == 0) mbar_arrive_expect_tx(&mbar_g[stage], (uint32_t)(nvalid * 512));
+            __syncwarp();
+            for (int u = lane; u < nvalid; u += 32)
+                bulk_load_1d(Gsm + ((size_t)stage * BG + u) * REC_GROW,
+                             p.G + ((size_t)t * B + b0 + u) * 8 * Hp + (size_t)dir * 4 * Hp + (size_t)cta * 128,
+                             512, &mbar_g[stage]);
+        }
+    } else if (role == 3) {
+        // ============================ exchange warp: slice -> L2 scratch -> multicast into every CTA of the cluster ============================
+        // The DSMEM port of an SM moves ~16 B/clk, in + out combined (measured: tools/micro/xch_bench.cu), so the 16 unicast
+        // copies of an all-gather cost ~60 cycles per KB of operand; a bulk store to an L2-resident scratch followed by ONE
+        // multicast bulk load costs ~750 cycles + 10 per KB and lands everywhere at once.
+        if (lane == 0) {
+            unsigned char* scr = p.xch + (size_t)cid * 2 * NC * SLICE;
+            const uint16_t mask = (uint16_t)((1u << NC) - 1u);
+            for (int s = 0; s + 1 < T && ok; ++s) {
+                ok = mbar_wait(&mbar_slice[s & 1], (uint32_t)((s >> 1) & 1));
+                if (!ok) break;
+                unsigned char* g = scr + ((size_t)(s & 1) * NC + cta) * SLICE;
+                bulk_store_s2g(g, smem_u32(Msm + (s & 1) * SLICE), (uint32_t)SLICE);
+                bulk_commit_group();
+                bulk_wait_group_all();
+                bulk_load_multicast(smem_u32(Bsm) + (uint32_t)((s + 1) & 1) * OPB + cta * (uint32_t)SLICE, g, (uint32_t)SLICE,
+                                    smem_u32(&mbar_op[(s + 1) & 1]), mask);
+            }
+        }
+        __syncwarp();
+    } else if (role == 1) {
+        // ============================ MMA issuers ============================
+        // forward operands are fp16: a_format = b_format = F16 (0); A (weights) from TMEM, B = m_{t-1} K-major from smem.
+        // The whole operand arrives at once (multicast), so each issuer waits ONCE per step and issues its half of the
+        // Hp/16 K steps back to back; every MMA ACCUMULATES onto the accumulator the compute warps pre-loaded with the
+        // hoisted x-part of the pre-activations (G tile), so issue order between the two threads does not matter.
+        constexpr uint32_t idesc = make_idesc_bf16_f32(128, BG, 0, 0) & ~((7u << 7) | (7u << 10));
+        const int iw = rw;
+        if (lane == 0) {
+            // LBO (next 8 units along K) = NUB*128 B, SBO (next 8 utterances) = 128 B; one K=16 MMA step = 2*NUB*128 B
+            const uint64_t bb0 = make_smem_desc_noswz(smem_u32(Bsm), NUB * 128, 128);
+            const uint32_t b_lo0 = (uint32_t)bb0, b_hi = (uint32_t)(bb0 >> 32);
+            const uint32_t d_tmem = tmem_base + REC_TMEM_ACC;
+            const int nk = Hp >> 4;
+            for (int s = 0; s < T && ok; ++s) {
+                REC_PROBE(0);
+                const uint32_t par = (uint32_t)(s & 1);
+                if (iw == 0 && s + 1 < T) mbar_arrive_expect_tx(&mbar_op[(s + 1) & 1], (uint32_t)(NC * SLICE));   // the buffer that step s fills
+                ok = mbar_wait(mbar_acc, (uint32_t)(s & 1));                 // accumulator = G tile of step s
+                if (ok && s > 0) ok = mbar_wait(&mbar_op[par], (uint32_t)(((s - 1) >> 1) & 1));
+                if (!ok) break;
+                REC_PROBE(1);
+                tc_fence_after();
+                const uint32_t b_lo_s = b_lo0 + ((par * OPB) >> 4);
+                if (s > 0) {                                                 // m_{-1} = 0: step 0 is the x-part alone
+#pragma unroll 4
+                    for (int kk = iw; kk < nk; kk += NIW)
+                        umma_f16_ts_lohi(d_tmem, tmem_base + 8 * kk, b_lo_s + (2 * NUB * 128 / 16) * kk, b_hi, idesc, 1u);
+                }
+                REC_PROBE(7);
+                umma_commit(mbar_mma);
+                REC_PROBE(2);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ============================ compute warps: (utterance block, TMEM lane quarter) ============================
+        const int ub = rw >> 2, q = rw & 3;                    // q == warp % 4: the TMEM lane quarter this warp may access
+        const int up = lane >> 2, g = lane & 3;
+        const int unit = (int)cta * 32 + q * 8 + up;
+        float wf = 0.f, wi = 0.f, wo = 0.f;
+        if (p.peep) {
+            wf = p.peep[(size_t)(dir * 3 + 0) * Hp + unit];
+            wi = p.peep[(size_t)(dir * 3 + 1) * Hp + unit];
+            wo = p.peep[(size_t)(dir * 3 + 2) * Hp + unit];
+        }
+        // this thread's two utterances: local rows ub*8 + 2g + j
+        int len_j[2];
+        float c_reg[2];
+        bool pad_j[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int b = b0 + ub * 8 + 2 * g + j;
+            pad_j[j] = b >= B;
+            len_j[j] = pad_j[j] ? 0 : p.lens[b];
+            c_reg[j] = 0.f;
+        }
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + ub * 8;
+        const float fbias = p.forget_bias;
+        const size_t out0 = (size_t)dir * Hp + unit;
+        // accumulator := hoisted x-part of step s2's pre-activations (G tile, forget bias folded in; padding utterances 0),
+        // then release the G stage and tell the issuers that they may accumulate onto it
+        auto load_acc = [&](int s2) {
+            const int stage = s2 % SG;
+            if (ok) ok = mbar_wait(&mbar_g[stage], (uint32_t)((s2 / SG) & 1));
+            const float* gt = Gsm + (size_t)stage * BG * REC_GROW + q * 32 + up;
+            uint32_t a0[4], a1[4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float* gr = gt + (ub * 8 + 2 * g + j) * REC_GROW;
+                a0[j] = pad_j[j] ? 0u : __float_as_uint(gr[0]);
+                a0[2 + j] = pad_j[j] ? 0u : __float_as_uint(gr[8]);
+                a1[j] = pad_j[j] ? 0u : __float_as_uint(gr[16] + fbias);
+                a1[2 + j] = pad_j[j] ? 0u : __float_as_uint(gr[24]);
+            }
+            tmem_st_16x256b_x1(t_addr, a0);
+            tmem_st_16x256b_x1(t_addr + (16u << 16), a1);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&mbar_gfree[stage]); mbar_arrive(mbar_acc); }
+        };
+        load_acc(0);
+
+        for (int s = 0; s < T; ++s) {
+            const int t = dir ? (T - 1 - s) : s;
+            REC_PROBE(8);
+            // rows of the quarter are gate-major: lanes [0,16) hold gates i,j ; lanes [16,32) gates f,o.  The accumulator
+            // already contains the x-part (put there by load_acc below), so this is the complete pre-activation.
+            if (ok) ok = mbar_wait(mbar_mma, (uint32_t)(s & 1));
+            REC_PROBE(10);
+            tc_fence_after();
+            float zi[2], zj[2], zf[2], zo[2];
+            {
+                uint32_t a0[4], a1[4];
+                tmem_ld_16x256b_x1(t_addr, a0);                       // (i | j) x 2 utts
+                tmem_ld_16x256b_x1(t_addr + (16u << 16), a1);         // (f | o)
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    zi[j] = __uint_as_float(a0[j]); zj[j] = __uint_as_float(a0[2 + j]);
+                    zf[j] = __uint_as_float(a1[j]); zo[j] = __uint_as_float(a1[2 + j]);
+                }
+            }
+            REC_PROBE(11);
+            float ig[2], fg[2], jt[2], cn[2], og[2], tc[2], mo[2];
+            bool live[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float cp = c_reg[j];
+                sig_sig_tanh(zi[j] + wi * cp, zf[j] + wf * cp, zj[j], ig[j], fg[j], jt[j]);
+                cn[j] = fg[j] * cp + ig[j] * jt[j];
+                sig_tanh(zo[j] + wo * cn[j], cn[j], og[j], tc[j]);
+                live[j] = t < len_j[j];
+                if (live[j]) c_reg[j] = cn[j];
+                mo[j] = live[j] ? og[j] * tc[j] : 0.f;
+            }
+            const __half2 mh = __floats2half2_rn(mo[0], mo[1]);
+            REC_PROBE(15);
+            if (s + 1 < T) {
+                // stage the warp's [8 utts][8 units] fp16 block = core matrix (q, ub) of this CTA's operand slice (double-
+                // buffered by step parity) and hand it to the exchange warp
+                __half* ms16 = reinterpret_cast<__half*>(Msm + (s & 1) * SLICE + (q * NUB + ub) * 128);
+                ms16[(2 * g) * 8 + up] = __low2half(mh);
+                ms16[(2 * g + 1) * 8 + up] = __high2half(mh);
+                fence_proxy_async_smem();                              // generic-proxy stores -> visible to the bulk (async-proxy) store
+                __syncwarp();
+                REC_PROBE(12);
+                if (lane == 0) mbar_arrive(&mbar_slice[s & 1]);
+                load_acc(s + 1);                                       // off the chain: the operand is >= 1000 cycles away
+            }
+            REC_PROBE(13);
+            // ---- off the critical path: outputs and saved activations ----
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int b = b0 + ub * 8 + 2 * g + j;
+                if (!pad_j[j]) {
+                    const size_t idx = ((size_t)t * B + b) * ld2 + out0;
+                    p.Mout[idx] = j ? __high2half(mh) : __low2half(mh);
+                    if (p.gates) {
+                        const __half2 g01 = __floats2half2_rn(ig[j], jt[j]), g23 = __floats2half2_rn(fg[j], og[j]);
+                        p.gates[idx] = make_uint2(*reinterpret_cast<const uint32_t*>(&g01), *reinterpret_cast<const uint32_t*>(&g23));
+                        p.cst[idx] = cn[j];
+                    }
+                    // final state = state at the last live step in this direction's own order
+                    const bool last = dir ? (t == 0 && live[j]) : (t == len_j[j] - 1);
+                    if (last && p.cfin) {
+                        p.cfin[((size_t)b * 2 + dir) * Hp + unit] = cn[j];
+                        p.mfin[((size_t)b * 2 + dir) * Hp + unit] = og[j] * tc[j];
+                    }
+                }
+            }
+            REC_PROBE(14);
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();          // nobody leaves while multicast traffic addressed to it may still be in flight
+    if (warp == NCW) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
+}
+
+// ---- BPTT v2 ----
+template <int BG> struct RecBwd2Cfg {
+    static constexpr int NUB = BG / 8;
+    static constexpr int NCW = 4 * NUB;                    // compute warps: (utterance block | M tile, TMEM lane quarter)
+    static constexpr int THREADS = 32 * (NCW + 4);         // + 4 MMA issuer warps (one per 128-unit M tile)
+    static constexpr int TPW = 16 / NCW;                   // (M tile, quarter) partial tiles per compute warp
+    static constexpr int PT = 32 * BG * 2;                 // bytes of one partial tile: [32 units][BG utts] bf16
+    static constexpr int BARS = 8;                         // mma[4] dz red[2] (+pad)
+    __host__ __device__ static size_t bp_bytes() { return (size_t)2 * BG * 128; }              // dz operand: 2 K blocks x BG rows x 128 B
+    __host__ __device__ static size_t red_bytes(int NC) { return (size_t)NC * PT; }            // one reduce buffer
+    static size_t smem_bytes(int NC) { return 1024 + 2 * bp_bytes() + 2 * red_bytes(NC) + (size_t)2 * 16 * PT + BARS * 8 + 64; }
+};
+
+template <int BG>
+__global__ void __launch_bounds__(RecBwd2Cfg<BG>::THREADS, 1)
+lstm_rec_bwd2_kernel(const RecBwdParams p)
+{
+    using Cfg = RecBwd2Cfg<BG>;
+    constexpr int NUB = Cfg::NUB, NCW = Cfg::NCW, TPW = Cfg::TPW, PT = Cfg::PT;
+    constexpr int NCH = BG / 8;                        // 16-byte chunks per partial-tile row (8 utterances each)
+    constexpr int SWS = 64 / BG;                       // row-swizzle period: chunk c of unit row u sits at c ^ ((u / SWS) & (NCH-1))
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = align_1024(smem_raw);
+    const int Hp = p.Hp, NC = p.NC, T = p.T, B = p.B;
+    const int MB = (Hp + 127) >> 7;                    // M tiles of 128 units
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int role = warp < NCW ? 0 : 1;
+    const int rw = role == 0 ? warp : warp - NCW;
+
+    // operand dz_t (K' = 128 gate rows), SW128 K-major; double-buffered by step parity: a CTA's reduce buffer can complete
+    // (and its next phase A start) while its OWN later M tiles of the previous step are still being multiplied
+    unsigned char* Bp = smem;                                                    // [2][2 K blocks][BG rows x 128 B]
+    unsigned char* red = Bp + 2 * Cfg::bp_bytes();                               // [2][NC][PT]
+    unsigned char* pst = red + 2 * Cfg::red_bytes(NC);                           // [2 step parities][16 tiles][PT] staging
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pst + (size_t)2 * 16 * PT);
+    uint64_t* mbar_mma = bars;                         // [4] partial dm tile j complete
+    uint64_t* mbar_dz = bars + 4;                      //     dz_t staged by all compute warps
+    uint64_t* mbar_red = bars + 5;                     // [2] partial dm slices from the whole cluster have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::BARS);
+
+    const uint32_t cta = cluster_ctarank();
+    const int cid = (int)cluster_id_x();
+    const int dir = cid & 1, bg = cid >> 1;
+    const int b0 = bg * BG;
+    const size_t ld2 = (size_t)2 * Hp, ld8 = (size_t)8 * Hp;
+    const uint32_t red_bytes = (uint32_t)Cfg::red_bytes(NC);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(&mbar_mma[i], 1);
+        mbar_init(mbar_dz, NCW);
+        mbar_init(&mbar_red[0], 1);
+        mbar_init(&mbar_red[1], 1);
+        fence_mbar_init();
+    }
+    if (warp == NCW) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // ---- W' -> tensor memory as A' = [units (lanes), own 128 gate rows (K')]: tile j in columns [64 j, 64 j + 64) ----
+    if (role == 0) {
+        const int q = warp & 3;
+        for (int jt = warp >> 2; jt < MB; jt += NUB) {
+            const int u = jt * 128 + q * 32 + lane;
+            const __nv_bfloat16* wrow = p.W + ((size_t)dir * Hp + (u < Hp ? u : 0)) * 4 * Hp + (size_t)cta * 128;
+            for (int ch = 0; ch < 8; ++ch) {
+                uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+                if (u < Hp) {
+                    v0 = __ldg(reinterpret_cast<const uint4*>(wrow + ch * 16));
+                    v1 = __ldg(reinterpret_cast<const uint4*>(wrow + ch * 16 + 8));
+                }
+                const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                tmem_st_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + jt * 64 + ch * 8, r);
+            }
+        }
+        tmem_st_wait();
+    }
+    if (threadIdx.x == 0 && T > 1) mbar_arrive_expect_tx(&mbar_red[0], red_bytes);   // armed before anybody can send
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+
+    long long* prof = (blockIdx.x == 0 && lane == 0 && rw == 0) ? g_rec_prof : nullptr;
+    const int prof_steps = g_rec_prof_steps;
+    bool ok = true;
+    if (role == 1) {
+        // ============================ MMA issuer warps: one 128-unit M tile each ============================
+        constexpr uint32_t idesc = make_idesc_bf16_f32(128, BG, 0, 0);           // bf16 x bf16, A (TMEM) K-major
+        const int jt = rw;
+        if (lane == 0 && jt < MB) {
+            const uint32_t a_tmem = tmem_base + jt * 64;
+            const uint64_t bb0 = make_smem_desc_sw128(smem_u32(Bp), 16, 1024);
+            const uint32_t b_lo0 = (uint32_t)bb0, b_hi = (uint32_t)(bb0 >> 32);
+            const uint32_t d_tmem = tmem_base + REC_TMEM_ACC + jt * BG;
+            for (int s = 0; s < T && ok; ++s) {
+                REC_PROBE(0);
+                ok = mbar_wait(mbar_dz, (uint32_t)(s & 1));                      // dz_t staged by all compute warps
+                if (!ok) break;
+                REC_PROBE(1);
+                // the reduce buffer the NEXT step's partials go to: its previous contents were consumed in phase A
+                // of this step (all compute warps arrived on mbar_dz after reading them)
+                if (jt == 0 && s + 2 < T) mbar_arrive_expect_tx(&mbar_red[(s + 1) & 1], red_bytes);
+                tc_fence_after();
+                if (s + 1 < T) {                      // the last step's dm_{-1} is never used
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        umma_f16_ts_lohi(d_tmem, a_tmem + 8 * kk,
+                                         b_lo0 + (uint32_t)(((s & 1) * (int)Cfg::bp_bytes() + (kk >> 2) * (BG * 128)) / 16 + (kk & 3) * 2), b_hi,
+                                         idesc, kk ? 1u : 0u);
+                }
+                REC_PROBE(7);
+                umma_commit(&mbar_mma[jt]);
+                REC_PROBE(2);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ============================ compute warps ============================
+        const int ub = rw >> 2, q = rw & 3;
+        const int up = lane >> 2, g = lane & 3;
+        const int ul = q * 8 + up;                          // local unit (0..31)
+        const int unit = (int)cta * 32 + ul;
+        float wf = 0.f, wi = 0.f, wo = 0.f;
+        if (p.peep) {
+            wf = p.peep[(size_t)(dir * 3 + 0) * Hp + unit];
+            wi = p.peep[(size_t)(dir * 3 + 1) * Hp + unit];
+            wo = p.peep[(size_t)(dir * 3 + 2) * Hp + unit];
+        }
+        int len_j[2];
+        float dcc[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int b = b0 + ub * 8 + 2 * g + j;
+            len_j[j] = (b < B) ? p.lens[b] : 0;
+            dcc[j] = 0.f;
+        }
+        float db[4] = {0.f, 0.f, 0.f, 0.f};
+        float dpf = 0.f, dpi = 0.f, dpo = 0.f;
+
+        // raw prefetch of the next step's saved activations: loads only, no arithmetic, so they stay in flight
+        // behind the current step.  Row indices advance by a constant stride per step.
+        struct Pre { uint2 gp[2]; float c[2], cp[2], dmo[2]; };
+        const long long row_stride = (dir ? 1 : -1) * (long long)B * (long long)ld2;      // elements per time step, in scan order
+        long long idx_j[2];                                                                // element index of (t(s), b_j, dir, unit)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int b = b0 + ub * 8 + 2 * g + j;
+            idx_j[j] = ((long long)(dir ? 0 : T - 1) * B + (b < B ? b : 0)) * (long long)ld2 + (long long)dir * Hp + unit;
+        }
+        auto load_pre = [&](int s, Pre& r) {          // loads step s (idx_j must already point at step s)
+            const int t = dir ? s : (T - 1 - s);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const bool live = (s < T) && (t < len_j[j]);
+                r.gp[j] = make_uint2(0u, 0u); r.c[j] = 0.f; r.cp[j] = 0.f; r.dmo[j] = 0.f;
+                if (live) {
+                    r.gp[j] = __ldg(p.gates + idx_j[j]);
+                    r.c[j] = __ldg(p.cst + idx_j[j]);
+                    r.dmo[j] = __ldg(p.dM + idx_j[j]);
+                    // previous step in the direction's own order: fwd t-1, bwd t+1 (zero initial state) = the row one
+                    // stride AHEAD in scan order
+                    const int tp = dir ? (t + 1) : (t - 1);
+                    const bool has_prev = dir ? (tp < len_j[j]) : (tp >= 0);
+                    if (has_prev) r.cp[j] = __ldg(p.cst + idx_j[j] + row_stride);
+                }
+            }
+        };
+        Pre cur, nxt;
+        load_pre(0, cur);
+        // reduce-buffer read offset of this thread: unit row ul, 16-byte chunk ub (swizzled), utterance pair g
+        const uint32_t rd_off = (uint32_t)(ul * (2 * BG) + ((ub ^ ((ul / SWS) & (NCH - 1))) << 4) + 4 * g);
+        // per-thread constants of the dz staging: smem offsets of the local MMA B operand and global columns
+        uint32_t bp_off[2][4];
+        int gcol[4];
+#pragma unroll
+        for (int gate = 0; gate < 4; ++gate) {
+            gcol[gate] = dir * 4 * Hp + packed_col(unit, gate);
+            const int kp = packed_col(ul, gate);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int bl = ub * 8 + 2 * g + j;
+                bp_off[j][gate] = (uint32_t)((kp >> 6) * (BG * 128) + (bl >> 3) * 1024 + (bl & 7) * 128 +
+                                             ((((kp & 63) >> 3) ^ (bl & 7)) << 4) + (kp & 7) * 2);
+            }
+        }
+        long long grow_j[2];                          // element index of dG row (t(s), b_j)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int b = b0 + ub * 8 + 2 * g + j;
+            grow_j[j] = ((long long)(dir ? 0 : T - 1) * B + (b < B ? b : 0)) * (long long)ld8;
+        }
+        const long long grow_stride = (dir ? 1 : -1) * (long long)B * (long long)ld8;
+        const uint32_t red_addr = smem_u32(red);
+
+        for (int s = 0; s < T; ++s) {
+            const int t = dir ? s : (T - 1 - s);
+            REC_PROBE(8);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) idx_j[j] += row_stride;
+            load_pre(s + 1, nxt);                                  // latency hidden behind this step
+            REC_PROBE(9);
+            // ---- phase A: dm_rec from the reduce buffer of the previous step, then dz_t ----
+            float dmr[2] = {0.f, 0.f};
+            if (s > 0) {
+                if (ok) ok = mbar_wait_cluster_acq(&mbar_red[(s - 1) & 1], (uint32_t)(((s - 1) >> 1) & 1));
+                REC_PROBE(10);
+                const unsigned char* rb = red + (size_t)((s - 1) & 1) * red_bytes + rd_off;
+                float2 accv[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+                int src = 0;
+                for (; src + 4 <= NC; src += 4) {                  // 4 independent loads in flight
+                    __nv_bfloat162 v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const __nv_bfloat162*>(rb + (size_t)(src + k) * PT);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(v[k]); accv[k].x += f.x; accv[k].y += f.y; }
+                }
+                for (; src < NC; ++src) {
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(rb + (size_t)src * PT));
+                    accv[0].x += f.x; accv[0].y += f.y;
+                }
+                dmr[0] = (accv[0].x + accv[1].x) + (accv[2].x + accv[3].x);
+                dmr[1] = (accv[0].y + accv[1].y) + (accv[2].y + accv[3].y);
+            }
+            unsigned char* Bps = Bp + (size_t)(s & 1) * Cfg::bp_bytes();
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int b = b0 + ub * 8 + 2 * g + j;
+                const bool live = t < len_j[j];
+                float dzi = 0.f, dzj = 0.f, dzf = 0.f, dzo = 0.f;
+                if (live) {
+                    const float2 g01 = __half22float2(*reinterpret_cast<const __half2*>(&cur.gp[j].x));
+                    const float2 g23 = __half22float2(*reinterpret_cast<const __half2*>(&cur.gp[j].y));
+                    const float ig = g01.x, jt = g01.y, fg = g23.x, og = g23.y, cp = cur.cp[j];
+                    const float tc = tanhf_fast(cur.c[j]);
+                    const float dm = cur.dmo[j] + dmr[j];
+                    dzo = dm * tc * og * (1.f - og);
+                    const float dc = dcc[j] + dm * og * (1.f - tc * tc) + dzo * wo;
+                    dzf = dc * cp * fg * (1.f - fg);
+                    dzi = dc * jt * ig * (1.f - ig);
+                    dzj = dc * ig * (1.f - jt * jt);
+                    dcc[j] = dc * fg + dzi * wi + dzf * wf;
+                    dpi += dzi * cp; dpf += dzf * cp; dpo += dzo * cur.c[j];
+                    db[0] += dzi; db[1] += dzj; db[2] += dzf; db[3] += dzo;
+                } else {
+                    dcc[j] = 0.f;
+                }
+                const float dzg[4] = {dzi, dzj, dzf, dzo};
+                // gate columns are gate-major inside each 8-unit group: col(unit, gate) = packed_col(unit, gate)
+                __nv_bfloat16* dgrow = p.dG + grow_j[j];
+#pragma unroll
+                for (int gate = 0; gate < 4; ++gate) {
+                    const __nv_bfloat16 v = __float2bfloat16(dzg[gate]);
+                    *reinterpret_cast<__nv_bfloat16*>(Bps + bp_off[j][gate]) = v;     // local MMA B operand dz_t (K-major, 128B swizzle)
+                    if (b < B) dgrow[gcol[gate]] = v;
+                }
+                grow_j[j] += grow_stride;
+            }
+            REC_PROBE(11);
+            fence_proxy_async_smem();                  // locally staged dz_t -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(mbar_dz);       // one arrival per warp (the fences of all its lanes precede it)
+            REC_PROBE(12);
+            // ---- phase B: partial dm_{t-1} tiles -> owners' reduce buffers (bulk DSMEM copies) ----
+            if (s + 1 < T) {
+#pragma unroll 1
+                for (int k = 0; k < TPW; ++k) {
+                    const int jt = (rw >> 2) + k * NUB;            // this warp's M tile; its TMEM lane quarter is q
+                    if (jt >= MB) break;
+                    if (ok) ok = mbar_wait(&mbar_mma[jt], (uint32_t)(s & 1));
+                    if (k == 0) { REC_PROBE(13); }
+                    tc_fence_after();
+                    // the 32 rows of this (tile, quarter) are 32 consecutive units of ONE owner CTA: stage them as a
+                    // [32 units][BG utts] bf16 tile (16-byte chunks XOR-swizzled by the unit row so that neither these
+                    // stores nor the owner's reads conflict) and ship it with a single bulk DSMEM copy
+                    unsigned char* pw = pst + (size_t)(((s & 1) * 16 + jt * 4 + q) * PT);
+#pragma unroll
+                    for (int h = 0; h < BG / 16; ++h) {
+                        uint32_t a[16];
+                        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + jt * BG + h * 16, a);
+                        tmem_ld_wait();
+                        const int sw = (lane / SWS) & (NCH - 1);
+                        uint4* row = reinterpret_cast<uint4*>(pw + lane * (2 * BG));
+                        row[(2 * h) ^ sw] = make_uint4(pack_bf16x2(__uint_as_float(a[0]), __uint_as_float(a[1])), pack_bf16x2(__uint_as_float(a[2]), __uint_as_float(a[3])),
+                                                       pack_bf16x2(__uint_as_float(a[4]), __uint_as_float(a[5])), pack_bf16x2(__uint_as_float(a[6]), __uint_as_float(a[7])));
+                        row[(2 * h + 1) ^ sw] = make_uint4(pack_bf16x2(__uint_as_float(a[8]), __uint_as_float(a[9])), pack_bf16x2(__uint_as_float(a[10]), __uint_as_float(a[11])),
+                                                           pack_bf16x2(__uint_as_float(a[12]), __uint_as_float(a[13])), pack_bf16x2(__uint_as_float(a[14]), __uint_as_float(a[15])));
+                    }
+                    __syncwarp();
+                    const int u0 = jt * 128 + q * 32;
+                    if (lane == 0 && u0 < Hp) {
+                        const uint32_t owner = (uint32_t)(u0 >> 5);
+                        fence_proxy_async_smem();
+                        bulk_copy_s2c(mapa_shared(red_addr + (uint32_t)(s & 1) * red_bytes + cta * (uint32_t)PT, owner),
+                                      smem_u32(pw), (uint32_t)PT, mapa_shared(smem_u32(&mbar_red[s & 1]), owner));
+                    }
+                }
+            }
+            tc_fence_before();
+            REC_PROBE(14);
+            cur = nxt;
+        }
+        // ---- parameter gradients held in registers: reduce the 4 lanes of a unit, then atomics ----
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) db[k] += __shfl_xor_sync(0xffffffffu, db[k], o);
+            dpf += __shfl_xor_sync(0xffffffffu, dpf, o);
+            dpi += __shfl_xor_sync(0xffffffffu, dpi, o);
+            dpo += __shfl_xor_sync(0xffffffffu, dpo, o);
+        }
+        if (g == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) atomicAdd(p.dbias + (size_t)dir * 4 * Hp + packed_col(unit, k), db[k]);
+            if (p.dpeep) {
+                atomicAdd(p.dpeep + (size_t)(dir * 3 + 0) * Hp + unit, dpf);
+                atomicAdd(p.dpeep + (size_t)(dir * 3 + 1) * Hp + unit, dpi);
+                atomicAdd(p.dpeep + (size_t)(dir * 3 + 2) * Hp + unit, dpo);
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == NCW) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
+}
+
+// ---- BPTT v3 (Hp = 512): 4 x 4 decomposition of the per-step product dm_{t-1} = W' dz_t ----
+// CTA x of the 16-CTA cluster owns 32 units (cell state, gate math) as before, but multiplies the [128 units of M tile
+// mr = x & 3] x [512 gate rows of K block kc = x >> 2] block of W' (resident in tensor memory).  Per step:
+//   all-gather of dz_t inside the group of 4 CTAs that own K block kc (= x's own group): each CTA stages its
+//     [BG utts x 128 gate rows] bf16 slice, bulk-stores it to an L2-resident scratch and multicasts it into the four CTAs;
+//   32 MMAs 128 x BG x 16 (two issuer threads, accumulating onto a pre-zeroed accumulator);
+//   reduce-scatter of the partial dm tile: quarter q of the accumulator belongs to owner CTA 4 mr + q -> ONE 64*BG-byte
+//     DSMEM copy per quarter; every owner receives 4 partial tiles (from the CTAs x' with x' & 3 == owner >> 2).
+// DSMEM traffic per CTA and step drops from 2 x BG KB (16-way reduce-scatter, the bottleneck of v1/v2: the SM's DSMEM
+// port moves ~16 B/clk in + out) to 2 x BG/4 KB; the all-gather rides the L2 multicast path (~750 cycles + 10 per KB).
+template <int BG> struct RecBwd3Cfg {
+    static constexpr int NUB = BG / 8;
+    static constexpr int NCW = 4 * NUB;                    // compute warps: (utterance block, TMEM lane quarter)
+    static constexpr int NIW = 2;                          // MMA issuer warps
+    static constexpr int THREADS = 32 * (NCW + NIW + 1);   // + exchange warp
+    static constexpr int SLICE = BG * 256;                 // dz slice of one CTA: 2 K sub-blocks x [BG rows x 128 B]
+    static constexpr int PT = 32 * BG * 2;                 // partial dm tile [32 units][BG utts] bf16
+    static constexpr int BARS = 10;                        // op[2] slice[2] red[2] acc mma (+pad)
+    static size_t smem_bytes() { return 1024 + 2 * 4 * (size_t)SLICE + 2 * (size_t)SLICE + 2 * 4 * (size_t)PT + 2 * 4 * (size_t)PT + BARS * 8 + 64; }
+};
+
+template <int BG>
+__global__ void __launch_bounds__(RecBwd3Cfg<BG>::THREADS, 1)
+lstm_rec_bwd3_kernel(const RecBwdParams p)
+{
+    using Cfg = RecBwd3Cfg<BG>;
+    constexpr int NUB = Cfg::NUB, NCW = Cfg::NCW, NIW = Cfg::NIW, SLICE = Cfg::SLICE, PT = Cfg::PT;
+    constexpr int NCH = BG / 8;                        // 16-byte chunks per partial-tile row (8 utterances each)
+    constexpr int SWS = 64 / BG;                       // row-swizzle period: chunk c of unit row u sits at c ^ ((u / SWS) & (NCH-1))
+    constexpr int Hp = 512, NC = 16;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = align_1024(smem_raw);
+    const int T = p.T, B = p.B;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int role = warp < NCW ? 0 : (warp < NCW + NIW ? 1 : 2);       // compute | MMA issuers | exchange
+    const int rw = role == 0 ? warp : warp - NCW;
+
+    unsigned char* Op = smem;                                        // [2 parities][4 src][2 K sub-blocks][BG rows x 128 B]  SW128 K-major
+    unsigned char* Stg = Op + 2 * 4 * SLICE;                         // [2 parities][SLICE]   own dz slice (same layout)
+    unsigned char* red = Stg + 2 * SLICE;                            // [2 parities][4 src][PT]
+    unsigned char* pst = red + 2 * 4 * PT;                           // [2 parities][4 quarters][PT]  partial-tile staging
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pst + 2 * 4 * PT);
+    uint64_t* mbar_op = bars;                          // [2] the four dz slices of this K block have landed
+    uint64_t* mbar_slice = bars + 2;                   // [2] own dz slice staged (count NCW)
+    uint64_t* mbar_red = bars + 4;                     // [2] four partial dm tiles have landed
+    uint64_t* mbar_acc = bars + 6;                     //     accumulator zeroed (count NCW)
+    uint64_t* mbar_mma = bars + 7;                     //     partial dm tile complete (count NIW)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::BARS);
+
+    const uint32_t cta = cluster_ctarank();
+    const int cid = (int)cluster_id_x();
+    const int dir = cid & 1, bg = cid >> 1;
+    const int b0 = bg * BG;
+    const int kc = (int)(cta >> 2), mr = (int)(cta & 3);
+    const size_t ld2 = (size_t)2 * Hp, ld8 = (size_t)8 * Hp;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar_op[0], 1); mbar_init(&mbar_op[1], 1);
+        mbar_init(&mbar_slice[0], NCW); mbar_init(&mbar_slice[1], NCW);
+        mbar_init(&mbar_red[0], 1); mbar_init(&mbar_red[1], 1);
+        mbar_init(mbar_acc, NCW);
+        mbar_init(mbar_mma, NIW);
+        fence_mbar_init();
+    }
+    if (warp == NCW) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // ---- W' block -> tensor memory: lane = unit of M tile mr, columns = the 512 packed gate rows of K block kc (bf16 pairs) ----
+    if (role == 0) {
+        const int q = warp & 3;
+        const __nv_bfloat16* wrow = p.W + ((size_t)dir * Hp + mr * 128 + q * 32 + lane) * 4 * Hp + (size_t)kc * 512;
+        for (int ch = warp >> 2; ch < 32; ch += NUB) {
+            const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(wrow + ch * 16));
+            const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(wrow + ch * 16 + 8));
+            const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            tmem_st_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + ch * 8, r);
+        }
+        // zero this warp's part of the accumulator (every MMA accumulates)
+        const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        tmem_st_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + (warp >> 2) * 8, z);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(mbar_acc);
+    }
+    if (threadIdx.x == 0 && T > 1) mbar_arrive_expect_tx(&mbar_red[0], 4u * PT);      // armed before anybody can send
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+
+    long long* prof = (blockIdx.x == 0 && lane == 0 && rw == 0 && role < 2) ? g_rec_prof : nullptr;
+    const int prof_steps = g_rec_prof_steps;
+    bool ok = true;
+    if (role == 2) {
+        // ============================ exchange warp: own dz slice -> L2 scratch -> multicast into the 4 CTAs of the group ============================
+        if (lane == 0) {
+            unsigned char* scr = p.xch + (size_t)cid * 2 * NC * SLICE;
+            const uint16_t mask = (uint16_t)(0xFu << (4 * kc));
+            for (int s = 0; s + 1 < T && ok; ++s) {
+                ok = mbar_wait(&mbar_slice[s & 1], (uint32_t)((s >> 1) & 1));
+                if (!ok) break;
+                unsigned char* g = scr + ((size_t)(s & 1) * NC + cta) * SLICE;
+                bulk_store_s2g(g, smem_u32(Stg + (s & 1) * SLICE), (uint32_t)SLICE);
+                bulk_commit_group();
+                bulk_wait_group_all();
+                bulk_load_multicast(smem_u32(Op) + (uint32_t)(((s & 1) * 4 + mr) * SLICE), g, (uint32_t)SLICE, smem_u32(&mbar_op[s & 1]), mask);
+            }
+        }
+        __syncwarp();
+    } else if (role == 1) {
+        // ============================ MMA issuers ============================
+        constexpr uint32_t idesc = make_idesc_bf16_f32(128, BG, 0, 0);           // bf16 x bf16, A (TMEM) K-major
+        const int iw = rw;
+        if (lane == 0) {
+            const uint64_t bb0 = make_smem_desc_sw128(smem_u32(Op), 16, 1024);
+            const uint32_t b_lo0 = (uint32_t)bb0, b_hi = (uint32_t)(bb0 >> 32);
+            const uint32_t d_tmem = tmem_base + REC_TMEM_ACC;
+            for (int s = 0; s + 1 < T && ok; ++s) {                               // the last step's dm_{-1} is never used
+                REC_PROBE(0);
+                if (iw == 0) mbar_arrive_expect_tx(&mbar_op[s & 1], 4u * SLICE);
+                ok = mbar_wait(mbar_acc, (uint32_t)(s & 1));                      // accumulator zeroed
+                if (ok) ok = mbar_wait(&mbar_op[s & 1], (uint32_t)((s >> 1) & 1)); // dz_t of the whole K block landed
+                if (!ok) break;
+                REC_PROBE(1);
+                // the reduce buffer the NEXT step's partials go to: its previous contents were consumed in phase A of
+                // this step (our own dz slice, part of the operand just awaited, was staged after reading them)
+                if (iw == 0 && s + 2 < T) mbar_arrive_expect_tx(&mbar_red[(s + 1) & 1], 4u * PT);
+                tc_fence_after();
+                const uint32_t b_lo_s = b_lo0 + (uint32_t)(((s & 1) * 4 * SLICE) >> 4);
+#pragma unroll 4
+                for (int idx = iw; idx < 32; idx += NIW) {                        // idx = src * 8 + kk
+                    const int src = idx >> 3, kk = idx & 7;
+                    umma_f16_ts_lohi(d_tmem, tmem_base + 8 * idx,
+                                     b_lo_s + (uint32_t)((src * SLICE + (kk >> 2) * (BG * 128)) / 16 + (kk & 3) * 2), b_hi, idesc, 1u);
+                }
+                REC_PROBE(7);
+                umma_commit(mbar_mma);
+                REC_PROBE(2);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ============================ compute warps ============================
+        const int ub = rw >> 2, q = rw & 3;
+        const int up = lane >> 2, g = lane & 3;
+        const int ul = q * 8 + up;                          // local unit (0..31)
+        const int unit = (int)cta * 32 + ul;
+        float wf = 0.f, wi = 0.f, wo = 0.f;
+        if (p.peep) {
+            wf = p.peep[(size_t)(dir * 3 + 0) * Hp + unit];
+            wi = p.peep[(size_t)(dir * 3 + 1) * Hp + unit];
+            wo = p.peep[(size_t)(dir * 3 + 2) * Hp + unit];
+        }
+        int len_j[2];
+        float dcc[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int b = b0 + ub * 8 + 2 * g + j;
+            len_j[j] = (b < B) ? p.lens[b] : 0;
+            dcc[j] = 0.f;
+        }
+        float db[4] = {0.f, 0.f, 0.f, 0.f};
+        float dpf = 0.f, dpi = 0.f, dpo = 0.f;
+
+        // raw prefetch of the next step's saved activations (loads only, stay in flight behind the current step)
+        struct Pre { uint2 gp[2]; float c[2], cp[2], dmo[2]; };
+        const long long row_stride = (dir ? 1 : -1) * (long long)B * (long long)ld2;      // elements per time step, in scan order
+        long long idx_j[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int b = b0 + ub * 8 + 2 * g + j;
+            idx_j[j] = ((long long)(dir ? 0 : T - 1) * B + (b < B ? b : 0)) * (long long)ld2 + (long long)dir * Hp + unit;
+        }
+        auto load_pre = [&](int s, Pre& r) {
+            const int t = dir ? s : (T - 1 - s);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const bool live = (s < T) && (t < len_j[j]);
+                r.gp[j] = make_uint2(0u, 0u); r.c[j] = 0.f; r.cp[j] = 0.f; r.dmo[j] = 0.f;
+                if (live) {
+                    r.gp[j] = __ldg(p.gates + idx_j[j]);
+                    r.c[j] = __ldg(p.cst + idx_j[j]);
+                    r.dmo[j] = __ldg(p.dM + idx_j[j]);
+                    const int tp = dir ? (t + 1) : (t - 1);
+                    const bool has_prev = dir ? (tp < len_j[j]) : (tp >= 0);
+                    if (has_prev) r.cp[j] = __ldg(p.cst + idx_j[j] + row_stride);
+                }
+            }
+        };
+        Pre cur, nxt;
+        load_pre(0, cur);
+        // reduce-buffer read offset of this thread: unit row ul, 16-byte chunk ub (swizzled), utterance pair g
+        const uint32_t rd_off = (uint32_t)(ul * (2 * BG) + ((ub ^ ((ul / SWS) & (NCH - 1))) << 4) + 4 * g);
+        // dz staging offsets (own slice, SW128 K-major: row = utterance, 64 gate rows per 128-byte row) and global columns
+        uint32_t bp_off[2][4];
+        int gcol[4];
+#pragma unroll
+        for (int gate = 0; gate < 4; ++gate) {
+            gcol[gate] = dir * 4 * Hp + packed_col(unit, gate);
+            const int kp = packed_col(ul, gate);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int bl = ub * 8 + 2 * g + j;
+                bp_off[j][gate] = (uint32_t)((kp >> 6) * (BG * 128) + (bl >> 3) * 1024 + (bl & 7) * 128 +
+                                             ((((kp & 63) >> 3) ^ (bl & 7)) << 4) + (kp & 7) * 2);
+            }
+        }
+        long long grow_j[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int b = b0 + ub * 8 + 2 * g + j;
+            grow_j[j] = ((long long)(dir ? 0 : T - 1) * B + (b < B ? b : 0)) * (long long)ld8;
+        }
+        const long long grow_stride = (dir ? 1 : -1) * (long long)B * (long long)ld8;
+        const uint32_t red_addr = smem_u32(red);
+        const uint32_t acc_addr = tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + ub * 8;
+
+        for (int s = 0; s < T; ++s) {
+            const int t = dir ? s : (T - 1 - s);
+            REC_PROBE(8);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) idx_j[j] += row_stride;
+            load_pre(s + 1, nxt);
+            REC_PROBE(9);
+            // ---- phase A: dm_rec = sum of the four partial tiles of the previous step, then dz_t ----
+            float dmr[2] = {0.f, 0.f};
+            if (s > 0) {
+                if (ok) ok = mbar_wait_cluster_acq(&mbar_red[(s - 1) & 1], (uint32_t)(((s - 1) >> 1) & 1));
+                REC_PROBE(10);
+                const unsigned char* rb = red + (size_t)((s - 1) & 1) * 4 * PT + rd_off;
+                __nv_bfloat162 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const __nv_bfloat162*>(rb + (size_t)k * PT);
+                const float2 f0 = __bfloat1622float2(v[0]), f1 = __bfloat1622float2(v[1]), f2 = __bfloat1622float2(v[2]), f3 = __bfloat1622float2(v[3]);
+                dmr[0] = (f0.x + f1.x) + (f2.x + f3.x);
+                dmr[1] = (f0.y + f1.y) + (f2.y + f3.y);
+            }
+            unsigned char* stg = Stg + (s & 1) * SLICE;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int b = b0 + ub * 8 + 2 * g + j;
+                const bool live = t < len_j[j];
+                float dzi = 0.f, dzj = 0.f, dzf = 0.f, dzo = 0.f;
+                if (live) {
+                    const float2 g01 = __half22float2(*reinterpret_cast<const __half2*>(&cur.gp[j].x));
+                    const float2 g23 = __half22float2(*reinterpret_cast<const __half2*>(&cur.gp[j].y));
+                    const float ig = g01.x, jt = g01.y, fg = g23.x, og = g23.y, cp = cur.cp[j];
+                    const float tc = tanhf_fast(cur.c[j]);
+                    const float dm = cur.dmo[j] + dmr[j];
+                    dzo = dm * tc * og * (1.f - og);
+                    const float dc = dcc[j] + dm * og * (1.f - tc * tc) + dzo * wo;
+                    dzf = dc * cp * fg * (1.f - fg);
+                    dzi = dc * jt * ig * (1.f - ig);
+                    dzj = dc * ig * (1.f - jt * jt);
+                    dcc[j] = dc * fg + dzi * wi + dzf * wf;
+                    dpi += dzi * cp; dpf += dzf * cp; dpo += dzo * cur.c[j];
+                    db[0] += dzi; db[1] += dzj; db[2] += dzf; db[3] += dzo;
+                } else {
+                    dcc[j] = 0.f;
+                }
+                const float dzg[4] = {dzi, dzj, dzf, dzo};
+                __nv_bfloat16* dgrow = p.dG + grow_j[j];
+#pragma unroll
+                for (int gate = 0; gate < 4; ++gate) {
+                    const __nv_bfloat16 v = __float2bfloat16(dzg[gate]);
+                    *reinterpret_cast<__nv_bfloat16*>(stg + bp_off[j][gate]) = v;     // own slice of the MMA B operand dz_t
+                    if (b < B) dgrow[gcol[gate]] = v;
+                }
+                grow_j[j] += grow_stride;
+            }
+            REC_PROBE(11);
+            if (s + 1 < T) {
+                fence_proxy_async_smem();                  // generic-proxy stores -> visible to the bulk (async-proxy) store
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&mbar_slice[s & 1]);
+                REC_PROBE(12);
+                // ---- phase B: quarter q of the partial dm tile -> owner CTA 4 mr + q (one bulk DSMEM copy per quarter) ----
+                if (ok) ok = mbar_wait(mbar_mma, (uint32_t)(s & 1));
+                REC_PROBE(13);
+                tc_fence_after();
+                uint32_t a[8];
+                tmem_ld_32x32b_x8(acc_addr, a);            // unit row = lane of the quarter, utterances ub*8 .. ub*8+7
+                tmem_ld_wait();
+                // staged as [32 units][BG utts] bf16, 16-byte chunks XOR-swizzled by the unit row (conflict-free here and
+                // for the owner's reads)
+                unsigned char* pw = pst + (size_t)(((s & 1) * 4 + q) * PT);
+                *reinterpret_cast<uint4*>(pw + lane * (2 * BG) + ((ub ^ ((lane / SWS) & (NCH - 1))) << 4)) =
+                    make_uint4(pack_bf16x2(__uint_as_float(a[0]), __uint_as_float(a[1])), pack_bf16x2(__uint_as_float(a[2]), __uint_as_float(a[3])),
+                               pack_bf16x2(__uint_as_float(a[4]), __uint_as_float(a[5])), pack_bf16x2(__uint_as_float(a[6]), __uint_as_float(a[7])));
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(NUB * 32) : "memory");   // the NUB warps of quarter q
+                if (ub == 0 && lane == 0) {
+                    const uint32_t owner = (uint32_t)(4 * mr + q);
+                    fence_proxy_async_smem();
+                    bulk_copy_s2c(mapa_shared(red_addr + (uint32_t)(((s & 1) * 4 + kc) * PT), owner),
+                                  smem_u32(pw), (uint32_t)PT, mapa_shared(smem_u32(&mbar_red[s & 1]), owner));
+                }
+                REC_PROBE(14);
+                // off the chain: zero our part of the accumulator for the next step's MMAs
+                const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                tmem_st_32x32b_x8(acc_addr, z);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(mbar_acc);
+            }
+            cur = nxt;
+        }
+        // ---- parameter gradients held in registers: reduce the 4 lanes of a unit, then atomics ----
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) db[k] += __shfl_xor_sync(0xffffffffu, db[k], o);
+            dpf += __shfl_xor_sync(0xffffffffu, dpf, o);
+            dpi += __shfl_xor_sync(0xffffffffu, dpi, o);
+            dpo += __shfl_xor_sync(0xffffffffu, dpo, o);
+        }
+        if (g == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) atomicAdd(p.dbias + (size_t)dir * 4 * Hp + packed_col(unit, k), db[k]);
+            if (p.dpeep) {
+                atomicAdd(p.dpeep + (size_t)(dir * 3 + 0) * Hp + unit, dpf);
+                atomicAdd(p.dpeep + (size_t)(dir * 3 + 1) * Hp + unit, dpi);
+                atomicAdd(p.dpeep + (size_t)(dir * 3 + 2) * Hp + unit, dpo);
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == NCW) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
+}
+
+// =================================================================================================
 // host side
 // =================================================================================================
 static bool rec_plan(int Hp, int& nc) {
     if (Hp < 64 || (Hp & 63) || Hp > 512) return false;
     nc = Hp / 32;                                   // 32 units (128 gate rows = one MMA M tile) per CTA
-    return RecFwdCfg<2>::smem_bytes(Hp / 64) <= 232448 && RecBwdCfg<2>::smem_bytes(nc) <= 232448;
+    return RecFwdCfg<2>::smem_bytes(Hp / 64) <= 232448 && RecBwdCfg<2>::smem_bytes(nc) <= 232448 &&
+           RecFwd2Cfg<32>::smem_bytes(Hp / 64) <= 232448 && RecBwd2Cfg<32>::smem_bytes(nc) <= 232448;
+}
+
+// kernel generation: 2 (default) = one lockstep group of 16/32 utterances per cluster; LCB_REC_V=1 selects the v1
+// kernels (two interleaved 16-utterance sub-groups) for A/B measurements
+static int rec_version() {
+    static int v = 0;
+    if (v == 0) { const char* e = getenv("LCB_REC_V"); v = (e && atoi(e) == 1) ? 1 : 2; }
+    return v;
 }
 
 template <typename K, typename P>
@@ -766,6 +1756,22 @@ static int choose_nsg(int B, int nc, int which) {
     return (2 * groups <= cap[which][nc]) ? 1 : 2;
 }
 
+// v2: utterances per cluster.  16 while every 16-utterance group gets its own resident cluster (shortest per-step chain),
+// 32 otherwise (half the clusters; the 32-MMA weight pass is paid once for 32 utterances).  LCB_REC_BG=16|32 overrides.
+static int choose_bg(int B, int nc, int which) {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("LCB_REC_BG"); forced = e ? atoi(e) : 0; }
+    if (forced == 16 || forced == 32) return forced;
+    static int cap[2][17];
+    if (cap[which][nc] == 0) {
+        int n = which ? max_clusters(lstm_rec_bwd2_kernel<16>, RecBwd2Cfg<16>::THREADS, RecBwd2Cfg<16>::smem_bytes(nc), nc)
+                      : max_clusters(lstm_rec_fwd2_kernel<16>, RecFwd2Cfg<16>::THREADS, RecFwd2Cfg<16>::smem_bytes(nc * 32 / 64), nc);
+        cap[which][nc] = n > 0 ? n : 1;
+    }
+    const int groups = (B + 15) / 16;
+    return (2 * groups <= cap[which][nc]) ? 16 : 32;
+}
+
 }  // namespace lcb
 
 using namespace lcb;
@@ -798,9 +1804,18 @@ extern "C" int lcb_lstm_rec_config(int Hp, int* units_per_cta_div32, int* cluste
     return LCB_OK;
 }
 
+// bytes of the L2 exchange scratch the v2 kernels use (per launch; must not be shared by concurrently running launches)
+extern "C" size_t lcb_lstm_rec_workspace_bytes(int B, int Hp)
+{
+    int nc;
+    if (!rec_plan(Hp, nc) || B <= 0) return 0;
+    const size_t clusters = 2 * (size_t)((B + 15) / 16);
+    return clusters * 2 * 16 * 8192;               // [cluster][2 step parities][16 CTAs][<= 8 KB slice (BPTT dz slice, 32 utterances)]
+}
+
 extern "C" int lcb_lstm_rec_fwd(const float* G, const void* WfoldT, const float* peep, const int32_t* lens,
                                 void* Mout, void* gates, float* cst, float* cfin, float* mfin,
-                                int T, int B, int Hp, float forget_bias, void* stream)
+                                int T, int B, int Hp, float forget_bias, void* workspace, size_t workspace_bytes, void* stream)
 {
     if (!G || !WfoldT || !lens || !Mout) return LCB_ERR_NULL_POINTER;
     if (T <= 0 || B <= 0) return LCB_ERR_BAD_SHAPE;
@@ -812,6 +1827,17 @@ extern "C" int lcb_lstm_rec_fwd(const float* G, const void* WfoldT, const float*
     p.G = G; p.Wt = (const __half*)WfoldT; p.peep = peep; p.lens = lens; p.Mout = (__half*)Mout;
     p.gates = (uint2*)gates; p.cst = cst; p.cfin = cfin; p.mfin = mfin;
     p.T = T; p.B = B; p.Hp = Hp; p.NC = nc; p.forget_bias = forget_bias;
+    static int xch_mode = -1;                      // LCB_REC_XCH=dsmem keeps the unicast DSMEM exchange (A/B measurements)
+    if (xch_mode < 0) { const char* e = getenv("LCB_REC_XCH"); xch_mode = (e && !strcmp(e, "dsmem")) ? 0 : 1; }
+    p.xch = (xch_mode && workspace && workspace_bytes >= lcb_lstm_rec_workspace_bytes(B, Hp)) ? (unsigned char*)workspace : nullptr;
+    if (workspace && ((uintptr_t)workspace & 15)) return LCB_ERR_MISALIGNED;
+    if (rec_version() == 2 && p.xch) {
+        const int bgs = choose_bg(B, nc, 0);
+        const int ncl2 = 2 * ((B + bgs - 1) / bgs);
+        if (bgs == 16)
+            return launch_cluster(lstm_rec_fwd2_kernel<16>, ncl2 * nc, RecFwd2Cfg<16>::THREADS, RecFwd2Cfg<16>::smem_bytes(Hp / 64), nc, (cudaStream_t)stream, p);
+        return launch_cluster(lstm_rec_fwd2_kernel<32>, ncl2 * nc, RecFwd2Cfg<32>::THREADS, RecFwd2Cfg<32>::smem_bytes(Hp / 64), nc, (cudaStream_t)stream, p);
+    }
     const int nsg = choose_nsg(B, nc, 0);
     const int ncl = 2 * ((B + REC_BG * nsg - 1) / (REC_BG * nsg));
     if (nsg == 1)
@@ -821,7 +1847,7 @@ extern "C" int lcb_lstm_rec_fwd(const float* G, const void* WfoldT, const float*
 
 extern "C" int lcb_lstm_rec_bwd(const float* dM, const void* gates, const float* cst, const void* Wfold, const float* peep,
                                 const int32_t* lens, void* dG, float* dbias, float* dpeep,
-                                int T, int B, int Hp, void* stream)
+                                int T, int B, int Hp, void* workspace, size_t workspace_bytes, void* stream)
 {
     if (!dM || !gates || !cst || !Wfold || !lens || !dG || !dbias) return LCB_ERR_NULL_POINTER;
     if (T <= 0 || B <= 0) return LCB_ERR_BAD_SHAPE;
@@ -833,6 +1859,22 @@ extern "C" int lcb_lstm_rec_bwd(const float* dM, const void* gates, const float*
     p.dM = dM; p.gates = (const uint2*)gates; p.cst = cst; p.W = (const __nv_bfloat16*)Wfold; p.peep = peep; p.lens = lens;
     p.dG = (__nv_bfloat16*)dG; p.dbias = dbias; p.dpeep = dpeep;
     p.T = T; p.B = B; p.Hp = Hp; p.NC = nc;
+    if (workspace && ((uintptr_t)workspace & 15)) return LCB_ERR_MISALIGNED;
+    p.xch = (workspace && workspace_bytes >= lcb_lstm_rec_workspace_bytes(B, Hp)) ? (unsigned char*)workspace : nullptr;
+    if (rec_version() == 2 && p.xch && Hp == 512 && !getenv("LCB_REC_BWD2")) {
+        const int bgs = choose_bg(B, nc, 1);
+        const int ncl3 = 2 * ((B + bgs - 1) / bgs);
+        if (bgs == 16)
+            return launch_cluster(lstm_rec_bwd3_kernel<16>, ncl3 * nc, RecBwd3Cfg<16>::THREADS, RecBwd3Cfg<16>::smem_bytes(), nc, (cudaStream_t)stream, p);
+        return launch_cluster(lstm_rec_bwd3_kernel<32>, ncl3 * nc, RecBwd3Cfg<32>::THREADS, RecBwd3Cfg<32>::smem_bytes(), nc, (cudaStream_t)stream, p);
+    }
+    if (rec_version() == 2) {
+        const int bgs = choose_bg(B, nc, 1);
+        const int ncl2 = 2 * ((B + bgs - 1) / bgs);
+        if (bgs == 16)
+            return launch_cluster(lstm_rec_bwd2_kernel<16>, ncl2 * nc, RecBwd2Cfg<16>::THREADS, RecBwd2Cfg<16>::smem_bytes(nc), nc, (cudaStream_t)stream, p);
+        return launch_cluster(lstm_rec_bwd2_kernel<32>, ncl2 * nc, RecBwd2Cfg<32>::THREADS, RecBwd2Cfg<32>::smem_bytes(nc), nc, (cudaStream_t)stream, p);
+    }
     const int nsg = choose_nsg(B, nc, 1);
     const int ncl = 2 * ((B + REC_BG * nsg - 1) / (REC_BG * nsg));
     if (nsg == 1)

@@ -233,6 +233,11 @@ __device__ __forceinline__ void tmem_ld_16x256b_x1(uint32_t taddr, uint32_t (&r)
     asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
 }
+// mirror of tmem_ld_16x256b_x1: thread t writes rows (t/4, t/4+8), columns 2*(t%4), 2*(t%4)+1 of the 16-lane slab
+__device__ __forceinline__ void tmem_st_16x256b_x1(uint32_t taddr, const uint32_t (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
 // commit all prior async tcgen05 ops of this thread to an mbarrier (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -297,6 +302,19 @@ __device__ __forceinline__ uint64_t make_smem_desc_noswz(uint32_t smem_addr, uin
 __device__ __forceinline__ void bulk_copy_s2c(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes, uint32_t mbar_cluster_addr) {
     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst_cluster_addr), "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr) : "memory");
+}
+// bulk store: own shared memory -> global (async proxy), tracked by the thread's bulk async-group
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, uint32_t src_cta_addr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(src_cta_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }        // writes performed
+__device__ __forceinline__ void bulk_wait_group_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }  // sources read
+// multicast bulk load: global -> the SAME shared-memory offset of every CTA in cta_mask, complete_tx on the mbarrier at the
+// same offset of each of them (the L2 response is replicated by the cluster crossbar: one L2 read, NC deliveries)
+__device__ __forceinline__ void bulk_load_multicast(uint32_t dst_cta_addr, const void* gsrc, uint32_t bytes, uint32_t mbar_cta_addr, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst_cta_addr), "l"(gsrc), "r"(bytes), "r"(mbar_cta_addr), "h"(cta_mask) : "memory");
 }
 // instruction descriptor for kind::f16: bf16 x bf16 -> f32
 __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N, int a_mn_major, int b_mn_major) {

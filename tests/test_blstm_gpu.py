@@ -65,6 +65,8 @@ def run_ours(cfg, params, x, lens, R=None):
     (320, 320, 120, 2, 16, 10, True),  # WSJ recipe cell: 5-CTA cluster, 64 units / CTA
     (512, 512, 120, 1, 8, 6, True),    # Libri-shape cell: 16-CTA (non-portable) cluster
     (384, 128, 64, 1, 4, 5, False),    # 12-CTA cluster
+    (512, 512, 120, 1, 50, 7, True),   # 32 utterances per cluster (MMA N = 32), ragged second group; 4x4 BPTT decomposition
+    (320, 320, 64, 1, 52, 6, True),    # 32 utterances per cluster on a 10-CTA cluster (1-D BPTT kernel)
 ])
 def test_forward_backward_vs_oracle(cuda_dev, H, P, D, L, B, T, peep):
     cfg, params, x, lens = make_case(H, P, D, L, B, T, peep)
