@@ -374,6 +374,8 @@ class BLSTMEncoder:
         overlap = side is not main
         side_done = {}                       # layer -> event: its side-stream work (reads of set k, dH) has finished
         dH = dXtop
+        if overlap:
+            side.wait_stream(main)           # the forward activations the side stream converts are complete
         for i in reversed(range(c.num_layers)):
             k = i & 1
             if overlap and (i + 2) in side_done:
@@ -381,8 +383,11 @@ class BLSTMEncoder:
             if c.keep_prob < 1.0:
                 self._dropout(dH, i)                # same (seed, index) mask as the forward pass, on the gradient
             X16 = ws["X0"] if i == 0 else ws["Hout"][i - 1]
-            X = _to_bf16(X16, ws["Xbf"][k][:X16.numel()].view(X16.shape))
-            M = _to_bf16(ws["M"][i], ws["Mbf"][k])
+            # bf16 copies of the fp16 forward activations for the wgrad GEMMs: only the side stream reads them, so it also
+            # makes them (in order behind layer i+1's wgrads, concurrently with this layer's BPTT on the main stream)
+            with torch.cuda.stream(side):
+                X = _to_bf16(X16, ws["Xbf"][k][:X16.numel()].view(X16.shape))
+                M = _to_bf16(ws["M"][i], ws["Mbf"][k])
             dM, dG = ws["dM"], ws["dG"][k]
             gWpT, gWh, gWx = ps.g("L%d/WpT" % i), ps.g("L%d/Wh" % i), ps.g("L%d/Wx" % i)
             for d in range(2):

@@ -41,19 +41,44 @@ __global__ void f16_to_bf16_kernel(const __half2* __restrict__ src, __nv_bfloat1
 // (DropoutWrapper(output_keep_prob) on the LSTM layer outputs, nnet/bilstm.py:128,137; the same call on the
 // bf16 gradient with the same seed is its backward)
 template <bool F16>
-__global__ void dropout16_kernel(uint16_t* __restrict__ x, size_t n, float inv_keep, uint32_t thr, uint64_t seed) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float v;
-        if constexpr (F16) v = __half2float(reinterpret_cast<__half*>(x)[i]);
-        else v = __bfloat162float(reinterpret_cast<__nv_bfloat16*>(x)[i]);
-        v = rng_keep(seed, i, thr) ? v * inv_keep : 0.f;
-        if constexpr (F16) reinterpret_cast<__half*>(x)[i] = __float2half_rn(sat_f16(v));
-        else reinterpret_cast<__nv_bfloat16*>(x)[i] = __float2bfloat16(v);
+__device__ __forceinline__ uint32_t drop2(uint32_t v2, bool k0, bool k1, float inv_keep) {
+    float lo, hi;
+    if constexpr (F16) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v2)); lo = f.x; hi = f.y; }
+    else { const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v2)); lo = f.x; hi = f.y; }
+    lo = k0 ? lo * inv_keep : 0.f;
+    hi = k1 ? hi * inv_keep : 0.f;
+    if constexpr (F16) return pack_f16x2(lo, hi);
+    else return pack_bf16x2(lo, hi);
+}
+// 8 elements (16 bytes) per thread and iteration, two hashes
+template <bool F16>
+__global__ void dropout16_kernel(uint16_t* __restrict__ x, size_t n, float inv_keep, uint32_t thr16, uint64_t seed) {
+    const size_t n8 = n >> 3;
+    uint4* x8 = reinterpret_cast<uint4*>(x);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 v = x8[i];
+        const uint64_t w0 = rng_u64(seed, 2 * i), w1 = rng_u64(seed, 2 * i + 1);
+        v.x = drop2<F16>(v.x, rng_keep16(w0, 0, thr16), rng_keep16(w0, 1, thr16), inv_keep);
+        v.y = drop2<F16>(v.y, rng_keep16(w0, 2, thr16), rng_keep16(w0, 3, thr16), inv_keep);
+        v.z = drop2<F16>(v.z, rng_keep16(w1, 0, thr16), rng_keep16(w1, 1, thr16), inv_keep);
+        v.w = drop2<F16>(v.w, rng_keep16(w1, 2, thr16), rng_keep16(w1, 3, thr16), inv_keep);
+        x8[i] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                 // tail (n not a multiple of 8)
+        for (size_t k = n8 << 3; k < n; ++k) {
+            const bool keep = rng_keep16(rng_u64(seed, k >> 2), (int)(k & 3), thr16);
+            float v;
+            if constexpr (F16) v = __half2float(reinterpret_cast<__half*>(x)[k]);
+            else v = __bfloat162float(reinterpret_cast<__nv_bfloat16*>(x)[k]);
+            v = keep ? v * inv_keep : 0.f;
+            if constexpr (F16) reinterpret_cast<__half*>(x)[k] = __float2half_rn(sat_f16(v));
+            else reinterpret_cast<__nv_bfloat16*>(x)[k] = __float2bfloat16(v);
+        }
     }
 }
-__global__ void dropout_mask_kernel(uint8_t* __restrict__ m, size_t n, uint32_t thr, uint64_t seed) {
+__global__ void dropout_mask_kernel(uint8_t* __restrict__ m, size_t n, uint32_t thr16, uint64_t seed) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        m[i] = rng_keep(seed, i, thr) ? 1 : 0;
+        m[i] = rng_keep16(rng_u64(seed, i >> 2), (int)(i & 3), thr16) ? 1 : 0;
 }
 
 // y += x on fp16 tensors (layer-0 residual: finput = finput + concat(fwd, bwd), nnet/bilstm.py:199-200)
@@ -186,9 +211,10 @@ extern "C" int lcb_dropout16(void* x, int dtype, size_t n, float keep_prob, unsi
     if (!x) return LCB_ERR_NULL_POINTER;
     if ((dtype != 1 && dtype != 2) || !(keep_prob > 0.f) || keep_prob > 1.f) return LCB_ERR_BAD_SHAPE;
     if (n == 0 || keep_prob == 1.f) return LCB_OK;
+    if ((uintptr_t)x & 15) return LCB_ERR_MISALIGNED;
     g_launches += 1;
-    if (dtype == 2) dropout16_kernel<true><<<grid_for(n, 2, 256), 256, 0, (cudaStream_t)stream>>>((uint16_t*)x, n, 1.f / keep_prob, keep_threshold(keep_prob), seed);
-    else dropout16_kernel<false><<<grid_for(n, 2, 256), 256, 0, (cudaStream_t)stream>>>((uint16_t*)x, n, 1.f / keep_prob, keep_threshold(keep_prob), seed);
+    if (dtype == 2) dropout16_kernel<true><<<grid_for(n, 16, 256), 256, 0, (cudaStream_t)stream>>>((uint16_t*)x, n, 1.f / keep_prob, keep_threshold16(keep_prob), seed);
+    else dropout16_kernel<false><<<grid_for(n, 16, 256), 256, 0, (cudaStream_t)stream>>>((uint16_t*)x, n, 1.f / keep_prob, keep_threshold16(keep_prob), seed);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }
 
@@ -197,7 +223,7 @@ extern "C" int lcb_dropout_mask(unsigned char* mask, size_t n, float keep_prob, 
     if (!mask) return LCB_ERR_NULL_POINTER;
     if (n == 0) return LCB_OK;
     g_launches += 1;
-    dropout_mask_kernel<<<grid_for(n, 2, 256), 256, 0, (cudaStream_t)stream>>>(mask, n, keep_threshold(keep_prob), seed);
+    dropout_mask_kernel<<<grid_for(n, 2, 256), 256, 0, (cudaStream_t)stream>>>(mask, n, keep_threshold16(keep_prob), seed);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }
 

@@ -37,7 +37,7 @@ struct OutFwdParams {
     int pis;               // row stride of pi in smem (odd)
     float tau;
     float inv_keep;        // 1 / keep_prob (1 when dropout is off)
-    uint32_t thr;          // keep threshold (0xffffffff: dropout off)
+    uint32_t thr;          // 16-bit keep threshold (65536: dropout off)
     unsigned long long seed_pi, seed_d;   // mask streams: mixture weights [N,K] (moe.py:46), expert logits [N,K*V] (moe.py:61)
 };
 
@@ -170,7 +170,7 @@ out_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                     const float inv = 1.f / sum;
                     // y_prior = dropout(softmax(...))  (moe.py:45-46): fold mask and 1/keep into the stored weights
                     for (int k = 0; k < K; ++k)
-                        pir[k] = rng_keep(p.seed_pi, (uint64_t)n * K + k, p.thr) ? pir[k] * inv * p.inv_keep : 0.f;
+                        pir[k] = rng_keepq(p.seed_pi, (uint64_t)n * K + k, p.thr) ? pir[k] * inv * p.inv_keep : 0.f;
                 } else {
                     const int c_base = (ps - (K > 0 ? 1 : 0)) * OUT_BN;
                     for (int c0 = 0; c0 < OUT_BN && c_base + c0 < KV; c0 += 32) {
@@ -182,7 +182,7 @@ out_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                             for (int j = 0; j < 32; ++j) {
                                 const int col = c_base + c0 + j;
                                 if (col < KV) {
-                                    if (rng_keep(p.seed_d, (uint64_t)n * KV + col, p.thr))      // dropout on tau*tanh (moe.py:61)
+                                    if (rng_keepq(p.seed_d, (uint64_t)n * KV + col, p.thr))      // dropout on tau*tanh (moe.py:61)
                                         accv += pir[kk] * tanhf_fast(__uint_as_float(r[j]) + __ldg(p.bias + col));
                                     if (++kk == K) {
                                         if (rowok) orow[vv] = p.tau * p.inv_keep * accv;
@@ -251,8 +251,8 @@ mos_bwd_kernel(const float* __restrict__ Z, const float* __restrict__ dY, __nv_b
         for (int c = lane; c < KV; c += 32) {
             const int v = c / K, k = c - v * K;
             const float th = tanhf_fast(z[c]);
-            const float m2 = rng_keep(seed_d, (uint64_t)n * KV + c, thr) ? inv_keep : 0.f;
-            const float m1 = rng_keep(seed_pi, (uint64_t)n * K + k, thr) ? inv_keep : 0.f;
+            const float m2 = rng_keepq(seed_d, (uint64_t)n * KV + c, thr) ? inv_keep : 0.f;
+            const float m1 = rng_keepq(seed_pi, (uint64_t)n * K + k, thr) ? inv_keep : 0.f;
             const float g = dy[v] * tau * m2;
             atomicAdd(&dpi[k], g * th * m1);                       // d loss / d pi_k
             dz[c] = __float2bfloat16(g * pi[k] * m1 * (1.f - th * th));
@@ -300,7 +300,7 @@ extern "C" int lcb_output_fwd(const void* X, int ldx, const void* Wall, const fl
     p.pis = (K | 1) + 2 * (K > 0 ? 0 : 0);
     p.tau = tau;
     p.inv_keep = 1.f / keep_prob;
-    p.thr = keep_threshold(keep_prob);
+    p.thr = keep_threshold16(keep_prob);
     p.seed_pi = seed; p.seed_d = seed ^ 0xD1B54A32D192ED03ull;
     const int rows = p.KV + K;
     CUtensorMap tx, tw, twp;
@@ -328,7 +328,7 @@ extern "C" int lcb_mos_bwd_dz(const float* Z, const float* dlogits, void* dZ, in
     int grid = (R + 7) / 8; if (grid > 148 * 8) grid = 148 * 8;
     const size_t smem = (size_t)8 * 2 * K * sizeof(float);
     g_launches += 1; mos_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(Z, dlogits, (__nv_bfloat16*)dZ, n0, R, ldz, T, B, V, K, tau,
-                                                            1.f / keep_prob, keep_threshold(keep_prob), seed, seed ^ 0xD1B54A32D192ED03ull);
+                                                            1.f / keep_prob, keep_threshold16(keep_prob), seed, seed ^ 0xD1B54A32D192ED03ull);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }
 

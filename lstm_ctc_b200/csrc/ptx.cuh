@@ -388,6 +388,24 @@ __host__ __device__ __forceinline__ uint32_t keep_threshold(float keep) {      /
 __host__ __device__ __forceinline__ bool rng_keep(uint64_t seed, uint64_t idx, uint32_t thr) {
     return thr == 0xffffffffu || rng_u32(seed, idx) < thr;
 }
+// cheaper stream for the big layer-output dropouts: ONE 64-bit hash decides four consecutive elements (16 bits each,
+// keep-probability granularity 2^-16)
+__host__ __device__ __forceinline__ uint64_t rng_u64(uint64_t seed, uint64_t idx) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint32_t keep_threshold16(float keep) {    // P(u16 < thr) = keep; 65536 = keep everything
+    double t = (double)keep * 65536.0 + 0.5;
+    return t >= 65536.0 ? 65536u : (uint32_t)t;
+}
+__host__ __device__ __forceinline__ bool rng_keep16(uint64_t word, int e, uint32_t thr16) {   // element e (0..3) of its 4-block
+    return (uint32_t)((word >> (16 * e)) & 0xffffu) < thr16;
+}
+__host__ __device__ __forceinline__ bool rng_keepq(uint64_t seed, uint64_t idx, uint32_t thr16) {   // same stream, one element
+    return thr16 >= 65536u || rng_keep16(rng_u64(seed, idx >> 2), (int)(idx & 3), thr16);
+}
 
 // ----------------------------------------------------------------------------------------
 // misc math
