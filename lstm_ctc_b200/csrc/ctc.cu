@@ -11,14 +11,16 @@
 //                   grad[b,t,:] = softmax (0 past seq_len / skipped utts), and the compact
 //                   per-frame log-probs the lattice needs: lpb[b,t] (blank) and lpl[b,t,j] (label j).
 //                   Reads logits once, writes grad once: the 8*T*B*V algorithmic bytes.
-//   ctc_alpha_beta: latency-bound lattice pass, one CTA (1..32 warps) per utterance, SPT
-//                   consecutive lattice states per thread in registers; log-space values are
-//                   kept in fp64 while exp/log run in fp32 on max-subtracted differences, so the
-//                   absolute error per step is ~1e-7 regardless of |alpha| (plain fp32 log-space,
-//                   which is what TF does, loses 1e-4..1e-3 at T~3000).  alpha is spilled to the
-//                   workspace; the beta sweep forms gamma = alpha*beta/p on the fly and applies
-//                   grad[b,t,l'_s] -= gamma with red.global.add (blank contributions are
-//                   pre-summed per thread).
+//   ctc_alpha_beta: latency-bound lattice pass, TWO CTAs (1..32 warps each) per utterance running
+//                   CONCURRENTLY: CTA 2b sweeps alpha forward in time, CTA 2b+1 sweeps beta backward
+//                   (the two recursions are independent; only gamma needs both), so the serial chain
+//                   is T steps instead of 2T.  SPT consecutive lattice states per thread in
+//                   registers; log-space values are kept in fp64 while exp/log run in fp32 on
+//                   max-subtracted differences, so the absolute error per step is ~1e-7 regardless
+//                   of |alpha| (plain fp32 log-space, which is what TF does, loses 1e-4..1e-3 at
+//                   T~3000).  Both sweeps spill their lattice rows to the workspace.
+//   ctc_gamma     : one warp per frame row: gamma = exp(alpha + beta - log p), grad[b,t,l'_s] -= gamma
+//                   with red.global.add (blank contributions pre-summed per warp).
 #include "ptx.cuh"
 #include "lstm_ctc_b200.h"
 
@@ -237,13 +239,12 @@ __device__ __forceinline__ void cta_sync() {
 //   nb   : double2[2][NT]                      neighbour exchange, parity double-buffered
 //   lpL  : float [2][TC][NT][SPT/2]            per-thread-private staged label log-probs
 //   lpB  : float [2][TC]  (each thread reads the broadcast copy; staged by thread 0..TC-1)
-//   aS   : double[2][TC][NT][SPT]              per-thread-private staged alpha (beta sweep only)
 template <int NW, int SPT>
 __global__ void __launch_bounds__(NW * 32)
 ctc_alpha_beta_kernel(const CtcMeta* __restrict__ meta, const int* __restrict__ lab, int LABP,
                       const float* __restrict__ lpb, const float* __restrict__ lpl, int LPP,
-                      double* __restrict__ alpha_ws, float* __restrict__ grad, float* __restrict__ loss,
-                      int T, int V, int TC)
+                      double* __restrict__ alpha_ws, double* __restrict__ beta_ws, double* __restrict__ logp_ws,
+                      float* __restrict__ loss, int T, int V, int TC)
 {
     constexpr int NT = NW * 32;
     constexpr int HL = SPT / 2;          // label slots per thread
@@ -251,22 +252,19 @@ ctc_alpha_beta_kernel(const CtcMeta* __restrict__ meta, const int* __restrict__ 
     double2* nb = reinterpret_cast<double2*>(smem_raw);                      // [2][NT]
     float* lpL = reinterpret_cast<float*>(nb + 2 * NT);                      // [2][TC][NT][HL]
     float* lpB = lpL + (size_t)2 * TC * NT * HL;                             // [2][TC] (padded to 4)
-    double* aS = reinterpret_cast<double*>(lpB + 2 * ((TC + 3) & ~3));       // [2][TC][NT][SPT]
     __shared__ double s_fin[2];
-    __shared__ double s_logp;
 
-    const int b = blockIdx.x;
+    const int b = blockIdx.x >> 1;
+    const int which = blockIdx.x & 1;                 // 0: alpha sweep (+ loss), 1: beta sweep
     const int tid = threadIdx.x;
     const CtcMeta mt = meta[b];
-    if (mt.skip) { if (tid == 0) loss[b] = 0.f; return; }
+    if (mt.skip) { if (tid == 0 && which == 0) { loss[b] = 0.f; logp_ws[b] = CTC_NEG; } return; }
     const int Tb = mt.Tb, L = mt.L, S = 2 * L + 1;
     const int s0 = tid * SPT;
-    const int blank = V - 1;
     const int* lb = lab + (size_t)b * LABP;
     const float* lpb_b = lpb + (size_t)b * T;
     const float* lpl_b = lpl + (size_t)b * T * LPP;
-    double* aw = alpha_ws + (size_t)b * T * (NT * SPT);
-    float* gb = grad + (size_t)b * T * V;
+    double* aw = (which ? beta_ws : alpha_ws) + (size_t)b * T * (NT * SPT);
 
     // per-state constants: odd local index i <-> label slot i/2 (s0 is even since SPT is even)
     int labv[HL];
@@ -290,15 +288,8 @@ ctc_alpha_beta_kernel(const CtcMeta* __restrict__ meta, const int* __restrict__ 
         }
         if (tid < nfr) cp_async<4>(lpB + buf * ((TC + 3) & ~3) + tid, lpb_b + t_first + tid);
     };
-    auto stage_alpha = [&](int buf, int t_first, int nfr) {
-        for (int f = 0; f < nfr; ++f) {
-            const double* src = aw + (size_t)(t_first + f) * (NT * SPT) + s0;
-            double* dst = aS + (((size_t)buf * TC + f) * NT + tid) * SPT;
-#pragma unroll
-            for (int q = 0; q < SPT / 2; ++q) cp_async<16>(dst + 2 * q, src + 2 * q);
-        }
-    };
 
+    if (which == 0) {
     double a[SPT];
     // =============================== alpha sweep ===============================
     {
@@ -370,12 +361,11 @@ ctc_alpha_beta_kernel(const CtcMeta* __restrict__ meta, const int* __restrict__ 
     __syncthreads();
     if (tid == 0) {
         double lp = lse2(s_fin[0], s_fin[1]);
-        s_logp = lp;
+        logp_ws[b] = lp;                            // <= CTC_ZERO_THRESH: no valid path, grad stays = softmax (TF behaviour)
         loss[b] = (lp <= CTC_ZERO_THRESH) ? INFINITY : (float)(-lp);
     }
-    __syncthreads();
-    const double logp = s_logp;
-    if (logp <= CTC_ZERO_THRESH) return;          // no valid path: grad stays = softmax (TF behaviour)
+    return;
+    }
 
     // =============================== beta sweep ===============================
     // e[i] = beta_t(s) + lp_t(l'_s)  ("beta with emission");  beta_{t-1}(s) = lse(e(s), e(s+1), skip ? e(s+2))
@@ -387,18 +377,13 @@ ctc_alpha_beta_kernel(const CtcMeta* __restrict__ meta, const int* __restrict__ 
         // chunk c covers frames [Tb - (c+1)*TC, Tb - c*TC) clipped at 0, processed descending
         auto chunk_first = [&](int c) { int f = Tb - (c + 1) * TC; return f < 0 ? 0 : f; };
         auto chunk_n = [&](int c) { return (Tb - c * TC) - chunk_first(c); };
-        __syncthreads();
         stage_lp(0, chunk_first(0), chunk_n(0));
-        stage_alpha(0, chunk_first(0), chunk_n(0));
         cp_async_commit();
         int par = 0;
         for (int c = 0; c < nchunks; ++c) {
             const int t_first = chunk_first(c);
             const int nfr = chunk_n(c);
-            if (c + 1 < nchunks) {
-                stage_lp((c + 1) & 1, chunk_first(c + 1), chunk_n(c + 1));
-                stage_alpha((c + 1) & 1, chunk_first(c + 1), chunk_n(c + 1));
-            }
+            if (c + 1 < nchunks) stage_lp((c + 1) & 1, chunk_first(c + 1), chunk_n(c + 1));
             cp_async_commit();
             cp_async_wait<1>();
             cta_sync<NW>();
@@ -412,20 +397,11 @@ ctc_alpha_beta_kernel(const CtcMeta* __restrict__ meta, const int* __restrict__ 
                     ll[k] = lpL[(((size_t)buf * TC + f) * NT + tid) * HL + k];
                     if (s0 / 2 + k >= L) ll[k] = 0.f;       // slots past L hold uninitialised workspace
                 }
-                // gamma_t(s) = exp(alpha_t(s) + beta_t(s) - logp)
-                const double* as_ = aS + (((size_t)buf * TC + f) * NT + tid) * SPT;
-                float gblank = 0.f;
-                float* grow = gb + (size_t)t * V;
+                {   // spill beta_t (without the emission at t, as TF defines it)
+                    double* dst = aw + (size_t)t * (NT * SPT) + s0;
 #pragma unroll
-                for (int i = 0; i < SPT; ++i) {
-                    if (s0 + i < S) {
-                        const double ex = as_[i] + be[i] - logp;
-                        const float gm = (ex < -80.0) ? 0.f : __expf((float)ex);
-                        if (i & 1) { if (gm != 0.f) atomicAdd(grow + labv[i >> 1], -gm); }
-                        else gblank += gm;
-                    }
+                    for (int q = 0; q < SPT / 2; ++q) *reinterpret_cast<double2*>(dst + 2 * q) = make_double2(be[2 * q], be[2 * q + 1]);
                 }
-                if (gblank != 0.f) atomicAdd(grow + blank, -gblank);
                 if (t == 0) break;
                 // e = beta_t + lp_t ; then beta_{t-1}
                 double e[SPT];
@@ -453,10 +429,44 @@ ctc_alpha_beta_kernel(const CtcMeta* __restrict__ meta, const int* __restrict__ 
 }
 
 // --------------------------------------------------------------------------------------------
+// gamma_t(s) = exp(alpha_t(s) + beta_t(s) - log p);  grad[b,t,l'_s] -= gamma_t(s).  One warp per frame row.
+__global__ void __launch_bounds__(256)
+ctc_gamma_kernel(const CtcMeta* __restrict__ meta, const int* __restrict__ lab, int LABP,
+                 const double* __restrict__ alpha_ws, const double* __restrict__ beta_ws, const double* __restrict__ logp_ws,
+                 float* __restrict__ grad, int B, int T, int V, int NS)
+{
+    const int lane = threadIdx.x & 31;
+    const long long rows = (long long)B * T;
+    const int blank = V - 1;
+    for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * 8) {
+        const int b = (int)(row / T), t = (int)(row - (long long)b * T);
+        const CtcMeta mt = meta[b];
+        if (mt.skip || t >= mt.Tb) continue;
+        const double logp = logp_ws[b];
+        if (logp <= CTC_ZERO_THRESH) continue;        // no valid path: grad stays = softmax
+        const int S = 2 * mt.L + 1;
+        const double* aw = alpha_ws + (size_t)row * NS;
+        const double* bw = beta_ws + (size_t)row * NS;
+        const int* lb = lab + (size_t)b * LABP;
+        float* grow = grad + (size_t)row * V;
+        float gblank = 0.f;
+        for (int s = lane; s < S; s += 32) {
+            const double ex = aw[s] + bw[s] - logp;
+            const float gm = (ex < -80.0) ? 0.f : __expf((float)ex);
+            if (s & 1) { if (gm != 0.f) atomicAdd(grow + lb[s >> 1], -gm); }
+            else gblank += gm;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gblank += __shfl_xor_sync(0xffffffffu, gblank, o);
+        if (lane == 0 && gblank != 0.f) atomicAdd(grow + blank, -gblank);
+    }
+}
+
+// --------------------------------------------------------------------------------------------
 struct CtcPlan {
     int NW, SPT, TC;
     int LABP, LPP;
-    size_t off_meta, off_lab, off_lpb, off_lpl, off_alpha, off_status, total;
+    size_t off_meta, off_lab, off_lpb, off_lpl, off_alpha, off_beta, off_logp, off_status, total;
     size_t smem;
 };
 
@@ -472,13 +482,12 @@ static bool ctc_make_plan(int B, int T, int V, int Lmax, CtcPlan& p) {
     p.LABP = (Lmax + 3) & ~3; if (p.LABP == 0) p.LABP = 4;
     p.LPP = NT * p.SPT / 2;                                  // one private slot group per thread
     // staging budget: ~64 KB per CTA
-    const size_t per_frame = (size_t)NT * (p.SPT / 2) * 4 + (size_t)NT * p.SPT * 8;
-    int tc = (int)((64 * 1024) / (2 * per_frame));
+    const size_t per_frame = (size_t)NT * (p.SPT / 2) * 4;
+    int tc = (int)((32 * 1024) / (2 * per_frame));
     if (tc < 1) tc = 1;
     if (tc > 32) tc = 32;
     p.TC = tc;
-    p.smem = (size_t)2 * NT * sizeof(double2) + (size_t)2 * tc * NT * (p.SPT / 2) * 4 + (size_t)2 * ((tc + 3) & ~3) * 4 +
-             (size_t)2 * tc * NT * p.SPT * 8 + 16;
+    p.smem = (size_t)2 * NT * sizeof(double2) + (size_t)2 * tc * NT * (p.SPT / 2) * 4 + (size_t)2 * ((tc + 3) & ~3) * 4 + 16;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t o = 0;
     p.off_status = o; o = al(o + 16);
@@ -487,6 +496,8 @@ static bool ctc_make_plan(int B, int T, int V, int Lmax, CtcPlan& p) {
     p.off_lpb = o; o = al(o + sizeof(float) * (size_t)B * T);
     p.off_lpl = o; o = al(o + sizeof(float) * (size_t)B * T * p.LPP);
     p.off_alpha = o; o = al(o + sizeof(double) * (size_t)B * T * NT * p.SPT);
+    p.off_beta = o; o = al(o + sizeof(double) * (size_t)B * T * NT * p.SPT);
+    p.off_logp = o; o = al(o + sizeof(double) * (size_t)B);
     p.total = o;
     return true;
 }
@@ -531,11 +542,15 @@ static void dispatch_softmax(const float* logits, float* grad, int B, int T, int
 
 template <int NW, int SPT>
 static cudaError_t launch_ab(const CtcPlan& p, int B, int T, int V, const CtcMeta* meta, const int* lab, const float* lpb,
-                             const float* lpl, double* alpha, float* grad, float* loss, cudaStream_t st)
+                             const float* lpl, double* alpha, double* beta, double* logp, float* grad, float* loss, cudaStream_t st)
 {
     cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_kernel<NW, SPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
-    ctc_alpha_beta_kernel<NW, SPT><<<B, NW * 32, p.smem, st>>>(meta, lab, p.LABP, lpb, lpl, p.LPP, alpha, grad, loss, T, V, p.TC);
+    ctc_alpha_beta_kernel<NW, SPT><<<2 * B, NW * 32, p.smem, st>>>(meta, lab, p.LABP, lpb, lpl, p.LPP, alpha, beta, logp, loss, T, V, p.TC);
+    const long long rows = (long long)B * T;
+    long long want = (rows + 7) / 8;
+    const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+    ctc_gamma_kernel<<<grid, 256, 0, st>>>(meta, lab, p.LABP, alpha, beta, logp, grad, B, T, V, NW * 32 * SPT);
     return cudaGetLastError();
 }
 
@@ -569,9 +584,11 @@ extern "C" int lcb_ctc_loss_grad_f32(const float* logits, const int64_t* labels,
     float* lpb = (float*)(ws + p.off_lpb);
     float* lpl = (float*)(ws + p.off_lpl);
     double* alpha = (double*)(ws + p.off_alpha);
+    double* beta = (double*)(ws + p.off_beta);
+    double* logp = (double*)(ws + p.off_logp);
 
     cudaMemsetAsync(status, 0, 16, st);
-    g_launches += 3; ctc_prep_kernel<<<(B + 3) / 4, 128, 0, st>>>(labels, Lmax, seq_len, B, T, V, meta, lab, p.LABP, status);
+    g_launches += 4; ctc_prep_kernel<<<(B + 3) / 4, 128, 0, st>>>(labels, Lmax, seq_len, B, T, V, meta, lab, p.LABP, status);
     if ((V & 3) == 0 && ((uintptr_t)logits & 15) == 0 && ((uintptr_t)grad & 15) == 0)
         dispatch_softmax<4>(logits, grad, B, T, V, meta, lab, p.LABP, lpb, lpl, p.LPP, st);
     else if ((V & 1) == 0 && ((uintptr_t)logits & 7) == 0 && ((uintptr_t)grad & 7) == 0)
@@ -579,12 +596,12 @@ extern "C" int lcb_ctc_loss_grad_f32(const float* logits, const int64_t* labels,
     else
         dispatch_softmax<1>(logits, grad, B, T, V, meta, lab, p.LABP, lpb, lpl, p.LPP, st);
     cudaError_t e = cudaSuccess;
-    if (p.NW == 1 && p.SPT == 2) e = launch_ab<1, 2>(p, B, T, V, meta, lab, lpb, lpl, alpha, grad, loss, st);
-    else if (p.NW == 4 && p.SPT == 2) e = launch_ab<4, 2>(p, B, T, V, meta, lab, lpb, lpl, alpha, grad, loss, st);
-    else if (p.NW == 4 && p.SPT == 4) e = launch_ab<4, 4>(p, B, T, V, meta, lab, lpb, lpl, alpha, grad, loss, st);
-    else if (p.NW == 4 && p.SPT == 8) e = launch_ab<4, 8>(p, B, T, V, meta, lab, lpb, lpl, alpha, grad, loss, st);
-    else if (p.NW == 8 && p.SPT == 8) e = launch_ab<8, 8>(p, B, T, V, meta, lab, lpb, lpl, alpha, grad, loss, st);
-    else e = launch_ab<32, 8>(p, B, T, V, meta, lab, lpb, lpl, alpha, grad, loss, st);
+    if (p.NW == 1 && p.SPT == 2) e = launch_ab<1, 2>(p, B, T, V, meta, lab, lpb, lpl, alpha, beta, logp, grad, loss, st);
+    else if (p.NW == 4 && p.SPT == 2) e = launch_ab<4, 2>(p, B, T, V, meta, lab, lpb, lpl, alpha, beta, logp, grad, loss, st);
+    else if (p.NW == 4 && p.SPT == 4) e = launch_ab<4, 4>(p, B, T, V, meta, lab, lpb, lpl, alpha, beta, logp, grad, loss, st);
+    else if (p.NW == 4 && p.SPT == 8) e = launch_ab<4, 8>(p, B, T, V, meta, lab, lpb, lpl, alpha, beta, logp, grad, loss, st);
+    else if (p.NW == 8 && p.SPT == 8) e = launch_ab<8, 8>(p, B, T, V, meta, lab, lpb, lpl, alpha, beta, logp, grad, loss, st);
+    else e = launch_ab<32, 8>(p, B, T, V, meta, lab, lpb, lpl, alpha, beta, logp, grad, loss, st);
     if (e != cudaSuccess) return LCB_ERR_CUDA;
     e = cudaGetLastError();
     return e == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
