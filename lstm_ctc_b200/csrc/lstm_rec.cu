@@ -730,6 +730,9 @@ __device__ __forceinline__ void sig_sig_tanh(float a, float b, float c, float& s
     sb = r * ea * ec;
     tc = 2.f * (r * ab) - 1.f;
 }
+__device__ __forceinline__ float tanh_ex2(float c) {
+    return 2.f * rcp_approx(1.f + ex2_approx(-2.8853900817779268f * clamp25(c))) - 1.f;
+}
 __device__ __forceinline__ void sig_tanh(float a, float c, float& sa, float& tc) {
     const float ea = 1.f + ex2_approx(-1.4426950408889634f * clamp25(a));
     const float ec = 1.f + ex2_approx(-2.8853900817779268f * clamp25(c));
@@ -1371,7 +1374,7 @@ template <int BG> struct RecBwd3Cfg {
 
 template <int BG>
 __global__ void __launch_bounds__(RecBwd3Cfg<BG>::THREADS, 1)
-lstm_rec_bwd3_kernel(const RecBwdParams p)
+lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap tmDG)
 {
     using Cfg = RecBwd3Cfg<BG>;
     constexpr int NUB = Cfg::NUB, NCW = Cfg::NCW, NIW = Cfg::NIW, SLICE = Cfg::SLICE, PT = Cfg::PT;
@@ -1402,7 +1405,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p)
     const int dir = cid & 1, bg = cid >> 1;
     const int b0 = bg * BG;
     const int kc = (int)(cta >> 2), mr = (int)(cta & 3);
-    const size_t ld2 = (size_t)2 * Hp, ld8 = (size_t)8 * Hp;
+    const size_t ld2 = (size_t)2 * Hp;
 
     if (threadIdx.x == 0) {
         mbar_init(&mbar_op[0], 1); mbar_init(&mbar_op[1], 1);
@@ -1446,18 +1449,33 @@ lstm_rec_bwd3_kernel(const RecBwdParams p)
     bool ok = true;
     if (role == 2) {
         // ============================ exchange warp: own dz slice -> L2 scratch -> multicast into the 4 CTAs of the group ============================
+        // The staged slice is also the layer output dG[t, b0.., own 128 packed gate columns]: two 128B-swizzled TMA tensor
+        // stores per step (rows past the batch end are clipped), off the serial chain.
         if (lane == 0) {
             unsigned char* scr = p.xch + (size_t)cid * 2 * NC * SLICE;
             const uint16_t mask = (uint16_t)(0xFu << (4 * kc));
-            for (int s = 0; s + 1 < T && ok; ++s) {
+            const int col0 = dir * 4 * Hp + (int)cta * 128;
+            for (int s = 0; s < T && ok; ++s) {
                 ok = mbar_wait(&mbar_slice[s & 1], (uint32_t)((s >> 1) & 1));
                 if (!ok) break;
-                unsigned char* g = scr + ((size_t)(s & 1) * NC + cta) * SLICE;
-                bulk_store_s2g(g, smem_u32(Stg + (s & 1) * SLICE), (uint32_t)SLICE);
-                bulk_commit_group();
-                bulk_wait_group_all();
-                bulk_load_multicast(smem_u32(Op) + (uint32_t)(((s & 1) * 4 + mr) * SLICE), g, (uint32_t)SLICE, smem_u32(&mbar_op[s & 1]), mask);
+                const uint32_t src = smem_u32(Stg + (s & 1) * SLICE);
+                const int t = dir ? s : (T - 1 - s);
+                if (s + 1 < T) {
+                    unsigned char* g = scr + ((size_t)(s & 1) * NC + cta) * SLICE;
+                    bulk_store_s2g(g, src, (uint32_t)SLICE);
+                    bulk_commit_group();
+                    bulk_wait_group_all();                 // scratch copy performed (and the dG stores of step s-1, long done)
+                    bulk_load_multicast(smem_u32(Op) + (uint32_t)(((s & 1) * 4 + mr) * SLICE), g, (uint32_t)SLICE, smem_u32(&mbar_op[s & 1]), mask);
+                    tma_store_3d(&tmDG, src, col0, b0, t);                     // behind the multicast: off the chain; read out of
+                    tma_store_3d(&tmDG, src + BG * 128, col0 + 64, b0, t);     // Stg[s&1] before step s+1's wait_group returns
+                    bulk_commit_group();
+                } else {
+                    tma_store_3d(&tmDG, src, col0, b0, t);
+                    tma_store_3d(&tmDG, src + BG * 128, col0 + 64, b0, t);
+                    bulk_commit_group();
+                }
             }
+            bulk_wait_group_all();                          // dG of the last steps is written before the kernel ends
         }
         __syncwarp();
     } else if (role == 1) {
@@ -1546,10 +1564,8 @@ lstm_rec_bwd3_kernel(const RecBwdParams p)
         const uint32_t rd_off = (uint32_t)(ul * (2 * BG) + ((ub ^ ((ul / SWS) & (NCH - 1))) << 4) + 4 * g);
         // dz staging offsets (own slice, SW128 K-major: row = utterance, 64 gate rows per 128-byte row) and global columns
         uint32_t bp_off[2][4];
-        int gcol[4];
 #pragma unroll
         for (int gate = 0; gate < 4; ++gate) {
-            gcol[gate] = dir * 4 * Hp + packed_col(unit, gate);
             const int kp = packed_col(ul, gate);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -1558,14 +1574,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p)
                                              ((((kp & 63) >> 3) ^ (bl & 7)) << 4) + (kp & 7) * 2);
             }
         }
-        long long grow_j[2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int b = b0 + ub * 8 + 2 * g + j;
-            grow_j[j] = ((long long)(dir ? 0 : T - 1) * B + (b < B ? b : 0)) * (long long)ld8;
-        }
-        const long long grow_stride = (dir ? 1 : -1) * (long long)B * (long long)ld8;
-        const uint32_t red_addr = smem_u32(red);
+        const uint32_t red_addr = smem_u32(red), stg_addr = smem_u32(Stg), pst_addr = smem_u32(pst);
         const uint32_t acc_addr = tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + ub * 8;
 
         for (int s = 0; s < T; ++s) {
@@ -1578,55 +1587,49 @@ lstm_rec_bwd3_kernel(const RecBwdParams p)
             // ---- phase A: dm_rec = sum of the four partial tiles of the previous step, then dz_t ----
             float dmr[2] = {0.f, 0.f};
             if (s > 0) {
-                if (ok) ok = mbar_wait_cluster_acq(&mbar_red[(s - 1) & 1], (uint32_t)(((s - 1) >> 1) & 1));
+                if (ok) ok = mbar_wait(&mbar_red[(s - 1) & 1], (uint32_t)(((s - 1) >> 1) & 1));   // async-proxy deliveries + complete_tx: a CTA-scope wait suffices
                 REC_PROBE(10);
-                const unsigned char* rb = red + (size_t)((s - 1) & 1) * 4 * PT + rd_off;
-                __nv_bfloat162 v[4];
+                const uint32_t rb = red_addr + (uint32_t)(((s - 1) & 1) * 4 * PT) + rd_off;
+                uint32_t v[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const __nv_bfloat162*>(rb + (size_t)k * PT);
-                const float2 f0 = __bfloat1622float2(v[0]), f1 = __bfloat1622float2(v[1]), f2 = __bfloat1622float2(v[2]), f3 = __bfloat1622float2(v[3]);
+                for (int k = 0; k < 4; ++k) v[k] = lds_b32(rb + (uint32_t)(k * PT));
+                const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[0])), f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[1])),
+                             f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[2])), f3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[3]));
                 dmr[0] = (f0.x + f1.x) + (f2.x + f3.x);
                 dmr[1] = (f0.y + f1.y) + (f2.y + f3.y);
             }
-            unsigned char* stg = Stg + (s & 1) * SLICE;
+            const uint32_t stg = stg_addr + (uint32_t)((s & 1) * SLICE);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int b = b0 + ub * 8 + 2 * g + j;
-                const bool live = t < len_j[j];
-                float dzi = 0.f, dzj = 0.f, dzf = 0.f, dzo = 0.f;
-                if (live) {
-                    const float2 g01 = __half22float2(*reinterpret_cast<const __half2*>(&cur.gp[j].x));
-                    const float2 g23 = __half22float2(*reinterpret_cast<const __half2*>(&cur.gp[j].y));
-                    const float ig = g01.x, jt = g01.y, fg = g23.x, og = g23.y, cp = cur.cp[j];
-                    const float tc = tanhf_fast(cur.c[j]);
-                    const float dm = cur.dmo[j] + dmr[j];
-                    dzo = dm * tc * og * (1.f - og);
-                    const float dc = dcc[j] + dm * og * (1.f - tc * tc) + dzo * wo;
-                    dzf = dc * cp * fg * (1.f - fg);
-                    dzi = dc * jt * ig * (1.f - ig);
-                    dzj = dc * ig * (1.f - jt * jt);
-                    dcc[j] = dc * fg + dzi * wi + dzf * wf;
-                    dpi += dzi * cp; dpf += dzf * cp; dpo += dzo * cur.c[j];
-                    db[0] += dzi; db[1] += dzj; db[2] += dzf; db[3] += dzo;
-                } else {
-                    dcc[j] = 0.f;
-                }
+                // branch-free: for a frame past the utterance end (or a padding utterance) the prefetch delivered zeros for
+                // the saved gates / cell state / dM, which makes every product below an exact 0 and resets the carried
+                // dc through fg = 0 -- so both cells' dependency chains interleave instead of running back to back
+                const float2 g01 = __half22float2(*reinterpret_cast<const __half2*>(&cur.gp[j].x));
+                const float2 g23 = __half22float2(*reinterpret_cast<const __half2*>(&cur.gp[j].y));
+                const float ig = g01.x, jt = g01.y, fg = g23.x, og = g23.y, cp = cur.cp[j];
+                const float tc = tanh_ex2(cur.c[j]);                   // same formula as the forward pass; tanh(0) == 0 exactly
+                const float dm = cur.dmo[j] + dmr[j];
+                const float dzo = dm * tc * og * (1.f - og);
+                const float dc = dcc[j] + dm * og * (1.f - tc * tc) + dzo * wo;
+                const float dzf = dc * cp * fg * (1.f - fg);
+                const float dzi = dc * jt * ig * (1.f - ig);
+                const float dzj = dc * ig * (1.f - jt * jt);
+                dcc[j] = dc * fg + dzi * wi + dzf * wf;
+                dpi += dzi * cp; dpf += dzf * cp; dpo += dzo * cur.c[j];
+                db[0] += dzi; db[1] += dzj; db[2] += dzf; db[3] += dzo;
                 const float dzg[4] = {dzi, dzj, dzf, dzo};
-                __nv_bfloat16* dgrow = p.dG + grow_j[j];
 #pragma unroll
                 for (int gate = 0; gate < 4; ++gate) {
                     const __nv_bfloat16 v = __float2bfloat16(dzg[gate]);
-                    *reinterpret_cast<__nv_bfloat16*>(stg + bp_off[j][gate]) = v;     // own slice of the MMA B operand dz_t
-                    if (b < B) dgrow[gcol[gate]] = v;
+                    sts_b16(stg + bp_off[j][gate], *reinterpret_cast<const uint16_t*>(&v));   // own slice of dz_t = MMA B operand = dG tile
                 }
-                grow_j[j] += grow_stride;
             }
             REC_PROBE(11);
+            fence_proxy_async_smem();                      // generic-proxy stores -> visible to the bulk (async-proxy) stores
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&mbar_slice[s & 1]);
+            REC_PROBE(12);
             if (s + 1 < T) {
-                fence_proxy_async_smem();                  // generic-proxy stores -> visible to the bulk (async-proxy) store
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&mbar_slice[s & 1]);
-                REC_PROBE(12);
                 // ---- phase B: quarter q of the partial dm tile -> owner CTA 4 mr + q (one bulk DSMEM copy per quarter) ----
                 if (ok) ok = mbar_wait(mbar_mma, (uint32_t)(s & 1));
                 REC_PROBE(13);
@@ -1636,16 +1639,17 @@ lstm_rec_bwd3_kernel(const RecBwdParams p)
                 tmem_ld_wait();
                 // staged as [32 units][BG utts] bf16, 16-byte chunks XOR-swizzled by the unit row (conflict-free here and
                 // for the owner's reads)
-                unsigned char* pw = pst + (size_t)(((s & 1) * 4 + q) * PT);
-                *reinterpret_cast<uint4*>(pw + lane * (2 * BG) + ((ub ^ ((lane / SWS) & (NCH - 1))) << 4)) =
-                    make_uint4(pack_bf16x2(__uint_as_float(a[0]), __uint_as_float(a[1])), pack_bf16x2(__uint_as_float(a[2]), __uint_as_float(a[3])),
-                               pack_bf16x2(__uint_as_float(a[4]), __uint_as_float(a[5])), pack_bf16x2(__uint_as_float(a[6]), __uint_as_float(a[7])));
+                const uint32_t pw = pst_addr + (uint32_t)(((s & 1) * 4 + q) * PT);
+                sts_v4(pw + lane * (2 * BG) + ((ub ^ ((lane / SWS) & (NCH - 1))) << 4),
+                       pack_bf16x2(__uint_as_float(a[0]), __uint_as_float(a[1])), pack_bf16x2(__uint_as_float(a[2]), __uint_as_float(a[3])),
+                       pack_bf16x2(__uint_as_float(a[4]), __uint_as_float(a[5])), pack_bf16x2(__uint_as_float(a[6]), __uint_as_float(a[7])));
                 asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(NUB * 32) : "memory");   // the NUB warps of quarter q
+                // (one bulk copy per quarter: 512 16-byte st.async per step were measured ~450 cycles slower than this)
                 if (ub == 0 && lane == 0) {
                     const uint32_t owner = (uint32_t)(4 * mr + q);
                     fence_proxy_async_smem();
                     bulk_copy_s2c(mapa_shared(red_addr + (uint32_t)(((s & 1) * 4 + kc) * PT), owner),
-                                  smem_u32(pw), (uint32_t)PT, mapa_shared(smem_u32(&mbar_red[s & 1]), owner));
+                                  pw, (uint32_t)PT, mapa_shared(smem_u32(&mbar_red[s & 1]), owner));
                 }
                 REC_PROBE(14);
                 // off the chain: zero our part of the accumulator for the next step's MMAs
@@ -1700,8 +1704,8 @@ static int rec_version() {
     return v;
 }
 
-template <typename K, typename P>
-static int launch_cluster(K kern, int grid, int threads, size_t smem, int nc, cudaStream_t st, const P& params) {
+template <typename K, typename... Args>
+static int launch_cluster(K kern, int grid, int threads, size_t smem, int nc, cudaStream_t st, const Args&... params) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return LCB_ERR_CUDA;
     if (nc > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return LCB_ERR_CUDA;
     cudaLaunchConfig_t cfg = {};
@@ -1717,7 +1721,7 @@ static int launch_cluster(K kern, int grid, int threads, size_t smem, int nc, cu
     cfg.attrs = at;
     cfg.numAttrs = 1;
     g_launches += 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, params);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, params...);
     if (e != cudaSuccess) { cudaGetLastError(); return LCB_ERR_CUDA; }
     return LCB_OK;
 }
@@ -1864,9 +1868,13 @@ extern "C" int lcb_lstm_rec_bwd(const float* dM, const void* gates, const float*
     if (rec_version() == 2 && p.xch && Hp == 512 && !getenv("LCB_REC_BWD2")) {
         const int bgs = choose_bg(B, nc, 1);
         const int ncl3 = 2 * ((B + bgs - 1) / bgs);
+        // dG as a 3-D tensor [T][B][8Hp] bf16, box = 64 columns x bgs utterances, 128B swizzle (= the MMA operand layout of a slice)
+        CUtensorMap tm;
+        if (((uintptr_t)dG & 15) || !make_tmap_3d(&tm, false, dG, (uint64_t)8 * Hp, (uint64_t)B, (uint64_t)T, (uint64_t)8 * Hp * 2,
+                                                  (uint64_t)B * 8 * Hp * 2, 64, (uint32_t)bgs, 1, true)) return LCB_ERR_CUDA;
         if (bgs == 16)
-            return launch_cluster(lstm_rec_bwd3_kernel<16>, ncl3 * nc, RecBwd3Cfg<16>::THREADS, RecBwd3Cfg<16>::smem_bytes(), nc, (cudaStream_t)stream, p);
-        return launch_cluster(lstm_rec_bwd3_kernel<32>, ncl3 * nc, RecBwd3Cfg<32>::THREADS, RecBwd3Cfg<32>::smem_bytes(), nc, (cudaStream_t)stream, p);
+            return launch_cluster(lstm_rec_bwd3_kernel<16>, ncl3 * nc, RecBwd3Cfg<16>::THREADS, RecBwd3Cfg<16>::smem_bytes(), nc, (cudaStream_t)stream, p, tm);
+        return launch_cluster(lstm_rec_bwd3_kernel<32>, ncl3 * nc, RecBwd3Cfg<32>::THREADS, RecBwd3Cfg<32>::smem_bytes(), nc, (cudaStream_t)stream, p, tm);
     }
     if (rec_version() == 2) {
         const int bgs = choose_bg(B, nc, 1);
