@@ -14,6 +14,7 @@
 // Operand layouts: A and B can each be K-major or MN-major (canonical SWIZZLE_128B layouts), which
 // gives forward (X*W), dgrad (dG*W^T) and wgrad (X^T*dG) from row-major tensors without transposes.
 #include <cuda_fp16.h>
+#include <string.h>
 #include "ptx.cuh"
 #include "tma_host.h"
 #include "lstm_ctc_b200.h"
@@ -34,7 +35,7 @@ template <int BN> struct GemmCfg {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;         // 16 KB
     static constexpr int B_BYTES = BN * GEMM_BK * 2;              // 16/32 KB
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;             // per-warp transpose staging
+    static constexpr int EPI_BYTES = 4 * 2 * 4096;                // per epilogue warp: two 32-row x 128 B staging boxes
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;
@@ -43,6 +44,7 @@ template <int BN> struct GemmCfg {
 template <int BN, bool A_MN, bool B_MN, int CT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmC, int tma_out,
                          void* __restrict__ Cptr, int ldc, const float* __restrict__ bias, int accumulate,
                          int M, int N, int K, uint32_t idesc, int splits)
 {
@@ -72,6 +74,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (tma_out) tma_prefetch_desc(&tmC);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
         fence_mbar_init();
@@ -152,10 +155,94 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         __syncwarp();
     } else {
         // ================= epilogue (warps 2..5) =================
+        // TMEM -> registers (lane = output row, 32 consecutive columns) -> +bias -> 128B-swizzled smem box of 32 rows x 128 B
+        // -> ONE TMA tensor store (or fp32 reduce-add for accumulate / split-K) per box; the TMA unit clips rows >= M and
+        // columns >= N.  Two boxes per warp so the next chunk is staged while the previous store drains.
         const int q = warp & 3;                               // TMEM lane quarter this warp may access
-        float* st = epi + (warp - 2) * (32 * 33);
         int acc = 0; uint32_t acc_phase = 0;
         bool ok = true;
+        if (tma_out) {
+            constexpr int CW = (CT == 0) ? 32 : 64;           // columns per box (128 B)
+            const uint32_t stage_base = smem_u32(epi) + (uint32_t)(warp - 2) * 8192u;
+            const bool reduce = (CT == 0) && (accumulate || splits > 1);
+            int buf = 0;
+            for (int work = blockIdx.x; work < nwork && ok; work += gridDim.x) {
+                const int tile = work % ntiles, split = work / ntiles;
+                const int m0 = (tile / tiles_n) * GEMM_BM;
+                const int n0 = (tile % tiles_n) * BN;
+                const bool skip = (split * kb_per >= nkb_all) || (m0 + q * 32 >= M);   // nothing accumulated / rows all outside
+                if (!mbar_wait(&tfull_bar[acc], acc_phase)) { ok = false; break; }
+                tc_fence_after();
+                const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+                if (!skip) {
+#pragma unroll 1
+                    for (int ch = 0; ch < BN / CW; ++ch) {
+                        const int c0 = n0 + ch * CW;
+                        if (c0 >= N) break;                   // warp-uniform
+                        uint32_t r[CW];
+                        {
+                            uint32_t (&ra)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[0]);
+                            tmem_ld_32x32b_x32(t_addr + ch * CW, ra);
+                            if constexpr (CW == 64) {
+                                uint32_t (&rb)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[32]);
+                                tmem_ld_32x32b_x32(t_addr + ch * CW + 32, rb);
+                            }
+                            tmem_ld_wait();
+                        }
+                        if (bias != nullptr && split == 0) {
+#pragma unroll
+                            for (int h = 0; h < CW / 32; ++h) {
+                                const int col = c0 + h * 32 + lane;
+                                const float bv = col < N ? bias[col] : 0.f;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    r[h * 32 + j] = __float_as_uint(__uint_as_float(r[h * 32 + j]) + __shfl_sync(0xffffffffu, bv, j));
+                            }
+                        }
+                        if (lane == 0) bulk_wait_group_read_pending<1>();   // the store that last used this box has read it
+                        __syncwarp();
+                        const uint32_t row_addr = stage_base + (uint32_t)buf * 4096u + (uint32_t)lane * 128u;
+                        const uint32_t sw = (uint32_t)(lane & 7);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            uint32_t w0, w1, w2, w3;
+                            if constexpr (CT == 0) {
+                                w0 = r[4 * c]; w1 = r[4 * c + 1]; w2 = r[4 * c + 2]; w3 = r[4 * c + 3];
+                            } else if constexpr (CT == 1) {
+                                w0 = pack_bf16x2(__uint_as_float(r[8 * c]), __uint_as_float(r[8 * c + 1]));
+                                w1 = pack_bf16x2(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
+                                w2 = pack_bf16x2(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]));
+                                w3 = pack_bf16x2(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
+                            } else {
+                                const __half2 h0 = __floats2half2_rn(__uint_as_float(r[8 * c]), __uint_as_float(r[8 * c + 1]));
+                                const __half2 h1 = __floats2half2_rn(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
+                                const __half2 h2 = __floats2half2_rn(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]));
+                                const __half2 h3 = __floats2half2_rn(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
+                                w0 = *reinterpret_cast<const uint32_t*>(&h0); w1 = *reinterpret_cast<const uint32_t*>(&h1);
+                                w2 = *reinterpret_cast<const uint32_t*>(&h2); w3 = *reinterpret_cast<const uint32_t*>(&h3);
+                            }
+                            sts_v4(row_addr + (((uint32_t)c ^ sw) << 4), w0, w1, w2, w3);
+                        }
+                        fence_proxy_async_smem();             // generic-proxy smem writes -> visible to the TMA (async proxy)
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (reduce) tma_reduce_add_2d(&tmC, stage_base + (uint32_t)buf * 4096u, c0, m0 + q * 32);
+                            else tma_store_2d(&tmC, stage_base + (uint32_t)buf * 4096u, c0, m0 + q * 32);
+                            bulk_commit_group();
+                        }
+                        buf ^= 1;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            if (lane == 0) bulk_wait_group_all();
+            __syncwarp();
+        } else {
+        // fallback for outputs the TMA cannot address (base or pitch not 16-byte aligned): smem-transposed scalar stores
+        float* st = epi + (warp - 2) * (32 * 33);
         for (int work = blockIdx.x; work < nwork && ok; work += gridDim.x) {
             const int tile = work % ntiles, split = work / ntiles;
             const int m0 = (tile / tiles_n) * GEMM_BM;
@@ -197,6 +284,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
         }
     }
     tc_fence_before();
@@ -242,6 +330,12 @@ template <int BN, bool A_MN, bool B_MN, int CT>
 static int launch_gemm(int M, int N, int K, const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc,
                        const float* bias, int accumulate, uint32_t fmt_bits, cudaStream_t st)
 {
+    // output through TMA stores when the tensor is addressable by a tensor map (16-byte aligned base and pitch)
+    const size_t es = CT == 0 ? 4 : 2;
+    const int tma_out = (((uintptr_t)C & 15) == 0 && (((size_t)ldc * es) & 15) == 0) ? 1 : 0;
+    CUtensorMap tc;
+    memset(&tc, 0, sizeof(tc));
+    if (tma_out && !make_tmap_2d_out(&tc, CT, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, CT == 0 ? 32 : 64)) return LCB_ERR_CUDA;
     const int tiles0 = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
     const int nkb0 = (K + GEMM_BK - 1) / GEMM_BK;
     // split-K for reductions with few output tiles (wgrad: K = frames): fill ~all SMs, >= 16 k-blocks per split
@@ -265,7 +359,7 @@ static int launch_gemm(int M, int N, int K, const CUtensorMap& ta, const CUtenso
     const int tiles = tiles0 * splits;
     int nsm = g_gemm_max_ctas;
     int grid = tiles < nsm ? tiles : nsm;
-    g_launches += 1; kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, C, ldc, bias, accumulate, M, N, K, idesc, splits);
+    g_launches += 1; kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tma_out, C, ldc, bias, accumulate, M, N, K, idesc, splits);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }
 

@@ -38,6 +38,24 @@ inline bool make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t rows, u
     return r == CUDA_SUCCESS;
 }
 
+// 2-D output tensor for TMA stores: row-major [rows, cols], leading dimension ld (elements); dtype 0 = fp32, 1 = bf16,
+// 2 = fp16; box = [box_rows, box_cols] with box_cols * elem_size == 128 B (one swizzle row), 128B swizzle.
+inline bool make_tmap_2d_out(CUtensorMap* m, int dtype, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                             uint32_t box_rows, uint32_t box_cols) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return false;
+    const uint64_t es = dtype == 0 ? 4 : 2;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {ld * es};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : (dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    CUresult r = enc(m, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 // 3-D tensor [d2, d1, d0] (d0 innermost) with byte strides s1 (dim1) and s2 (dim2); fp32 or bf16.
 inline bool make_tmap_3d(CUtensorMap* m, bool is_f32, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                          uint64_t s1_bytes, uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2,
