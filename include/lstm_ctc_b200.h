@@ -42,6 +42,9 @@ const char* lcb_status_string(int status);
 int lcb_device_error(int reset);
 /* number of kernels this library has launched in this process; reset != 0 zeroes the counter. */
 long long lcb_launch_count(int reset);
+/* kernels launched on the library's behalf by a replayed CUDA graph (the host wrapper captured n of them once and
+ * adds n per replay, so the counter keeps meaning "kernels of this library that ran"). */
+void lcb_launch_count_add(long long n);
 
 /* ---- CTC loss + gradient ---------------------------------------------------------------
  * replaces: tf.nn.ctc_loss(labels, inputs, sequence_length,

@@ -57,6 +57,7 @@ _SIGS = {
     "lcb_status_string": (ctypes.c_char_p, [c_int]),
     "lcb_device_error": (c_int, [c_int]),
     "lcb_launch_count": (ctypes.c_longlong, [c_int]),
+    "lcb_launch_count_add": (None, [ctypes.c_longlong]),
     "lcb_ctc_workspace_bytes": (c_size_t, [c_int] * 4),
     "lcb_ctc_loss_grad_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                       c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -126,10 +126,12 @@ def _to_bf16(src, dst):
     return dst
 
 
-def _split_bf16(src):
+def _split_bf16(src, hi=None, lo=None):
     L = _lib.lib()
-    hi = torch.empty(src.shape, dtype=BF16, device=src.device)
-    lo = torch.empty(src.shape, dtype=BF16, device=src.device)
+    if hi is None:
+        hi = torch.empty(src.shape, dtype=BF16, device=src.device)
+    if lo is None:
+        lo = torch.empty(src.shape, dtype=BF16, device=src.device)
     _lib.check(L.lcb_split_f32_bf16(_lib.ptr(src), _lib.ptr(hi), _lib.ptr(lo), src.numel(), _lib.stream_ptr()),
                "lcb_split_f32_bf16")
     return hi, lo
@@ -155,6 +157,10 @@ class BLSTMEncoder:
         self._stale = True
         self.wstream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None   # wgrad side stream
         self.overlap_wgrad = True
+        self.rstream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None   # operand-refresh side stream
+        self.use_graphs = True
+        self._refresh_graphs = None
+        self._refresh_done = None
         self.seed_base = 777           # reference default --seed (nnet-train.py:141-142)
         self.step_id = 0
         mt = _lib.ctypes.c_int()
@@ -233,46 +239,94 @@ class BLSTMEncoder:
     def mark_stale(self):
         self._stale = True
 
+    def _refresh_layer(self, i):
+        """16-bit GEMM operands of layer i + its folded recurrent weights W' = W_proj * W_h (fp32-accurate via a 3-term
+        split-bf16 product on the tensor cores).  Every destination buffer is allocated once and then rewritten in place, so
+        the launch sequence can be replayed from a CUDA graph."""
+        c = self.cfg
+        ps = self.params
+        bf = self._bf
+        bf[("Wx16", i)] = _cast16(ps.w("L%d/Wx" % i), F16, bf.get(("Wx16", i)))
+        bf[("Wx", i)] = _cast16(ps.w("L%d/Wx" % i), BF16, bf.get(("Wx", i)))
+        bf[("WpT16", i)] = _cast16(ps.w("L%d/WpT" % i), F16, bf.get(("WpT16", i)))
+        Wh_hi, Wh_lo = _split_bf16(ps.w("L%d/Wh" % i), bf.get(("Wh", i)), bf.get(("Wh_lo", i)))
+        Wp_hi, Wp_lo = _split_bf16(ps.w("L%d/WpT" % i), bf.get(("WpT", i)), bf.get(("WpT_lo", i)))
+        bf[("Wh", i)], bf[("Wh_lo", i)], bf[("WpT", i)], bf[("WpT_lo", i)] = Wh_hi, Wh_lo, Wp_hi, Wp_lo
+        fold = bf.get(("fold32", i))
+        if fold is None:
+            fold = torch.empty(8 * c.Hp, c.Hp, dtype=F32, device=self.device)
+        for d in range(2):
+            rows = slice(d * 4 * c.Hp, (d + 1) * 4 * c.Hp)
+            # W'^T[g,h] = sum_p Wh[g,p] * WpT[p,h]
+            gemm(Wh_hi[rows], Wp_hi[d], 0, 1, out=fold[rows])
+            gemm(Wh_hi[rows], Wp_lo[d], 0, 1, out=fold[rows], accumulate=True)
+            gemm(Wh_lo[rows], Wp_hi[d], 0, 1, out=fold[rows], accumulate=True)
+        bf[("fold32", i)] = fold
+        bf[("fold16", i)] = _cast16(fold, F16, bf.get(("fold16", i)))   # forward recurrence: (W')^T, fp16
+        # BPTT keeps W' itself ([units, packed gate cols], bf16) in tensor memory: same product, other orientation
+        foldb = bf.get(("foldb32", i))
+        if foldb is None:
+            foldb = torch.empty(2 * c.Hp, 4 * c.Hp, dtype=F32, device=self.device)
+        for d in range(2):
+            rows = slice(d * 4 * c.Hp, (d + 1) * 4 * c.Hp)
+            out = foldb[d * c.Hp:(d + 1) * c.Hp]
+            # W'[u,g] = sum_p WpT[p,u] * Wh[g,p]
+            gemm(Wp_hi[d], Wh_hi[rows], 1, 0, out=out)
+            gemm(Wp_lo[d], Wh_hi[rows], 1, 0, out=out, accumulate=True)
+            gemm(Wp_hi[d], Wh_lo[rows], 1, 0, out=out, accumulate=True)
+        bf[("foldb32", i)] = foldb
+        bf[("fold", i)] = _cast16(foldb, BF16, bf.get(("fold", i)))
+
     def refresh_operands(self):
-        """bf16 GEMM operands + folded recurrent weights W' = W_proj * W_h (fp32-accurate via a
-        3-term split-bf16 product on the tensor cores)."""
+        """Rebuild the 16-bit operands after a weight update (once per step).  ~100 tiny launches: the first call runs them
+        eagerly (allocating the buffers), the second captures them into two CUDA graphs -- layer 0 (replayed on the calling
+        stream) and layers 1.. (replayed on a side stream, so they execute on the SMs layer 0's recurrence leaves idle;
+        forward() waits on `_refresh_done` before it touches layer 1)."""
         if not self._stale:
             return
         c = self.cfg
-        ps = self.params
-        for i in range(c.num_layers):
-            self._bf[("Wx16", i)] = _cast16(ps.w("L%d/Wx" % i), F16, self._bf.get(("Wx16", i)))
-            self._bf[("Wx", i)] = _cast16(ps.w("L%d/Wx" % i), BF16, self._bf.get(("Wx", i)))
-            self._bf[("WpT16", i)] = _cast16(ps.w("L%d/WpT" % i), F16, self._bf.get(("WpT16", i)))
-            Wh_hi, Wh_lo = _split_bf16(ps.w("L%d/Wh" % i))
-            Wp_hi, Wp_lo = _split_bf16(ps.w("L%d/WpT" % i))
-            fold = self._bf.get(("fold32", i))
-            if fold is None:
-                fold = torch.empty(8 * c.Hp, c.Hp, dtype=F32, device=self.device)
-            for d in range(2):
-                rows = slice(d * 4 * c.Hp, (d + 1) * 4 * c.Hp)
-                # W'^T[g,h] = sum_p Wh[g,p] * WpT[p,h]
-                gemm(Wh_hi[rows], Wp_hi[d], 0, 1, out=fold[rows])
-                gemm(Wh_hi[rows], Wp_lo[d], 0, 1, out=fold[rows], accumulate=True)
-                gemm(Wh_lo[rows], Wp_hi[d], 0, 1, out=fold[rows], accumulate=True)
-            self._bf[("Wh", i)] = Wh_hi
-            self._bf[("WpT", i)] = Wp_hi
-            self._bf[("fold32", i)] = fold
-            self._bf[("fold16", i)] = _cast16(fold, F16, self._bf.get(("fold16", i)))   # forward recurrence: (W')^T, fp16
-            # BPTT keeps W' itself ([units, packed gate cols], bf16) in tensor memory: same product, other orientation
-            foldb = self._bf.get(("foldb32", i))
-            if foldb is None:
-                foldb = torch.empty(2 * c.Hp, 4 * c.Hp, dtype=F32, device=self.device)
-            for d in range(2):
-                rows = slice(d * 4 * c.Hp, (d + 1) * 4 * c.Hp)
-                out = foldb[d * c.Hp:(d + 1) * c.Hp]
-                # W'[u,g] = sum_p WpT[p,u] * Wh[g,p]
-                gemm(Wp_hi[d], Wh_hi[rows], 1, 0, out=out)
-                gemm(Wp_lo[d], Wh_hi[rows], 1, 0, out=out, accumulate=True)
-                gemm(Wp_hi[d], Wh_lo[rows], 1, 0, out=out, accumulate=True)
-            self._bf[("foldb32", i)] = foldb
-            self._bf[("fold", i)] = _cast16(foldb, BF16, self._bf.get(("fold", i)))
+        self._refresh_done = None
+        have_buffers = ("fold", c.num_layers - 1) in self._bf
+        if not (self.use_graphs and have_buffers and self.device.type == "cuda"):
+            for i in range(c.num_layers):
+                self._refresh_layer(i)
+            self._stale = False
+            return
+        main = torch.cuda.current_stream()
+        if self._refresh_graphs is None:
+            torch.cuda.synchronize()
+            L = _lib.lib()
+            n0 = L.lcb_launch_count(0)
+            g0 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g0, capture_error_mode="thread_local"):   # the pipeline prefetch thread may pin memory meanwhile
+                self._refresh_layer(0)
+            n1 = L.lcb_launch_count(0)
+            g1 = None
+            if c.num_layers > 1:
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1, capture_error_mode="thread_local"):
+                    for i in range(1, c.num_layers):
+                        self._refresh_layer(i)
+            n2 = L.lcb_launch_count(0)
+            L.lcb_launch_count_add(-(n2 - n0))        # captured, not run
+            self._refresh_graphs = (g0, g1)
+            self._refresh_nodes = n2 - n0
+        g0, g1 = self._refresh_graphs
+        _lib.lib().lcb_launch_count_add(self._refresh_nodes)
+        if g1 is not None:
+            self.rstream.wait_stream(main)            # the weights the graph reads were written on the calling stream
+            with torch.cuda.stream(self.rstream):
+                g1.replay()
+                ev = torch.cuda.Event()
+                ev.record(self.rstream)
+            self._refresh_done = ev
+        g0.replay()
         self._stale = False
+
+    def _await_refresh(self):
+        if self._refresh_done is not None:
+            torch.cuda.current_stream().wait_event(self._refresh_done)
+            self._refresh_done = None
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, T, B, training):
@@ -321,6 +375,8 @@ class BLSTMEncoder:
         _lib.check(L.lcb_pack_input(_lib.ptr(nnet_input), _lib.ptr(ws["X0"]), B, T, D, c.Dp0, st), "lcb_pack_input")
         X = ws["X0"]
         for i in range(c.num_layers):
+            if i == 1:
+                self._await_refresh()               # layers 1.. were refreshed on the side stream during layer 0's recurrence
             gemm(X, self._bf[("Wx16", i)], 0, 0, out=ws["G"], bias=self.params.w("L%d/bias" % i))
             peep = self.params.w("L%d/peep" % i) if c.use_peepholes else None
             gates = ws["gates"][i] if training else None
@@ -376,45 +432,22 @@ class BLSTMEncoder:
         dH = dXtop
         if overlap:
             side.wait_stream(main)           # the forward activations the side stream converts are complete
-        for i in reversed(range(c.num_layers)):
+
+        def wgrad(i, dH_this, after):
+            """Weight gradients of layer i on the side stream.  `after` = event on the main stream behind the serial chain
+            (dX, dropout, dM GEMMs) of the layer BELOW, so these GEMMs never take SMs from it: the BPTT launch that follows
+            leaves them 84 idle SMs for ~3.8 ms (capped grid); layer 0's run alone on the whole chip."""
             k = i & 1
-            if overlap and (i + 2) in side_done:
-                main.wait_event(side_done[i + 2])             # buffer set k is free again
-            if c.keep_prob < 1.0:
-                self._dropout(dH, i)                # same (seed, index) mask as the forward pass, on the gradient
-            X16 = ws["X0"] if i == 0 else ws["Hout"][i - 1]
-            # bf16 copies of the fp16 forward activations for the wgrad GEMMs: only the side stream reads them, so it also
-            # makes them (in order behind layer i+1's wgrads, concurrently with this layer's BPTT on the main stream)
-            with torch.cuda.stream(side):
-                X = _to_bf16(X16, ws["Xbf"][k][:X16.numel()].view(X16.shape))
-                M = _to_bf16(ws["M"][i], ws["Mbf"][k])
-            dM, dG = ws["dM"], ws["dG"][k]
+            dG = ws["dG"][k]
             gWpT, gWh, gWx = ps.g("L%d/WpT" % i), ps.g("L%d/Wh" % i), ps.g("L%d/Wx" % i)
-            for d in range(2):
-                # dM = dH * W_p^T
-                gemm(dH[:, d * c.P:(d + 1) * c.P], self._bf[("WpT", i)][d], 0, 1, out=dM[:, d * c.Hp:(d + 1) * c.Hp])
-            peep = ps.w("L%d/peep" % i) if c.use_peepholes else None
-            gpeep = ps.g("L%d/peep" % i) if c.use_peepholes else None
-            _lib.check(L.lcb_lstm_rec_bwd(_lib.ptr(dM), _lib.ptr(ws["gates"][i]), _lib.ptr(ws["cst"][i]),
-                                          _lib.ptr(self._bf[("fold", i)]), _lib.ptr(peep),
-                                          _lib.ptr(seq_len), _lib.ptr(dG), _lib.ptr(ps.g("L%d/bias" % i)), _lib.ptr(gpeep),
-                                          T, B, c.Hp, _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(), _lib.stream_ptr()), "lcb_lstm_rec_bwd")
-            ev_dg = None
-            if overlap:
-                ev_dg = torch.cuda.Event()
-                ev_dg.record(main)
-            dH_this = dH
-            if i > 0:
-                dXn = ws["dX"][k]
-                if overlap and (i + 1) in side_done:
-                    main.wait_event(side_done[i + 1])         # layer i+1's wgrad still reads this buffer as its dH
-                gemm(dG, self._bf[("Wx", i)], 0, 1, out=dXn)        # dX = dG * W_x
-                dH = dXn
-            # ---- weight gradients of layer i (side stream) ----
+            X16 = ws["X0"] if i == 0 else ws["Hout"][i - 1]
             with torch.cuda.stream(side):
                 if overlap:
-                    side.wait_event(ev_dg)
-                    old_cap = L.lcb_gemm_set_max_ctas(80)      # the SMs not owned by the next layer's BPTT clusters
+                    side.wait_event(after)
+                    old_cap = L.lcb_gemm_set_max_ctas(80 if i > 0 else 148)
+                # bf16 copies of the fp16 forward activations (tcgen05 kind::f16 cannot mix f16 x bf16 operands)
+                X = _to_bf16(X16, ws["Xbf"][k][:X16.numel()].view(X16.shape))
+                M = _to_bf16(ws["M"][i], ws["Mbf"][k])
                 for d in range(2):
                     dHd = dH_this[:, d * c.P:(d + 1) * c.P]
                     Md = M[:, d * c.Hp:(d + 1) * c.Hp]
@@ -446,6 +479,43 @@ class BLSTMEncoder:
                     ev = torch.cuda.Event()
                     ev.record(side)
                     side_done[i] = ev
+
+        def mark():
+            if not overlap:
+                return None
+            ev = torch.cuda.Event()
+            ev.record(main)
+            return ev
+
+        pending = None                       # (layer, its dH): weight gradients not yet enqueued
+        for i in reversed(range(c.num_layers)):
+            k = i & 1
+            if overlap and (i + 2) in side_done:
+                main.wait_event(side_done[i + 2])             # buffer set k is free again
+            if c.keep_prob < 1.0:
+                self._dropout(dH, i)                # same (seed, index) mask as the forward pass, on the gradient
+            dM, dG = ws["dM"], ws["dG"][k]
+            for d in range(2):
+                # dM = dH * W_p^T
+                gemm(dH[:, d * c.P:(d + 1) * c.P], self._bf[("WpT", i)][d], 0, 1, out=dM[:, d * c.Hp:(d + 1) * c.Hp])
+            chain_issued = mark()                             # behind BPTT(i+1) and this layer's dropout / dM GEMMs
+            peep = ps.w("L%d/peep" % i) if c.use_peepholes else None
+            gpeep = ps.g("L%d/peep" % i) if c.use_peepholes else None
+            _lib.check(L.lcb_lstm_rec_bwd(_lib.ptr(dM), _lib.ptr(ws["gates"][i]), _lib.ptr(ws["cst"][i]),
+                                          _lib.ptr(self._bf[("fold", i)]), _lib.ptr(peep),
+                                          _lib.ptr(seq_len), _lib.ptr(dG), _lib.ptr(ps.g("L%d/bias" % i)), _lib.ptr(gpeep),
+                                          T, B, c.Hp, _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(), _lib.stream_ptr()), "lcb_lstm_rec_bwd")
+            if pending is not None:
+                wgrad(pending[0], pending[1], chain_issued)   # layer i+1's weight gradients run beside this BPTT
+            dH_this = dH
+            if i > 0:
+                dXn = ws["dX"][k]
+                if overlap and (i + 1) in side_done:
+                    main.wait_event(side_done[i + 1])         # layer i+1's wgrad still reads this buffer as its dH
+                gemm(dG, self._bf[("Wx", i)], 0, 1, out=dXn)        # dX = dG * W_x
+                dH = dXn
+            pending = (i, dH_this)
+        wgrad(pending[0], pending[1], mark())
         if overlap:
             main.wait_stream(side)
         return None

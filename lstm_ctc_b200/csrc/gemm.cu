@@ -338,12 +338,19 @@ static int launch_gemm(int M, int N, int K, const CUtensorMap& ta, const CUtenso
     if (tma_out && !make_tmap_2d_out(&tc, CT, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, CT == 0 ? 32 : 64)) return LCB_ERR_CUDA;
     const int tiles0 = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
     const int nkb0 = (K + GEMM_BK - 1) / GEMM_BK;
-    // split-K for reductions with few output tiles (wgrad: K = frames): fill ~all SMs, >= 16 k-blocks per split
+    // split-K for reductions whose output tiles do not fill the persistent grid evenly (wgrad: K = frames): work item =
+    // (tile, K split), all of equal cost and dealt round-robin, so the run time is ceil(tiles*s / ctas) rounds of K/s.
+    // Pick the s that minimises rounds/s, with a small charge per extra split for its fp32 reduce-add traffic.
     int splits = 1;
-    if (CT == 0 && tiles0 <= 74 && nkb0 >= 64) {
-        splits = (148 + tiles0 - 1) / tiles0;
-        if (splits > nkb0 / 16) splits = nkb0 / 16;
-        if (splits < 1) splits = 1;
+    const int ctas = g_gemm_max_ctas;
+    if (CT == 0 && tiles0 < 2 * ctas && nkb0 >= 64) {
+        int smax = nkb0 / 16; if (smax > 48) smax = 48;
+        double best = 1e30;
+        for (int s = 1; s <= smax; ++s) {
+            const int rounds = (tiles0 * s + ctas - 1) / ctas;
+            const double cost = (double)rounds / s * (1.0 + 0.015 * (s - 1));
+            if (cost < best - 1e-9) { best = cost; splits = s; }
+        }
     }
     if (splits > 1 && !accumulate) {      // partial sums are added atomically: start from zero
         if (cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st) != cudaSuccess) return LCB_ERR_CUDA;
@@ -467,6 +474,8 @@ extern "C" long long lcb_launch_count(int reset)
     if (reset) lcb::g_launches = 0;
     return v;
 }
+
+extern "C" void lcb_launch_count_add(long long n) { lcb::g_launches += n; }
 
 extern "C" const char* lcb_status_string(int s)
 {
