@@ -129,6 +129,14 @@ size_t lcb_lstm_rec_workspace_bytes(int B, int Hp);
 int lcb_lstm_rec_fwd(const float* G, const void* WfoldT, const float* peep, const int32_t* lens,
                      void* Mout, void* gates, float* cst, float* cfin, float* mfin,
                      int T, int B, int Hp, float forget_bias, void* workspace, size_t workspace_bytes, void* stream);
+/* Same, for scan steps [s_begin, s_end) only (scan step s is frame s of the forward direction and frame T-1-s of the
+ * backward direction).  A launch with s_begin > 0 resumes from the saved cst / Mout rows of scan step s_begin-1 (so gates
+ * and cst must be given); launches over consecutive ranges in stream order equal one launch over [0, T).  This lets the
+ * caller start the recurrence when only the first frames' pre-activations G exist and compute the rest beside it. */
+int lcb_lstm_rec_fwd_range(const float* G, const void* WfoldT, const float* peep, const int32_t* lens,
+                           void* Mout, void* gates, float* cst, float* cfin, float* mfin,
+                           int T, int B, int Hp, float forget_bias, int s_begin, int s_end,
+                           void* workspace, size_t workspace_bytes, void* stream);
 /* BPTT of the above (replaces tf.gradients through the while_loop, nnet/graph.py:190-191).
  *   dM    [T*B, 2Hp] f32   d loss / d m_t arriving from the output projection
  *   Wfold [2*Hp, 4Hp] bf16 W' = W_proj*W_h per direction: rows = units, cols = packed gate columns

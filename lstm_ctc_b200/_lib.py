@@ -71,6 +71,7 @@ _SIGS = {
     "lcb_debug_rec_profile": (c_int, [c_void_p, c_int]),
     "lcb_lstm_rec_workspace_bytes": (c_size_t, [c_int, c_int]),
     "lcb_lstm_rec_fwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
+    "lcb_lstm_rec_fwd_range": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "lcb_lstm_rec_bwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "lcb_pack_input": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "lcb_cast_f32_16": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p]),

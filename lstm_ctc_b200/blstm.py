@@ -159,6 +159,8 @@ class BLSTMEncoder:
         self.overlap_wgrad = True
         self.rstream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None   # operand-refresh side stream
         self.use_graphs = True
+        self.pstream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None   # projection of the later frames
+        self.head_frac = 0.3           # fraction of the scan steps whose pre-activations are projected before the recurrence starts
         self._refresh_graphs = None
         self._refresh_done = None
         self.seed_base = 777           # reference default --seed (nnet-train.py:141-142)
@@ -377,15 +379,44 @@ class BLSTMEncoder:
         for i in range(c.num_layers):
             if i == 1:
                 self._await_refresh()               # layers 1.. were refreshed on the side stream during layer 0's recurrence
-            gemm(X, self._bf[("Wx16", i)], 0, 0, out=ws["G"], bias=self.params.w("L%d/bias" % i))
             peep = self.params.w("L%d/peep" % i) if c.use_peepholes else None
             gates = ws["gates"][i] if training else None
             cst = ws["cst"][i] if training else None
             last = (i == c.num_layers - 1)
-            _lib.check(L.lcb_lstm_rec_fwd(_lib.ptr(ws["G"]), _lib.ptr(self._bf[("fold16", i)]), _lib.ptr(peep), _lib.ptr(seq_len),
-                                          _lib.ptr(ws["M"][i]), _lib.ptr(gates), _lib.ptr(cst),
-                                          _lib.ptr(ws["cfin"]) if last else None, _lib.ptr(ws["mfin"]) if last else None,
-                                          T, B, c.Hp, c.forget_bias, _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(), st), "lcb_lstm_rec_fwd")
+            W16, bias, G = self._bf[("Wx16", i)], self.params.w("L%d/bias" % i), ws["G"]
+
+            def rec(s0, s1):
+                _lib.check(L.lcb_lstm_rec_fwd_range(_lib.ptr(G), _lib.ptr(self._bf[("fold16", i)]), _lib.ptr(peep), _lib.ptr(seq_len),
+                                                    _lib.ptr(ws["M"][i]), _lib.ptr(gates), _lib.ptr(cst),
+                                                    _lib.ptr(ws["cfin"]) if last else None, _lib.ptr(ws["mfin"]) if last else None,
+                                                    T, B, c.Hp, c.forget_bias, s0, s1, _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(),
+                                                    _lib.stream_ptr()), "lcb_lstm_rec_fwd_range")
+
+            Tc = int(math.ceil(self.head_frac * T)) if (training and self.pstream is not None) else 0
+            if Tc < 16 or 2 * Tc > T:
+                gemm(X, W16, 0, 0, out=G, bias=bias)
+                rec(0, T)
+            else:
+                # The recurrence needs G only for the frames it is about to visit: project the first Tc scan steps of each
+                # direction (frames [0,Tc) for the forward, [T-Tc,T) for the backward cells), start the recurrence on them, and
+                # project the remaining rows on a side stream on the SMs the 64 recurrence CTAs leave idle.
+                H4, nh, nt = 4 * c.Hp, Tc * B, (T - Tc) * B
+                main = torch.cuda.current_stream()
+                gemm(X[:nh], W16[:H4], 0, 0, out=G[:nh, :H4], bias=bias[:H4])
+                gemm(X[nt:], W16[H4:], 0, 0, out=G[nt:, H4:], bias=bias[H4:])
+                head_done = torch.cuda.Event()
+                head_done.record(main)
+                rec(0, Tc)
+                with torch.cuda.stream(self.pstream):
+                    self.pstream.wait_event(head_done)
+                    old_cap = L.lcb_gemm_set_max_ctas(84)
+                    gemm(X[nh:], W16[:H4], 0, 0, out=G[nh:, :H4], bias=bias[:H4])
+                    gemm(X[:nt], W16[H4:], 0, 0, out=G[:nt, H4:], bias=bias[H4:])
+                    L.lcb_gemm_set_max_ctas(old_cap)
+                    tail_done = torch.cuda.Event()
+                    tail_done.record(self.pstream)
+                main.wait_event(tail_done)
+                rec(Tc, T)
             Hout = ws["Hout"][i]
             for d in range(2):
                 gemm(ws["M"][i][:, d * c.Hp:(d + 1) * c.Hp], self._bf[("WpT16", i)][d], 0, 0, out=Hout[:, d * c.P:(d + 1) * c.P])
@@ -441,14 +472,21 @@ class BLSTMEncoder:
             dG = ws["dG"][k]
             gWpT, gWh, gWx = ps.g("L%d/WpT" % i), ps.g("L%d/Wh" % i), ps.g("L%d/Wx" % i)
             X16 = ws["X0"] if i == 0 else ws["Hout"][i - 1]
+            split = overlap and i == 0        # nothing runs beside layer 0's weight gradients: direction 1 goes to the main stream
             with torch.cuda.stream(side):
-                if overlap:
+                if overlap and not split:
                     side.wait_event(after)
-                    old_cap = L.lcb_gemm_set_max_ctas(80 if i > 0 else 148)
-                # bf16 copies of the fp16 forward activations (tcgen05 kind::f16 cannot mix f16 x bf16 operands)
+                # bf16 copies of the fp16 forward activations (tcgen05 kind::f16 cannot mix f16 x bf16 operands); layer 0's are
+                # made while its BPTT still runs
                 X = _to_bf16(X16, ws["Xbf"][k][:X16.numel()].view(X16.shape))
                 M = _to_bf16(ws["M"][i], ws["Mbf"][k])
-                for d in range(2):
+                if split:
+                    converted = torch.cuda.Event()
+                    converted.record(side)
+                    side.wait_event(after)
+                if overlap:
+                    old_cap = L.lcb_gemm_set_max_ctas(80 if i > 0 else 148)
+                def direction(d):
                     dHd = dH_this[:, d * c.P:(d + 1) * c.P]
                     Md = M[:, d * c.Hp:(d + 1) * c.Hp]
                     dGd = dG[:, d * 4 * c.Hp:(d + 1) * 4 * c.Hp]
@@ -469,8 +507,20 @@ class BLSTMEncoder:
                         # dW_p^T[p,h] += sum_g Wh[g,p] * dW'^T[g,h]
                         gemm(self._bf[("Wh", i)][rows], df_hi, 1, 1, out=gWpT[d], accumulate=True)
                         gemm(self._bf[("Wh", i)][rows], df_lo, 1, 1, out=gWpT[d], accumulate=True)
+
+                direction(0)
+                if split:
+                    with torch.cuda.stream(main):
+                        main.wait_event(converted)
+                        direction(1)
+                        dir1_done = torch.cuda.Event()
+                        dir1_done.record(main)
+                else:
+                    direction(1)
                 # dW_x[g,k] = sum_n dz_n[g] * x_n[k]   (both directions at once)
                 gemm(dG, X, 1, 1, out=gWx)
+                if split:
+                    side.wait_event(dir1_done)
                 if overlap:
                     L.lcb_gemm_set_max_ctas(old_cap)
                 if bucket_ready is not None:

@@ -63,6 +63,8 @@ struct RecFwdParams {
     int T, B, Hp, NC;
     float forget_bias;
     unsigned char* xch;           // v2: L2 exchange scratch [clusters][2][NC][slice] (nullptr: DSMEM copies)
+    int s_begin, s_end;           // v2: scan steps [s_begin, s_end) of this launch (t = s forward, T-1-s backward direction);
+                                  // a launch with s_begin > 0 resumes from the saved cst / Mout of step s_begin - 1
 };
 
 struct RecBwdParams {
@@ -796,10 +798,23 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
         fence_mbar_init();
     }
     if (warp == NCW) tmem_alloc<512>(tmem_slot);
-    {   // m_{-1} = 0
+    const int S0 = p.s_begin, S = p.s_end - p.s_begin;      // this launch runs scan steps S0 .. S0+S-1 (local index s = 0..S-1)
+    {   // operand buffer 0 := m of the step before S0 (0 for a fresh start; a padded frame's saved m is 0 as well)
         uint4* bz = reinterpret_cast<uint4*>(Bsm);
         const int n16 = (int)(2 * OPB / 16);
         for (int i = threadIdx.x; i < n16; i += blockDim.x) bz[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (S0 > 0) {
+            __syncthreads();
+            const int tp = dir ? (T - S0) : (S0 - 1);
+            const int pieces = (Hp >> 3) * BG;               // 16-byte pieces: (unit chunk of 8, utterance)
+            for (int i = threadIdx.x; i < pieces; i += blockDim.x) {
+                const int u = i % BG, ch = i / BG;
+                if (b0 + u < B) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(p.Mout + ((size_t)tp * B + b0 + u) * ld2 + (size_t)dir * Hp + ch * 8);
+                    *reinterpret_cast<uint4*>(Bsm + ((size_t)ch * NUB + (u >> 3)) * 128 + (u & 7) * 16) = v;
+                }
+            }
+        }
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -830,14 +845,14 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
     bool ok = true;
     if (role == 2) {
         // ============================ loader warp: G tile prefetch, one 512-byte bulk copy per lane ============================
-        for (int s = 0; s < T; ++s) {
+        for (int s = 0; s < S; ++s) {
             const int stage = s % SG;
             if (s >= SG) {              // wait until the compute warps drained this stage (step s - SG)
                 if (lane == 0 && ok) ok = mbar_wait(&mbar_gfree[stage], (uint32_t)(((s - SG) / SG) & 1));
                 ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
                 if (!ok) break;
             }
-            const int t = dir ? (T - 1 - s) : s;
+            const int t = dir ? (T - 1 - (S0 + s)) : (S0 + s);
             if (lane == 0) mbar_arrive_expect_tx(&mbar_g[stage], (uint32_t)(nvalid * 512));
             __syncwarp();
             for (int u = lane; u < nvalid; u += 32)
@@ -853,7 +868,7 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
         if (lane == 0) {
             unsigned char* scr = p.xch + (size_t)cid * 2 * NC * SLICE;
             const uint16_t mask = (uint16_t)((1u << NC) - 1u);
-            for (int s = 0; s + 1 < T && ok; ++s) {
+            for (int s = 0; s + 1 < S && ok; ++s) {
                 ok = mbar_wait(&mbar_slice[s & 1], (uint32_t)((s >> 1) & 1));
                 if (!ok) break;
                 unsigned char* g = scr + ((size_t)(s & 1) * NC + cta) * SLICE;
@@ -879,17 +894,17 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
             const uint32_t b_lo0 = (uint32_t)bb0, b_hi = (uint32_t)(bb0 >> 32);
             const uint32_t d_tmem = tmem_base + REC_TMEM_ACC;
             const int nk = Hp >> 4;
-            for (int s = 0; s < T && ok; ++s) {
+            for (int s = 0; s < S && ok; ++s) {
                 REC_PROBE(0);
                 const uint32_t par = (uint32_t)(s & 1);
-                if (iw == 0 && s + 1 < T) mbar_arrive_expect_tx(&mbar_op[(s + 1) & 1], (uint32_t)(NC * SLICE));   // the buffer that step s fills
+                if (iw == 0 && s + 1 < S) mbar_arrive_expect_tx(&mbar_op[(s + 1) & 1], (uint32_t)(NC * SLICE));   // the buffer that step s fills
                 ok = mbar_wait(mbar_acc, (uint32_t)(s & 1));                 // accumulator = G tile of step s
                 if (ok && s > 0) ok = mbar_wait(&mbar_op[par], (uint32_t)(((s - 1) >> 1) & 1));
                 if (!ok) break;
                 REC_PROBE(1);
                 tc_fence_after();
                 const uint32_t b_lo_s = b_lo0 + ((par * OPB) >> 4);
-                if (s > 0) {                                                 // m_{-1} = 0: step 0 is the x-part alone
+                if (S0 + s > 0) {                                            // m_{-1} = 0: scan step 0 is the x-part alone
 #pragma unroll 4
                     for (int kk = iw; kk < nk; kk += NIW)
                         umma_f16_ts_lohi(d_tmem, tmem_base + 8 * kk, b_lo_s + (2 * NUB * 128 / 16) * kk, b_hi, idesc, 1u);
@@ -921,6 +936,10 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
             pad_j[j] = b >= B;
             len_j[j] = pad_j[j] ? 0 : p.lens[b];
             c_reg[j] = 0.f;
+            if (S0 > 0 && !pad_j[j]) {                     // resume: the carried cell state is the saved c of the previous scan step
+                const int tp = dir ? (T - S0) : (S0 - 1);  // (a backward-direction utterance that has not started yet carries 0)
+                if (tp < len_j[j]) c_reg[j] = p.cst[((size_t)tp * B + b) * ((size_t)2 * Hp) + (size_t)dir * Hp + unit];
+            }
         }
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + ub * 8;
         const float fbias = p.forget_bias;
@@ -949,8 +968,8 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
         };
         load_acc(0);
 
-        for (int s = 0; s < T; ++s) {
-            const int t = dir ? (T - 1 - s) : s;
+        for (int s = 0; s < S; ++s) {
+            const int t = dir ? (T - 1 - (S0 + s)) : (S0 + s);
             REC_PROBE(8);
             // rows of the quarter are gate-major: lanes [0,16) hold gates i,j ; lanes [16,32) gates f,o.  The accumulator
             // already contains the x-part (put there by load_acc below), so this is the complete pre-activation.
@@ -984,7 +1003,7 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
             }
             const __half2 mh = __floats2half2_rn(mo[0], mo[1]);
             REC_PROBE(15);
-            if (s + 1 < T) {
+            if (s + 1 < S) {
                 // stage the warp's [8 utts][8 units] fp16 block = core matrix (q, ub) of this CTA's operand slice (double-
                 // buffered by step parity) and hand it to the exchange warp
                 __half* ms16 = reinterpret_cast<__half*>(Msm + (s & 1) * SLICE + (q * NUB + ub) * 128);
@@ -1821,8 +1840,19 @@ extern "C" int lcb_lstm_rec_fwd(const float* G, const void* WfoldT, const float*
                                 void* Mout, void* gates, float* cst, float* cfin, float* mfin,
                                 int T, int B, int Hp, float forget_bias, void* workspace, size_t workspace_bytes, void* stream)
 {
+    return lcb_lstm_rec_fwd_range(G, WfoldT, peep, lens, Mout, gates, cst, cfin, mfin, T, B, Hp, forget_bias, 0, T,
+                                  workspace, workspace_bytes, stream);
+}
+
+extern "C" int lcb_lstm_rec_fwd_range(const float* G, const void* WfoldT, const float* peep, const int32_t* lens,
+                                      void* Mout, void* gates, float* cst, float* cfin, float* mfin,
+                                      int T, int B, int Hp, float forget_bias, int s_begin, int s_end,
+                                      void* workspace, size_t workspace_bytes, void* stream)
+{
     if (!G || !WfoldT || !lens || !Mout) return LCB_ERR_NULL_POINTER;
     if (T <= 0 || B <= 0) return LCB_ERR_BAD_SHAPE;
+    if (s_begin < 0 || s_end > T || s_begin >= s_end) return LCB_ERR_BAD_SHAPE;
+    if (s_begin > 0 && !cst) return LCB_ERR_NULL_POINTER;       // resuming reads the saved cell state
     if ((cfin == nullptr) != (mfin == nullptr) || (gates == nullptr) != (cst == nullptr)) return LCB_ERR_NULL_POINTER;
     int nc;
     if (!rec_plan(Hp, nc)) return LCB_ERR_UNSUPPORTED;
@@ -1830,7 +1860,7 @@ extern "C" int lcb_lstm_rec_fwd(const float* G, const void* WfoldT, const float*
     RecFwdParams p;
     p.G = G; p.Wt = (const __half*)WfoldT; p.peep = peep; p.lens = lens; p.Mout = (__half*)Mout;
     p.gates = (uint2*)gates; p.cst = cst; p.cfin = cfin; p.mfin = mfin;
-    p.T = T; p.B = B; p.Hp = Hp; p.NC = nc; p.forget_bias = forget_bias;
+    p.T = T; p.B = B; p.Hp = Hp; p.NC = nc; p.forget_bias = forget_bias; p.s_begin = s_begin; p.s_end = s_end;
     static int xch_mode = -1;                      // LCB_REC_XCH=dsmem keeps the unicast DSMEM exchange (A/B measurements)
     if (xch_mode < 0) { const char* e = getenv("LCB_REC_XCH"); xch_mode = (e && !strcmp(e, "dsmem")) ? 0 : 1; }
     p.xch = (xch_mode && workspace && workspace_bytes >= lcb_lstm_rec_workspace_bytes(B, Hp)) ? (unsigned char*)workspace : nullptr;
@@ -1842,6 +1872,7 @@ extern "C" int lcb_lstm_rec_fwd(const float* G, const void* WfoldT, const float*
             return launch_cluster(lstm_rec_fwd2_kernel<16>, ncl2 * nc, RecFwd2Cfg<16>::THREADS, RecFwd2Cfg<16>::smem_bytes(Hp / 64), nc, (cudaStream_t)stream, p);
         return launch_cluster(lstm_rec_fwd2_kernel<32>, ncl2 * nc, RecFwd2Cfg<32>::THREADS, RecFwd2Cfg<32>::smem_bytes(Hp / 64), nc, (cudaStream_t)stream, p);
     }
+    if (s_begin != 0 || s_end != T) return LCB_ERR_UNSUPPORTED;  // the v1 kernels run whole sequences only
     const int nsg = choose_nsg(B, nc, 0);
     const int ncl = 2 * ((B + REC_BG * nsg - 1) / (REC_BG * nsg));
     if (nsg == 1)

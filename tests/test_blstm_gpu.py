@@ -105,3 +105,37 @@ def test_final_state_encoder(cuda_dev):
     e = enc.encoder_state().cpu().double()
     assert e.shape == enc_ref.shape
     assert (e - enc_ref).abs().max().item() < 3e-2 * enc_ref.abs().max().item()
+
+
+@pytest.mark.parametrize("H,B,T", [(512, 40, 64), (128, 16, 70), (320, 52, 60)])
+def test_split_recurrence_equals_whole(cuda_dev, H, B, T):
+    """lcb_lstm_rec_fwd_range: projecting the first scan steps, starting the recurrence on them and resuming it after the
+    rest of the projection (BLSTMEncoder.head_frac) gives the same activations, saved states and final states as one launch,
+    with ragged lengths (utterances that end / start inside either part) -- and still matches the oracle."""
+    from lstm_ctc_b200.blstm import BLSTMEncoder, ModelConfig
+    cfg, params, x, lens = make_case(H, H, 24, 2, B, T, True, seed=11)
+    lens[1] = 3                                   # ends inside the head part of the forward scan, starts in the tail of the backward one
+    x[1, 3:] = 0
+    dev = torch.device("cuda:0")
+    outs = []
+    for frac in (0.0, 0.3):
+        enc = BLSTMEncoder(ModelConfig(nnet_config(cfg)), dev)
+        enc.from_tf_dict(params)
+        enc.head_frac = frac
+        out = enc.forward(x.float().to(dev), lens.to(dev), training=True).float().clone()
+        ws = enc._workspace(T, B, True)
+        outs.append((out, [m.float().clone() for m in ws["M"]], [c.clone() for c in ws["cst"]], enc.encoder_state().clone()))
+    torch.cuda.synchronize()
+    from lstm_ctc_b200 import _lib
+    assert _lib.lib().lcb_device_error(1) == 0
+    (o0, m0, c0, e0), (o1, m1, c1, e1) = outs
+    valid = (torch.arange(T).unsqueeze(1) < lens.unsqueeze(0)).reshape(T * B).to(dev)      # rows n = t*B + b of live frames
+    assert (o0 - o1).abs().max().item() < 2e-3 * o0.abs().max().item()
+    for a, b in zip(m0, m1):
+        assert (a - b).abs().max().item() < 2e-3
+    for a, b in zip(c0, c1):
+        assert (a[valid] - b[valid]).abs().max().item() < 2e-3 * max(1.0, a[valid].abs().max().item())
+    assert (e0 - e1).abs().max().item() < 2e-3 * max(1.0, e0.abs().max().item())
+    ref, _ = oracle.blstm_forward(params, cfg, x, lens)
+    out_bt = o1.view(T, B, -1).permute(1, 0, 2).cpu().double()
+    assert (out_bt - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
