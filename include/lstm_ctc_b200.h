@@ -80,6 +80,14 @@ int lcb_gemm16(int M, int N, int K,
                const void* B, int ldb, int b_layout, int b_dtype,
                void* C, int ldc, int c_dtype,
                const float* bias, int accumulate, void* stream);
+/* Same, with inverted dropout fused into the epilogue: C = dropout(op(A)*op(B) + bias), where element (row, col) of C uses
+ * element mask_base + row*ldc + col of the counter-based mask stream of lcb_dropout16 / lcb_dropout_mask (seed).  Replaces
+ * DropoutWrapper(output_keep_prob) on the layer output h = m*W_proj (nnet/bilstm.py:128,137) and, with the same seed, the
+ * mask on its gradient.  keep_prob == 1: identical to lcb_gemm16.  Needs a 16-byte aligned C and (mask_base | ldc) % 4 == 0. */
+int lcb_gemm16_dropout(int M, int N, int K, const void* A, int lda, int a_layout, int a_dtype,
+                       const void* B, int ldb, int b_layout, int b_dtype,
+                       void* C, int ldc, int c_dtype, const float* bias, int accumulate,
+                       float keep_prob, unsigned long long seed, unsigned long long mask_base, void* stream);
 /* caps the persistent grid of subsequent lcb_gemm16 launches (1..148 CTAs); returns the previous cap.  Used when a
  * GEMM runs on a side stream next to a cluster kernel that owns part of the SMs. */
 int lcb_gemm_set_max_ctas(int n);

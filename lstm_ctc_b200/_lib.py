@@ -78,6 +78,8 @@ _SIGS = {
     "lcb_gemm_set_max_ctas": (c_int, [c_int]),
     "lcb_gemm16": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                            c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "lcb_gemm16_dropout": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                                   c_void_p, c_int, c_int, c_void_p, c_int, c_float, ctypes.c_ulonglong, ctypes.c_ulonglong, c_void_p]),
     "lcb_gemm16_simt_check": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                       c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "lcb_split_f32_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

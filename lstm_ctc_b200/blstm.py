@@ -418,10 +418,12 @@ class BLSTMEncoder:
                 main.wait_event(tail_done)
                 rec(Tc, T)
             Hout = ws["Hout"][i]
+            # h = m * W_proj with DropoutWrapper(output_keep_prob) (bilstm.py:128,137) applied in the GEMM epilogue: element
+            # [n, d*P + p] of Hout uses element n*2P + d*P + p of the layer's mask stream
+            drop = (c.keep_prob, self.dropout_seed(i)) if (training and c.keep_prob < 1.0) else None
             for d in range(2):
-                gemm(ws["M"][i][:, d * c.Hp:(d + 1) * c.Hp], self._bf[("WpT16", i)][d], 0, 0, out=Hout[:, d * c.P:(d + 1) * c.P])
-            if training and c.keep_prob < 1.0:
-                self._dropout(Hout, i)              # DropoutWrapper(output_keep_prob), bilstm.py:128,137
+                gemm(ws["M"][i][:, d * c.Hp:(d + 1) * c.Hp], self._bf[("WpT16", i)][d], 0, 0, out=Hout[:, d * c.P:(d + 1) * c.P],
+                     dropout=(drop + (d * c.P,)) if drop else None)
             if i == 0 and c.residual0:              # finput = finput + concat(...)  iff input_dim == 2*num_projects (bilstm.py:199-200)
                 _lib.check(L.lcb_add_f16(_lib.ptr(Hout), _lib.ptr(ws["X0"]), Hout.numel(), st), "lcb_add_f16")
             X = Hout
@@ -441,7 +443,7 @@ class BLSTMEncoder:
         return torch.cat(out, 1)
 
     # ------------------------------------------------------------------ backward
-    def backward(self, dXtop, bucket_ready=None):
+    def backward(self, dXtop, bucket_ready=None, top_dropped=False):
         """dXtop [T*B, 2P] bf16 = d loss / d encoder output.  Accumulates parameter gradients into
         params.gflat (which the caller zeroed).  bucket_ready(name_list) is called as soon as the
         gradients of a layer are final (data-parallel all-reduce hook).
@@ -542,7 +544,7 @@ class BLSTMEncoder:
             k = i & 1
             if overlap and (i + 2) in side_done:
                 main.wait_event(side_done[i + 2])             # buffer set k is free again
-            if c.keep_prob < 1.0:
+            if c.keep_prob < 1.0 and i == c.num_layers - 1 and not top_dropped:
                 self._dropout(dH, i)                # same (seed, index) mask as the forward pass, on the gradient
             dM, dG = ws["dM"], ws["dG"][k]
             for d in range(2):
@@ -562,7 +564,9 @@ class BLSTMEncoder:
                 dXn = ws["dX"][k]
                 if overlap and (i + 1) in side_done:
                     main.wait_event(side_done[i + 1])         # layer i+1's wgrad still reads this buffer as its dH
-                gemm(dG, self._bf[("Wx", i)], 0, 1, out=dXn)        # dX = dG * W_x
+                # dX = dG * W_x, with the mask of layer i-1's output dropout (same seed and indices as forward) in the epilogue
+                gemm(dG, self._bf[("Wx", i)], 0, 1, out=dXn,
+                     dropout=(c.keep_prob, self.dropout_seed(i - 1), 0) if c.keep_prob < 1.0 else None)
                 dH = dXn
             pending = (i, dH_this)
         wgrad(pending[0], pending[1], mark())

@@ -30,6 +30,16 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;          // 64 bf16 = 128 B = one swizzle row
 constexpr int GEMM_THREADS = 192;
 
+// optional inverted dropout fused into the epilogue (DropoutWrapper(output_keep_prob) of nnet/bilstm.py:128,137 on the layer
+// output, and the same mask on its gradient): element (row, col) of C is element base + row*ldc + col of the counter-based
+// mask stream of lcb_dropout16 / lcb_dropout_mask.  thr16 >= 65536: off.
+struct GemmDropout {
+    uint32_t thr16;
+    float inv_keep;
+    unsigned long long seed;
+    unsigned long long base;
+};
+
 template <int BN> struct GemmCfg {
     static constexpr int STAGES = (BN == 256) ? 4 : 6;
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;         // 16 KB
@@ -46,7 +56,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmC, int tma_out,
                          void* __restrict__ Cptr, int ldc, const float* __restrict__ bias, int accumulate,
-                         int M, int N, int K, uint32_t idesc, int splits)
+                         int M, int N, int K, uint32_t idesc, int splits, const GemmDropout drop)
 {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
@@ -199,6 +209,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                                     r[h * 32 + j] = __float_as_uint(__uint_as_float(r[h * 32 + j]) + __shfl_sync(0xffffffffu, bv, j));
                             }
                         }
+                        if (drop.thr16 < 65536u) {                // one 64-bit hash decides four consecutive elements
+                            const unsigned long long e0 = drop.base + (unsigned long long)(m0 + q * 32 + lane) * (unsigned long long)ldc
+                                                          + (unsigned long long)c0;
+#pragma unroll
+                            for (int j4 = 0; j4 < CW / 4; ++j4) {
+                                const uint64_t w = rng_u64(drop.seed, (e0 >> 2) + j4);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    float v = rng_keep16(w, e, drop.thr16) ? __uint_as_float(r[4 * j4 + e]) * drop.inv_keep : 0.f;
+                                    if constexpr (CT == 2) v = fminf(fmaxf(v, -65504.f), 65504.f);
+                                    r[4 * j4 + e] = __float_as_uint(v);
+                                }
+                            }
+                        }
                         if (lane == 0) bulk_wait_group_read_pending<1>();   // the store that last used this box has read it
                         __syncwarp();
                         const uint32_t row_addr = stage_base + (uint32_t)buf * 4096u + (uint32_t)lane * 128u;
@@ -328,13 +352,14 @@ __global__ void gemm_simt_check_kernel(int M, int N, int K, const void* A, int a
 
 template <int BN, bool A_MN, bool B_MN, int CT>
 static int launch_gemm(int M, int N, int K, const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc,
-                       const float* bias, int accumulate, uint32_t fmt_bits, cudaStream_t st)
+                       const float* bias, int accumulate, uint32_t fmt_bits, cudaStream_t st, const GemmDropout& drop)
 {
     // output through TMA stores when the tensor is addressable by a tensor map (16-byte aligned base and pitch)
     const size_t es = CT == 0 ? 4 : 2;
     const int tma_out = (((uintptr_t)C & 15) == 0 && (((size_t)ldc * es) & 15) == 0) ? 1 : 0;
     CUtensorMap tc;
     memset(&tc, 0, sizeof(tc));
+    if (drop.thr16 < 65536u && (!tma_out || ((drop.base | (unsigned long long)ldc) & 3ull))) return LCB_ERR_MISALIGNED;
     if (tma_out && !make_tmap_2d_out(&tc, CT, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, CT == 0 ? 32 : 64)) return LCB_ERR_CUDA;
     const int tiles0 = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
     const int nkb0 = (K + GEMM_BK - 1) / GEMM_BK;
@@ -343,7 +368,7 @@ static int launch_gemm(int M, int N, int K, const CUtensorMap& ta, const CUtenso
     // Pick the s that minimises rounds/s, with a small charge per extra split for its fp32 reduce-add traffic.
     int splits = 1;
     const int ctas = g_gemm_max_ctas;
-    if (CT == 0 && tiles0 < 2 * ctas && nkb0 >= 64) {
+    if (CT == 0 && tiles0 < 2 * ctas && nkb0 >= 64 && drop.thr16 >= 65536u) {
         int smax = nkb0 / 16; if (smax > 48) smax = 48;
         double best = 1e30;
         for (int s = 1; s <= smax; ++s) {
@@ -366,26 +391,26 @@ static int launch_gemm(int M, int N, int K, const CUtensorMap& ta, const CUtenso
     const int tiles = tiles0 * splits;
     int nsm = g_gemm_max_ctas;
     int grid = tiles < nsm ? tiles : nsm;
-    g_launches += 1; kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tma_out, C, ldc, bias, accumulate, M, N, K, idesc, splits);
+    g_launches += 1; kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tma_out, C, ldc, bias, accumulate, M, N, K, idesc, splits, drop);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }
 
 template <int BN, int CT>
 static int dispatch_layout(int a_layout, int b_layout, int M, int N, int K, const CUtensorMap& ta, const CUtensorMap& tb,
-                           void* C, int ldc, const float* bias, int accumulate, uint32_t fmt, cudaStream_t st)
+                           void* C, int ldc, const float* bias, int accumulate, uint32_t fmt, cudaStream_t st, const GemmDropout& drop)
 {
-    if (!a_layout && !b_layout) return launch_gemm<BN, false, false, CT>(M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st);
-    if (!a_layout && b_layout) return launch_gemm<BN, false, true, CT>(M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st);
-    if (a_layout && !b_layout) return launch_gemm<BN, true, false, CT>(M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st);
-    return launch_gemm<BN, true, true, CT>(M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st);
+    if (!a_layout && !b_layout) return launch_gemm<BN, false, false, CT>(M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop);
+    if (!a_layout && b_layout) return launch_gemm<BN, false, true, CT>(M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop);
+    if (a_layout && !b_layout) return launch_gemm<BN, true, false, CT>(M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop);
+    return launch_gemm<BN, true, true, CT>(M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop);
 }
 template <int BN>
 static int dispatch_ct(int c_dtype, int a_layout, int b_layout, int M, int N, int K, const CUtensorMap& ta, const CUtensorMap& tb,
-                       void* C, int ldc, const float* bias, int accumulate, uint32_t fmt, cudaStream_t st)
+                       void* C, int ldc, const float* bias, int accumulate, uint32_t fmt, cudaStream_t st, const GemmDropout& drop)
 {
-    if (c_dtype == 0) return dispatch_layout<BN, 0>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st);
-    if (c_dtype == 1) return dispatch_layout<BN, 1>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st);
-    return dispatch_layout<BN, 2>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st);
+    if (c_dtype == 0) return dispatch_layout<BN, 0>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop);
+    if (c_dtype == 1) return dispatch_layout<BN, 1>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop);
+    return dispatch_layout<BN, 2>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop);
 }
 
 }  // namespace lcb
@@ -409,6 +434,20 @@ extern "C" int lcb_gemm16(int M, int N, int K, const void* A, int lda, int a_lay
                           const void* B, int ldb, int b_layout, int b_dtype,
                           void* C, int ldc, int c_dtype, const float* bias, int accumulate, void* stream)
 {
+    return lcb_gemm16_dropout(M, N, K, A, lda, a_layout, a_dtype, B, ldb, b_layout, b_dtype, C, ldc, c_dtype, bias, accumulate,
+                              1.0f, 0ull, 0ull, stream);
+}
+
+extern "C" int lcb_gemm16_dropout(int M, int N, int K, const void* A, int lda, int a_layout, int a_dtype,
+                                  const void* B, int ldb, int b_layout, int b_dtype,
+                                  void* C, int ldc, int c_dtype, const float* bias, int accumulate,
+                                  float keep_prob, unsigned long long seed, unsigned long long mask_base, void* stream)
+{
+    if (!(keep_prob > 0.f) || keep_prob > 1.f) return LCB_ERR_BAD_SHAPE;
+    if (keep_prob < 1.f && accumulate) return LCB_ERR_UNSUPPORTED;
+    GemmDropout drop;
+    drop.thr16 = keep_prob < 1.f ? keep_threshold16(keep_prob) : 65536u;
+    drop.inv_keep = 1.f / keep_prob; drop.seed = seed; drop.base = mask_base;
     int rc = gemm_check_args(M, N, K, A, lda, a_layout, a_dtype, B, ldb, b_layout, b_dtype, C, ldc, c_dtype, accumulate);
     if (rc != LCB_OK) return rc;
     if ((lda & 7) || (ldb & 7) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) return LCB_ERR_MISALIGNED;
@@ -427,8 +466,8 @@ extern "C" int lcb_gemm16(int M, int N, int K, const void* A, int lda, int a_lay
     if (!ok) return LCB_ERR_CUDA;
     // instruction-descriptor operand formats: 0 = F16, 1 = BF16 (a: bits 7-9, b: bits 10-12)
     const uint32_t fmt = ((a_dtype == 1 ? 1u : 0u) << 7) | ((b_dtype == 1 ? 1u : 0u) << 10);
-    if (bn256) return dispatch_ct<256>(c_dtype, a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st);
-    return dispatch_ct<128>(c_dtype, a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st);
+    if (bn256) return dispatch_ct<256>(c_dtype, a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop);
+    return dispatch_ct<128>(c_dtype, a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop);
 }
 
 extern "C" int lcb_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_layout, const void* B, int ldb,

@@ -197,10 +197,12 @@ class AcousticModel:
         gW, gb = self.params.g("out/Wall"), self.params.g("out/ball")
         dXtop = ws["dXtop"]
         ro = self.rows_out
+        # the top BiLSTM layer's output dropout acts on d loss / d encoder output: fused into the GEMMs that produce it
+        top_drop = (c.keep_prob, self.enc.dropout_seed(c.num_layers - 1)) if c.keep_prob < 1.0 else None
         if c.K == 0:
             dZ = ws["dZ"]
             _lib.check(L.lcb_pack_dlogits(_lib.ptr(dlogits), _lib.ptr(dZ), T, B, c.V, self.ldz, st), "lcb_pack_dlogits")
-            gemm(dZ[:, :ro], self._outbf, 0, 1, out=dXtop)                       # dX = dZ * W^T
+            gemm(dZ[:, :ro], self._outbf, 0, 1, out=dXtop, dropout=top_drop and top_drop + (0,))   # dX = dZ * W^T (+ top layer's mask)
             gemm(dZ[:, :ro], Xbf, 1, 1, out=gW)                                   # dW^T = dZ^T * X
             _lib.check(L.lcb_colsum(_lib.ptr(dZ), 1, N, ro, self.ldz, _lib.ptr(gb), st), "lcb_colsum")
         else:
@@ -211,12 +213,12 @@ class AcousticModel:
                 gemm(X16[n0:n0 + r], self._out16, 0, 0, out=Z[:, :ro], bias=self.params.w("out/ball"))   # recompute z
                 _lib.check(L.lcb_mos_bwd_dz(_lib.ptr(Z), _lib.ptr(dlogits), _lib.ptr(dZ), n0, r, self.ldz, T, B, c.V, c.K,
                                             c.tau, c.keep_prob, self._out_seed, st), "lcb_mos_bwd_dz")
-                gemm(dZ[:, :ro], self._outbf, 0, 1, out=dXtop[n0:n0 + r])
+                gemm(dZ[:, :ro], self._outbf, 0, 1, out=dXtop[n0:n0 + r], dropout=top_drop and top_drop + (n0 * 2 * c.P,))
                 gemm(dZ[:, :ro], Xbf[n0:n0 + r], 1, 1, out=gW, accumulate=(ci > 0))
                 _lib.check(L.lcb_colsum(_lib.ptr(dZ), 1, r, ro, self.ldz, _lib.ptr(gb), st), "lcb_colsum")
         if bucket_ready is not None:
             bucket_ready(["out/Wall", "out/ball"])
-        self.enc.backward(dXtop, bucket_ready)
+        self.enc.backward(dXtop, bucket_ready, top_dropped=top_drop is not None)
 
     # ------------------------------------------------------------------ loss
     def ctc(self, logits, labels, seq_len, check_labels=True):

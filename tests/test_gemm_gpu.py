@@ -106,3 +106,34 @@ def test_gemm_split_k_wgrad_shape(cuda_dev, accumulate):
     R = A.float().t() @ B.float() + (C0[:, 8:8 + N] if accumulate else 0)
     assert (out - R).abs().max() < 5e-3 * (K ** 0.5) * 0.01 + 1e-2
     assert torch.equal(Cfull[:, :8], C0[:, :8]) and torch.equal(Cfull[:, 8 + N:], C0[:, 8 + N:])   # neighbours untouched
+
+
+@pytest.mark.parametrize("odt", [torch.float16, torch.bfloat16, torch.float32])
+def test_fused_dropout_equals_separate_pass(cuda_dev, odt):
+    """lcb_gemm16_dropout: the epilogue mask is the (seed, element index) stream of lcb_dropout16 / lcb_dropout_mask --
+    written into a column slice of a wider tensor (mask_base = column offset, row stride = ldc), as the BiLSTM layer
+    output uses it -- so it is bit-identical to the GEMM followed by the separate dropout pass."""
+    from lstm_ctc_b200 import _lib
+    from lstm_ctc_b200.gemm import gemm
+    d = torch.device("cuda:0")
+    torch.manual_seed(5)
+    M, N, K, ld, off = 1000, 192, 136, 448, 64
+    A = (torch.randn(M, K, device=d) * 0.3).half()
+    B = (torch.randn(N, K, device=d) * 0.3).half()
+    keep, seed = 0.8, 0x1234567890ABCDEF
+    full = torch.zeros(M, ld, device=d, dtype=odt)
+    gemm(A, B, 0, 0, out=full[:, off:off + N], dropout=(keep, seed, off))
+    ref = torch.zeros(M, ld, device=d, dtype=odt)
+    gemm(A, B, 0, 0, out=ref[:, off:off + N])
+    mask = torch.empty(M * ld, dtype=torch.uint8, device=d)
+    _lib.check(_lib.lib().lcb_dropout_mask(_lib.ptr(mask), M * ld, keep, seed, _lib.stream_ptr()), "mask")
+    mask = mask.view(M, ld).bool()
+    want = torch.where(mask, ref.float() / keep, torch.zeros((), device=d)).to(odt)
+    torch.cuda.synchronize()
+    got, want = full[:, off:off + N].float(), want[:, off:off + N].float()
+    assert 0.75 < mask.float().mean().item() < 0.85
+    # the fused epilogue scales in fp32 and rounds once; the two-pass reference rounds, scales and rounds again
+    tol = {torch.float32: 1e-6, torch.float16: 2e-3, torch.bfloat16: 1.2e-2}[odt]
+    assert (got - want).abs().max().item() <= tol * max(1.0, want.abs().max().item())
+    assert torch.equal(got == 0, want == 0)
+    assert full[:, :off].abs().max().item() == 0 and full[:, off + N:].abs().max().item() == 0
