@@ -223,6 +223,17 @@ int lcb_greedy_decode(const float* logits, const int32_t* seq_len, int32_t* out,
 int lcb_posterior(const float* logits, float* out, long long rows, int V, float smooth_factor,
                   int apply_log, const float* log_prior, void* stream);
 
+/* ---- data formats either side of the path ------------------------------------
+ * replaces: _splice / _subsample of nnet/tfrecord.py:28-51 (edge-replicated +-context splicing, then every
+ *           subsample-th frame; output length floor(len / subsample)), applied to the zero-padded minibatch ON THE DEVICE.
+ *   in   [B, T, D] f32, lens [B] int32  ->  out [B, Tout, D*(1+lc+rc)] f32 (0 past the new length), lens_out [B] (nullable)
+ *   subsample <= 1: no subsampling.  Tout >= T / max(subsample, 1). */
+int lcb_splice_subsample(const float* in, const int32_t* lens, float* out, int32_t* lens_out,
+                         int B, int T, int D, int left_context, int right_context, int subsample, int Tout, void* stream);
+/* CRC-32C (Castagnoli, reflected 0x82F63B78) of a HOST buffer, continuing from `crc` (0 to start): the checksum of the
+ * TFRecord framing written by tf.python_io.TFRecordWriter (nnet/tfrecord.py:132) -- masked as ((c >> 15 | c << 17) + 0xa282ead8). */
+uint32_t lcb_crc32c(const void* data, size_t n, uint32_t crc);
+
 #ifdef __cplusplus
 }
 #endif

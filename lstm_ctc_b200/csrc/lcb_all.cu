@@ -7,3 +7,4 @@
 #include "mos.cu"
 #include "optim.cu"
 #include "decode.cu"
+#include "io.cu"

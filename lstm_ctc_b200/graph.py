@@ -105,8 +105,15 @@ class _Graph:
         x = batch["nnet_input"].to(dev, non_blocking=True)
         lens = batch["sequence_length"].to(dev, non_blocking=True)
         y = batch["nnet_target"].to(dev, non_blocking=True)
+        seq_len_host = batch["sequence_length"]
+        if self.source.device_splice is not None:                     # _splice / _subsample of tfrecord.py:28-51, on the device
+            from .tfrecord import splice_subsample_device
+            lc, rc, sub = self.source.device_splice
+            x, lens = splice_subsample_device(x, lens, lc, rc, sub)
+            seq_len_host = seq_len_host // max(sub, 1)
+            batch = dict(batch, sequence_length=seq_len_host)
         size = int((batch["nnet_target"] != -1).sum())                # graph.py:105-106
-        out = {"size": size, "sequence_length": batch["sequence_length"].numpy(), "summary": None,
+        out = {"size": size, "sequence_length": seq_len_host.numpy(), "summary": None,
                "raw_target": batch["nnet_target"].numpy()}
         if "train" in wanted:
             tc = self.train_cfg
@@ -151,8 +158,13 @@ class _Graph:
     def _infer(self, batch, wanted):
         m = self.model
         x = batch["nnet_input"].to(m.device, non_blocking=True).unsqueeze(0)      # graph.py:227
-        T = x.shape[1]
         lens = torch.tensor([batch["sequence_length"]], dtype=torch.int32, device=m.device)
+        if self.source.device_splice is not None:
+            from .tfrecord import splice_subsample_device
+            lc, rc, sub = self.source.device_splice
+            x, lens = splice_subsample_device(x, lens, lc, rc, sub)
+            batch = dict(batch, sequence_length=int(batch["sequence_length"]) // max(sub, 1))
+        T = x.shape[1]
         logits = m.forward_logits(x, lens, training=False)[0]                       # squeeze, graph.py:234
         out = {"filename": batch["filename"], "sequence_length": batch["sequence_length"]}
         if "logits" in wanted:

@@ -30,6 +30,11 @@ class PipelineTensor:
 class _BatchSource:
     def __init__(self, dataset, input_dim, batch_size, sequential=False):
         self.dataset, self.input_dim, self.batch_size, self.sequential = dataset, input_dim, batch_size, sequential
+        # (left_context, right_context, subsample) still to be applied -- on the device, by the Session -- when the dataset
+        # yields raw frames (tfrecord.dataset_from_tfrecords(device_splice=True)); host tensors then have the raw width
+        self.device_splice = getattr(dataset, "device_splice", None)
+        if self.device_splice is not None and not sequential:
+            self.input_dim = getattr(dataset, "raw_input_dim", input_dim)
         self._it = None
         self.pin = torch.cuda.is_available()
 
@@ -118,7 +123,9 @@ def create_pipeline_sequential(filename, tfrecord, num_epochs=1):
                     d = dict(r)
                     d["filename"] = f
                     yield d
-    src = _BatchSource(_Zip(), None, 1, sequential=True)
+    zipped = _Zip()
+    zipped.device_splice = getattr(tfrecord, "device_splice", None)
+    src = _BatchSource(zipped, None, 1, sequential=True)
     pipeline = {k: PipelineTensor(src, k) for k in ("filename", "nnet_input", "sequence_length")}
     return src.initialize, pipeline
 
