@@ -53,6 +53,18 @@ def train_flops_per_frame(w):
     return 3.0 * f
 
 
+def recurrent_flops_per_frame(w):
+    """The serial h_{t-1} * W_hh part of the forward flops (both directions, all layers) -- done inside the recurrence
+    kernels (forward) and the BPTT kernels (its dgrad); only its weight gradient is a bulk GEMM."""
+    return w["num_layers"] * 2 * 2.0 * w["P"] * 4 * w["H"]
+
+
+def gemm_family_flops_per_frame(w):
+    """Algorithmic flops the bulk GEMM launches of one training step carry per valid frame: everything of SURVEY 8(d)'s
+    3 x F_fwd except the recurrent product's forward and dgrad (which run in lstm_rec_fwd / lstm_rec_bwd)."""
+    return train_flops_per_frame(w) - 2.0 * recurrent_flops_per_frame(w)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -268,7 +280,7 @@ def main():
     dev_err = L.lcb_device_error(0)
 
     # ---- per-kernel durations, measured live with CUDA events on the launching stream ----
-    kt = kernel_breakdown(model, x, lens, y, w) if rank == 0 else None
+    kt = kernel_breakdown(model, x, lens, y, w, frames_local) if rank == 0 else None
 
     # ---- e2e through the public API with HOST buffers (H2D of inputs + D2H of the loss every step) ----
     e2e = None
@@ -303,7 +315,7 @@ def _peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
-def kernel_breakdown(model, x, lens, y, w):
+def kernel_breakdown(model, x, lens, y, w, frames):
     """Time each kernel family of one training step with CUDA events on the launching stream (one extra
     instrumented step after the timed region; the un-instrumented timed region above is the headline)."""
     from lstm_ctc_b200 import _lib, gemm as gemm_mod, blstm as blstm_mod, model as model_mod, ctc as ctc_mod
@@ -358,19 +370,24 @@ def kernel_breakdown(model, x, lens, y, w):
     Hp = (H + 63) // 64 * 64
     roof = None
     if dom in ("lstm_rec_fwd", "lstm_rec_bwd"):
-        # algorithmic flops of one launch: the folded recurrent product m_{t-1} W' for both directions, all steps
-        flops = 2.0 * 2 * T * B * Hp * 4 * Hp
-        ms1 = kernels[dom]["ms_total"] / kernels[dom]["launches"]
-        ach = flops / (ms1 * 1e-3) / 1e12
+        # algorithmic flops of the family per step: the folded recurrent product m_{t-1} W' (or its dgrad W' dz_t), both
+        # directions, all layers, VALID frames only (padded frames are not algorithmic work)
+        flops = recurrent_flops_per_frame(w) * frames
+        ms_all = kernels[dom]["ms_total"]
+        ach = flops / (ms_all * 1e-3) / 1e12
         roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus,
                 "traffic": None, "peak_source": how + " sustained (kernel timed inside a long step)",
-                "note": "serial recurrence: latency-bound (one barrier.cluster per time step); us_per_time_step = %.3f" % (ms1 * 1e3 / T)}
+                "note": "serial recurrence: latency-bound, not tensor- or HBM-bound (2 x T dependent steps per layer, 64 of 148 SMs); "
+                        "us_per_time_step = %.3f" % (ms_all * 1e3 / (Ltot * T))}
     elif dom == "gemm":
-        flops = train_flops_per_frame(w) * B * T
+        flops = gemm_family_flops_per_frame(w) * frames
         ms1 = kernels[dom]["ms_total"]
         ach = flops / (ms1 * 1e-3) / 1e12
-        roof = {"kernel": "gemm16 (all bulk GEMMs of the step)", "bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s",
-                "frac": ach / tf_sus, "traffic": None, "peak_source": how + " sustained"}
+        roof = {"kernel": "gemm16 (all bulk GEMMs of the step: projections, dgrad, wgrad, output layer)", "bound": "tensor",
+                "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": None,
+                "peak_source": how + " sustained",
+                "note": "algorithmic flops over VALID frames / summed GEMM launch time (weight-gradient GEMMs run on a capped grid "
+                        "beside the BPTT clusters, so their launch time overlaps other kernels)"}
     else:
         bytes_ = 8.0 * T * B * w["V"]
         ms1 = kernels.get("ctc_loss_grad", {"ms_total": 1.0, "launches": 1})

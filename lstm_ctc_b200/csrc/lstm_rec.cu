@@ -892,7 +892,10 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
             // LBO (next 8 units along K) = NUB*128 B, SBO (next 8 utterances) = 128 B; one K=16 MMA step = 2*NUB*128 B
             const uint64_t bb0 = make_smem_desc_noswz(smem_u32(Bsm), NUB * 128, 128);
             const uint32_t b_lo0 = (uint32_t)bb0, b_hi = (uint32_t)(bb0 >> 32);
-            const uint32_t d_tmem = tmem_base + REC_TMEM_ACC;
+            // each issuer accumulates into ITS OWN accumulator (columns [iw*BG, iw*BG + BG)): the tensor pipe executes one
+            // thread's MMAs in issue order, so both partial sums -- and the sum the compute warps form from them -- are
+            // bit-reproducible run to run and independent of how the two threads interleave
+            const uint32_t d_tmem = tmem_base + REC_TMEM_ACC + (uint32_t)(iw * BG);
             const int nk = Hp >> 4;
             for (int s = 0; s < S && ok; ++s) {
                 REC_PROBE(0);
@@ -961,6 +964,9 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
             }
             tmem_st_16x256b_x1(t_addr, a0);
             tmem_st_16x256b_x1(t_addr + (16u << 16), a1);
+            const uint32_t zz[4] = {0u, 0u, 0u, 0u};               // the second issuer's accumulator starts from zero
+            tmem_st_16x256b_x1(t_addr + BG, zz);
+            tmem_st_16x256b_x1(t_addr + BG + (16u << 16), zz);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -978,14 +984,16 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
             tc_fence_after();
             float zi[2], zj[2], zf[2], zo[2];
             {
-                uint32_t a0[4], a1[4];
-                tmem_ld_16x256b_x1(t_addr, a0);                       // (i | j) x 2 utts
+                uint32_t a0[4], a1[4], b0[4], b1[4];
+                tmem_ld_16x256b_x1(t_addr, a0);                       // (i | j) x 2 utts: x-part + issuer 0's K steps
                 tmem_ld_16x256b_x1(t_addr + (16u << 16), a1);         // (f | o)
+                tmem_ld_16x256b_x1(t_addr + BG, b0);                  // issuer 1's K steps
+                tmem_ld_16x256b_x1(t_addr + BG + (16u << 16), b1);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    zi[j] = __uint_as_float(a0[j]); zj[j] = __uint_as_float(a0[2 + j]);
-                    zf[j] = __uint_as_float(a1[j]); zo[j] = __uint_as_float(a1[2 + j]);
+                    zi[j] = __uint_as_float(a0[j]) + __uint_as_float(b0[j]); zj[j] = __uint_as_float(a0[2 + j]) + __uint_as_float(b0[2 + j]);
+                    zf[j] = __uint_as_float(a1[j]) + __uint_as_float(b1[j]); zo[j] = __uint_as_float(a1[2 + j]) + __uint_as_float(b1[2 + j]);
                 }
             }
             REC_PROBE(11);
@@ -1453,6 +1461,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
         // zero this warp's part of the accumulator (every MMA accumulates)
         const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
         tmem_st_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + (warp >> 2) * 8, z);
+        tmem_st_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + BG + (warp >> 2) * 8, z);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -1504,7 +1513,9 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
         if (lane == 0) {
             const uint64_t bb0 = make_smem_desc_sw128(smem_u32(Op), 16, 1024);
             const uint32_t b_lo0 = (uint32_t)bb0, b_hi = (uint32_t)(bb0 >> 32);
-            const uint32_t d_tmem = tmem_base + REC_TMEM_ACC;
+            // one accumulator per issuer (columns [iw*BG, iw*BG + BG)): each thread's MMAs execute in its issue order, so the
+            // partial sums and their sum in phase B are bit-reproducible whatever the interleaving of the two threads
+            const uint32_t d_tmem = tmem_base + REC_TMEM_ACC + (uint32_t)(iw * BG);
             for (int s = 0; s + 1 < T && ok; ++s) {                               // the last step's dm_{-1} is never used
                 REC_PROBE(0);
                 if (iw == 0) mbar_arrive_expect_tx(&mbar_op[s & 1], 4u * SLICE);
@@ -1653,9 +1664,12 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
                 if (ok) ok = mbar_wait(mbar_mma, (uint32_t)(s & 1));
                 REC_PROBE(13);
                 tc_fence_after();
-                uint32_t a[8];
+                uint32_t a[8], a2[8];
                 tmem_ld_32x32b_x8(acc_addr, a);            // unit row = lane of the quarter, utterances ub*8 .. ub*8+7
+                tmem_ld_32x32b_x8(acc_addr + BG, a2);      // the second issuer's partial sum
                 tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = __float_as_uint(__uint_as_float(a[i]) + __uint_as_float(a2[i]));
                 // staged as [32 units][BG utts] bf16, 16-byte chunks XOR-swizzled by the unit row (conflict-free here and
                 // for the owner's reads)
                 const uint32_t pw = pst_addr + (uint32_t)(((s & 1) * 4 + q) * PT);
@@ -1674,6 +1688,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
                 // off the chain: zero our part of the accumulator for the next step's MMAs
                 const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
                 tmem_st_32x32b_x8(acc_addr, z);
+                tmem_st_32x32b_x8(acc_addr + BG, z);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();

@@ -49,7 +49,8 @@ out_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* tiles = smem;
     float* pi_s = reinterpret_cast<float*>(smem + OUT_STAGES * OUT_STAGE_BYTES);            // [128][pis]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(pi_s + (size_t)OUT_BM * p.pis + 2);
+    float* bias_s = pi_s + (size_t)OUT_BM * p.pis;                                          // [KV + K] copy of the bias
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + p.KV + p.K + 2);
     bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bars) + 7) & ~(uintptr_t)7);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + OUT_STAGES;
@@ -70,6 +71,7 @@ out_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
+    for (int i = threadIdx.x; i < p.KV + p.K; i += blockDim.x) bias_s[i] = p.bias[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -178,12 +180,37 @@ out_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                         tmem_ld_32x32b_x32(t_addr + c0, r);
                         tmem_ld_wait();
                         if (K > 0) {
+                            // phase 1 (independent per column -> instruction-level parallelism): th[j] = dropout mask * tanh(z + b).
+                            // One 64-bit hash decides four consecutive elements of the [N, K*V] mask stream (moe.py:61); the
+                            // element index n*KV + col is not 4-aligned in general, so the hash is refreshed at block boundaries.
+                            float th[32];
+                            const int colb = c_base + c0;
+                            if (p.thr < 65536u) {
+                                const unsigned long long e0 = (unsigned long long)n * (unsigned long long)KV + (unsigned long long)colb;
+                                const int ph = (int)(e0 & 3ull);
+                                unsigned long long W[9];                   // the <= 9 four-element blocks these 32 columns touch
+#pragma unroll
+                                for (int q4 = 0; q4 < 9; ++q4) W[q4] = rng_u64(p.seed_d, (e0 >> 2) + q4);
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const int e = (ph + j) & 3;
+                                    const unsigned long long wd = (ph + (j & 3) >= 4) ? W[(j >> 2) + 1] : W[j >> 2];
+                                    const bool keep = rng_keep16(wd, e, p.thr);
+                                    const float bz = (colb + j < KV) ? bias_s[colb + j] : 0.f;
+                                    th[j] = keep ? tanhf_fast(__uint_as_float(r[j]) + bz) : 0.f;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const float bz = (colb + j < KV) ? bias_s[colb + j] : 0.f;
+                                    th[j] = tanhf_fast(__uint_as_float(r[j]) + bz);
+                                }
+                            }
+                            // phase 2 (serial in k): y_v = tau/keep * sum_k pi_k * th_k
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
-                                const int col = c_base + c0 + j;
-                                if (col < KV) {
-                                    if (rng_keepq(p.seed_d, (uint64_t)n * KV + col, p.thr))      // dropout on tau*tanh (moe.py:61)
-                                        accv += pir[kk] * tanhf_fast(__uint_as_float(r[j]) + __ldg(p.bias + col));
+                                if (colb + j < KV) {
+                                    accv = fmaf(pir[kk], th[j], accv);
                                     if (++kk == K) {
                                         if (rowok) orow[vv] = p.tau * p.inv_keep * accv;
                                         ++vv; kk = 0; accv = 0.f;
@@ -307,7 +334,8 @@ extern "C" int lcb_output_fwd(const void* X, int ldx, const void* Wall, const fl
     if (!make_tmap_2d_bf16(&tx, X, (uint64_t)p.N, (uint64_t)D2, (uint64_t)ldx, OUT_BM, OUT_BK)) return LCB_ERR_CUDA;
     if (!make_tmap_2d_bf16(&tw, Wall, (uint64_t)rows, (uint64_t)D2, (uint64_t)D2, OUT_BN, OUT_BK)) return LCB_ERR_CUDA;
     if (!make_tmap_2d_bf16(&twp, Wall, (uint64_t)rows, (uint64_t)D2, (uint64_t)D2, (uint32_t)p.Kp16, OUT_BK)) return LCB_ERR_CUDA;
-    const size_t smem = 1024 + (size_t)OUT_STAGES * OUT_STAGE_BYTES + (size_t)OUT_BM * p.pis * 4 + 512;
+    const size_t smem = 1024 + (size_t)OUT_STAGES * OUT_STAGE_BYTES + (size_t)OUT_BM * p.pis * 4 + (size_t)(p.KV + K + 2) * 4 + 512;
+    if (smem > 227 * 1024) return LCB_ERR_UNSUPPORTED;
     static size_t smem_set = 0;
     if (smem > smem_set) {
         if (cudaFuncSetAttribute(out_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return LCB_ERR_CUDA;

@@ -68,7 +68,7 @@ def random_tf_variables(cfg: ModelConfig, seed=None) -> Dict[str, torch.Tensor]:
 class AcousticModel:
     """Weights, activations and the forward / loss / backward / update sequence for one GPU."""
 
-    MOS_BWD_ROWS = 16384          # row chunk of the recompute backward (dz chunk stays L2 resident)
+    MOS_BWD_ROWS = 32768          # row chunk of the recompute backward (z + dz of a chunk, 115 MB at K*V = 576, stay L2 resident)
 
     def __init__(self, nnet_config: dict, device=None, seed=None, init=True):
         self.cfg = c = ModelConfig(nnet_config)
