@@ -130,12 +130,14 @@ def test_split_recurrence_equals_whole(cuda_dev, H, B, T):
     assert _lib.lib().lcb_device_error(1) == 0
     (o0, m0, c0, e0), (o1, m1, c1, e1) = outs
     valid = (torch.arange(T).unsqueeze(1) < lens.unsqueeze(0)).reshape(T * B).to(dev)      # rows n = t*B + b of live frames
-    assert (o0 - o1).abs().max().item() < 2e-3 * o0.abs().max().item()
+    # bit-identical: the split changes launches, not arithmetic (each MMA issuer thread owns its accumulator, so the sum
+    # order inside a time step is fixed)
+    assert torch.equal(o0, o1)
     for a, b in zip(m0, m1):
-        assert (a - b).abs().max().item() < 2e-3
+        assert torch.equal(a, b)
     for a, b in zip(c0, c1):
-        assert (a[valid] - b[valid]).abs().max().item() < 2e-3 * max(1.0, a[valid].abs().max().item())
-    assert (e0 - e1).abs().max().item() < 2e-3 * max(1.0, e0.abs().max().item())
+        assert torch.equal(a[valid], b[valid])
+    assert torch.equal(e0, e1)
     ref, _ = oracle.blstm_forward(params, cfg, x, lens)
     out_bt = o1.view(T, B, -1).permute(1, 0, 2).cpu().double()
     assert (out_bt - ref).abs().max().item() < 1e-2 * ref.abs().max().item()

@@ -80,7 +80,7 @@ def test_cli_init_train_validate_forward(cuda_dev, tmp_path, capfd):
     for (k, a), (_, b), n in zip(arks[0], arks[1], lens):
         assert a.shape == (n // 3, V)
         assert np.allclose(np.exp(a).sum(1), 1.0, atol=1e-4)
-        assert np.allclose(a, b, atol=2e-3)       # same inputs bit for bit; the recurrence's MMA issue order is not deterministic
+        assert np.array_equal(a, b)               # same inputs bit for bit -> same posteriors bit for bit
     # unsupported objective: fatal log + exit 1 (nnet-train.py:70-77)
     with pytest.raises(SystemExit) as e:
         cli.nnet_validate([scp, cfg, n1, "--batch-size", "4"])
