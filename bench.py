@@ -394,6 +394,16 @@ def kernel_breakdown(model, x, lens, y, w, frames):
         ach = bytes_ / (ms1["ms_total"] / ms1["launches"] * 1e-3) / 1e9
         roof = {"kernel": "ctc_loss_grad", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                 "traffic": None, "peak_source": how}
+    # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed `ncu --set full`
+    # capture of this same command (profiles/r01_ncu_traffic.json; null if the capture does not cover this workload)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        ent = tr.get(w.get("desc", ""), {}).get(dom if dom != "gemm" else "gemm")
+        if ent is not None:
+            roof["traffic"] = ent["dram_bytes_per_launch"]
+            roof["traffic_source"] = ent["source"]
+    except Exception:
+        pass
     return {"kernels": kernels, "roofline": roof}
 
 

@@ -94,17 +94,49 @@ class _Graph:
         self.reducer = _dist.GradientAllReducer(self.model.params)
         self.reducer.broadcast_weights()
         self._scal = torch.zeros(2, dtype=torch.float64, device=self.model.device)
+        self._staged = None            # (batch, device tensors, copy-done event) of the NEXT step, or the OutOfRangeError to raise
+        self._copy_stream = None
+        self._staged_epoch = 0
+
+    # host -> device staging ------------------------------------------------------
+    def _stage(self):
+        """Pull the next minibatch from the pipeline and start its host->device copy on the copy stream, so that it overlaps
+        the step that is still running (the reference's tf.data pipeline prefetches the same way, tfrecord.py:122-123).
+        End of data is remembered and raised by the step that would have consumed the batch."""
+        self._staged_epoch = getattr(self.source, "epoch_id", 0)
+        try:
+            batch = self.source.next()
+        except OutOfRangeError as e:
+            self._staged = e
+            return
+        dev = self.model.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(self._copy_stream):
+            x = batch["nnet_input"].to(dev, non_blocking=True)
+            lens = batch["sequence_length"].to(dev, non_blocking=True)
+            y = batch["nnet_target"].to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._staged = (batch, x, lens, y, ev)
 
     # one sess.run ----------------------------------------------------------------
     def step(self, wanted):
-        batch = self.source.next()                                   # may raise OutOfRangeError
         m = self.model
         dev = m.device
         if self.mode == "infer":
-            return self._infer(batch, wanted)
-        x = batch["nnet_input"].to(dev, non_blocking=True)
-        lens = batch["sequence_length"].to(dev, non_blocking=True)
-        y = batch["nnet_target"].to(dev, non_blocking=True)
+            return self._infer(self.source.next(), wanted)           # may raise OutOfRangeError
+        if self._staged is None or self._staged_epoch != getattr(self.source, "epoch_id", 0):
+            self._stage()                                             # first step, or the pipeline was re-initialised
+        staged, self._staged = self._staged, None
+        if isinstance(staged, OutOfRangeError):
+            self._staged = staged                                     # stay exhausted
+            raise staged
+        batch, x, lens, y, copied = staged
+        torch.cuda.current_stream().wait_event(copied)
+        for t in (x, lens, y):
+            t.record_stream(torch.cuda.current_stream())
+        self._stage()                                                 # next batch's copy runs beside this step
         seq_len_host = batch["sequence_length"]
         if self.source.device_splice is not None:                     # _splice / _subsample of tfrecord.py:28-51, on the device
             from .tfrecord import splice_subsample_device

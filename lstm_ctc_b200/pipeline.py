@@ -41,6 +41,7 @@ class _BatchSource:
     def initialize(self):
         """(Re)start the epoch.  Batches are assembled into pinned memory by a background thread, two ahead
         (the reference's tf.data pipeline prefetches on host threads as well, tfrecord.py:122-123)."""
+        self.epoch_id = getattr(self, "epoch_id", 0) + 1      # consumers drop anything they staged from the previous epoch
         self._it = iter(self.dataset)
         self._q = queue.Queue(maxsize=2)
         self._thread = threading.Thread(target=self._producer, args=(self._it, self._q), daemon=True)
