@@ -8,6 +8,7 @@ Same entry points, argument meaning and returned dict keys as the reference:
 The returned values are `Node` handles; `Session.run(nodes)` pulls ONE minibatch from the pipeline and
 executes the step on the sm_100a kernels (the equivalent of one sess.run of the reference, funcs.py:40-41).
 """
+import os
 import sys
 
 import numpy as np
@@ -17,6 +18,7 @@ from . import _lib
 from .model import AcousticModel
 from .pipeline import OutOfRangeError, PipelineTensor  # noqa: F401
 from . import dist as _dist
+from . import tf_bundle
 
 
 class Node:
@@ -37,17 +39,28 @@ def trainable_variables():
 
 class Saver:
     """tf.train.Saver(tf.trainable_variables()): trainable variables ONLY, in the reference's TF names
-    (no optimizer slots, no global_step -- nnet-train.py:83-84,95)."""
+    (no optimizer slots, no global_step -- nnet-train.py:83-84,95).
+
+    On disk a checkpoint is what TF's Saver writes for the same call: the V2 tensor bundle `<path>.index` +
+    `<path>.data-00000-of-00001` (+ the directory's `checkpoint` state file), written and read by `tf_bundle` without
+    TensorFlow, so `nnet.$iter` prefixes are interchangeable with the reference's (scripts/train.sh:123-124).  `restore`
+    also accepts the `torch.save` dict earlier versions of this package wrote at the bare path."""
 
     def __init__(self, var_list=None):
         self.model = var_list if var_list is not None else _default_model[0]
 
     def save(self, sess, path):
-        torch.save(self.model.state_dict(), path)
+        tf_bundle.write_bundle(path, self.model.state_dict())
         return path
 
     def restore(self, sess, path):
-        self.model.load_state_dict(torch.load(path, map_location="cpu"))
+        if tf_bundle.bundle_exists(path):
+            sd = {k: torch.from_numpy(v) for k, v in tf_bundle.read_bundle(path).items()}
+        elif os.path.isfile(path):
+            sd = torch.load(path, map_location="cpu")
+        else:
+            raise tf_bundle.BundleError("no checkpoint at %r (neither %s.index nor a state-dict file)" % (path, path))
+        self.model.load_state_dict(sd)
 
 
 def get_create_logits(string):

@@ -9,7 +9,7 @@ from lstm_ctc_b200.model import random_tf_variables
 
 H = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-T = 200
+T = int(sys.argv[3]) if len(sys.argv) > 3 else 200
 dev = torch.device("cuda:0")
 cfg = ModelConfig({"input_dim": 120, "num_layers": 1, "num_neurons": H, "num_projects": H, "num_targets": 72, "use_peepholes": True, "dropout_rate": 1.0})
 enc = BLSTMEncoder(cfg, dev)
