@@ -743,32 +743,42 @@ __device__ __forceinline__ void sig_tanh(float a, float c, float& sa, float& tc)
     tc = 2.f * (r * ea) - 1.f;
 }
 
-template <int BG> struct RecFwd2Cfg {
+// NSG = 2 (BG = 16 only): TWO independent 16-utterance groups per cluster share the resident weights.  Each has its own
+// warps, operand buffers, barriers, accumulators and exchange scratch and steps on its own; they meet only in the tensor
+// pipe.  Measured (profiles/r01_recprobe_fwd_nsg2.txt): the per-step chain of a 16-utterance group is ~3100 cycles against
+// ~3800 for a 32-utterance one (1 KB slices, half the operand ingress, half the gate math per thread-step), and the
+// 32-MMA weight pass (~1150 cycles whatever N is) of one group hides behind the exchange + gate math of the other.
+template <int BG, int NSG = 1> struct RecFwd2Cfg {
+    static_assert(NSG == 1 || BG == 16, "two sub-groups only for 16-utterance groups");
     static constexpr int NUB = BG / 8;                     // utterance blocks of 8 (core-matrix rows of the MMA B operand)
     static constexpr int NCW = 4 * NUB;                    // compute warps: (utterance block, TMEM lane quarter)
     static constexpr int NIW = 2;                          // MMA issuer warps: one thread issues a 128xBGx16 MMA every ~65 cycles,
                                                            // the tensor pipe retires one every ~36 -> two issuers keep it busy
-    static constexpr int THREADS = 32 * (NCW + NIW + 2);   // + loader warp + exchange warp
+    static constexpr int WPS = NCW + NIW + 2;              // warps per sub-group: + loader warp + exchange warp (multiple of 4)
+    static constexpr int THREADS = 32 * WPS * NSG;
     static constexpr int SLICE = 512 * NUB;                // bytes of one CTA's m_t slice: 32 units x BG utterances, fp16
     static constexpr int BARS = 1 + 2 * REC_SG + 2 + 2 + 1; // mma g[SG] gfree[SG] op[2] slice[2] acc
     __host__ __device__ static size_t op_bytes(int KB) { return (size_t)KB * 8 * NUB * 128; }    // one operand buffer (all K blocks)
     __host__ __device__ static size_t g_bytes() { return (size_t)REC_SG * BG * REC_GROW * 4; }
-    static size_t smem_bytes(int KB) { return 1024 + 2 * op_bytes(KB) + g_bytes() + 2 * SLICE + BARS * 8 + 64; }
+    __host__ __device__ static size_t sg_bytes(int KB) { return (2 * op_bytes(KB) + g_bytes() + 2 * SLICE + BARS * 8 + 1023) & ~(size_t)1023; }
+    static size_t smem_bytes(int KB) { return 1024 + NSG * sg_bytes(KB) + 64; }
 };
 
-template <int BG>
-__global__ void __launch_bounds__(RecFwd2Cfg<BG>::THREADS, 1)
+template <int BG, int NSG>
+__global__ void __launch_bounds__(RecFwd2Cfg<BG, NSG>::THREADS, 1)
 lstm_rec_fwd2_kernel(const RecFwdParams p)
 {
-    using Cfg = RecFwd2Cfg<BG>;
-    constexpr int SG = REC_SG, NUB = Cfg::NUB, NCW = Cfg::NCW, NIW = Cfg::NIW, SLICE = Cfg::SLICE;
+    using Cfg = RecFwd2Cfg<BG, NSG>;
+    constexpr int SG = REC_SG, NUB = Cfg::NUB, NCW = Cfg::NCW, NIW = Cfg::NIW, SLICE = Cfg::SLICE, WPS = Cfg::WPS;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = align_1024(smem_raw);
+    unsigned char* smem_all = align_1024(smem_raw);
     const int Hp = p.Hp, KB = Hp >> 6, NC = p.NC, T = p.T, B = p.B;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int role = warp < NCW ? 0 : (warp < NCW + NIW ? 1 : warp - NCW - NIW + 2);   // 0 compute | 1 MMA issuers | 2 loader | 3 exchange
-    const int rw = role == 0 ? warp : warp - NCW;
+    const int sg = warp / WPS, wl = warp - sg * WPS;       // sub-group, warp inside it (WPS % 4 == 0: wl % 4 == warp % 4)
+    int role = wl < NCW ? 0 : (wl < NCW + NIW ? 1 : wl - NCW - NIW + 2);   // 0 compute | 1 MMA issuers | 2 loader | 3 exchange
+    const int rw = role == 0 ? wl : wl - NCW;
     const uint32_t OPB = (uint32_t)Cfg::op_bytes(KB);
+    unsigned char* smem = smem_all + (size_t)sg * Cfg::sg_bytes(KB);
 
     // operand m_{t-1}: no-swizzle K-major core matrices (8 utterances x 8 units = 128 B), index (unit/8)*NUB + utt/8
     unsigned char* Bsm = smem;                                                   // [2][KB*8][NUB][128 B]
@@ -781,15 +791,19 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
     uint64_t* mbar_op = bars + 1 + 2 * SG;             // [2]  operand buffer: the slices of all NC CTAs have landed
     uint64_t* mbar_slice = bars + 3 + 2 * SG;          // [2]  this CTA's m_t slice is staged for the exchange warp
     uint64_t* mbar_acc = bars + 5 + 2 * SG;            //      the accumulator holds the next step's x-part (G tile): MMAs may accumulate
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::BARS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_all + (size_t)NSG * Cfg::sg_bytes(KB));
+    volatile int* pipe_turn = reinterpret_cast<volatile int*>(tmem_slot + 1);   // NSG = 2: whose weight pass the tensor pipe runs next
+    int* pipe_cnt = reinterpret_cast<int*>(tmem_slot + 2);
+    if (threadIdx.x == 0) { *pipe_turn = 0; *pipe_cnt = 0; }
 
     const uint32_t cta = cluster_ctarank();
     const int cid = (int)cluster_id_x();
-    const int dir = cid & 1, bg = cid >> 1;
-    const int b0 = bg * BG;                            // first utterance of this cluster's group
+    const int dir = cid & 1, bg = (cid >> 1) * NSG + sg;
+    const int b0 = bg * BG;                            // first utterance of this sub-group
     const size_t ld2 = (size_t)2 * Hp;
+    const int tl = (int)threadIdx.x - sg * WPS * 32;   // thread inside the sub-group
 
-    if (threadIdx.x == 0) {
+    if (tl == 0) {
         mbar_init(mbar_mma, NIW);
         mbar_init(mbar_acc, NCW);
         for (int s = 0; s < SG; ++s) { mbar_init(&mbar_g[s], 1); mbar_init(&mbar_gfree[s], NCW); }
@@ -802,12 +816,12 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
     {   // operand buffer 0 := m of the step before S0 (0 for a fresh start; a padded frame's saved m is 0 as well)
         uint4* bz = reinterpret_cast<uint4*>(Bsm);
         const int n16 = (int)(2 * OPB / 16);
-        for (int i = threadIdx.x; i < n16; i += blockDim.x) bz[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tl; i < n16; i += WPS * 32) bz[i] = make_uint4(0u, 0u, 0u, 0u);
         if (S0 > 0) {
             __syncthreads();
             const int tp = dir ? (T - S0) : (S0 - 1);
             const int pieces = (Hp >> 3) * BG;               // 16-byte pieces: (unit chunk of 8, utterance)
-            for (int i = threadIdx.x; i < pieces; i += blockDim.x) {
+            for (int i = tl; i < pieces; i += WPS * 32) {
                 const int u = i % BG, ch = i / BG;
                 if (b0 + u < B) {
                     const uint4 v = *reinterpret_cast<const uint4*>(p.Mout + ((size_t)tp * B + b0 + u) * ld2 + (size_t)dir * Hp + ch * 8);
@@ -823,10 +837,10 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
     const uint32_t tmem_base = *tmem_slot;
 
     // ---- W'^T slice -> tensor memory: row r of the slice lives in TMEM lane r, 16 fp16 per 8 columns ----
-    if (role == 0) {
+    if (role == 0) {                                   // (the compute warps of all sub-groups share the work)
         const int q = warp & 3;
         const __half* wrow = p.Wt + ((size_t)dir * 4 * Hp + (size_t)cta * 128 + q * 32 + lane) * Hp;
-        for (int ch = warp >> 2; ch < Hp / 16; ch += NUB) {
+        for (int ch = sg * NUB + (wl >> 2); ch < Hp / 16; ch += NUB * NSG) {
             const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(wrow + ch * 16));
             const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(wrow + ch * 16 + 8));
             const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -838,9 +852,12 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
     cluster_sync_all();          // weights resident; every CTA of the cluster is initialised before any multicast traffic
     tc_fence_after();
 
-    long long* prof = (blockIdx.x == 0 && lane == 0 && (role == 1 || (role == 0 && rw == 0))) ? g_rec_prof : nullptr;
-    const int prof_steps = g_rec_prof_steps;
+    // (debug probes: bits 16.. of the step count select the sub-group that is sampled)
+    long long* prof = (blockIdx.x == 0 && lane == 0 && sg == (g_rec_prof_steps >> 16) && ((role == 1 && rw == 0) || (role == 0 && rw == 0))) ? g_rec_prof : nullptr;
+    const int prof_steps = g_rec_prof_steps & 0xffff;
     const int nvalid = (B - b0) < BG ? (B - b0) : BG;           // utterances of this group that exist
+    if (nvalid <= 0) role = 4;                                  // an empty second sub-group (in every CTA of the cluster alike) idles
+    const bool paired = NSG == 2 && (cid >> 1) * NSG * BG + BG < B;   // both sub-groups of this cluster hold utterances
 
     bool ok = true;
     if (role == 2) {
@@ -866,7 +883,7 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
         // copies of an all-gather cost ~60 cycles per KB of operand; a bulk store to an L2-resident scratch followed by ONE
         // multicast bulk load costs ~750 cycles + 10 per KB and lands everywhere at once.
         if (lane == 0) {
-            unsigned char* scr = p.xch + (size_t)cid * 2 * NC * SLICE;
+            unsigned char* scr = p.xch + (size_t)(cid * NSG + sg) * 2 * NC * SLICE;
             const uint16_t mask = (uint16_t)((1u << NC) - 1u);
             for (int s = 0; s + 1 < S && ok; ++s) {
                 ok = mbar_wait(&mbar_slice[s & 1], (uint32_t)((s >> 1) & 1));
@@ -895,7 +912,7 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
             // each issuer accumulates into ITS OWN accumulator (columns [iw*BG, iw*BG + BG)): the tensor pipe executes one
             // thread's MMAs in issue order, so both partial sums -- and the sum the compute warps form from them -- are
             // bit-reproducible run to run and independent of how the two threads interleave
-            const uint32_t d_tmem = tmem_base + REC_TMEM_ACC + (uint32_t)(iw * BG);
+            const uint32_t d_tmem = tmem_base + REC_TMEM_ACC + (uint32_t)(sg * 2 * BG + iw * BG);
             const int nk = Hp >> 4;
             for (int s = 0; s < S && ok; ++s) {
                 REC_PROBE(0);
@@ -905,6 +922,15 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
                 if (ok && s > 0) ok = mbar_wait(&mbar_op[par], (uint32_t)(((s - 1) >> 1) & 1));
                 if (!ok) break;
                 REC_PROBE(1);
+                // Two sub-groups: the weight passes take strict turns.  Issued at the same time they would share the tensor
+                // pipe, both finish late and the sub-groups fall into phase (measured: 1430-cycle passes, no gain); one
+                // after the other, each pass runs at full rate under the other sub-group's exchange and gate math.
+                if (paired) {
+                    uint32_t spins = 0;
+                    while (*pipe_turn != sg) { if ((++spins & 0xfffu) == 0 && dev_has_error()) { ok = false; break; } }
+                    if (!ok) break;
+                }
+                REC_PROBE(4);
                 tc_fence_after();
                 const uint32_t b_lo_s = b_lo0 + ((par * OPB) >> 4);
                 if (S0 + s > 0) {                                            // m_{-1} = 0: scan step 0 is the x-part alone
@@ -914,11 +940,12 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
                 }
                 REC_PROBE(7);
                 umma_commit(mbar_mma);
+                if (paired && atomicAdd(pipe_cnt, 1) == NIW - 1) { *pipe_cnt = 0; __threadfence_block(); *pipe_turn = sg ^ 1; }
                 REC_PROBE(2);
             }
         }
         __syncwarp();
-    } else {
+    } else if (role == 0) {
         // ============================ compute warps: (utterance block, TMEM lane quarter) ============================
         const int ub = rw >> 2, q = rw & 3;                    // q == warp % 4: the TMEM lane quarter this warp may access
         const int up = lane >> 2, g = lane & 3;
@@ -944,7 +971,7 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
                 if (tp < len_j[j]) c_reg[j] = p.cst[((size_t)tp * B + b) * ((size_t)2 * Hp) + (size_t)dir * Hp + unit];
             }
         }
-        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + ub * 8;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + sg * 2 * BG + ub * 8;
         const float fbias = p.forget_bias;
         const size_t out0 = (size_t)dir * Hp + unit;
         // accumulator := hoisted x-part of step s2's pre-activations (G tile, forget bias folded in; padding utterances 0),
@@ -1388,32 +1415,39 @@ lstm_rec_bwd2_kernel(const RecBwdParams p)
 //     DSMEM copy per quarter; every owner receives 4 partial tiles (from the CTAs x' with x' & 3 == owner >> 2).
 // DSMEM traffic per CTA and step drops from 2 x BG KB (16-way reduce-scatter, the bottleneck of v1/v2: the SM's DSMEM
 // port moves ~16 B/clk in + out) to 2 x BG/4 KB; the all-gather rides the L2 multicast path (~750 cycles + 10 per KB).
-template <int BG> struct RecBwd3Cfg {
+// NSG = 2 (BG = 16): two independent 16-utterance groups per cluster share the resident weights, as in lstm_rec_fwd2_kernel;
+// their weight passes take strict turns on the tensor pipe.  Warp order: all compute warps (so that warp % 4 stays the
+// TMEM lane quarter), then the issuers, then the exchange warps.
+template <int BG, int NSG = 1> struct RecBwd3Cfg {
+    static_assert(NSG == 1 || BG == 16, "two sub-groups only for 16-utterance groups");
     static constexpr int NUB = BG / 8;
-    static constexpr int NCW = 4 * NUB;                    // compute warps: (utterance block, TMEM lane quarter)
-    static constexpr int NIW = 2;                          // MMA issuer warps
-    static constexpr int THREADS = 32 * (NCW + NIW + 1);   // + exchange warp
+    static constexpr int NCW = 4 * NUB;                    // compute warps per sub-group: (utterance block, TMEM lane quarter)
+    static constexpr int NIW = 2;                          // MMA issuer warps per sub-group
+    static constexpr int THREADS = 32 * NSG * (NCW + NIW + 1);   // + one exchange warp per sub-group
     static constexpr int SLICE = BG * 256;                 // dz slice of one CTA: 2 K sub-blocks x [BG rows x 128 B]
     static constexpr int PT = 32 * BG * 2;                 // partial dm tile [32 units][BG utts] bf16
     static constexpr int BARS = 10;                        // op[2] slice[2] red[2] acc mma (+pad)
-    static size_t smem_bytes() { return 1024 + 2 * 4 * (size_t)SLICE + 2 * (size_t)SLICE + 2 * 4 * (size_t)PT + 2 * 4 * (size_t)PT + BARS * 8 + 64; }
+    __host__ __device__ static constexpr size_t sg_bytes() { return (2 * 4 * (size_t)SLICE + 2 * (size_t)SLICE + 2 * 4 * (size_t)PT + 2 * 4 * (size_t)PT + BARS * 8 + 1023) & ~(size_t)1023; }
+    static size_t smem_bytes() { return 1024 + NSG * sg_bytes() + 64; }
 };
 
-template <int BG>
-__global__ void __launch_bounds__(RecBwd3Cfg<BG>::THREADS, 1)
+template <int BG, int NSG>
+__global__ void __launch_bounds__(RecBwd3Cfg<BG, NSG>::THREADS, 1)
 lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap tmDG)
 {
-    using Cfg = RecBwd3Cfg<BG>;
+    using Cfg = RecBwd3Cfg<BG, NSG>;
     constexpr int NUB = Cfg::NUB, NCW = Cfg::NCW, NIW = Cfg::NIW, SLICE = Cfg::SLICE, PT = Cfg::PT;
     constexpr int NCH = BG / 8;                        // 16-byte chunks per partial-tile row (8 utterances each)
     constexpr int SWS = 64 / BG;                       // row-swizzle period: chunk c of unit row u sits at c ^ ((u / SWS) & (NCH-1))
     constexpr int Hp = 512, NC = 16;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = align_1024(smem_raw);
+    unsigned char* smem_all = align_1024(smem_raw);
     const int T = p.T, B = p.B;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int role = warp < NCW ? 0 : (warp < NCW + NIW ? 1 : 2);       // compute | MMA issuers | exchange
-    const int rw = role == 0 ? warp : warp - NCW;
+    int role = warp < NSG * NCW ? 0 : (warp < NSG * (NCW + NIW) ? 1 : 2);       // compute | MMA issuers | exchange
+    const int sg = role == 0 ? warp / NCW : (role == 1 ? (warp - NSG * NCW) / NIW : warp - NSG * (NCW + NIW));
+    const int rw = role == 0 ? warp - sg * NCW : (role == 1 ? warp - NSG * NCW - sg * NIW : 0);
+    unsigned char* smem = smem_all + (size_t)sg * Cfg::sg_bytes();
 
     unsigned char* Op = smem;                                        // [2 parities][4 src][2 K sub-blocks][BG rows x 128 B]  SW128 K-major
     unsigned char* Stg = Op + 2 * 4 * SLICE;                         // [2 parities][SLICE]   own dz slice (same layout)
@@ -1425,16 +1459,20 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
     uint64_t* mbar_red = bars + 4;                     // [2] four partial dm tiles have landed
     uint64_t* mbar_acc = bars + 6;                     //     accumulator zeroed (count NCW)
     uint64_t* mbar_mma = bars + 7;                     //     partial dm tile complete (count NIW)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::BARS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_all + (size_t)NSG * Cfg::sg_bytes());
+    volatile int* pipe_turn = reinterpret_cast<volatile int*>(tmem_slot + 1);   // NSG = 2: whose weight pass the tensor pipe runs next
+    int* pipe_cnt = reinterpret_cast<int*>(tmem_slot + 2);
+    if (threadIdx.x == 0) { *pipe_turn = 0; *pipe_cnt = 0; }
 
     const uint32_t cta = cluster_ctarank();
     const int cid = (int)cluster_id_x();
-    const int dir = cid & 1, bg = cid >> 1;
+    const int dir = cid & 1, bg = (cid >> 1) * NSG + sg;
     const int b0 = bg * BG;
+    const bool paired = NSG == 2 && (cid >> 1) * NSG * BG + BG < B;   // both sub-groups of this cluster hold utterances
     const int kc = (int)(cta >> 2), mr = (int)(cta & 3);
     const size_t ld2 = (size_t)2 * Hp;
 
-    if (threadIdx.x == 0) {
+    if (lane == 0 && role == 0 && rw == 0) {
         mbar_init(&mbar_op[0], 1); mbar_init(&mbar_op[1], 1);
         mbar_init(&mbar_slice[0], NCW); mbar_init(&mbar_slice[1], NCW);
         mbar_init(&mbar_red[0], 1); mbar_init(&mbar_red[1], 1);
@@ -1442,7 +1480,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
         mbar_init(mbar_mma, NIW);
         fence_mbar_init();
     }
-    if (warp == NCW) tmem_alloc<512>(tmem_slot);
+    if (warp == NSG * NCW) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -1452,7 +1490,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
     if (role == 0) {
         const int q = warp & 3;
         const __nv_bfloat16* wrow = p.W + ((size_t)dir * Hp + mr * 128 + q * 32 + lane) * 4 * Hp + (size_t)kc * 512;
-        for (int ch = warp >> 2; ch < 32; ch += NUB) {
+        for (int ch = sg * NUB + (rw >> 2); ch < 32; ch += NUB * NSG) {        // (the compute warps of all sub-groups share the work)
             const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(wrow + ch * 16));
             const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(wrow + ch * 16 + 8));
             const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -1460,27 +1498,28 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
         }
         // zero this warp's part of the accumulator (every MMA accumulates)
         const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-        tmem_st_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + (warp >> 2) * 8, z);
-        tmem_st_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + BG + (warp >> 2) * 8, z);
+        tmem_st_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + sg * 2 * BG + (rw >> 2) * 8, z);
+        tmem_st_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + sg * 2 * BG + BG + (rw >> 2) * 8, z);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(mbar_acc);
     }
-    if (threadIdx.x == 0 && T > 1) mbar_arrive_expect_tx(&mbar_red[0], 4u * PT);      // armed before anybody can send
+    if (lane == 0 && role == 0 && rw == 0 && T > 1) mbar_arrive_expect_tx(&mbar_red[0], 4u * PT);      // armed before anybody can send
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
 
-    long long* prof = (blockIdx.x == 0 && lane == 0 && rw == 0 && role < 2) ? g_rec_prof : nullptr;
-    const int prof_steps = g_rec_prof_steps;
+    long long* prof = (blockIdx.x == 0 && lane == 0 && rw == 0 && role < 2 && sg == (g_rec_prof_steps >> 16)) ? g_rec_prof : nullptr;
+    const int prof_steps = g_rec_prof_steps & 0xffff;
     bool ok = true;
+    if (b0 >= B) role = 3;                             // an empty second sub-group (in every CTA of the cluster alike) idles
     if (role == 2) {
         // ============================ exchange warp: own dz slice -> L2 scratch -> multicast into the 4 CTAs of the group ============================
         // The staged slice is also the layer output dG[t, b0.., own 128 packed gate columns]: two 128B-swizzled TMA tensor
         // stores per step (rows past the batch end are clipped), off the serial chain.
         if (lane == 0) {
-            unsigned char* scr = p.xch + (size_t)cid * 2 * NC * SLICE;
+            unsigned char* scr = p.xch + (size_t)(cid * NSG + sg) * 2 * NC * SLICE;
             const uint16_t mask = (uint16_t)(0xFu << (4 * kc));
             const int col0 = dir * 4 * Hp + (int)cta * 128;
             for (int s = 0; s < T && ok; ++s) {
@@ -1515,7 +1554,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
             const uint32_t b_lo0 = (uint32_t)bb0, b_hi = (uint32_t)(bb0 >> 32);
             // one accumulator per issuer (columns [iw*BG, iw*BG + BG)): each thread's MMAs execute in its issue order, so the
             // partial sums and their sum in phase B are bit-reproducible whatever the interleaving of the two threads
-            const uint32_t d_tmem = tmem_base + REC_TMEM_ACC + (uint32_t)(iw * BG);
+            const uint32_t d_tmem = tmem_base + REC_TMEM_ACC + (uint32_t)(sg * 2 * BG + iw * BG);
             for (int s = 0; s + 1 < T && ok; ++s) {                               // the last step's dm_{-1} is never used
                 REC_PROBE(0);
                 if (iw == 0) mbar_arrive_expect_tx(&mbar_op[s & 1], 4u * SLICE);
@@ -1526,6 +1565,12 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
                 // the reduce buffer the NEXT step's partials go to: its previous contents were consumed in phase A of
                 // this step (our own dz slice, part of the operand just awaited, was staged after reading them)
                 if (iw == 0 && s + 2 < T) mbar_arrive_expect_tx(&mbar_red[(s + 1) & 1], 4u * PT);
+                if (paired) {                                                     // strict turns (see lstm_rec_fwd2_kernel)
+                    uint32_t spins = 0;
+                    while (*pipe_turn != sg) { if ((++spins & 0xfffu) == 0 && dev_has_error()) { ok = false; break; } }
+                    if (!ok) break;
+                }
+                REC_PROBE(4);
                 tc_fence_after();
                 const uint32_t b_lo_s = b_lo0 + (uint32_t)(((s & 1) * 4 * SLICE) >> 4);
 #pragma unroll 4
@@ -1536,11 +1581,12 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
                 }
                 REC_PROBE(7);
                 umma_commit(mbar_mma);
+                if (paired && atomicAdd(pipe_cnt, 1) == NIW - 1) { *pipe_cnt = 0; __threadfence_block(); *pipe_turn = sg ^ 1; }
                 REC_PROBE(2);
             }
         }
         __syncwarp();
-    } else {
+    } else if (role == 0) {
         // ============================ compute warps ============================
         const int ub = rw >> 2, q = rw & 3;
         const int up = lane >> 2, g = lane & 3;
@@ -1605,7 +1651,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
             }
         }
         const uint32_t red_addr = smem_u32(red), stg_addr = smem_u32(Stg), pst_addr = smem_u32(pst);
-        const uint32_t acc_addr = tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + ub * 8;
+        const uint32_t acc_addr = tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + sg * 2 * BG + ub * 8;
 
         for (int s = 0; s < T; ++s) {
             const int t = dir ? s : (T - 1 - s);
@@ -1676,7 +1722,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
                 sts_v4(pw + lane * (2 * BG) + ((ub ^ ((lane / SWS) & (NCH - 1))) << 4),
                        pack_bf16x2(__uint_as_float(a[0]), __uint_as_float(a[1])), pack_bf16x2(__uint_as_float(a[2]), __uint_as_float(a[3])),
                        pack_bf16x2(__uint_as_float(a[4]), __uint_as_float(a[5])), pack_bf16x2(__uint_as_float(a[6]), __uint_as_float(a[7])));
-                asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(NUB * 32) : "memory");   // the NUB warps of quarter q
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + sg * 4 + q), "n"(NUB * 32) : "memory");   // the NUB warps of quarter q of this sub-group
                 // (one bulk copy per quarter: 512 16-byte st.async per step were measured ~450 cycles slower than this)
                 if (ub == 0 && lane == 0) {
                     const uint32_t owner = (uint32_t)(4 * mr + q);
@@ -1717,7 +1763,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
     }
     tc_fence_before();
     cluster_sync_all();
-    if (warp == NCW) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
+    if (warp == NSG * NCW) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
 }
 
 // =================================================================================================
@@ -1736,6 +1782,12 @@ static int rec_version() {
     static int v = 0;
     if (v == 0) { const char* e = getenv("LCB_REC_V"); v = (e && atoi(e) == 1) ? 1 : 2; }
     return v;
+}
+
+static bool rec_pair() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LCB_REC_PAIR"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v != 0;
 }
 
 template <typename K, typename... Args>
@@ -1803,7 +1855,7 @@ static int choose_bg(int B, int nc, int which) {
     static int cap[2][17];
     if (cap[which][nc] == 0) {
         int n = which ? max_clusters(lstm_rec_bwd2_kernel<16>, RecBwd2Cfg<16>::THREADS, RecBwd2Cfg<16>::smem_bytes(nc), nc)
-                      : max_clusters(lstm_rec_fwd2_kernel<16>, RecFwd2Cfg<16>::THREADS, RecFwd2Cfg<16>::smem_bytes(nc * 32 / 64), nc);
+                      : max_clusters(lstm_rec_fwd2_kernel<16, 1>, RecFwd2Cfg<16>::THREADS, RecFwd2Cfg<16>::smem_bytes(nc * 32 / 64), nc);
         cap[which][nc] = n > 0 ? n : 1;
     }
     const int groups = (B + 15) / 16;
@@ -1884,8 +1936,12 @@ extern "C" int lcb_lstm_rec_fwd_range(const float* G, const void* WfoldT, const 
         const int bgs = choose_bg(B, nc, 0);
         const int ncl2 = 2 * ((B + bgs - 1) / bgs);
         if (bgs == 16)
-            return launch_cluster(lstm_rec_fwd2_kernel<16>, ncl2 * nc, RecFwd2Cfg<16>::THREADS, RecFwd2Cfg<16>::smem_bytes(Hp / 64), nc, (cudaStream_t)stream, p);
-        return launch_cluster(lstm_rec_fwd2_kernel<32>, ncl2 * nc, RecFwd2Cfg<32>::THREADS, RecFwd2Cfg<32>::smem_bytes(Hp / 64), nc, (cudaStream_t)stream, p);
+            return launch_cluster(lstm_rec_fwd2_kernel<16, 1>, ncl2 * nc, RecFwd2Cfg<16>::THREADS, RecFwd2Cfg<16>::smem_bytes(Hp / 64), nc, (cudaStream_t)stream, p);
+        // too many 16-utterance groups for one wave of clusters: two of them per cluster, stepping independently
+        // (LCB_REC_PAIR=0 keeps the older single lockstep group of 32 for A/B measurements)
+        if (rec_pair() && RecFwd2Cfg<16, 2>::smem_bytes(Hp / 64) <= 232448)
+            return launch_cluster(lstm_rec_fwd2_kernel<16, 2>, ncl2 * nc, RecFwd2Cfg<16, 2>::THREADS, RecFwd2Cfg<16, 2>::smem_bytes(Hp / 64), nc, (cudaStream_t)stream, p);
+        return launch_cluster(lstm_rec_fwd2_kernel<32, 1>, ncl2 * nc, RecFwd2Cfg<32>::THREADS, RecFwd2Cfg<32>::smem_bytes(Hp / 64), nc, (cudaStream_t)stream, p);
     }
     if (s_begin != 0 || s_end != T) return LCB_ERR_UNSUPPORTED;  // the v1 kernels run whole sequences only
     const int nsg = choose_nsg(B, nc, 0);
@@ -1912,15 +1968,19 @@ extern "C" int lcb_lstm_rec_bwd(const float* dM, const void* gates, const float*
     if (workspace && ((uintptr_t)workspace & 15)) return LCB_ERR_MISALIGNED;
     p.xch = (workspace && workspace_bytes >= lcb_lstm_rec_workspace_bytes(B, Hp)) ? (unsigned char*)workspace : nullptr;
     if (rec_version() == 2 && p.xch && Hp == 512 && !getenv("LCB_REC_BWD2")) {
-        const int bgs = choose_bg(B, nc, 1);
-        const int ncl3 = 2 * ((B + bgs - 1) / bgs);
+        const int bgs0 = choose_bg(B, nc, 1);
+        const bool pair = bgs0 == 32 && rec_pair();      // two 16-utterance sub-groups per cluster instead of one group of 32
+        const int bgs = pair ? 16 : bgs0;
+        const int ncl3 = 2 * ((B + bgs0 - 1) / bgs0);
         // dG as a 3-D tensor [T][B][8Hp] bf16, box = 64 columns x bgs utterances, 128B swizzle (= the MMA operand layout of a slice)
         CUtensorMap tm;
         if (((uintptr_t)dG & 15) || !make_tmap_3d(&tm, false, dG, (uint64_t)8 * Hp, (uint64_t)B, (uint64_t)T, (uint64_t)8 * Hp * 2,
                                                   (uint64_t)B * 8 * Hp * 2, 64, (uint32_t)bgs, 1, true)) return LCB_ERR_CUDA;
+        if (pair)
+            return launch_cluster(lstm_rec_bwd3_kernel<16, 2>, ncl3 * nc, RecBwd3Cfg<16, 2>::THREADS, RecBwd3Cfg<16, 2>::smem_bytes(), nc, (cudaStream_t)stream, p, tm);
         if (bgs == 16)
-            return launch_cluster(lstm_rec_bwd3_kernel<16>, ncl3 * nc, RecBwd3Cfg<16>::THREADS, RecBwd3Cfg<16>::smem_bytes(), nc, (cudaStream_t)stream, p, tm);
-        return launch_cluster(lstm_rec_bwd3_kernel<32>, ncl3 * nc, RecBwd3Cfg<32>::THREADS, RecBwd3Cfg<32>::smem_bytes(), nc, (cudaStream_t)stream, p, tm);
+            return launch_cluster(lstm_rec_bwd3_kernel<16, 1>, ncl3 * nc, RecBwd3Cfg<16>::THREADS, RecBwd3Cfg<16>::smem_bytes(), nc, (cudaStream_t)stream, p, tm);
+        return launch_cluster(lstm_rec_bwd3_kernel<32, 1>, ncl3 * nc, RecBwd3Cfg<32>::THREADS, RecBwd3Cfg<32>::smem_bytes(), nc, (cudaStream_t)stream, p, tm);
     }
     if (rec_version() == 2) {
         const int bgs = choose_bg(B, nc, 1);

@@ -57,7 +57,9 @@ def test_cli_init_train_validate_forward(cuda_dev, tmp_path, capfd):
     n0, n1 = os.path.join(tmp, "nnet.0"), os.path.join(tmp, "nnet.1")
     cli.nnet_init([scp, cfg, n0, "--objective", "ctc", "--batch-size", "4"])
     err = capfd.readouterr().err
-    assert "INFO:tensorflow:cv_loss = " in err and os.path.exists(n0)
+    assert "INFO:tensorflow:cv_loss = " in err
+    # the model is a TF checkpoint-V2 bundle under the prefix, as tf.train.Saver leaves it (nnet-init.py:77-79)
+    assert os.path.exists(n0 + ".index") and os.path.exists(n0 + ".data-00000-of-00001") and os.path.exists(os.path.join(tmp, "checkpoint"))
     cv0 = float(err.split("cv_loss = ")[1].split()[0])
     for it in range(3):                                               # three "epochs", each a fresh process in the reference
         cli.nnet_train([scp, cfg, n0 if it == 0 else n1, n1, "--objective", "ctc", "--optimizer", "adam", "--learn-rate", "0.004",

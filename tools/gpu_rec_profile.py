@@ -22,12 +22,13 @@ NS = 64
 buf = torch.zeros(NS * 16, dtype=torch.int64, device=dev)
 enc.forward(x, lens, training=True)
 torch.cuda.synchronize()
-L.lcb_debug_rec_profile(_lib.ptr(buf), NS)
+SGP = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+L.lcb_debug_rec_profile(_lib.ptr(buf), NS | (SGP << 16))
 enc.forward(x, lens, training=True)
 torch.cuda.synchronize()
 L.lcb_debug_rec_profile(None, 0)
 p = buf.cpu().numpy().reshape(NS, 16)
-names = {0: "ctl:start", 1: "ctl:op_ready", 4: "ctl:blk1_ready", 5: "ctl:blk2_ready", 6: "ctl:blk3_ready", 7: "ctl:mma_issued", 2: "ctl:mma_committed", 12: "cmp:fenced",
+names = {0: "ctl:start", 1: "ctl:op_ready", 4: "ctl:turn_acquired", 5: "ctl:blk2_ready", 6: "ctl:blk3_ready", 7: "ctl:mma_issued", 2: "ctl:mma_committed", 12: "cmp:fenced",
          8: "cmp:start", 9: "cmp:g_ready", 10: "cmp:mma_done", 11: "cmp:tmem_ld", 12: "cmp:z_read", 15: "cmp:math_done", 13: "cmp:sent_dsmem", 14: "cmp:global_stores"}
 print("H=%d B=%d  cluster: MT=%d NC=%d" % (H, B, enc.rec_mt, enc.rec_nc))
 steps = range(20, 60)

@@ -26,12 +26,13 @@ enc.backward(dX)
 torch.cuda.synchronize()
 enc.forward(x, lens, training=True)
 torch.cuda.synchronize()
-L.lcb_debug_rec_profile(_lib.ptr(buf), NS)
+SGP = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+L.lcb_debug_rec_profile(_lib.ptr(buf), NS | (SGP << 16))
 enc.backward(dX)
 torch.cuda.synchronize()
 L.lcb_debug_rec_profile(None, 0)
 p = buf.cpu().numpy().reshape(NS, 16)
-names = {0: "iss:start", 1: "iss:dz_ready", 7: "iss:mma_issued", 2: "iss:committed", 8: "cmp:start", 9: "cmp:prefetch_issued",
+names = {0: "iss:start", 1: "iss:dz_ready", 4: "iss:turn_acquired", 7: "iss:mma_issued", 2: "iss:committed", 8: "cmp:start", 9: "cmp:prefetch_issued",
          10: "cmp:red_ready", 11: "cmp:dz_done", 12: "cmp:arrived", 13: "cmp:mma_done", 14: "cmp:sent"}
 print("BPTT H=%d B=%d NC=%d" % (H, B, enc.rec_nc))
 print("step period: median %.0f cycles" % np.median(np.diff(p[20:60, 8])))
