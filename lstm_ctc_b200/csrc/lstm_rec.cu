@@ -773,7 +773,7 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem_all = align_1024(smem_raw);
     const int Hp = p.Hp, KB = Hp >> 6, NC = p.NC, T = p.T, B = p.B;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int sg = warp / WPS, wl = warp - sg * WPS;       // sub-group, warp inside it (WPS % 4 == 0: wl % 4 == warp % 4)
     int role = wl < NCW ? 0 : (wl < NCW + NIW ? 1 : wl - NCW - NIW + 2);   // 0 compute | 1 MMA issuers | 2 loader | 3 exchange
     const int rw = role == 0 ? wl : wl - NCW;
@@ -834,7 +834,7 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // (warp-uniform to the compiler as well)
 
     // ---- W'^T slice -> tensor memory: row r of the slice lives in TMEM lane r, 16 fp16 per 8 columns ----
     if (role == 0) {                                   // (the compute warps of all sub-groups share the work)
@@ -905,44 +905,47 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
         // hoisted x-part of the pre-activations (G tile), so issue order between the two threads does not matter.
         constexpr uint32_t idesc = make_idesc_bf16_f32(128, BG, 0, 0) & ~((7u << 7) | (7u << 10));
         const int iw = rw;
-        if (lane == 0) {
-            // LBO (next 8 units along K) = NUB*128 B, SBO (next 8 utterances) = 128 B; one K=16 MMA step = 2*NUB*128 B
-            const uint64_t bb0 = make_smem_desc_noswz(smem_u32(Bsm), NUB * 128, 128);
-            const uint32_t b_lo0 = (uint32_t)bb0, b_hi = (uint32_t)(bb0 >> 32);
-            // each issuer accumulates into ITS OWN accumulator (columns [iw*BG, iw*BG + BG)): the tensor pipe executes one
-            // thread's MMAs in issue order, so both partial sums -- and the sum the compute warps form from them -- are
-            // bit-reproducible run to run and independent of how the two threads interleave
-            const uint32_t d_tmem = tmem_base + REC_TMEM_ACC + (uint32_t)(sg * 2 * BG + iw * BG);
-            const int nk = Hp >> 4;
-            for (int s = 0; s < S && ok; ++s) {
-                REC_PROBE(0);
-                const uint32_t par = (uint32_t)(s & 1);
-                if (iw == 0 && s + 1 < S) mbar_arrive_expect_tx(&mbar_op[(s + 1) & 1], (uint32_t)(NC * SLICE));   // the buffer that step s fills
-                ok = mbar_wait(mbar_acc, (uint32_t)(s & 1));                 // accumulator = G tile of step s
-                if (ok && s > 0) ok = mbar_wait(&mbar_op[par], (uint32_t)(((s - 1) >> 1) & 1));
+        // The issuer warp stays converged and its address arithmetic warp-uniform (canonical warp index, broadcast TMEM base);
+        // one elected lane issues and commits.
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        // LBO (next 8 units along K) = NUB*128 B, SBO (next 8 utterances) = 128 B; one K=16 MMA step = 2*NUB*128 B
+        const uint64_t bb0 = make_smem_desc_noswz(smem_u32(Bsm), NUB * 128, 128);
+        const uint32_t b_lo0 = (uint32_t)bb0, b_hi = (uint32_t)(bb0 >> 32);
+        // each issuer accumulates into ITS OWN accumulator (columns [iw*BG, iw*BG + BG)): the tensor pipe executes one
+        // thread's MMAs in issue order, so the partial sums -- and the sum the compute warps form from them -- are
+        // bit-reproducible run to run and independent of how issuer threads interleave
+        const uint32_t d_tmem = tmem_base + REC_TMEM_ACC + (uint32_t)((sg * NIW + iw) * BG);
+        const int nk = Hp >> 4;
+        for (int s = 0; s < S && ok; ++s) {
+            REC_PROBE(0);
+            const uint32_t par = (uint32_t)(s & 1);
+            if (leader && iw == 0 && s + 1 < S) mbar_arrive_expect_tx(&mbar_op[(s + 1) & 1], (uint32_t)(NC * SLICE));   // the buffer that step s fills
+            ok = mbar_wait(mbar_acc, (uint32_t)(s & 1));                 // accumulator = G tile of step s
+            if (ok && s > 0) ok = mbar_wait(&mbar_op[par], (uint32_t)(((s - 1) >> 1) & 1));
+            if (!ok) break;
+            REC_PROBE(1);
+            // Two sub-groups: the weight passes take strict turns.  Issued at the same time they would share the tensor
+            // pipe, both finish late and the sub-groups fall into phase (measured: 1430-cycle passes, no gain); one
+            // after the other, each pass runs at full rate under the other sub-group's exchange and gate math.
+            if (paired) {
+                uint32_t spins = 0;
+                while (*pipe_turn != sg) { if ((++spins & 0xfffu) == 0 && dev_has_error()) { ok = false; break; } }
                 if (!ok) break;
-                REC_PROBE(1);
-                // Two sub-groups: the weight passes take strict turns.  Issued at the same time they would share the tensor
-                // pipe, both finish late and the sub-groups fall into phase (measured: 1430-cycle passes, no gain); one
-                // after the other, each pass runs at full rate under the other sub-group's exchange and gate math.
-                if (paired) {
-                    uint32_t spins = 0;
-                    while (*pipe_turn != sg) { if ((++spins & 0xfffu) == 0 && dev_has_error()) { ok = false; break; } }
-                    if (!ok) break;
-                }
-                REC_PROBE(4);
-                tc_fence_after();
-                const uint32_t b_lo_s = b_lo0 + ((par * OPB) >> 4);
-                if (S0 + s > 0) {                                            // m_{-1} = 0: scan step 0 is the x-part alone
+            }
+            REC_PROBE(4);
+            tc_fence_after();
+            const uint32_t b_lo_s = b_lo0 + ((par * OPB) >> 4);
+            if (S0 + s > 0) {                                            // m_{-1} = 0: scan step 0 is the x-part alone
 #pragma unroll 4
-                    for (int kk = iw; kk < nk; kk += NIW)
-                        umma_f16_ts_lohi(d_tmem, tmem_base + 8 * kk, b_lo_s + (2 * NUB * 128 / 16) * kk, b_hi, idesc, 1u);
-                }
-                REC_PROBE(7);
+                for (int kk = iw; kk < nk; kk += NIW)
+                    umma_f16_ts_elect(d_tmem, tmem_base + 8 * kk, b_lo_s + (2 * NUB * 128 / 16) * kk, b_hi, idesc, leader);
+            }
+            REC_PROBE(7);
+            if (leader) {
                 umma_commit(mbar_mma);
                 if (paired && atomicAdd(pipe_cnt, 1) == NIW - 1) { *pipe_cnt = 0; __threadfence_block(); *pipe_turn = sg ^ 1; }
-                REC_PROBE(2);
             }
+            REC_PROBE(2);
         }
         __syncwarp();
     } else if (role == 0) {
@@ -971,7 +974,7 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
                 if (tp < len_j[j]) c_reg[j] = p.cst[((size_t)tp * B + b) * ((size_t)2 * Hp) + (size_t)dir * Hp + unit];
             }
         }
-        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + sg * 2 * BG + ub * 8;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + sg * NIW * BG + ub * 8;
         const float fbias = p.forget_bias;
         const size_t out0 = (size_t)dir * Hp + unit;
         // accumulator := hoisted x-part of step s2's pre-activations (G tile, forget bias folded in; padding utterances 0),
@@ -991,9 +994,11 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
             }
             tmem_st_16x256b_x1(t_addr, a0);
             tmem_st_16x256b_x1(t_addr + (16u << 16), a1);
-            const uint32_t zz[4] = {0u, 0u, 0u, 0u};               // the second issuer's accumulator starts from zero
-            tmem_st_16x256b_x1(t_addr + BG, zz);
-            tmem_st_16x256b_x1(t_addr + BG + (16u << 16), zz);
+            if (NIW > 1) {
+                const uint32_t zz[4] = {0u, 0u, 0u, 0u};               // the second issuer's accumulator starts from zero
+                tmem_st_16x256b_x1(t_addr + BG, zz);
+                tmem_st_16x256b_x1(t_addr + BG + (16u << 16), zz);
+            }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -1011,11 +1016,13 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
             tc_fence_after();
             float zi[2], zj[2], zf[2], zo[2];
             {
-                uint32_t a0[4], a1[4], b0[4], b1[4];
+                uint32_t a0[4], a1[4], b0[4] = {0u, 0u, 0u, 0u}, b1[4] = {0u, 0u, 0u, 0u};
                 tmem_ld_16x256b_x1(t_addr, a0);                       // (i | j) x 2 utts: x-part + issuer 0's K steps
                 tmem_ld_16x256b_x1(t_addr + (16u << 16), a1);         // (f | o)
-                tmem_ld_16x256b_x1(t_addr + BG, b0);                  // issuer 1's K steps
-                tmem_ld_16x256b_x1(t_addr + BG + (16u << 16), b1);
+                if (NIW > 1) {
+                    tmem_ld_16x256b_x1(t_addr + BG, b0);              // issuer 1's K steps
+                    tmem_ld_16x256b_x1(t_addr + BG + (16u << 16), b1);
+                }
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
@@ -1443,7 +1450,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem_all = align_1024(smem_raw);
     const int T = p.T, B = p.B;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
     int role = warp < NSG * NCW ? 0 : (warp < NSG * (NCW + NIW) ? 1 : 2);       // compute | MMA issuers | exchange
     const int sg = role == 0 ? warp / NCW : (role == 1 ? (warp - NSG * NCW) / NIW : warp - NSG * (NCW + NIW));
     const int rw = role == 0 ? warp - sg * NCW : (role == 1 ? warp - NSG * NCW - sg * NIW : 0);
@@ -1484,7 +1491,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // (warp-uniform to the compiler as well)
 
     // ---- W' block -> tensor memory: lane = unit of M tile mr, columns = the 512 packed gate rows of K block kc (bf16 pairs) ----
     if (role == 0) {
@@ -1498,8 +1505,8 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
         }
         // zero this warp's part of the accumulator (every MMA accumulates)
         const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-        tmem_st_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + sg * 2 * BG + (rw >> 2) * 8, z);
-        tmem_st_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + sg * 2 * BG + BG + (rw >> 2) * 8, z);
+        tmem_st_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + sg * NIW * BG + (rw >> 2) * 8, z);
+        tmem_st_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + sg * NIW * BG + BG + (rw >> 2) * 8, z);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -1549,41 +1556,43 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
         // ============================ MMA issuers ============================
         constexpr uint32_t idesc = make_idesc_bf16_f32(128, BG, 0, 0);           // bf16 x bf16, A (TMEM) K-major
         const int iw = rw;
-        if (lane == 0) {
-            const uint64_t bb0 = make_smem_desc_sw128(smem_u32(Op), 16, 1024);
-            const uint32_t b_lo0 = (uint32_t)bb0, b_hi = (uint32_t)(bb0 >> 32);
-            // one accumulator per issuer (columns [iw*BG, iw*BG + BG)): each thread's MMAs execute in its issue order, so the
-            // partial sums and their sum in phase B are bit-reproducible whatever the interleaving of the two threads
-            const uint32_t d_tmem = tmem_base + REC_TMEM_ACC + (uint32_t)(sg * 2 * BG + iw * BG);
-            for (int s = 0; s + 1 < T && ok; ++s) {                               // the last step's dm_{-1} is never used
-                REC_PROBE(0);
-                if (iw == 0) mbar_arrive_expect_tx(&mbar_op[s & 1], 4u * SLICE);
-                ok = mbar_wait(mbar_acc, (uint32_t)(s & 1));                      // accumulator zeroed
-                if (ok) ok = mbar_wait(&mbar_op[s & 1], (uint32_t)((s >> 1) & 1)); // dz_t of the whole K block landed
+        // converged issuer warp, warp-uniform address arithmetic, one elected lane issues and commits (see umma_f16_ts_elect)
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        const uint64_t bb0 = make_smem_desc_sw128(smem_u32(Op), 16, 1024);
+        const uint32_t b_lo0 = (uint32_t)bb0, b_hi = (uint32_t)(bb0 >> 32);
+        // one accumulator per issuer (columns [iw*BG, iw*BG + BG)): each thread's MMAs execute in its issue order, so the
+        // partial sums and their sum in phase B are bit-reproducible whatever the interleaving of the issuer threads
+        const uint32_t d_tmem = tmem_base + REC_TMEM_ACC + (uint32_t)((sg * NIW + iw) * BG);
+        for (int s = 0; s + 1 < T && ok; ++s) {                               // the last step's dm_{-1} is never used
+            REC_PROBE(0);
+            if (leader && iw == 0) mbar_arrive_expect_tx(&mbar_op[s & 1], 4u * SLICE);
+            ok = mbar_wait(mbar_acc, (uint32_t)(s & 1));                      // accumulator zeroed
+            if (ok) ok = mbar_wait(&mbar_op[s & 1], (uint32_t)((s >> 1) & 1)); // dz_t of the whole K block landed
+            if (!ok) break;
+            REC_PROBE(1);
+            // the reduce buffer the NEXT step's partials go to: its previous contents were consumed in phase A of
+            // this step (our own dz slice, part of the operand just awaited, was staged after reading them)
+            if (leader && iw == 0 && s + 2 < T) mbar_arrive_expect_tx(&mbar_red[(s + 1) & 1], 4u * PT);
+            if (paired) {                                                     // strict turns (see lstm_rec_fwd2_kernel)
+                uint32_t spins = 0;
+                while (*pipe_turn != sg) { if ((++spins & 0xfffu) == 0 && dev_has_error()) { ok = false; break; } }
                 if (!ok) break;
-                REC_PROBE(1);
-                // the reduce buffer the NEXT step's partials go to: its previous contents were consumed in phase A of
-                // this step (our own dz slice, part of the operand just awaited, was staged after reading them)
-                if (iw == 0 && s + 2 < T) mbar_arrive_expect_tx(&mbar_red[(s + 1) & 1], 4u * PT);
-                if (paired) {                                                     // strict turns (see lstm_rec_fwd2_kernel)
-                    uint32_t spins = 0;
-                    while (*pipe_turn != sg) { if ((++spins & 0xfffu) == 0 && dev_has_error()) { ok = false; break; } }
-                    if (!ok) break;
-                }
-                REC_PROBE(4);
-                tc_fence_after();
-                const uint32_t b_lo_s = b_lo0 + (uint32_t)(((s & 1) * 4 * SLICE) >> 4);
+            }
+            REC_PROBE(4);
+            tc_fence_after();
+            const uint32_t b_lo_s = b_lo0 + (uint32_t)(((s & 1) * 4 * SLICE) >> 4);
 #pragma unroll 4
-                for (int idx = iw; idx < 32; idx += NIW) {                        // idx = src * 8 + kk
-                    const int src = idx >> 3, kk = idx & 7;
-                    umma_f16_ts_lohi(d_tmem, tmem_base + 8 * idx,
-                                     b_lo_s + (uint32_t)((src * SLICE + (kk >> 2) * (BG * 128)) / 16 + (kk & 3) * 2), b_hi, idesc, 1u);
-                }
-                REC_PROBE(7);
+            for (int idx = iw; idx < 32; idx += NIW) {                        // idx = src * 8 + kk
+                const int src = idx >> 3, kk = idx & 7;
+                umma_f16_ts_elect(d_tmem, tmem_base + 8 * idx,
+                                  b_lo_s + (uint32_t)((src * SLICE + (kk >> 2) * (BG * 128)) / 16 + (kk & 3) * 2), b_hi, idesc, leader);
+            }
+            REC_PROBE(7);
+            if (leader) {
                 umma_commit(mbar_mma);
                 if (paired && atomicAdd(pipe_cnt, 1) == NIW - 1) { *pipe_cnt = 0; __threadfence_block(); *pipe_turn = sg ^ 1; }
-                REC_PROBE(2);
             }
+            REC_PROBE(2);
         }
         __syncwarp();
     } else if (role == 0) {
@@ -1651,7 +1660,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
             }
         }
         const uint32_t red_addr = smem_u32(red), stg_addr = smem_u32(Stg), pst_addr = smem_u32(pst);
-        const uint32_t acc_addr = tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + sg * 2 * BG + ub * 8;
+        const uint32_t acc_addr = tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + sg * NIW * BG + ub * 8;
 
         for (int s = 0; s < T; ++s) {
             const int t = dir ? s : (T - 1 - s);

@@ -48,7 +48,10 @@ def test_training_graph_loss_decreases_and_logs(cuda_dev, capsys, tmp_path):
     # checkpoint of trainable variables only, TF names
     path = str(tmp_path / "nnet.1")
     nnet.Saver(nnet.trainable_variables()).save(sess, path)
-    sd = torch.load(path)
+    from lstm_ctc_b200 import tf_bundle
+    import os
+    assert os.path.exists(path + ".index") and os.path.exists(path + ".data-00000-of-00001")   # TF checkpoint-V2 bundle under the prefix
+    sd = {k: torch.from_numpy(a) for k, a in tf_bundle.read_bundle(path).items()}
     assert "fd0/frnn0/kernel" in sd and sd["fd0/frnn0/kernel"].shape == (20 + 32, 4 * 64) and "Variable_3" in sd
     assert not any(k.startswith(("m/", "v/", "global_step")) for k in sd)
 
