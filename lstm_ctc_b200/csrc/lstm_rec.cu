@@ -45,6 +45,9 @@ __device__ long long* g_rec_prof = nullptr;
 __device__ int g_rec_prof_steps = 0;
 #define REC_PROBE(slot) do { if (prof && s < prof_steps) prof[(size_t)s * 16 + (slot)] = clock64(); } while (0)
 
+#ifndef LCB_REC_NIW
+#define LCB_REC_NIW 2             // issuer warps of the v2 forward / v3 BPTT kernels (measured: 1 issuer = 657-cycle passes, 2 = 526)
+#endif
 constexpr int REC_BG = 16;        // utterances per cluster
 constexpr int REC_GROW = 132;     // padded fp32 row of a staged G tile: 2*132 = 8 (mod 32) -> conflict-free gate reads
 constexpr int REC_SG = 8;         // G prefetch ring depth
@@ -752,9 +755,8 @@ template <int BG, int NSG = 1> struct RecFwd2Cfg {
     static_assert(NSG == 1 || BG == 16, "two sub-groups only for 16-utterance groups");
     static constexpr int NUB = BG / 8;                     // utterance blocks of 8 (core-matrix rows of the MMA B operand)
     static constexpr int NCW = 4 * NUB;                    // compute warps: (utterance block, TMEM lane quarter)
-    static constexpr int NIW = 2;                          // MMA issuer warps: one thread issues a 128xBGx16 MMA every ~65 cycles,
-                                                           // the tensor pipe retires one every ~36 -> two issuers keep it busy
-    static constexpr int WPS = NCW + NIW + 2;              // warps per sub-group: + loader warp + exchange warp (multiple of 4)
+    static constexpr int NIW = LCB_REC_NIW;                // MMA issuer warps (each with its own accumulator)
+    static constexpr int WPS = NCW + NIW + 2;              // warps per sub-group: + loader warp + exchange warp
     static constexpr int THREADS = 32 * WPS * NSG;
     static constexpr int SLICE = 512 * NUB;                // bytes of one CTA's m_t slice: 32 units x BG utterances, fp16
     static constexpr int BARS = 1 + 2 * REC_SG + 2 + 2 + 1; // mma g[SG] gfree[SG] op[2] slice[2] acc
@@ -774,7 +776,10 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
     unsigned char* smem_all = align_1024(smem_raw);
     const int Hp = p.Hp, KB = Hp >> 6, NC = p.NC, T = p.T, B = p.B;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
-    const int sg = warp / WPS, wl = warp - sg * WPS;       // sub-group, warp inside it (WPS % 4 == 0: wl % 4 == warp % 4)
+    // warp order: the compute warps of all sub-groups first (warp % 4 stays the TMEM lane quarter), then per sub-group its
+    // issuer(s), loader and exchange warp
+    const int sg = warp < NSG * NCW ? warp / NCW : (warp - NSG * NCW) / (NIW + 2);
+    const int wl = warp < NSG * NCW ? warp - sg * NCW : NCW + (warp - NSG * NCW) - sg * (NIW + 2);     // warp inside the sub-group
     int role = wl < NCW ? 0 : (wl < NCW + NIW ? 1 : wl - NCW - NIW + 2);   // 0 compute | 1 MMA issuers | 2 loader | 3 exchange
     const int rw = role == 0 ? wl : wl - NCW;
     const uint32_t OPB = (uint32_t)Cfg::op_bytes(KB);
@@ -801,9 +806,8 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
     const int dir = cid & 1, bg = (cid >> 1) * NSG + sg;
     const int b0 = bg * BG;                            // first utterance of this sub-group
     const size_t ld2 = (size_t)2 * Hp;
-    const int tl = (int)threadIdx.x - sg * WPS * 32;   // thread inside the sub-group
 
-    if (tl == 0) {
+    if (role == 0 && rw == 0 && lane == 0) {
         mbar_init(mbar_mma, NIW);
         mbar_init(mbar_acc, NCW);
         for (int s = 0; s < SG; ++s) { mbar_init(&mbar_g[s], 1); mbar_init(&mbar_gfree[s], NCW); }
@@ -811,21 +815,28 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
         mbar_init(&mbar_slice[0], NCW); mbar_init(&mbar_slice[1], NCW);
         fence_mbar_init();
     }
-    if (warp == NCW) tmem_alloc<512>(tmem_slot);
+    if (warp == NSG * NCW) tmem_alloc<512>(tmem_slot);
     const int S0 = p.s_begin, S = p.s_end - p.s_begin;      // this launch runs scan steps S0 .. S0+S-1 (local index s = 0..S-1)
-    {   // operand buffer 0 := m of the step before S0 (0 for a fresh start; a padded frame's saved m is 0 as well)
-        uint4* bz = reinterpret_cast<uint4*>(Bsm);
+    {   // operand buffer 0 := m of the step before S0 (0 for a fresh start; a padded frame's saved m is 0 as well); the
+        // whole block fills the buffers of every sub-group
         const int n16 = (int)(2 * OPB / 16);
-        for (int i = tl; i < n16; i += WPS * 32) bz[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int g2 = 0; g2 < NSG; ++g2) {
+            uint4* bz = reinterpret_cast<uint4*>(smem_all + (size_t)g2 * Cfg::sg_bytes(KB));
+            for (int i = threadIdx.x; i < n16; i += blockDim.x) bz[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
         if (S0 > 0) {
             __syncthreads();
             const int tp = dir ? (T - S0) : (S0 - 1);
             const int pieces = (Hp >> 3) * BG;               // 16-byte pieces: (unit chunk of 8, utterance)
-            for (int i = tl; i < pieces; i += WPS * 32) {
-                const int u = i % BG, ch = i / BG;
-                if (b0 + u < B) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(p.Mout + ((size_t)tp * B + b0 + u) * ld2 + (size_t)dir * Hp + ch * 8);
-                    *reinterpret_cast<uint4*>(Bsm + ((size_t)ch * NUB + (u >> 3)) * 128 + (u & 7) * 16) = v;
+            for (int g2 = 0; g2 < NSG; ++g2) {
+                unsigned char* Bs2 = smem_all + (size_t)g2 * Cfg::sg_bytes(KB);
+                const int b02 = ((cid >> 1) * NSG + g2) * BG;
+                for (int i = threadIdx.x; i < pieces; i += blockDim.x) {
+                    const int u = i % BG, ch = i / BG;
+                    if (b02 + u < B) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(p.Mout + ((size_t)tp * B + b02 + u) * ld2 + (size_t)dir * Hp + ch * 8);
+                        *reinterpret_cast<uint4*>(Bs2 + ((size_t)ch * NUB + (u >> 3)) * 128 + (u & 7) * 16) = v;
+                    }
                 }
             }
         }
@@ -1083,7 +1094,7 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
     }
     tc_fence_before();
     cluster_sync_all();          // nobody leaves while multicast traffic addressed to it may still be in flight
-    if (warp == NCW) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
+    if (warp == NSG * NCW) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
 }
 
 // ---- BPTT v2 ----
@@ -1111,7 +1122,7 @@ lstm_rec_bwd2_kernel(const RecBwdParams p)
     unsigned char* smem = align_1024(smem_raw);
     const int Hp = p.Hp, NC = p.NC, T = p.T, B = p.B;
     const int MB = (Hp + 127) >> 7;                    // M tiles of 128 units
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int role = warp < NCW ? 0 : 1;
     const int rw = role == 0 ? warp : warp - NCW;
 
@@ -1144,7 +1155,7 @@ lstm_rec_bwd2_kernel(const RecBwdParams p)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // (warp-uniform to the compiler as well)
 
     // ---- W' -> tensor memory as A' = [units (lanes), own 128 gate rows (K')]: tile j in columns [64 j, 64 j + 64) ----
     if (role == 0) {
@@ -1176,7 +1187,9 @@ lstm_rec_bwd2_kernel(const RecBwdParams p)
         // ============================ MMA issuer warps: one 128-unit M tile each ============================
         constexpr uint32_t idesc = make_idesc_bf16_f32(128, BG, 0, 0);           // bf16 x bf16, A (TMEM) K-major
         const int jt = rw;
-        if (lane == 0 && jt < MB) {
+        // converged issuer warp, warp-uniform address arithmetic, one elected lane issues and commits (see umma_f16_ts_elect)
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        if (jt < MB) {
             const uint32_t a_tmem = tmem_base + jt * 64;
             const uint64_t bb0 = make_smem_desc_sw128(smem_u32(Bp), 16, 1024);
             const uint32_t b_lo0 = (uint32_t)bb0, b_hi = (uint32_t)(bb0 >> 32);
@@ -1188,17 +1201,17 @@ lstm_rec_bwd2_kernel(const RecBwdParams p)
                 REC_PROBE(1);
                 // the reduce buffer the NEXT step's partials go to: its previous contents were consumed in phase A
                 // of this step (all compute warps arrived on mbar_dz after reading them)
-                if (jt == 0 && s + 2 < T) mbar_arrive_expect_tx(&mbar_red[(s + 1) & 1], red_bytes);
+                if (leader && jt == 0 && s + 2 < T) mbar_arrive_expect_tx(&mbar_red[(s + 1) & 1], red_bytes);
                 tc_fence_after();
                 if (s + 1 < T) {                      // the last step's dm_{-1} is never used
+                    const uint32_t b_lo_s = b_lo0 + (uint32_t)(((s & 1) * (int)Cfg::bp_bytes()) / 16);
+                    umma_f16_ts_elect<false>(d_tmem, a_tmem, b_lo_s, b_hi, idesc, leader);
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)
-                        umma_f16_ts_lohi(d_tmem, a_tmem + 8 * kk,
-                                         b_lo0 + (uint32_t)(((s & 1) * (int)Cfg::bp_bytes() + (kk >> 2) * (BG * 128)) / 16 + (kk & 3) * 2), b_hi,
-                                         idesc, kk ? 1u : 0u);
+                    for (int kk = 1; kk < 8; ++kk)
+                        umma_f16_ts_elect<true>(d_tmem, a_tmem + 8 * kk, b_lo_s + (uint32_t)(((kk >> 2) * (BG * 128)) / 16 + (kk & 3) * 2), b_hi, idesc, leader);
                 }
                 REC_PROBE(7);
-                umma_commit(&mbar_mma[jt]);
+                if (leader) umma_commit(&mbar_mma[jt]);
                 REC_PROBE(2);
             }
         }
@@ -1429,7 +1442,7 @@ template <int BG, int NSG = 1> struct RecBwd3Cfg {
     static_assert(NSG == 1 || BG == 16, "two sub-groups only for 16-utterance groups");
     static constexpr int NUB = BG / 8;
     static constexpr int NCW = 4 * NUB;                    // compute warps per sub-group: (utterance block, TMEM lane quarter)
-    static constexpr int NIW = 2;                          // MMA issuer warps per sub-group
+    static constexpr int NIW = LCB_REC_NIW;                // MMA issuer warps per sub-group (each with its own accumulator)
     static constexpr int THREADS = 32 * NSG * (NCW + NIW + 1);   // + one exchange warp per sub-group
     static constexpr int SLICE = BG * 256;                 // dz slice of one CTA: 2 K sub-blocks x [BG rows x 128 B]
     static constexpr int PT = 32 * BG * 2;                 // partial dm tile [32 units][BG utts] bf16
@@ -1506,7 +1519,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
         // zero this warp's part of the accumulator (every MMA accumulates)
         const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
         tmem_st_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + sg * NIW * BG + (rw >> 2) * 8, z);
-        tmem_st_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + sg * NIW * BG + BG + (rw >> 2) * 8, z);
+        if (NIW > 1) tmem_st_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + sg * NIW * BG + BG + (rw >> 2) * 8, z);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -1721,10 +1734,12 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
                 tc_fence_after();
                 uint32_t a[8], a2[8];
                 tmem_ld_32x32b_x8(acc_addr, a);            // unit row = lane of the quarter, utterances ub*8 .. ub*8+7
-                tmem_ld_32x32b_x8(acc_addr + BG, a2);      // the second issuer's partial sum
+                if (NIW > 1) tmem_ld_32x32b_x8(acc_addr + BG, a2);      // the second issuer's partial sum
                 tmem_ld_wait();
+                if (NIW > 1) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) a[i] = __float_as_uint(__uint_as_float(a[i]) + __uint_as_float(a2[i]));
+                    for (int i = 0; i < 8; ++i) a[i] = __float_as_uint(__uint_as_float(a[i]) + __uint_as_float(a2[i]));
+                }
                 // staged as [32 units][BG utts] bf16, 16-byte chunks XOR-swizzled by the unit row (conflict-free here and
                 // for the owner's reads)
                 const uint32_t pw = pst_addr + (uint32_t)(((s & 1) * 4 + q) * PT);
@@ -1743,7 +1758,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
                 // off the chain: zero our part of the accumulator for the next step's MMAs
                 const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
                 tmem_st_32x32b_x8(acc_addr, z);
-                tmem_st_32x32b_x8(acc_addr + BG, z);
+                if (NIW > 1) tmem_st_32x32b_x8(acc_addr + BG, z);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();

@@ -260,15 +260,25 @@ __device__ __forceinline__ void umma_f16_ts_lohi(uint32_t tmem_d, uint32_t tmem_
 // The same, issued from a CONVERGED warp by the lane whose `leader` flag is set: when the operands are warp-uniform
 // expressions the compiler keeps them in uniform registers, instead of the ELECT / 4 x R2UR / branch waterfall it wraps
 // around every MMA issued from inside an `if (lane == 0)` region (~65 cycles per MMA and thread).
+template <bool ACCUMULATE = true>
 __device__ __forceinline__ void umma_f16_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi,
                                                   uint32_t idesc, uint32_t leader) {
-    asm volatile(
-        "{\n\t.reg .pred pe;\n\t.reg .b64 db;\n\t"
-        "mov.b64 db, {%2, %3};\n\t"
-        "setp.ne.b32 pe, %5, 0;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, 1;\n\t}\n"
-        ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(leader)
-        : "memory");
+    if (ACCUMULATE)
+        asm volatile(
+            "{\n\t.reg .pred pe;\n\t.reg .b64 db;\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "setp.ne.b32 pe, %5, 0;\n\t"
+            "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, 1;\n\t}\n"
+            ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(leader)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred pe;\n\t.reg .b64 db;\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "setp.ne.b32 pe, %5, 0;\n\t"
+            "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, 0;\n\t}\n"
+            ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(leader)
+            : "memory");
 }
 // registers -> TMEM: thread i of the warp writes 8 consecutive 32-bit columns of lane (quarter base + i)
 __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
