@@ -13,6 +13,7 @@ flat fp32 buffer; `to_tf_dict` / `from_tf_dict` convert to/from the reference's 
 shapes (fd{i}/frnn{i}/kernel, .../bias, .../w_{f,i,o}_diag, .../projection/kernel; bilstm.py:125-165).
 """
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -160,7 +161,8 @@ class BLSTMEncoder:
         self.rstream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None   # operand-refresh side stream
         self.use_graphs = True
         self.pstream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None   # projection of the later frames
-        self.head_frac = 0.3           # fraction of the scan steps whose pre-activations are projected before the recurrence starts
+        # fraction of the scan steps whose pre-activations are projected before the recurrence starts (LCB_HEAD_FRAC overrides)
+        self.head_frac = float(os.environ.get("LCB_HEAD_FRAC", "0.36"))
         self._refresh_graphs = None
         self._refresh_done = None
         self.seed_base = 777           # reference default --seed (nnet-train.py:141-142)

@@ -71,7 +71,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // provably warp-uniform: the producer and issuer warps
+                                                                                // stay converged, their operands in uniform registers
     const int lane = threadIdx.x & 31;
     const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
     const int tiles_n = (N + BN - 1) / BN;
@@ -93,11 +94,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        // (converged warp, one elected lane issues: no per-instruction ELECT / R2UR waterfall, see ptx.cuh)
+        {
+            const uint32_t leader = elect_one() ? 1u : 0u;
             int stage = 0; uint32_t phase = 0;
             bool ok = true;
             for (int work = blockIdx.x; work < nwork && ok; work += gridDim.x) {
@@ -107,21 +110,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 const int kb0 = split * kb_per, kb1 = min(nkb_all, kb0 + kb_per);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     if (!mbar_wait(&empty_bar[stage], phase ^ 1)) { ok = false; break; }
-                    unsigned char* sa = tiles + stage * Cfg::STAGE_BYTES;
-                    unsigned char* sb = sa + Cfg::A_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    const uint32_t sa = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + Cfg::A_BYTES;
+                    const uint32_t fb = smem_u32(&full_bar[stage]);
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     const int k0 = kb * GEMM_BK;
                     if constexpr (!A_MN) {
-                        tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);
+                        tma_load_2d_elect(sa, &tmA, fb, k0, m0, leader);
                     } else {
 #pragma unroll
-                        for (int bx = 0; bx < GEMM_BM / 64; ++bx) tma_load_2d(sa + bx * 8192, &tmA, &full_bar[stage], m0 + bx * 64, k0);
+                        for (int bx = 0; bx < GEMM_BM / 64; ++bx) tma_load_2d_elect(sa + bx * 8192, &tmA, fb, m0 + bx * 64, k0, leader);
                     }
                     if constexpr (!B_MN) {
-                        tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+                        tma_load_2d_elect(sb, &tmB, fb, k0, n0, leader);
                     } else {
 #pragma unroll
-                        for (int bx = 0; bx < BN / 64; ++bx) tma_load_2d(sb + bx * 8192, &tmB, &full_bar[stage], n0 + bx * 64, k0);
+                        for (int bx = 0; bx < BN / 64; ++bx) tma_load_2d_elect(sb + bx * 8192, &tmB, fb, n0 + bx * 64, k0, leader);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -130,7 +134,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         __syncwarp();
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        {
+            const uint32_t leader = elect_one() ? 1u : 0u;
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             bool ok = true;
@@ -153,12 +158,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                                                     : make_smem_desc_sw128(sa + k * 32, 16, 1024);
                         const uint64_t bdesc = B_MN ? make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
                                                     : make_smem_desc_sw128(sb + k * 32, 16, 1024);
-                        umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if (k == 0 && kb == kb0) umma_f16_ss_elect<false>(d_tmem, adesc, bdesc, idesc, leader);   // first MMA of the tile overwrites
+                        else umma_f16_ss_elect<true>(d_tmem, adesc, bdesc, idesc, leader);
                     }
-                    umma_commit(&empty_bar[stage]);           // smem slot reusable once these MMAs retire
+                    if (leader) umma_commit(&empty_bar[stage]);           // smem slot reusable once these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);                 // accumulator complete
+                if (leader) umma_commit(&tfull_bar[acc]);                 // accumulator complete
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }

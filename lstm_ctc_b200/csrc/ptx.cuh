@@ -234,6 +234,28 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uin
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// SS form issued from a converged warp by the lane whose `leader` flag is set (see umma_f16_ts_elect); the accumulate flag
+// is a template literal (a run-time predicate operand costs ~10 cycles per MMA)
+template <bool ACCUMULATE>
+__device__ __forceinline__ void umma_f16_ss_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t leader) {
+    if (ACCUMULATE)
+        asm volatile(
+            "{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %4, 0;\n\t"
+            "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, 1;\n\t}\n"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(leader) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %4, 0;\n\t"
+            "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, 0;\n\t}\n"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_elect(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %5, 0;\n\t"
+        "@pe cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}\n"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(leader)
+        : "memory");
+}
 // same, descriptors given as (lo, hi) words: only `lo` (start address field) changes between k-steps, so the
 // issue loop is one integer add per operand instead of rebuilding 64-bit descriptors
 __device__ __forceinline__ void umma_f16_ss_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
