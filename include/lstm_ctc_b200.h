@@ -153,6 +153,17 @@ int lcb_lstm_rec_fwd_range(const float* G, const void* WfoldT, const float* peep
 int lcb_lstm_rec_bwd(const float* dM, const void* gates, const float* cst, const void* Wfold, const float* peep,
                      const int32_t* lens, void* dG, float* dbias, float* dpeep,
                      int T, int B, int Hp, void* workspace, size_t workspace_bytes, void* stream);
+/* The same over scan steps [s_begin, s_end) only (scan step s visits frame T-1-s in the forward, s in the backward direction --
+ * the reverse of the forward pass).  A launch with s_end < T leaves, per cell, the recurrent part of d loss / d m of the next
+ * step and the carried d loss / d c in `carry` ([B,2,Hp,2] f32); a launch with s_begin > 0 resumes from them.  Launches over
+ * consecutive ranges in stream order equal one launch over [0, T) bit for bit (dbias / dpeep accumulate), so the caller can
+ * start BPTT when only the last frames' dM exist and compute the rest beside it.  LCB_ERR_UNSUPPORTED for a partial range
+ * unless lcb_lstm_rec_bwd_can_split(Hp). */
+int lcb_lstm_rec_bwd_range(const float* dM, const void* gates, const float* cst, const void* Wfold, const float* peep,
+                           const int32_t* lens, void* dG, float* dbias, float* dpeep,
+                           int T, int B, int Hp, int s_begin, int s_end, float* carry,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int lcb_lstm_rec_bwd_can_split(int Hp);
 
 /* ---- HBM-bound helpers -----------------------------------------------------------------
  * lcb_pack_input: pipeline tensor nnet_input [B,T,D] f32 (nnet/pipeline.py:35-61) -> time-major

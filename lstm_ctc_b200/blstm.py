@@ -163,6 +163,7 @@ class BLSTMEncoder:
         self.pstream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None   # projection of the later frames
         # fraction of the scan steps whose pre-activations are projected before the recurrence starts (LCB_HEAD_FRAC overrides)
         self.head_frac = float(os.environ.get("LCB_HEAD_FRAC", "0.36"))
+        self.bwd_split_frac = float(os.environ.get("LCB_BWD_SPLIT_FRAC", "0"))   # > 0: BPTT as two launches (lcb_lstm_rec_bwd_range)
         self._refresh_graphs = None
         self._refresh_done = None
         self.seed_base = 777           # reference default --seed (nnet-train.py:141-142)
@@ -555,10 +556,18 @@ class BLSTMEncoder:
             chain_issued = mark()                             # behind BPTT(i+1) and this layer's dropout / dM GEMMs
             peep = ps.w("L%d/peep" % i) if c.use_peepholes else None
             gpeep = ps.g("L%d/peep" % i) if c.use_peepholes else None
-            _lib.check(L.lcb_lstm_rec_bwd(_lib.ptr(dM), _lib.ptr(ws["gates"][i]), _lib.ptr(ws["cst"][i]),
-                                          _lib.ptr(self._bf[("fold", i)]), _lib.ptr(peep),
-                                          _lib.ptr(seq_len), _lib.ptr(dG), _lib.ptr(ps.g("L%d/bias" % i)), _lib.ptr(gpeep),
-                                          T, B, c.Hp, _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(), _lib.stream_ptr()), "lcb_lstm_rec_bwd")
+            # BPTT in one launch, or (bwd_split_frac > 0, cells the 4 x 4 kernel serves) as two launches over consecutive scan
+            # ranges joined by the carry buffer -- bit-identical; the hook for computing late rows of dM beside the first range
+            Tb = int(math.ceil(self.bwd_split_frac * T)) if self.bwd_split_frac > 0 and L.lcb_lstm_rec_bwd_can_split(c.Hp) else 0
+            ranges = [(0, T)] if (Tb < 1 or Tb >= T) else [(0, Tb), (Tb, T)]
+            if len(ranges) > 1 and "bwd_carry" not in ws:
+                ws["bwd_carry"] = torch.empty(B * 2 * c.Hp * 2, dtype=F32, device=self.device)
+            for (s0, s1) in ranges:
+                _lib.check(L.lcb_lstm_rec_bwd_range(_lib.ptr(dM), _lib.ptr(ws["gates"][i]), _lib.ptr(ws["cst"][i]),
+                                                    _lib.ptr(self._bf[("fold", i)]), _lib.ptr(peep),
+                                                    _lib.ptr(seq_len), _lib.ptr(dG), _lib.ptr(ps.g("L%d/bias" % i)), _lib.ptr(gpeep),
+                                                    T, B, c.Hp, s0, s1, _lib.ptr(ws.get("bwd_carry")),
+                                                    _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(), _lib.stream_ptr()), "lcb_lstm_rec_bwd_range")
             if pending is not None:
                 wgrad(pending[0], pending[1], chain_issued)   # layer i+1's weight gradients run beside this BPTT
             dH_this = dH

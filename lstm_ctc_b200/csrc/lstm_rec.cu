@@ -82,6 +82,9 @@ struct RecBwdParams {
     float* dpeep;                 // [2][3][Hp] += (nullable)
     int T, B, Hp, NC;
     unsigned char* xch;           // v3: L2 exchange scratch [clusters][2][NC][dz slice]
+    int s_begin, s_end;           // v3: scan steps [s_begin, s_end) of this launch (t = T-1-s forward, s backward direction)
+    float* carry;                 // v3: [B][2][Hp][2] (recurrent dm, carried dc) handed from one launch to the next (nullable
+                                  //     when the launch covers [0, T))
 };
 
 __device__ __forceinline__ unsigned char* align_1024(unsigned char* p) {
@@ -1463,6 +1466,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem_all = align_1024(smem_raw);
     const int T = p.T, B = p.B;
+    const int S0 = p.s_begin, S = p.s_end - p.s_begin;   // this launch runs scan steps S0 .. S0+S-1 (local index s = 0..S-1)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
     int role = warp < NSG * NCW ? 0 : (warp < NSG * (NCW + NIW) ? 1 : 2);       // compute | MMA issuers | exchange
     const int sg = role == 0 ? warp / NCW : (role == 1 ? (warp - NSG * NCW) / NIW : warp - NSG * (NCW + NIW));
@@ -1525,7 +1529,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
         __syncwarp();
         if (lane == 0) mbar_arrive(mbar_acc);
     }
-    if (lane == 0 && role == 0 && rw == 0 && T > 1) mbar_arrive_expect_tx(&mbar_red[0], 4u * PT);      // armed before anybody can send
+    if (lane == 0 && role == 0 && rw == 0 && S0 + 1 < T) mbar_arrive_expect_tx(&mbar_red[0], 4u * PT);      // armed before anybody can send
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
@@ -1542,12 +1546,12 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
             unsigned char* scr = p.xch + (size_t)(cid * NSG + sg) * 2 * NC * SLICE;
             const uint16_t mask = (uint16_t)(0xFu << (4 * kc));
             const int col0 = dir * 4 * Hp + (int)cta * 128;
-            for (int s = 0; s < T && ok; ++s) {
+            for (int s = 0; s < S && ok; ++s) {
                 ok = mbar_wait(&mbar_slice[s & 1], (uint32_t)((s >> 1) & 1));
                 if (!ok) break;
                 const uint32_t src = smem_u32(Stg + (s & 1) * SLICE);
-                const int t = dir ? s : (T - 1 - s);
-                if (s + 1 < T) {
+                const int t = dir ? (S0 + s) : (T - 1 - (S0 + s));
+                if (S0 + s + 1 < T) {
                     unsigned char* g = scr + ((size_t)(s & 1) * NC + cta) * SLICE;
                     bulk_store_s2g(g, src, (uint32_t)SLICE);
                     bulk_commit_group();
@@ -1576,7 +1580,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
         // one accumulator per issuer (columns [iw*BG, iw*BG + BG)): each thread's MMAs execute in its issue order, so the
         // partial sums and their sum in phase B are bit-reproducible whatever the interleaving of the issuer threads
         const uint32_t d_tmem = tmem_base + REC_TMEM_ACC + (uint32_t)((sg * NIW + iw) * BG);
-        for (int s = 0; s + 1 < T && ok; ++s) {                               // the last step's dm_{-1} is never used
+        for (int s = 0; s < S && S0 + s + 1 < T && ok; ++s) {                 // the last step's dm_{-1} is never used
             REC_PROBE(0);
             if (leader && iw == 0) mbar_arrive_expect_tx(&mbar_op[s & 1], 4u * SLICE);
             ok = mbar_wait(mbar_acc, (uint32_t)(s & 1));                      // accumulator zeroed
@@ -1585,7 +1589,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
             REC_PROBE(1);
             // the reduce buffer the NEXT step's partials go to: its previous contents were consumed in phase A of
             // this step (our own dz slice, part of the operand just awaited, was staged after reading them)
-            if (leader && iw == 0 && s + 2 < T) mbar_arrive_expect_tx(&mbar_red[(s + 1) & 1], 4u * PT);
+            if (leader && iw == 0 && s + 1 < S && S0 + s + 2 < T) mbar_arrive_expect_tx(&mbar_red[(s + 1) & 1], 4u * PT);
             if (paired) {                                                     // strict turns (see lstm_rec_fwd2_kernel)
                 uint32_t spins = 0;
                 while (*pipe_turn != sg) { if ((++spins & 0xfffu) == 0 && dev_has_error()) { ok = false; break; } }
@@ -1628,6 +1632,18 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
             len_j[j] = (b < B) ? p.lens[b] : 0;
             dcc[j] = 0.f;
         }
+        // a launch that resumes (S0 > 0) takes the recurrent dm of its first step and the carried dc from the previous launch
+        float dm_in[2] = {0.f, 0.f};
+        if (S0 > 0) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int b = b0 + ub * 8 + 2 * g + j;
+                if (b < B) {
+                    const float2 cv = *reinterpret_cast<const float2*>(p.carry + (((size_t)b * 2 + dir) * Hp + unit) * 2);
+                    dm_in[j] = cv.x; dcc[j] = cv.y;
+                }
+            }
+        }
         float db[4] = {0.f, 0.f, 0.f, 0.f};
         float dpf = 0.f, dpi = 0.f, dpo = 0.f;
 
@@ -1638,9 +1654,9 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int b = b0 + ub * 8 + 2 * g + j;
-            idx_j[j] = ((long long)(dir ? 0 : T - 1) * B + (b < B ? b : 0)) * (long long)ld2 + (long long)dir * Hp + unit;
+            idx_j[j] = ((long long)(dir ? S0 : T - 1 - S0) * B + (b < B ? b : 0)) * (long long)ld2 + (long long)dir * Hp + unit;
         }
-        auto load_pre = [&](int s, Pre& r) {
+        auto load_pre = [&](int s, Pre& r) {              // s: GLOBAL scan step
             const int t = dir ? s : (T - 1 - s);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -1657,7 +1673,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
             }
         };
         Pre cur, nxt;
-        load_pre(0, cur);
+        load_pre(S0, cur);
         // reduce-buffer read offset of this thread: unit row ul, 16-byte chunk ub (swizzled), utterance pair g
         const uint32_t rd_off = (uint32_t)(ul * (2 * BG) + ((ub ^ ((ul / SWS) & (NCH - 1))) << 4) + 4 * g);
         // dz staging offsets (own slice, SW128 K-major: row = utterance, 64 gate rows per 128-byte row) and global columns
@@ -1675,26 +1691,28 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
         const uint32_t red_addr = smem_u32(red), stg_addr = smem_u32(Stg), pst_addr = smem_u32(pst);
         const uint32_t acc_addr = tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + sg * NIW * BG + ub * 8;
 
-        for (int s = 0; s < T; ++s) {
-            const int t = dir ? s : (T - 1 - s);
+        auto reduce_partials = [&](int sp, float (&dmr)[2]) {          // sum of the four partial tiles sent in (local) step sp
+            const uint32_t rb = red_addr + (uint32_t)((sp & 1) * 4 * PT) + rd_off;
+            uint32_t v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = lds_b32(rb + (uint32_t)(k * PT));
+            const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[0])), f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[1])),
+                         f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[2])), f3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[3]));
+            dmr[0] = (f0.x + f1.x) + (f2.x + f3.x);
+            dmr[1] = (f0.y + f1.y) + (f2.y + f3.y);
+        };
+        for (int s = 0; s < S; ++s) {
             REC_PROBE(8);
 #pragma unroll
             for (int j = 0; j < 2; ++j) idx_j[j] += row_stride;
-            load_pre(s + 1, nxt);
+            load_pre(S0 + s + 1, nxt);
             REC_PROBE(9);
             // ---- phase A: dm_rec = sum of the four partial tiles of the previous step, then dz_t ----
-            float dmr[2] = {0.f, 0.f};
+            float dmr[2] = {dm_in[0], dm_in[1]};
             if (s > 0) {
                 if (ok) ok = mbar_wait(&mbar_red[(s - 1) & 1], (uint32_t)(((s - 1) >> 1) & 1));   // async-proxy deliveries + complete_tx: a CTA-scope wait suffices
                 REC_PROBE(10);
-                const uint32_t rb = red_addr + (uint32_t)(((s - 1) & 1) * 4 * PT) + rd_off;
-                uint32_t v[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = lds_b32(rb + (uint32_t)(k * PT));
-                const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[0])), f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[1])),
-                             f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[2])), f3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[3]));
-                dmr[0] = (f0.x + f1.x) + (f2.x + f3.x);
-                dmr[1] = (f0.y + f1.y) + (f2.y + f3.y);
+                reduce_partials(s - 1, dmr);
             }
             const uint32_t stg = stg_addr + (uint32_t)((s & 1) * SLICE);
 #pragma unroll
@@ -1727,7 +1745,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
             __syncwarp();
             if (lane == 0) mbar_arrive(&mbar_slice[s & 1]);
             REC_PROBE(12);
-            if (s + 1 < T) {
+            if (S0 + s + 1 < T) {
                 // ---- phase B: quarter q of the partial dm tile -> owner CTA 4 mr + q (one bulk DSMEM copy per quarter) ----
                 if (ok) ok = mbar_wait(mbar_mma, (uint32_t)(s & 1));
                 REC_PROBE(13);
@@ -1765,6 +1783,17 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
                 if (lane == 0) mbar_arrive(mbar_acc);
             }
             cur = nxt;
+        }
+        // ---- hand-over to the launch that continues at scan step S0 + S: recurrent dm of its first step, carried dc ----
+        if (S0 + S < T) {
+            float dmr[2] = {0.f, 0.f};
+            if (ok) ok = mbar_wait(&mbar_red[(S - 1) & 1], (uint32_t)(((S - 1) >> 1) & 1));
+            reduce_partials(S - 1, dmr);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int b = b0 + ub * 8 + 2 * g + j;
+                if (b < B) *reinterpret_cast<float2*>(p.carry + (((size_t)b * 2 + dir) * Hp + unit) * 2) = make_float2(dmr[j], dcc[j]);
+            }
         }
         // ---- parameter gradients held in registers: reduce the 4 lanes of a unit, then atomics ----
 #pragma unroll
@@ -1979,8 +2008,27 @@ extern "C" int lcb_lstm_rec_bwd(const float* dM, const void* gates, const float*
                                 const int32_t* lens, void* dG, float* dbias, float* dpeep,
                                 int T, int B, int Hp, void* workspace, size_t workspace_bytes, void* stream)
 {
+    return lcb_lstm_rec_bwd_range(dM, gates, cst, Wfold, peep, lens, dG, dbias, dpeep, T, B, Hp, 0, T, nullptr,
+                                  workspace, workspace_bytes, stream);
+}
+
+// 1 when lcb_lstm_rec_bwd_range accepts partial ranges for this cell size (the 4 x 4 kernel, Hp = 512, with its scratch)
+extern "C" int lcb_lstm_rec_bwd_can_split(int Hp)
+{
+    return (rec_version() == 2 && Hp == 512 && !getenv("LCB_REC_BWD2")) ? 1 : 0;
+}
+
+extern "C" int lcb_lstm_rec_bwd_range(const float* dM, const void* gates, const float* cst, const void* Wfold, const float* peep,
+                                      const int32_t* lens, void* dG, float* dbias, float* dpeep,
+                                      int T, int B, int Hp, int s_begin, int s_end, float* carry,
+                                      void* workspace, size_t workspace_bytes, void* stream)
+{
     if (!dM || !gates || !cst || !Wfold || !lens || !dG || !dbias) return LCB_ERR_NULL_POINTER;
     if (T <= 0 || B <= 0) return LCB_ERR_BAD_SHAPE;
+    if (s_begin < 0 || s_end > T || s_begin >= s_end) return LCB_ERR_BAD_SHAPE;
+    const bool whole = s_begin == 0 && s_end == T;
+    if (!whole && !carry) return LCB_ERR_NULL_POINTER;
+    if (carry && ((uintptr_t)carry & 7)) return LCB_ERR_MISALIGNED;
     if ((peep == nullptr) != (dpeep == nullptr)) return LCB_ERR_NULL_POINTER;
     int nc;
     if (!rec_plan(Hp, nc)) return LCB_ERR_UNSUPPORTED;
@@ -1988,9 +2036,10 @@ extern "C" int lcb_lstm_rec_bwd(const float* dM, const void* gates, const float*
     RecBwdParams p;
     p.dM = dM; p.gates = (const uint2*)gates; p.cst = cst; p.W = (const __nv_bfloat16*)Wfold; p.peep = peep; p.lens = lens;
     p.dG = (__nv_bfloat16*)dG; p.dbias = dbias; p.dpeep = dpeep;
-    p.T = T; p.B = B; p.Hp = Hp; p.NC = nc;
+    p.T = T; p.B = B; p.Hp = Hp; p.NC = nc; p.s_begin = s_begin; p.s_end = s_end; p.carry = carry;
     if (workspace && ((uintptr_t)workspace & 15)) return LCB_ERR_MISALIGNED;
     p.xch = (workspace && workspace_bytes >= lcb_lstm_rec_workspace_bytes(B, Hp)) ? (unsigned char*)workspace : nullptr;
+    if (!whole && !(lcb_lstm_rec_bwd_can_split(Hp) && p.xch)) return LCB_ERR_UNSUPPORTED;
     if (rec_version() == 2 && p.xch && Hp == 512 && !getenv("LCB_REC_BWD2")) {
         const int bgs0 = choose_bg(B, nc, 1);
         const bool pair = bgs0 == 32 && rec_pair();      // two 16-utterance sub-groups per cluster instead of one group of 32
