@@ -162,7 +162,8 @@ class BLSTMEncoder:
         self.use_graphs = True
         self.pstream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None   # projection of the later frames
         # fraction of the scan steps whose pre-activations are projected before the recurrence starts (LCB_HEAD_FRAC overrides)
-        self.head_frac = float(os.environ.get("LCB_HEAD_FRAC", "0.36"))
+        self.head_fracs = [float(v) for v in os.environ.get("LCB_HEAD_FRACS", "0.36").split(",") if v]
+        self.overlap_hproj = os.environ.get("LCB_OVERLAP_HPROJ", "1") != "0"   # output projection of finished chunks on the side stream
         self.bwd_split_frac = float(os.environ.get("LCB_BWD_SPLIT_FRAC", "0"))   # > 0: BPTT as two launches (lcb_lstm_rec_bwd_range)
         self._refresh_graphs = None
         self._refresh_done = None
@@ -363,6 +364,15 @@ class BLSTMEncoder:
         return ws
 
     # ------------------------------------------------------------------ forward
+    @property
+    def head_frac(self):
+        """First recurrence-launch boundary as a fraction of T (0: one launch); setting it selects a two-launch schedule."""
+        return self.head_fracs[0] if self.head_fracs else 0.0
+
+    @head_frac.setter
+    def head_frac(self, v):
+        self.head_fracs = [float(v)] if v and v > 0 else []
+
     def forward(self, nnet_input, seq_len, training=True):
         """nnet_input [B,T,D] f32 cuda (zero padded), seq_len [B] int32 cuda.
         Returns the encoder output [T*B, 2P] fp16 (time-major rows n = t*B + b)."""
@@ -395,38 +405,82 @@ class BLSTMEncoder:
                                                     T, B, c.Hp, c.forget_bias, s0, s1, _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(),
                                                     _lib.stream_ptr()), "lcb_lstm_rec_fwd_range")
 
-            Tc = int(math.ceil(self.head_frac * T)) if (training and self.pstream is not None) else 0
-            if Tc < 16 or 2 * Tc > T:
-                gemm(X, W16, 0, 0, out=G, bias=bias)
-                rec(0, T)
-            else:
-                # The recurrence needs G only for the frames it is about to visit: project the first Tc scan steps of each
-                # direction (frames [0,Tc) for the forward, [T-Tc,T) for the backward cells), start the recurrence on them, and
-                # project the remaining rows on a side stream on the SMs the 64 recurrence CTAs leave idle.
-                H4, nh, nt = 4 * c.Hp, Tc * B, (T - Tc) * B
-                main = torch.cuda.current_stream()
-                gemm(X[:nh], W16[:H4], 0, 0, out=G[:nh, :H4], bias=bias[:H4])
-                gemm(X[nt:], W16[H4:], 0, 0, out=G[nt:, H4:], bias=bias[H4:])
-                head_done = torch.cuda.Event()
-                head_done.record(main)
-                rec(0, Tc)
-                with torch.cuda.stream(self.pstream):
-                    self.pstream.wait_event(head_done)
-                    old_cap = L.lcb_gemm_set_max_ctas(84)
-                    gemm(X[nh:], W16[:H4], 0, 0, out=G[nh:, :H4], bias=bias[:H4])
-                    gemm(X[:nt], W16[H4:], 0, 0, out=G[:nt, H4:], bias=bias[H4:])
-                    L.lcb_gemm_set_max_ctas(old_cap)
-                    tail_done = torch.cuda.Event()
-                    tail_done.record(self.pstream)
-                main.wait_event(tail_done)
-                rec(Tc, T)
             Hout = ws["Hout"][i]
             # h = m * W_proj with DropoutWrapper(output_keep_prob) (bilstm.py:128,137) applied in the GEMM epilogue: element
             # [n, d*P + p] of Hout uses element n*2P + d*P + p of the layer's mask stream
             drop = (c.keep_prob, self.dropout_seed(i)) if (training and c.keep_prob < 1.0) else None
-            for d in range(2):
-                gemm(ws["M"][i][:, d * c.Hp:(d + 1) * c.Hp], self._bf[("WpT16", i)][d], 0, 0, out=Hout[:, d * c.P:(d + 1) * c.P],
-                     dropout=(drop + (d * c.P,)) if drop else None)
+
+            def hproj(s0, s1):
+                """Output projection of the frames scan steps [s0, s1) visited: rows [s0,s1) of the forward, [T-s1,T-s0) of the
+                backward direction's column half."""
+                for d, (r0, r1) in enumerate(((s0 * B, s1 * B), ((T - s1) * B, (T - s0) * B))):
+                    gemm(ws["M"][i][r0:r1, d * c.Hp:(d + 1) * c.Hp], self._bf[("WpT16", i)][d], 0, 0,
+                         out=Hout[r0:r1, d * c.P:(d + 1) * c.P],
+                         dropout=(drop + (r0 * 2 * c.P + d * c.P,)) if drop else None)
+
+            # scan-step boundaries of the recurrence launches (training, side stream available, long enough sequences)
+            bounds = []
+            if training and self.pstream is not None:
+                for fr in self.head_fracs:
+                    b_ = int(math.ceil(fr * T))
+                    if b_ >= 16 and b_ <= T - 16 and (not bounds or b_ >= bounds[-1] + 16):
+                        bounds.append(b_)
+            if not bounds:
+                gemm(X, W16, 0, 0, out=G, bias=bias)
+                rec(0, T)
+                hproj(0, T)
+            else:
+                # The recurrence needs G only for the frames it is about to visit: project the first scan steps of each direction
+                # (frames [0,b0) for the forward, [T-b0,T) for the backward cells) on the whole chip, start the recurrence on them,
+                # and project the following chunks, in the order the scan needs them, on a side stream on the SMs the 64
+                # recurrence CTAs leave idle (grid capped); each further recurrence launch resumes bit-identically
+                # (lcb_lstm_rec_fwd_range).  Chunks grow geometrically: the capped GEMM of chunk k+1 (1.17 ms per full sequence)
+                # has to fit under the recurrence of chunks <= k (2.13 ms per full sequence).  The output projection of a chunk
+                # follows on the side stream once its recurrence is done; only the last chunk's stays on the main stream.
+                H4 = 4 * c.Hp
+                main = torch.cuda.current_stream()
+                bounds = bounds + [T]
+
+                def proj(s0, s1):
+                    r0, r1 = s0 * B, s1 * B
+                    gemm(X[r0:r1], W16[:H4], 0, 0, out=G[r0:r1, :H4], bias=bias[:H4])
+                    r0, r1 = (T - s1) * B, (T - s0) * B
+                    gemm(X[r0:r1], W16[H4:], 0, 0, out=G[r0:r1, H4:], bias=bias[H4:])
+
+                proj(0, bounds[0])
+                head_done = torch.cuda.Event()
+                head_done.record(main)
+                chunk_ready = []
+                with torch.cuda.stream(self.pstream):
+                    self.pstream.wait_event(head_done)
+                    old_cap = L.lcb_gemm_set_max_ctas(84)
+                    for k in range(1, len(bounds)):
+                        proj(bounds[k - 1], bounds[k])
+                        ev = torch.cuda.Event()
+                        ev.record(self.pstream)
+                        chunk_ready.append(ev)
+                    L.lcb_gemm_set_max_ctas(old_cap)
+                prev = 0
+                for k, b_ in enumerate(bounds):
+                    if k > 0:
+                        main.wait_event(chunk_ready[k - 1])
+                    rec(prev, b_)
+                    if k + 1 < len(bounds) and self.overlap_hproj:
+                        rec_done = torch.cuda.Event()
+                        rec_done.record(main)
+                        with torch.cuda.stream(self.pstream):
+                            self.pstream.wait_event(rec_done)
+                            old_cap = L.lcb_gemm_set_max_ctas(84)
+                            hproj(prev, b_)
+                            L.lcb_gemm_set_max_ctas(old_cap)
+                    prev = b_
+                if self.overlap_hproj:
+                    hproj(bounds[-2], T)
+                    hp_done = torch.cuda.Event()
+                    hp_done.record(self.pstream)
+                    main.wait_event(hp_done)
+                else:
+                    hproj(0, T)
             if i == 0 and c.residual0:              # finput = finput + concat(...)  iff input_dim == 2*num_projects (bilstm.py:199-200)
                 _lib.check(L.lcb_add_f16(_lib.ptr(Hout), _lib.ptr(ws["X0"]), Hout.numel(), st), "lcb_add_f16")
             X = Hout

@@ -118,17 +118,18 @@ def test_split_recurrence_equals_whole(cuda_dev, H, B, T):
     x[1, 3:] = 0
     dev = torch.device("cuda:0")
     outs = []
-    for frac in (0.0, 0.3):
+    for fracs in ([], [0.3], [0.25, 0.5, 0.75]):
         enc = BLSTMEncoder(ModelConfig(nnet_config(cfg)), dev)
         enc.from_tf_dict(params)
-        enc.head_frac = frac
+        enc.head_fracs = fracs
         out = enc.forward(x.float().to(dev), lens.to(dev), training=True).float().clone()
         ws = enc._workspace(T, B, True)
         outs.append((out, [m.float().clone() for m in ws["M"]], [c.clone() for c in ws["cst"]], enc.encoder_state().clone()))
     torch.cuda.synchronize()
     from lstm_ctc_b200 import _lib
     assert _lib.lib().lcb_device_error(1) == 0
-    (o0, m0, c0, e0), (o1, m1, c1, e1) = outs
+    (o0, m0, c0, e0), (o1, m1, c1, e1), (o2, m2, c2, e2) = outs
+    assert torch.equal(o0, o2) and torch.equal(e0, e2) and all(torch.equal(a, b) for a, b in zip(m0, m2))     # four launches
     valid = (torch.arange(T).unsqueeze(1) < lens.unsqueeze(0)).reshape(T * B).to(dev)      # rows n = t*B + b of live frames
     # bit-identical: the split changes launches, not arithmetic (each MMA issuer thread owns its accumulator, so the sum
     # order inside a time step is fixed)
