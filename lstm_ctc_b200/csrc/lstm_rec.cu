@@ -17,13 +17,14 @@
 // keeps them RESIDENT IN TENSOR MEMORY for the whole sequence (128 lanes x Hp/2 columns, fp16): the per-step
 // product uses the TS form of tcgen05.mma (A from TMEM), so the weights are never re-read through the
 // shared-memory port -- measured, the SS form was bound at ~40 cycles per 128x16x16 MMA by exactly that.
-// Per step: two issuer warps (K halves, own accumulators) issue D[128 gate rows, 16 utts] = W'^T_slice *
-// m_{t-1}^T; 8 compute warps read their accumulator fragment with tcgen05.ld.16x256b (the packing above puts
+// Per step: two issuer warps (K halves, own accumulators; converged, one elected lane, warp-uniform operands --
+// see the v2 section) issue D[128 gate rows, 16 utts] = W'^T_slice * m_{t-1}^T; 8 compute warps read their accumulator fragment with tcgen05.ld.16x256b (the packing above puts
 // the four gates of a unit in ONE thread), add the prefetched G tile, apply gates / peepholes / cell update
-// / length mask in registers (the fp32 cell state never leaves registers), push m_t (fp16) into the operand
-// buffer of every CTA of the cluster with st.async (DSMEM, completion counted on the receiver's mbarrier --
-// no barrier.cluster and no release fence in the loop), then write m_t and the saved activations to HBM off
-// the critical path.  A loader warp keeps an 8-deep ring of G tiles in flight (one bulk copy per lane).
+// / length mask in registers (the fp32 cell state never leaves registers), hand the CTA's m_t slice (fp16) to an
+// exchange warp that bulk-stores it to an L2-resident scratch and multicasts it into the operand buffer of every CTA
+// of the cluster (completion counted on the receivers' mbarriers -- no barrier.cluster and no release fence in the
+// loop; the v1 kernels at the top of the file still push it with st.async over DSMEM), then write m_t and the saved
+// activations to HBM off the critical path.  A loader warp keeps an 8-deep ring of G tiles in flight (one bulk copy per lane).
 // The backward direction is the same scan in descending absolute time under the mask t < len[b]
 // (state stays at its zero initial value until t = len[b]-1), so no reversed copies are ever made.
 //
@@ -714,14 +715,17 @@ lstm_rec_bwd_kernel(const RecBwdParams p)
 }
 
 // =================================================================================================
-// v2 kernels: ONE group of BG utterances per cluster, in lockstep (MMA N = BG, BG = 16 or 32)
+// v2 kernels (the ones the library launches): groups of BG utterances step in lockstep through a cluster (MMA N = BG)
 //
-// Measured on the v1 kernels (profiles/r01_recprobe_*): a 128 x 16 x 16 tcgen05.mma costs ~36 cycles whatever N <= 64 is
-// (the 4 KB weight operand streams at ~128 B/clk), so two interleaved 16-utterance sub-groups pay the 32-MMA pass
-// (~1150 cycles) twice per step pair.  v2 issues it once for 32 utterances; the cluster then runs in lockstep and the
-// per-step chain is  commit->wake, tcgen05.ld, gate math (MUFU-bound: 5 ex2 + 2 rcp per cell with shared reciprocals),
-// slice barrier + 16 bulk DSMEM copies of 512*BG/8 bytes, ingress (BG KB per CTA at ~17 B/clk) overlapped with the
-// K-block-pipelined MMA issue.
+// Per step:  operand m_{t-1} lands (multicast)  ->  32 MMAs 128 x BG x 16, A = weights from TMEM (TS form)  ->  commit->wake,
+// tcgen05.ld, gate math (MUFU-bound: 5 ex2 + 2 rcp per cell with shared reciprocals)  ->  the CTA's slice of m_t is staged,
+// bulk-stored to an L2-resident scratch and multicast into every CTA of the cluster.
+// THE MMA ISSUE.  The first versions issued the MMAs from inside an `if (lane == 0)` region; the compiler then wraps every
+// tcgen05.mma in an ELECT / 4 x R2UR / branch "waterfall" (its operands live in per-thread registers) and one thread issues one
+// MMA per ~65 cycles -- the 32-MMA pass took ~1150 cycles whatever N was and was mistaken for a TMEM-bandwidth limit.  With the
+// issuer warp converged, a canonical (shuffled) warp index and TMEM base, and the issuing lane selected by a predicate inside
+// the asm (umma_f16_ts_elect), the operands stay in uniform registers: a pass is ~420 cycles at N = 16 and ~600 at N = 32
+// (profiles/r01_recprobe_fwd_uniform_issue.txt).  Two issuer warps (own accumulators) still beat one (526 vs 657 cycles).
 // =================================================================================================
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -751,9 +755,10 @@ __device__ __forceinline__ void sig_tanh(float a, float c, float& sa, float& tc)
 
 // NSG = 2 (BG = 16 only): TWO independent 16-utterance groups per cluster share the resident weights.  Each has its own
 // warps, operand buffers, barriers, accumulators and exchange scratch and steps on its own; they meet only in the tensor
-// pipe.  Measured (profiles/r01_recprobe_fwd_nsg2.txt): the per-step chain of a 16-utterance group is ~3100 cycles against
-// ~3800 for a 32-utterance one (1 KB slices, half the operand ingress, half the gate math per thread-step), and the
-// 32-MMA weight pass (~1150 cycles whatever N is) of one group hides behind the exchange + gate math of the other.
+// pipe, where their weight passes take strict turns.  Measured (H = 512, B = 64, profiles/r01_recprobe_fwd_uniform_issue.txt):
+// 2400-2460 cycles per step for both groups against ~2900 for one lockstep group of 32 (1 KB slices, half the operand
+// ingress, half the gate math per thread-step; one group's exchange hides behind the other's pass and gate math); a
+// 16-utterance group alone in a cluster steps in ~1970 cycles, but 8 such clusters are not co-resident on a B200 (7).
 template <int BG, int NSG = 1> struct RecFwd2Cfg {
     static_assert(NSG == 1 || BG == 16, "two sub-groups only for 16-utterance groups");
     static constexpr int NUB = BG / 8;                     // utterance blocks of 8 (core-matrix rows of the MMA B operand)
@@ -938,9 +943,10 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
             if (ok && s > 0) ok = mbar_wait(&mbar_op[par], (uint32_t)(((s - 1) >> 1) & 1));
             if (!ok) break;
             REC_PROBE(1);
-            // Two sub-groups: the weight passes take strict turns.  Issued at the same time they would share the tensor
-            // pipe, both finish late and the sub-groups fall into phase (measured: 1430-cycle passes, no gain); one
-            // after the other, each pass runs at full rate under the other sub-group's exchange and gate math.
+            // Two sub-groups: the weight passes take strict turns.  Issued at the same time they share the tensor pipe, both
+            // finish late and the sub-groups fall into phase; one after the other, each pass runs at full rate under the other
+            // sub-group's exchange and gate math (without turns: forward equal, BPTT 3330 -> 3560 cycles per step,
+            // profiles/r01_rec_experiments_lock_stasync.txt).
             if (paired) {
                 uint32_t spins = 0;
                 while (*pipe_turn != sg) { if ((++spins & 0xfffu) == 0 && dev_has_error()) { ok = false; break; } }
@@ -1900,7 +1906,7 @@ static int choose_nsg(int B, int nc, int which) {
 }
 
 // v2: utterances per cluster.  16 while every 16-utterance group gets its own resident cluster (shortest per-step chain),
-// 32 otherwise (half the clusters; the 32-MMA weight pass is paid once for 32 utterances).  LCB_REC_BG=16|32 overrides.
+// 32 otherwise -- as two independent 16-utterance sub-groups (rec_pair()), or one lockstep group of 32.  LCB_REC_BG=16|32 overrides.
 static int choose_bg(int B, int nc, int which) {
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("LCB_REC_BG"); forced = e ? atoi(e) : 0; }
