@@ -163,7 +163,7 @@ class BLSTMEncoder:
         self.pstream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None   # projection of the later frames
         # fraction of the scan steps whose pre-activations are projected before the recurrence starts (LCB_HEAD_FRAC overrides)
         self.head_fracs = [float(v) for v in os.environ.get("LCB_HEAD_FRACS", "0.36").split(",") if v]
-        self.overlap_hproj = os.environ.get("LCB_OVERLAP_HPROJ", "1") != "0"   # output projection of finished chunks on the side stream
+        self.overlap_hproj = os.environ.get("LCB_OVERLAP_HPROJ", "0") != "0"   # output projection of finished chunks on the side stream (c3: +-0, c2: 15 % slower -> off)
         self.bwd_split_frac = float(os.environ.get("LCB_BWD_SPLIT_FRAC", "0"))   # > 0: BPTT as two launches (lcb_lstm_rec_bwd_range)
         self._refresh_graphs = None
         self._refresh_done = None
