@@ -165,6 +165,12 @@ class BLSTMEncoder:
         self.head_fracs = [float(v) for v in os.environ.get("LCB_HEAD_FRACS", "0.36").split(",") if v]
         self.overlap_hproj = os.environ.get("LCB_OVERLAP_HPROJ", "0") != "0"   # output projection of finished chunks on the side stream (c3: +-0, c2: 15 % slower -> off)
         self.bwd_split_frac = float(os.environ.get("LCB_BWD_SPLIT_FRAC", "0"))   # > 0: BPTT as two launches (lcb_lstm_rec_bwd_range)
+        # > 0.5: BPTT of layers 1.. as two launches at this fraction of the scan; the rows of dX (and of the next layer's dM) whose
+        # dG is final in BOTH directions after the first launch are computed beside the second one (backward(), "early rows")
+        self.bwd_early_frac = float(os.environ.get("LCB_BWD_EARLY_FRAC", "0.7"))
+        self.xstream = (torch.cuda.Stream(device=device, priority=int(os.environ.get("LCB_XSTREAM_PRIO", "0")))
+                        if torch.cuda.is_available() else None)   # early rows of dX / dM
+        self.early_cap = int(os.environ.get("LCB_EARLY_CAP", "84"))   # persistent-grid cap of those GEMMs (84 SMs idle beside BPTT)
         self._refresh_graphs = None
         self._refresh_done = None
         self.seed_base = 777           # reference default --seed (nnet-train.py:141-142)
@@ -356,7 +362,8 @@ class BLSTMEncoder:
                 # double-buffered by layer parity: the wgrad GEMMs of layer i run on a side stream while the main
                 # stream already produces layer i-1's tensors
                 ws["dG"] = [torch.empty(N, 8 * c.Hp, dtype=BF16, device=dev) for _ in range(2)]
-                ws["dX"] = [torch.empty(N, 2 * c.P, dtype=BF16, device=dev) for _ in range(2)]
+                # three, by layer % 3: layer i's dX is written (early rows) while layer i+1's wgrad still reads ITS dH = layer i+2's dX
+                ws["dX"] = [torch.empty(N, 2 * c.P, dtype=BF16, device=dev) for _ in range(3)]
                 ws["dfold"] = [torch.empty(4 * c.Hp, c.Hp, dtype=F32, device=dev) for _ in range(2)]
                 ws["Xbf"] = [torch.empty(N * max(c.Dp0, 2 * c.P), dtype=BF16, device=dev) for _ in range(2)]   # bf16 copies for wgrad
                 ws["Mbf"] = [torch.empty(N, 2 * c.Hp, dtype=BF16, device=dev) for _ in range(2)]
@@ -596,6 +603,30 @@ class BLSTMEncoder:
             ev.record(main)
             return ev
 
+        def dm_rows(i, dH_, r0, r1):
+            """dM[r0:r1] = dH[r0:r1] * W_p^T of layer i, both directions"""
+            if r1 <= r0:
+                return
+            for d in range(2):
+                gemm(dH_[r0:r1, d * c.P:(d + 1) * c.P], self._bf[("WpT", i)][d], 0, 1, out=ws["dM"][r0:r1, d * c.Hp:(d + 1) * c.Hp])
+
+        def dx_rows(i, dG_, dXn_, r0, r1):
+            """dX[r0:r1] = dG[r0:r1] * W_x of layer i, with the mask of layer i-1's output dropout (same seed and element indices as
+            the forward pass) in the epilogue"""
+            if r1 <= r0:
+                return
+            gemm(dG_[r0:r1], self._bf[("Wx", i)], 0, 1, out=dXn_[r0:r1],
+                 dropout=(c.keep_prob, self.dropout_seed(i - 1), r0 * 2 * c.P) if c.keep_prob < 1.0 else None)
+
+        # "Early rows": scan step s of BPTT visits frame T-1-s in the forward and frame s in the backward direction, so after the
+        # scan steps [0, Tb) with Tb > T/2 the frames [T-Tb, Tb) have their final dG in BOTH directions.  Their rows of dX -- and of
+        # the dM of the layer below, which needs nothing else -- are computed on a side stream beside the launch over
+        # [Tb, T); only the rows of the first and last T-Tb frames stay on the serial chain between two layers' BPTT.
+        Tb = int(math.ceil(self.bwd_early_frac * T)) if (overlap and self.xstream is not None and self.bwd_early_frac > 0.5
+                                                          and L.lcb_lstm_rec_bwd_can_split(c.Hp)) else 0
+        if Tb < T - Tb + 16 or T - Tb < 16:
+            Tb = 0
+        early = None                         # (first row, end row, event): rows of dH and of this layer's dM made on xstream
         pending = None                       # (layer, its dH): weight gradients not yet enqueued
         for i in reversed(range(c.num_layers)):
             k = i & 1
@@ -604,34 +635,56 @@ class BLSTMEncoder:
             if c.keep_prob < 1.0 and i == c.num_layers - 1 and not top_dropped:
                 self._dropout(dH, i)                # same (seed, index) mask as the forward pass, on the gradient
             dM, dG = ws["dM"], ws["dG"][k]
-            for d in range(2):
-                # dM = dH * W_p^T
-                gemm(dH[:, d * c.P:(d + 1) * c.P], self._bf[("WpT", i)][d], 0, 1, out=dM[:, d * c.Hp:(d + 1) * c.Hp])
+            # dM = dH * W_p^T
+            if early is None:
+                dm_rows(i, dH, 0, N)
+            else:
+                dm_rows(i, dH, 0, early[0])
+                dm_rows(i, dH, early[1], N)
+                main.wait_event(early[2])
+                early = None
             chain_issued = mark()                             # behind BPTT(i+1) and this layer's dropout / dM GEMMs
             peep = ps.w("L%d/peep" % i) if c.use_peepholes else None
             gpeep = ps.g("L%d/peep" % i) if c.use_peepholes else None
-            # BPTT in one launch, or (bwd_split_frac > 0, cells the 4 x 4 kernel serves) as two launches over consecutive scan
-            # ranges joined by the carry buffer -- bit-identical; the hook for computing late rows of dM beside the first range
-            Tb = int(math.ceil(self.bwd_split_frac * T)) if self.bwd_split_frac > 0 and L.lcb_lstm_rec_bwd_can_split(c.Hp) else 0
-            ranges = [(0, T)] if (Tb < 1 or Tb >= T) else [(0, Tb), (Tb, T)]
+            # BPTT in one launch, or as two launches over consecutive scan ranges joined by the carry buffer -- bit-identical
+            # (lcb_lstm_rec_bwd_range): at Tb for the early rows above (layers 1..), or at bwd_split_frac (experiments)
+            if Tb > 0 and i > 0:
+                ranges = [(0, Tb), (Tb, T)]
+            else:
+                Ts = int(math.ceil(self.bwd_split_frac * T)) if self.bwd_split_frac > 0 and L.lcb_lstm_rec_bwd_can_split(c.Hp) else 0
+                ranges = [(0, T)] if (Ts < 1 or Ts >= T) else [(0, Ts), (Ts, T)]
             if len(ranges) > 1 and "bwd_carry" not in ws:
                 ws["bwd_carry"] = torch.empty(B * 2 * c.Hp * 2, dtype=F32, device=self.device)
+            dXn = ws["dX"][i % 3] if i > 0 else None
             for (s0, s1) in ranges:
                 _lib.check(L.lcb_lstm_rec_bwd_range(_lib.ptr(dM), _lib.ptr(ws["gates"][i]), _lib.ptr(ws["cst"][i]),
                                                     _lib.ptr(self._bf[("fold", i)]), _lib.ptr(peep),
                                                     _lib.ptr(seq_len), _lib.ptr(dG), _lib.ptr(ps.g("L%d/bias" % i)), _lib.ptr(gpeep),
                                                     T, B, c.Hp, s0, s1, _lib.ptr(ws.get("bwd_carry")),
                                                     _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(), _lib.stream_ptr()), "lcb_lstm_rec_bwd_range")
+                if Tb > 0 and i > 0 and s1 == Tb:
+                    first_done = torch.cuda.Event()
+                    first_done.record(main)
+                    r0, r1 = (T - Tb) * B, Tb * B
+                    with torch.cuda.stream(self.xstream):
+                        self.xstream.wait_event(first_done)
+                        old_cap = L.lcb_gemm_set_max_ctas(self.early_cap)
+                        dx_rows(i, dG, dXn, r0, r1)
+                        dm_rows(i - 1, dXn, r0, r1)
+                        L.lcb_gemm_set_max_ctas(old_cap)
+                        ev = torch.cuda.Event()
+                        ev.record(self.xstream)
+                    early = (r0, r1, ev)
             if pending is not None:
                 wgrad(pending[0], pending[1], chain_issued)   # layer i+1's weight gradients run beside this BPTT
             dH_this = dH
             if i > 0:
-                dXn = ws["dX"][k]
-                if overlap and (i + 1) in side_done:
-                    main.wait_event(side_done[i + 1])         # layer i+1's wgrad still reads this buffer as its dH
-                # dX = dG * W_x, with the mask of layer i-1's output dropout (same seed and indices as forward) in the epilogue
-                gemm(dG, self._bf[("Wx", i)], 0, 1, out=dXn,
-                     dropout=(c.keep_prob, self.dropout_seed(i - 1), 0) if c.keep_prob < 1.0 else None)
+                # dX = dG * W_x (layer i+1's wgrad reads ITS dH from another of the three buffers)
+                if early is None:
+                    dx_rows(i, dG, dXn, 0, N)
+                else:
+                    dx_rows(i, dG, dXn, 0, early[0])
+                    dx_rows(i, dG, dXn, early[1], N)
                 dH = dXn
             pending = (i, dH_this)
         wgrad(pending[0], pending[1], mark())

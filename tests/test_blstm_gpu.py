@@ -164,6 +164,7 @@ def test_split_bptt_equals_whole(cuda_dev, B, T, frac):
         enc = BLSTMEncoder(ModelConfig(nnet_config(cfg)), dev)
         enc.from_tf_dict(params)
         enc.bwd_split_frac = f
+        enc.bwd_early_frac = 0.0
         enc.forward(x.float().to(dev), lens.to(dev), training=True)
         enc.params.gflat.zero_()
         enc.backward(dtop.clone())
@@ -176,5 +177,43 @@ def test_split_bptt_equals_whole(cuda_dev, B, T, frac):
         assert torch.equal(a, b)
     # parameter gradients: same dz, but bias / peephole sums are atomically accumulated per launch and the weight-gradient
     # GEMMs use split-K reduce-adds -> equal up to fp32 summation order
+    assert (g0 - g1).abs().max().item() <= 1e-5 * g0.abs().max().item()
+    assert g0.abs().max().item() > 0
+
+
+@pytest.mark.parametrize("B,T,frac,keep", [(40, 96, 0.75, 0.8), (64, 80, 0.6, 1.0), (24, 130, 0.85, 0.9)])
+def test_early_rows_schedule_equals_serial(cuda_dev, B, T, frac, keep):
+    """backward() with bwd_early_frac: BPTT of layers 1.. in two launches, the rows of dX (fused dropout mask addressed by
+    absolute element index) and of the next layer's dM whose dG is final after the first launch computed on a side stream
+    beside the second -- three layers so that the three dX buffers rotate.  Same dz bit for bit in every layer that is still
+    held (layer 0's depends on every dX above it), parameter gradients equal up to fp32 summation order."""
+    from lstm_ctc_b200 import _lib
+    from lstm_ctc_b200.blstm import BLSTMEncoder, ModelConfig
+    H = 512
+    assert _lib.lib().lcb_lstm_rec_bwd_can_split(H) == 1
+    cfg, params, x, lens = make_case(H, H, 24, 3, B, T, True, seed=21)
+    lens[1] = 5
+    x[1, 5:] = 0
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    dtop = (torch.randn(T * B, 2 * H, generator=g) * 0.1).to(dev).bfloat16()
+    nc = nnet_config(cfg)
+    nc["dropout_rate"] = keep
+    res = []
+    for f in (0.0, frac):
+        enc = BLSTMEncoder(ModelConfig(nc), dev)
+        enc.from_tf_dict(params)
+        enc.bwd_early_frac = f
+        enc.forward(x.float().to(dev), lens.to(dev), training=True)
+        enc.params.gflat.zero_()
+        enc.backward(dtop.clone())
+        ws = enc._workspace(T, B, True)
+        torch.cuda.synchronize()
+        res.append(([d.clone() for d in ws["dG"]], enc.params.gflat.clone(), ws["dX"][1].clone()))
+    assert _lib.lib().lcb_device_error(1) == 0
+    (dg0, g0, dx0), (dg1, g1, dx1) = res
+    assert torch.equal(dx0, dx1)                   # layer 1's dX (= layer 0's dH), all rows
+    for a, b in zip(dg0, dg1):
+        assert torch.equal(a, b)
     assert (g0 - g1).abs().max().item() <= 1e-5 * g0.abs().max().item()
     assert g0.abs().max().item() > 0
