@@ -322,6 +322,8 @@ def kernel_breakdown(model, x, lens, y, w, frames):
     L = _lib.lib()
     spans = {}
 
+    gemm_calls = []                 # (class, flops, start, end) of every bulk GEMM launch of the instrumented step
+
     def timed(name, fn):
         def wrap(*a, **k):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -329,6 +331,15 @@ def kernel_breakdown(model, x, lens, y, w, frames):
             r = fn(*a, **k)
             e.record()
             spans.setdefault(name, []).append((s, e))
+            if name == "gemm":
+                A, Bm = a[0], a[1]
+                al = a[2] if len(a) > 2 else k.get("a_layout", 0)
+                bl = a[3] if len(a) > 3 else k.get("b_layout", 0)
+                M_, K_ = (A.shape[0], A.shape[1]) if al == 0 else (A.shape[1], A.shape[0])
+                N_ = Bm.shape[0] if bl == 0 else Bm.shape[1]
+                cls = {(0, 0): "forward (X*W^T: projections, h-projection, output recompute)", (0, 1): "dgrad (dG*W)",
+                       (1, 1): "wgrad (X^T*dG, K = frames)"}.get((al, bl), "other")
+                gemm_calls.append((cls, 2.0 * M_ * N_ * K_, s, e))
             return r
         return wrap
 
@@ -353,6 +364,7 @@ def kernel_breakdown(model, x, lens, y, w, frames):
     try:
         for _ in range(2):
             spans.clear()
+            del gemm_calls[:]
             model.loss_and_grad(x, lens, y, check_labels=False)
             model.optimizer_step("adam", 4e-4)
             torch.cuda.synchronize()
@@ -394,6 +406,23 @@ def kernel_breakdown(model, x, lens, y, w, frames):
         ach = bytes_ / (ms1["ms_total"] / ms1["launches"] * 1e-3) / 1e9
         roof = {"kernel": "ctc_loss_grad", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                 "traffic": None, "peak_source": how}
+    # per-class GEMM throughput of the same instrumented step (launched flops incl. padded frames / launch time); launches of
+    # >= 20 GFLOP only, so the tiny weight-folding GEMMs do not blur the classes.  The forward projections' tails and all
+    # weight gradients run on a CAPPED grid (84 / 80 of 148 SMs) beside the recurrence, by design.
+    classes = {}
+    for cls, fl, s_, e_ in gemm_calls:
+        if fl < 2e10:
+            continue
+        c_ = classes.setdefault(cls, {"launches": 0, "flops": 0.0, "ms_total": 0.0})
+        c_["launches"] += 1
+        c_["flops"] += fl
+        c_["ms_total"] += s_.elapsed_time(e_)
+    for c_ in classes.values():
+        c_["tflops"] = c_["flops"] / (c_["ms_total"] * 1e-3) / 1e12 if c_["ms_total"] > 0 else 0.0
+        c_["frac_of_sustained_peak"] = c_["tflops"] / tf_sus
+        del c_["flops"]
+    if roof is not None and classes:
+        roof["gemm_classes"] = classes
     # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed `ncu --set full`
     # capture of this same command (profiles/r01_ncu_traffic.json; null if the capture does not cover this workload)
     try:

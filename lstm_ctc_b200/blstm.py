@@ -165,9 +165,10 @@ class BLSTMEncoder:
         self.head_fracs = [float(v) for v in os.environ.get("LCB_HEAD_FRACS", "0.36").split(",") if v]
         self.overlap_hproj = os.environ.get("LCB_OVERLAP_HPROJ", "0") != "0"   # output projection of finished chunks on the side stream (c3: +-0, c2: 15 % slower -> off)
         self.bwd_split_frac = float(os.environ.get("LCB_BWD_SPLIT_FRAC", "0"))   # > 0: BPTT as two launches (lcb_lstm_rec_bwd_range)
-        # > 0.5: BPTT of layers 1.. as two launches at this fraction of the scan; the rows of dX (and of the next layer's dM) whose
-        # dG is final in BOTH directions after the first launch are computed beside the second one (backward(), "early rows")
-        self.bwd_early_frac = float(os.environ.get("LCB_BWD_EARLY_FRAC", "0.7"))
+        # increasing fractions > 0.5 of the scan at which BPTT of layers 1.. is cut into consecutive launches; the rows of dX (and of
+        # the next layer's dM) whose dG is final in BOTH directions after a launch are computed beside the next one (backward(),
+        # "early rows").  Empty: one launch.
+        self.bwd_early_fracs = [float(v) for v in os.environ.get("LCB_BWD_EARLY_FRACS", "0.67,0.85").split(",") if v]
         self.xstream = (torch.cuda.Stream(device=device, priority=int(os.environ.get("LCB_XSTREAM_PRIO", "0")))
                         if torch.cuda.is_available() else None)   # early rows of dX / dM
         self.early_cap = int(os.environ.get("LCB_EARLY_CAP", "84"))   # persistent-grid cap of those GEMMs (84 SMs idle beside BPTT)
@@ -547,6 +548,11 @@ class BLSTMEncoder:
                 X = _to_bf16(X16, ws["Xbf"][k][:X16.numel()].view(X16.shape))
                 M = _to_bf16(ws["M"][i], ws["Mbf"][k])
                 if split:
+                    # dW_p^T = dH^T * M needs nothing from layer 0's BPTT: both directions run beside it (capped grid)
+                    cap0 = L.lcb_gemm_set_max_ctas(80)
+                    for d in range(2):
+                        gemm(dH_this[:, d * c.P:(d + 1) * c.P], M[:, d * c.Hp:(d + 1) * c.Hp], 1, 1, out=gWpT[d])
+                    L.lcb_gemm_set_max_ctas(cap0)
                     converted = torch.cuda.Event()
                     converted.record(side)
                     side.wait_event(after)
@@ -557,7 +563,8 @@ class BLSTMEncoder:
                     Md = M[:, d * c.Hp:(d + 1) * c.Hp]
                     dGd = dG[:, d * 4 * c.Hp:(d + 1) * 4 * c.Hp]
                     # dW_p^T[p,h] = sum_n dH[n,p] * M[n,h]
-                    gemm(dHd, Md, 1, 1, out=gWpT[d])
+                    if not split:
+                        gemm(dHd, Md, 1, 1, out=gWpT[d])
                     dfold = ws["dfold"][d]
                     if T > 1:
                         # dW'^T[g,h] = sum_n dz_n[g] * m_prev(n)[h]; prev = t-1 (fwd) / t+1 (bwd): a row shift of B
@@ -621,11 +628,15 @@ class BLSTMEncoder:
         # "Early rows": scan step s of BPTT visits frame T-1-s in the forward and frame s in the backward direction, so after the
         # scan steps [0, Tb) with Tb > T/2 the frames [T-Tb, Tb) have their final dG in BOTH directions.  Their rows of dX -- and of
         # the dM of the layer below, which needs nothing else -- are computed on a side stream beside the launch over
-        # [Tb, T); only the rows of the first and last T-Tb frames stay on the serial chain between two layers' BPTT.
-        Tb = int(math.ceil(self.bwd_early_frac * T)) if (overlap and self.xstream is not None and self.bwd_early_frac > 0.5
-                                                          and L.lcb_lstm_rec_bwd_can_split(c.Hp)) else 0
-        if Tb < T - Tb + 16 or T - Tb < 16:
-            Tb = 0
+        # [Tb, T); only the rows of the first and last T-Tb frames stay on the serial chain between two layers' BPTT.  With several
+        # cuts each launch releases the two bands of frames between its cut and the previous one.
+        cuts = []
+        if overlap and self.xstream is not None and L.lcb_lstm_rec_bwd_can_split(c.Hp):
+            for fr in self.bwd_early_fracs:
+                Tb = int(math.ceil(fr * T))
+                lo = cuts[-1] + 16 if cuts else (T - Tb) + 16       # first cut: at least 16 frames final in both directions
+                if fr > 0.5 and Tb >= lo and T - Tb >= 16:
+                    cuts.append(Tb)
         early = None                         # (first row, end row, event): rows of dH and of this layer's dM made on xstream
         pending = None                       # (layer, its dH): weight gradients not yet enqueued
         for i in reversed(range(c.num_layers)):
@@ -648,33 +659,37 @@ class BLSTMEncoder:
             gpeep = ps.g("L%d/peep" % i) if c.use_peepholes else None
             # BPTT in one launch, or as two launches over consecutive scan ranges joined by the carry buffer -- bit-identical
             # (lcb_lstm_rec_bwd_range): at Tb for the early rows above (layers 1..), or at bwd_split_frac (experiments)
-            if Tb > 0 and i > 0:
-                ranges = [(0, Tb), (Tb, T)]
+            if cuts and i > 0:
+                ranges = list(zip([0] + cuts, cuts + [T]))
             else:
                 Ts = int(math.ceil(self.bwd_split_frac * T)) if self.bwd_split_frac > 0 and L.lcb_lstm_rec_bwd_can_split(c.Hp) else 0
                 ranges = [(0, T)] if (Ts < 1 or Ts >= T) else [(0, Ts), (Ts, T)]
             if len(ranges) > 1 and "bwd_carry" not in ws:
                 ws["bwd_carry"] = torch.empty(B * 2 * c.Hp * 2, dtype=F32, device=self.device)
             dXn = ws["dX"][i % 3] if i > 0 else None
+            prev_cut = None
             for (s0, s1) in ranges:
                 _lib.check(L.lcb_lstm_rec_bwd_range(_lib.ptr(dM), _lib.ptr(ws["gates"][i]), _lib.ptr(ws["cst"][i]),
                                                     _lib.ptr(self._bf[("fold", i)]), _lib.ptr(peep),
                                                     _lib.ptr(seq_len), _lib.ptr(dG), _lib.ptr(ps.g("L%d/bias" % i)), _lib.ptr(gpeep),
                                                     T, B, c.Hp, s0, s1, _lib.ptr(ws.get("bwd_carry")),
                                                     _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(), _lib.stream_ptr()), "lcb_lstm_rec_bwd_range")
-                if Tb > 0 and i > 0 and s1 == Tb:
-                    first_done = torch.cuda.Event()
-                    first_done.record(main)
-                    r0, r1 = (T - Tb) * B, Tb * B
+                if cuts and i > 0 and s1 < T:
+                    # frames final in both directions now: [T-s1, s1), minus those the previous cut already released
+                    blocks = [(T - s1, s1)] if prev_cut is None else [(T - s1, T - prev_cut), (prev_cut, s1)]
+                    prev_cut = s1
+                    launched = torch.cuda.Event()
+                    launched.record(main)
                     with torch.cuda.stream(self.xstream):
-                        self.xstream.wait_event(first_done)
+                        self.xstream.wait_event(launched)
                         old_cap = L.lcb_gemm_set_max_ctas(self.early_cap)
-                        dx_rows(i, dG, dXn, r0, r1)
-                        dm_rows(i - 1, dXn, r0, r1)
+                        for (t0, t1) in blocks:
+                            dx_rows(i, dG, dXn, t0 * B, t1 * B)
+                            dm_rows(i - 1, dXn, t0 * B, t1 * B)
                         L.lcb_gemm_set_max_ctas(old_cap)
                         ev = torch.cuda.Event()
                         ev.record(self.xstream)
-                    early = (r0, r1, ev)
+                    early = ((T - s1) * B, s1 * B, ev)
             if pending is not None:
                 wgrad(pending[0], pending[1], chain_issued)   # layer i+1's weight gradients run beside this BPTT
             dH_this = dH

@@ -296,6 +296,96 @@ mos_bwd_kernel(const float* __restrict__ Z, const float* __restrict__ dY, __nv_b
     }
 }
 
+// The same, four consecutive expert columns per lane (K % 4 == 0, ldz % 4 == 0, 16-byte aligned rows): one float4 load, ONE
+// hash word per mask stream per four elements (the streams give 16 bits to each of four consecutive element indices, and both
+// n*K*V + c and n*K + k are multiples of four here), one 8-byte store.  FIXEDK (128 % K == 0): a lane meets the same four experts
+// in every iteration, so d loss / d pi accumulates in registers and is reduced with shuffles; otherwise shared-memory atomics.
+// The scalar kernel above spent ~200 instructions per element on the per-element hashes, the division and the atomics.
+template <bool FIXEDK>
+__global__ void __launch_bounds__(256)
+mos_bwd_v4_kernel(const float* __restrict__ Z, const float* __restrict__ dY, __nv_bfloat16* __restrict__ dZ,
+                  int n0, int R, int ldz, int T, int B, int V, int K, float tau,
+                  float inv_keep, uint32_t thr, unsigned long long seed_pi, unsigned long long seed_d)
+{
+    extern __shared__ float sm[];                     // per warp: dpi[K], pi[K] (masked: pi * m1), m1[K]
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* dpi = sm + (size_t)w * 3 * K;
+    float* pi = dpi + K;
+    float* m1s = pi + K;
+    const int KV = K * V;
+    const bool drop = thr < 65536u;
+    const int q = K >> 2;                              // lanes per period of the expert index (FIXEDK)
+    const int vstep = FIXEDK ? 128 / K : 0;
+    for (int r = blockIdx.x * 8 + w; r < R; r += gridDim.x * 8) {
+        const int n = n0 + r;
+        const int t = n / B, b = n - t * B;
+        const float* z = Z + (size_t)r * ldz;
+        const float* dy = dY + ((size_t)b * T + t) * V;
+        __nv_bfloat16* dz = dZ + (size_t)r * ldz;
+        // prior softmax, mixture-weight mask
+        float mx = -INFINITY;
+        for (int k = lane; k < K; k += 32) mx = fmaxf(mx, z[KV + k]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float s = 0.f;
+        for (int k = lane; k < K; k += 32) { const float e = __expf(z[KV + k] - mx); pi[k] = e; s += e; if (!FIXEDK) dpi[k] = 0.f; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float inv = 1.f / s;
+        for (int k4 = lane * 4; k4 < K; k4 += 128) {
+            const uint64_t word = drop ? rng_u64(seed_pi, ((uint64_t)n * K + k4) >> 2) : 0ull;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) m1s[k4 + e] = (!drop || rng_keep16(word, e, thr)) ? inv_keep : 0.f;
+        }
+        __syncwarp();
+        for (int k = lane; k < K; k += 32) pi[k] *= inv;          // plain pi (softmax backward needs it unmasked)
+        __syncwarp();
+        // expert columns: dz = dy * pi * tau * (1 - tanh^2);  dpi[k] += dy * tau * tanh
+        // forward: y_v = sum_k pi'_k * tau * th_k * m2/keep,  pi'_k = pi_k * m1/keep
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        int v = FIXEDK ? (lane * 4) / K : 0;
+        const int kfix = FIXEDK ? lane * 4 - v * K : 0;
+        for (int c = lane * 4; c < KV; c += 128) {
+            int k;
+            if (FIXEDK) k = kfix; else { v = c / K; k = c - v * K; }
+            const float4 z4 = *reinterpret_cast<const float4*>(z + c);
+            const uint64_t word = drop ? rng_u64(seed_d, ((uint64_t)n * KV + c) >> 2) : 0ull;
+            const float dyv = dy[v] * tau;
+            const float4 p4 = *reinterpret_cast<const float4*>(pi + k);
+            const float4 a4 = *reinterpret_cast<const float4*>(m1s + k);
+            const float zz[4] = {z4.x, z4.y, z4.z, z4.w}, pp[4] = {p4.x, p4.y, p4.z, p4.w}, aa[4] = {a4.x, a4.y, a4.z, a4.w};
+            float o4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float th = tanhf_fast(zz[e]);
+                const float g = (!drop || rng_keep16(word, e, thr)) ? dyv * inv_keep : 0.f;
+                const float gm = g * aa[e];
+                if (FIXEDK) acc[e] += gm * th; else if (gm != 0.f) atomicAdd(&dpi[k + e], gm * th);
+                o4[e] = gm * pp[e] * (1.f - th * th);
+            }
+            *reinterpret_cast<uint2*>(dz + c) = make_uint2(pack_bf16x2(o4[0], o4[1]), pack_bf16x2(o4[2], o4[3]));
+            if (FIXEDK) v += vstep;
+        }
+        if (FIXEDK) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float a = acc[e];
+                for (int o = 16; o >= q; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (lane < q) dpi[lane * 4 + e] = a;
+            }
+        }
+        __syncwarp();
+        // softmax backward: dlogit_k = pi_k * (dpi_k - sum_j pi_j dpi_j)
+        float dot = 0.f;
+        for (int k = lane; k < K; k += 32) dot += pi[k] * dpi[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        for (int k = lane; k < K; k += 32) dz[KV + k] = __float2bfloat16(pi[k] * (dpi[k] - dot));
+        for (int c = KV + K + lane; c < ldz; c += 32) dz[c] = __float2bfloat16(0.f);
+        __syncwarp();
+    }
+}
+
 // dlogits [B,T,V] f32 batch-major -> [N, ldo] bf16 time-major (pad columns zero): the affine layer's dZ
 __global__ void pack_dlogits_kernel(const float* __restrict__ dY, __nv_bfloat16* __restrict__ out, int T, int B, int V, int ldo) {
     const size_t total = (size_t)T * B * ldo;
@@ -354,9 +444,24 @@ extern "C" int lcb_mos_bwd_dz(const float* Z, const float* dlogits, void* dZ, in
     if (!Z || !dlogits || !dZ) return LCB_ERR_NULL_POINTER;
     if (R <= 0 || K <= 0 || V <= 0 || ldz < K * V + K) return LCB_ERR_BAD_SHAPE;
     int grid = (R + 7) / 8; if (grid > 148 * 8) grid = 148 * 8;
-    const size_t smem = (size_t)8 * 2 * K * sizeof(float);
-    g_launches += 1; mos_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(Z, dlogits, (__nv_bfloat16*)dZ, n0, R, ldz, T, B, V, K, tau,
-                                                            1.f / keep_prob, keep_threshold16(keep_prob), seed, seed ^ 0xD1B54A32D192ED03ull);
+    const float inv_keep = 1.f / keep_prob;
+    const uint32_t thr = keep_threshold16(keep_prob);
+    const unsigned long long seed_d = seed ^ 0xD1B54A32D192ED03ull;
+    const bool vec = (K % 4 == 0) && (ldz % 4 == 0) && (((uintptr_t)Z & 15) == 0) && (((uintptr_t)dZ & 7) == 0);
+    g_launches += 1;
+    if (vec) {
+        const size_t smem = (size_t)8 * 3 * K * sizeof(float);
+        if (128 % K == 0)
+            mos_bwd_v4_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(Z, dlogits, (__nv_bfloat16*)dZ, n0, R, ldz, T, B, V, K, tau,
+                                                                                inv_keep, thr, seed, seed_d);
+        else
+            mos_bwd_v4_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(Z, dlogits, (__nv_bfloat16*)dZ, n0, R, ldz, T, B, V, K, tau,
+                                                                                 inv_keep, thr, seed, seed_d);
+    } else {
+        const size_t smem = (size_t)8 * 2 * K * sizeof(float);
+        mos_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(Z, dlogits, (__nv_bfloat16*)dZ, n0, R, ldz, T, B, V, K, tau,
+                                                                  inv_keep, thr, seed, seed_d);
+    }
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }
 

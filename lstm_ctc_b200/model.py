@@ -178,6 +178,16 @@ class AcousticModel:
         ws = self._out_ws(T, B)
         keep = c.keep_prob if training else 1.0
         self._out_seed = self.enc.dropout_seed(255)
+        self._xbf_done = None
+        if training and self.enc.wstream is not None:
+            # bf16 copy of the encoder output for the output layer's weight gradient: made on the side stream beside the output
+            # layer and the CTC sweep (both leave most of the chip idle) instead of at the head of backward()
+            main = torch.cuda.current_stream()
+            self.enc.wstream.wait_stream(main)
+            with torch.cuda.stream(self.enc.wstream):
+                _to_bf16(X, ws["Xbf"])
+                self._xbf_done = torch.cuda.Event()
+                self._xbf_done.record(self.enc.wstream)
         _lib.check(L.lcb_output_fwd(_lib.ptr(X), X.stride(0), _lib.ptr(self._out16), _lib.ptr(self.params.w("out/ball")),
                                     _lib.ptr(ws["logits"]), T, B, 2 * c.P, c.V, c.K, c.tau, keep, self._out_seed,
                                     _lib.stream_ptr()), "lcb_output_fwd")
@@ -193,7 +203,12 @@ class AcousticModel:
         N = T * B
         ws = self._out_ws(T, B)
         st = _lib.stream_ptr()
-        Xbf = _to_bf16(X16, ws["Xbf"])
+        if getattr(self, "_xbf_done", None) is not None:
+            torch.cuda.current_stream().wait_event(self._xbf_done)
+            self._xbf_done = None
+            Xbf = ws["Xbf"]
+        else:
+            Xbf = _to_bf16(X16, ws["Xbf"])
         gW, gb = self.params.g("out/Wall"), self.params.g("out/ball")
         dXtop = ws["dXtop"]
         ro = self.rows_out

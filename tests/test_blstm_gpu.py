@@ -164,7 +164,7 @@ def test_split_bptt_equals_whole(cuda_dev, B, T, frac):
         enc = BLSTMEncoder(ModelConfig(nnet_config(cfg)), dev)
         enc.from_tf_dict(params)
         enc.bwd_split_frac = f
-        enc.bwd_early_frac = 0.0
+        enc.bwd_early_fracs = []
         enc.forward(x.float().to(dev), lens.to(dev), training=True)
         enc.params.gflat.zero_()
         enc.backward(dtop.clone())
@@ -181,9 +181,9 @@ def test_split_bptt_equals_whole(cuda_dev, B, T, frac):
     assert g0.abs().max().item() > 0
 
 
-@pytest.mark.parametrize("B,T,frac,keep", [(40, 96, 0.75, 0.8), (64, 80, 0.6, 1.0), (24, 130, 0.85, 0.9)])
-def test_early_rows_schedule_equals_serial(cuda_dev, B, T, frac, keep):
-    """backward() with bwd_early_frac: BPTT of layers 1.. in two launches, the rows of dX (fused dropout mask addressed by
+@pytest.mark.parametrize("B,T,fracs,keep", [(40, 96, [0.75], 0.8), (64, 80, [0.6], 1.0), (24, 130, [0.65, 0.85], 0.9)])
+def test_early_rows_schedule_equals_serial(cuda_dev, B, T, fracs, keep):
+    """backward() with bwd_early_fracs: BPTT of layers 1.. in two or three launches, the rows of dX (fused dropout mask addressed by
     absolute element index) and of the next layer's dM whose dG is final after the first launch computed on a side stream
     beside the second -- three layers so that the three dX buffers rotate.  Same dz bit for bit in every layer that is still
     held (layer 0's depends on every dX above it), parameter gradients equal up to fp32 summation order."""
@@ -200,10 +200,10 @@ def test_early_rows_schedule_equals_serial(cuda_dev, B, T, frac, keep):
     nc = nnet_config(cfg)
     nc["dropout_rate"] = keep
     res = []
-    for f in (0.0, frac):
+    for f in ([], fracs):
         enc = BLSTMEncoder(ModelConfig(nc), dev)
         enc.from_tf_dict(params)
-        enc.bwd_early_frac = f
+        enc.bwd_early_fracs = f
         enc.forward(x.float().to(dev), lens.to(dev), training=True)
         enc.params.gflat.zero_()
         enc.backward(dtop.clone())

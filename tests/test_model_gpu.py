@@ -37,6 +37,7 @@ CASES = {
     "affine": dict(input_dim=40, num_layers=2, num_neurons=128, num_projects=64, num_targets=20, use_peepholes=True, num_experts=0),
     "mos_k4": dict(input_dim=24, num_layers=1, num_neurons=64, num_projects=64, num_targets=13, use_peepholes=False, num_experts=4),
     "mos_k8_v72": dict(input_dim=40, num_layers=2, num_neurons=128, num_projects=128, num_targets=72, use_peepholes=True, num_experts=8),
+    "mos_k12": dict(input_dim=24, num_layers=1, num_neurons=64, num_projects=64, num_targets=11, use_peepholes=True, num_experts=12),
     "mos_k5_odd": dict(input_dim=16, num_layers=1, num_neurons=64, num_projects=32, num_targets=31, use_peepholes=True, num_experts=5),
 }
 
@@ -141,12 +142,13 @@ def _mask(n, keep, seed, dev):
     return m.cpu().double()
 
 
-def test_dropout_parity_with_exported_masks(cuda_dev):
+@pytest.mark.parametrize("case", ["mos_k4", "mos_k12", "mos_k5_odd"])
+def test_dropout_parity_with_exported_masks(cuda_dev, case):
     """keep_prob = 0.8 on LSTM layer outputs (bilstm.py:128,137), mixture weights (moe.py:46) and expert logits
     (moe.py:61).  TF's RNG stream cannot be matched, so the kernels' counter-based masks are exported and fed to
     the oracle: logits, loss and gradients must then agree at the usual tolerance."""
     from lstm_ctc_b200.model import AcousticModel
-    cfg = oracle.OracleConfig(**CASES["mos_k4"])
+    cfg = oracle.OracleConfig(**CASES[case])      # K = 4: vectorised mixture backward, experts fixed per lane; 12: atomics; 5: scalar kernel
     cfg.num_layers = 2
     params = oracle.init_params(cfg, seed=31, bias_scale=0.1)
     B, T, keep = 5, 14, 0.8
