@@ -169,6 +169,7 @@ class BLSTMEncoder:
         # the next layer's dM) whose dG is final in BOTH directions after a launch are computed beside the next one (backward(),
         # "early rows").  Empty: one launch.
         self.bwd_early_fracs = [float(v) for v in os.environ.get("LCB_BWD_EARLY_FRACS", "0.67,0.85").split(",") if v]
+        self.l0_released = os.environ.get("LCB_L0_RELEASED", "1") != "0"   # layer 0's frame-sum gradients over released frames
         self.xstream = (torch.cuda.Stream(device=device, priority=int(os.environ.get("LCB_XSTREAM_PRIO", "0")))
                         if torch.cuda.is_available() else None)   # early rows of dX / dM
         self.early_cap = int(os.environ.get("LCB_EARLY_CAP", "84"))   # persistent-grid cap of those GEMMs (84 SMs idle beside BPTT)
@@ -531,10 +532,26 @@ class BLSTMEncoder:
         if overlap:
             side.wait_stream(main)           # the forward activations the side stream converts are complete
 
-        def wgrad(i, dH_this, after):
+        def dfold_rows(d, r0, r1, M, dG_, acc):
+            """share of the rows [r0, r1) of dz in dW'^T[g,h] = sum_n dz_n[g] * m_prev(n)[h] of direction d (prev = the row B
+            before / after): into ws["dfold"][d], accumulating if acc"""
+            if d == 0:
+                r0 = max(r0, B)
+            else:
+                r1 = min(r1, N - B)
+            if r1 <= r0:
+                return
+            sh = -B if d == 0 else B
+            gemm(dG_[r0:r1, d * 4 * c.Hp:(d + 1) * 4 * c.Hp], M[r0 + sh:r1 + sh, d * c.Hp:(d + 1) * c.Hp], 1, 1,
+                 out=ws["dfold"][d], accumulate=acc)
+
+        def wgrad(i, dH_this, after, released=()):
             """Weight gradients of layer i on the side stream.  `after` = event on the main stream behind the serial chain
             (dX, dropout, dM GEMMs) of the layer BELOW, so these GEMMs never take SMs from it: the BPTT launch that follows
-            leaves them 84 idle SMs for ~3.8 ms (capped grid); layer 0's run alone on the whole chip."""
+            leaves them 84 idle SMs for ~3.8 ms (capped grid); layer 0's run alone on the whole chip.
+            `released` (layer 0): [(frame blocks, event)] -- frames whose dG was final after a partial BPTT launch; their share of
+            the frame-sums dW' and dW_x is accumulated beside the remaining launches, only the outer frames' share is left for the
+            tail after BPTT."""
             k = i & 1
             dG = ws["dG"][k]
             gWpT, gWh, gWx = ps.g("L%d/WpT" % i), ps.g("L%d/Wh" % i), ps.g("L%d/Wx" % i)
@@ -552,10 +569,20 @@ class BLSTMEncoder:
                     cap0 = L.lcb_gemm_set_max_ctas(80)
                     for d in range(2):
                         gemm(dH_this[:, d * c.P:(d + 1) * c.P], M[:, d * c.Hp:(d + 1) * c.Hp], 1, 1, out=gWpT[d])
+                    done_blocks = []
+                    for blocks, ev in released:
+                        side.wait_event(ev)
+                        for (t0, t1) in blocks:
+                            for d in range(2):
+                                dfold_rows(d, t0 * B, t1 * B, M, dG, bool(done_blocks))
+                            gemm(dG[t0 * B:t1 * B], X[t0 * B:t1 * B], 1, 1, out=gWx, accumulate=bool(done_blocks))
+                            done_blocks.append((t0, t1))
                     L.lcb_gemm_set_max_ctas(cap0)
                     converted = torch.cuda.Event()
                     converted.record(side)
                     side.wait_event(after)
+                    # frames not covered yet: the two outer bands (or everything)
+                    rest = [(0, T)] if not done_blocks else [(0, min(b[0] for b in done_blocks)), (max(b[1] for b in done_blocks), T)]
                 if overlap:
                     old_cap = L.lcb_gemm_set_max_ctas(80 if i > 0 else 148)
                 def direction(d):
@@ -568,7 +595,10 @@ class BLSTMEncoder:
                     dfold = ws["dfold"][d]
                     if T > 1:
                         # dW'^T[g,h] = sum_n dz_n[g] * m_prev(n)[h]; prev = t-1 (fwd) / t+1 (bwd): a row shift of B
-                        if d == 0:
+                        if split and done_blocks:
+                            for (t0, t1) in rest:
+                                dfold_rows(d, t0 * B, t1 * B, M, dG, True)
+                        elif d == 0:
                             gemm(dGd[B:], Md[:N - B], 1, 1, out=dfold)
                         else:
                             gemm(dGd[:N - B], Md[B:], 1, 1, out=dfold)
@@ -591,7 +621,12 @@ class BLSTMEncoder:
                 else:
                     direction(1)
                 # dW_x[g,k] = sum_n dz_n[g] * x_n[k]   (both directions at once)
-                gemm(dG, X, 1, 1, out=gWx)
+                if split and done_blocks:
+                    for (t0, t1) in rest:
+                        if t1 > t0:
+                            gemm(dG[t0 * B:t1 * B], X[t0 * B:t1 * B], 1, 1, out=gWx, accumulate=True)
+                else:
+                    gemm(dG, X, 1, 1, out=gWx)
                 if split:
                     side.wait_event(dir1_done)
                 if overlap:
@@ -637,6 +672,7 @@ class BLSTMEncoder:
                 lo = cuts[-1] + 16 if cuts else (T - Tb) + 16       # first cut: at least 16 frames final in both directions
                 if fr > 0.5 and Tb >= lo and T - Tb >= 16:
                     cuts.append(Tb)
+        released0 = []
         early = None                         # (first row, end row, event): rows of dH and of this layer's dM made on xstream
         pending = None                       # (layer, its dH): weight gradients not yet enqueued
         for i in reversed(range(c.num_layers)):
@@ -659,7 +695,7 @@ class BLSTMEncoder:
             gpeep = ps.g("L%d/peep" % i) if c.use_peepholes else None
             # BPTT in one launch, or as two launches over consecutive scan ranges joined by the carry buffer -- bit-identical
             # (lcb_lstm_rec_bwd_range): at Tb for the early rows above (layers 1..), or at bwd_split_frac (experiments)
-            if cuts and i > 0:
+            if cuts:
                 ranges = list(zip([0] + cuts, cuts + [T]))
             else:
                 Ts = int(math.ceil(self.bwd_split_frac * T)) if self.bwd_split_frac > 0 and L.lcb_lstm_rec_bwd_can_split(c.Hp) else 0
@@ -674,12 +710,16 @@ class BLSTMEncoder:
                                                     _lib.ptr(seq_len), _lib.ptr(dG), _lib.ptr(ps.g("L%d/bias" % i)), _lib.ptr(gpeep),
                                                     T, B, c.Hp, s0, s1, _lib.ptr(ws.get("bwd_carry")),
                                                     _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(), _lib.stream_ptr()), "lcb_lstm_rec_bwd_range")
-                if cuts and i > 0 and s1 < T:
+                if cuts and s1 < T:
                     # frames final in both directions now: [T-s1, s1), minus those the previous cut already released
                     blocks = [(T - s1, s1)] if prev_cut is None else [(T - s1, T - prev_cut), (prev_cut, s1)]
                     prev_cut = s1
                     launched = torch.cuda.Event()
                     launched.record(main)
+                    if i == 0:
+                        if self.l0_released:
+                            released0.append((blocks, launched))      # layer 0 has no dX: its weight gradients use the released frames
+                        continue
                     with torch.cuda.stream(self.xstream):
                         self.xstream.wait_event(launched)
                         old_cap = L.lcb_gemm_set_max_ctas(self.early_cap)
@@ -702,7 +742,7 @@ class BLSTMEncoder:
                     dx_rows(i, dG, dXn, early[1], N)
                 dH = dXn
             pending = (i, dH_this)
-        wgrad(pending[0], pending[1], mark())
+        wgrad(pending[0], pending[1], mark(), released0)
         if overlap:
             main.wait_stream(side)
         return None
