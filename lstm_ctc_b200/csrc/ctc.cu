@@ -475,7 +475,9 @@ static bool ctc_make_plan(int B, int T, int V, int Lmax, CtcPlan& p) {
     struct Cfg { int nw, spt; };
     // fewest states per thread first: the sweep is a serial chain of T steps whose length grows with the per-thread
     // instruction count (measured 4.4 cycles per issued instruction at one warp per scheduler), a CTA barrier costs less
-    const Cfg cfgs[] = {{1, 2}, {4, 2}, {8, 2}, {16, 2}, {16, 4}, {32, 4}, {32, 8}};
+    // (idle threads still execute the sweep: at L = 300 the 16 x 2 plan kept 41 % of its warps busy with padding states and the
+    // kernel is XU-pipe bound there -- MUFU + f64<->f32 conversions -- so the warp count follows S closely)
+    const Cfg cfgs[] = {{1, 2}, {2, 2}, {4, 2}, {6, 2}, {8, 2}, {10, 2}, {12, 2}, {16, 2}, {16, 4}, {32, 4}, {32, 8}};
     bool ok = false;
     for (const Cfg& c : cfgs)
         if (S <= c.nw * 32 * c.spt) { p.NW = c.nw; p.SPT = c.spt; ok = true; break; }
@@ -599,6 +601,10 @@ extern "C" int lcb_ctc_loss_grad_f32(const float* logits, const int64_t* labels,
         dispatch_softmax<1>(logits, grad, B, T, V, meta, lab, p.LABP, lpb, lpl, p.LPP, st);
     cudaError_t e = cudaSuccess;
     if (p.NW == 1 && p.SPT == 2) e = launch_ab<1, 2>(p, B, T, V, meta, lab, lpb, lpl, alpha, beta, logp, grad, loss, st);
+    else if (p.NW == 2 && p.SPT == 2) e = launch_ab<2, 2>(p, B, T, V, meta, lab, lpb, lpl, alpha, beta, logp, grad, loss, st);
+    else if (p.NW == 6 && p.SPT == 2) e = launch_ab<6, 2>(p, B, T, V, meta, lab, lpb, lpl, alpha, beta, logp, grad, loss, st);
+    else if (p.NW == 10 && p.SPT == 2) e = launch_ab<10, 2>(p, B, T, V, meta, lab, lpb, lpl, alpha, beta, logp, grad, loss, st);
+    else if (p.NW == 12 && p.SPT == 2) e = launch_ab<12, 2>(p, B, T, V, meta, lab, lpb, lpl, alpha, beta, logp, grad, loss, st);
     else if (p.NW == 4 && p.SPT == 2) e = launch_ab<4, 2>(p, B, T, V, meta, lab, lpb, lpl, alpha, beta, logp, grad, loss, st);
     else if (p.NW == 8 && p.SPT == 2) e = launch_ab<8, 2>(p, B, T, V, meta, lab, lpb, lpl, alpha, beta, logp, grad, loss, st);
     else if (p.NW == 16 && p.SPT == 2) e = launch_ab<16, 2>(p, B, T, V, meta, lab, lpb, lpl, alpha, beta, logp, grad, loss, st);

@@ -62,10 +62,14 @@ def _random_case(rng, B, T, V, Lmax, scale=3.0, full_len=False):
 
 @pytest.mark.parametrize("B,T,V,Lmax", [
     (8, 50, 30, 10),      # 1 warp / 2 states per thread
-    (5, 120, 72, 60),     # 4 warps x 2
-    (4, 300, 72, 120),    # 4 warps x 4
-    (3, 700, 31, 300),    # 4 warps x 8, odd V (scalar path)
-    (2, 1100, 500, 520),  # 8 warps x 8
+    (5, 120, 72, 60),     # 2 warps x 2
+    (3, 400, 72, 180),    # 6 warps x 2
+    (3, 500, 40, 230),    # 8 warps x 2
+    (2, 800, 72, 350),    # 12 warps x 2
+    (2, 1000, 30, 450),   # 16 warps x 2
+    (4, 300, 72, 120),    # 4 warps x 2
+    (3, 700, 31, 300),    # 10 warps x 2, odd V (scalar path)
+    (2, 1100, 500, 520),  # 16 warps x 4
     (3, 64, 5000, 20),    # CTA-per-row softmax
     (2, 40, 9000, 8),     # big-row fallback
     (4, 30, 2, 3),        # V = 2: only blank + one label
