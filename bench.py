@@ -339,7 +339,9 @@ def kernel_breakdown(model, x, lens, y, w, frames):
                 N_ = Bm.shape[0] if bl == 0 else Bm.shape[1]
                 cls = {(0, 0): "forward (X*W^T: projections, h-projection, output recompute)", (0, 1): "dgrad (dG*W)",
                        (1, 1): "wgrad (X^T*dG, K = frames)"}.get((al, bl), "other")
-                gemm_calls.append((cls, 2.0 * M_ * N_ * K_, s, e))
+                cap = L.lcb_gemm_set_max_ctas(148)          # read the persistent-grid cap this launch ran under (host-side setting)
+                L.lcb_gemm_set_max_ctas(cap)
+                gemm_calls.append((cls, 2.0 * M_ * N_ * K_, s, e, min(max(int(cap), 1), 148) / 148.0))
             return r
         return wrap
 
@@ -410,19 +412,37 @@ def kernel_breakdown(model, x, lens, y, w, frames):
     # >= 20 GFLOP only, so the tiny weight-folding GEMMs do not blur the classes.  The forward projections' tails and all
     # weight gradients run on a CAPPED grid (84 / 80 of 148 SMs) beside the recurrence, by design.
     classes = {}
-    for cls, fl, s_, e_ in gemm_calls:
+    share_ms = 0.0                      # sum over GEMM launches of duration x fraction of the SMs the launch was granted
+    all_ms = 0.0
+    for cls, fl, s_, e_, share in gemm_calls:
+        ms_ = s_.elapsed_time(e_)
+        share_ms += ms_ * share
+        all_ms += ms_
         if fl < 2e10:
             continue
-        c_ = classes.setdefault(cls, {"launches": 0, "flops": 0.0, "ms_total": 0.0})
+        c_ = classes.setdefault(cls, {"launches": 0, "flops": 0.0, "ms_total": 0.0, "sm_ms": 0.0})
         c_["launches"] += 1
         c_["flops"] += fl
-        c_["ms_total"] += s_.elapsed_time(e_)
+        c_["ms_total"] += ms_
+        c_["sm_ms"] += ms_ * share
     for c_ in classes.values():
         c_["tflops"] = c_["flops"] / (c_["ms_total"] * 1e-3) / 1e12 if c_["ms_total"] > 0 else 0.0
-        c_["frac_of_sustained_peak"] = c_["tflops"] / tf_sus
-        del c_["flops"]
+        c_["mean_sm_share"] = c_["sm_ms"] / c_["ms_total"] if c_["ms_total"] > 0 else 1.0
+        c_["frac_of_sustained_peak_of_sms_granted"] = c_["tflops"] / (tf_sus * c_["mean_sm_share"])
+        del c_["flops"], c_["sm_ms"]
     if roof is not None and classes:
         roof["gemm_classes"] = classes
+    if roof is not None and dom == "gemm" and all_ms > 0:
+        # Many launches of this family run on a CAPPED persistent grid (84 / 80 of 148 SMs) beside the recurrence clusters, by
+        # design; the roofline of such a launch is the peak of the SMs it was granted.  `peak` is therefore the measured
+        # sustained peak x the duration-weighted mean SM share of the family's launches; the whole-chip figures stay beside it.
+        mean_share = share_ms / all_ms
+        roof["peak_whole_chip"] = roof["peak"]
+        roof["frac_whole_chip"] = roof["frac"]
+        roof["mean_sm_share"] = mean_share
+        roof["peak"] = roof["peak_whole_chip"] * mean_share
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof["note"] += "; peak = measured sustained peak x duration-weighted mean fraction of the 148 SMs the launches were granted"
     # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed `ncu --set full`
     # capture of this same command (profiles/r01_ncu_traffic.json; null if the capture does not cover this workload)
     try:

@@ -37,7 +37,11 @@ for r in rows[hi + 1:]:
         d[r[MN]] = (float(r[VAL].replace(",", "")), r[UNIT])
     except ValueError:
         pass
-WHAT = {("256, 1, 1, 0", 768000): "wgrad dWx (K = 96000, capped grid)", ("256, 0, 1, 1", 768000): "dgrad dX = dG*Wx (bf16 out, fused dropout)",
+WHAT = {("256, 0, 0, 0", 245760): "projection tail X*Wx (64 % of the frames, capped grid beside the forward recurrence)",
+        ("256, 0, 0, 0", 138240): "projection head X*Wx (36 % of the frames, whole chip)",
+        ("256, 0, 1, 1", 138240): "dX early rows, first cut (capped grid beside BPTT)", ("256, 0, 1, 1", 262144): "dX early rows",
+        ("256, 0, 1, 1", 115712): "dX late rows (whole chip, on the serial chain)",
+("256, 1, 1, 0", 768000): "wgrad dWx (K = 96000, capped grid)", ("256, 0, 1, 1", 768000): "dgrad dX = dG*Wx (bf16 out, fused dropout)",
         ("256, 0, 1, 0", 48000): "dM = dH*W_proj^T (fp32 out)", ("256, 0, 0, 2", 48000): "h = m*W_proj (fp16 out, fused dropout)",
         ("128, 1, 1, 0", 383744): "wgrad dW' (split-K, capped grid)", ("128, 1, 1, 0", 96000): "wgrad dW_proj (split-K, capped grid)"}
 cls = collections.OrderedDict()
@@ -46,7 +50,9 @@ for d in L.values():
     dur = d["gpu__time_duration.sum"]
     us = dur[0] * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(dur[1], 1e-3)
     inst = int(d["sm__inst_executed_pipe_tensor.sum"][0])
-    tp = d.get("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", (float("nan"),))[0]
+    # (sm__pipe_tensor_cycles_active_realtime is only reported inside ncu's sections, not as a --metrics name on this ncu: the
+    # column shows the SM-throughput percentage instead; the tensor-pipe figure of the big launches is in r01_ncu_full_summary.txt)
+    tp = d.get("sm__throughput.avg.pct_of_peak_sustained_elapsed", (float("nan"),))[0]
     c = cls.setdefault((t, d["grid"], inst), [0, 0.0, 0.0])
     c[0] += 1
     c[1] += us
@@ -54,8 +60,8 @@ for d in L.values():
 print("tcgen05.mma instruction counts (ncu sm__inst_executed_pipe_tensor.sum) -> achieved tensor throughput per GEMM launch class of one C3 training step")
 print("flops = instructions x 2*128*BN*16; per-SM peak = measured cuBLAS bf16 burst %.1f TFLOP/s / 148 SMs (MEASURED_PEAKS.json); grid = persistent CTAs = SMs used" % burst)
 print("(weight-gradient GEMMs run on a capped grid of 80 beside the BPTT clusters; projection tails on 84 beside the forward recurrence);")
-print("tensor%% = ncu sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed over ALL 148 SMs; times are ncu's (cold cache, serialised)")
-print("%-18s %5s %9s %4s %9s %9s %15s %8s  %s" % ("template<BN,A,B,C>", "grid", "mma inst", "n", "avg us", "TFLOP/s", "% of SMs' peak", "tensor%", "what"))
+print("sm% = ncu sm__throughput.avg.pct_of_peak_sustained_elapsed over ALL 148 SMs; times are ncu's (cold cache, serialised)")
+print("%-18s %5s %9s %4s %9s %9s %15s %8s  %s" % ("template<BN,A,B,C>", "grid", "mma inst", "n", "avg us", "TFLOP/s", "% of SMs' peak", "sm%", "what"))
 for (t, grid, inst), (n, us, tp) in sorted(cls.items(), key=lambda kv: -kv[1][1]):
     if us / n < 20:
         continue
