@@ -183,6 +183,12 @@ int lcb_dropout_mask(unsigned char* mask, size_t n, float keep_prob, unsigned lo
 int lcb_colsum(const void* src, int src_dtype, int rows, int cols, int ld, float* out, void* stream);
 /* y += x on fp16 tensors, n even: the layer-0 residual  finput = finput + concat(fwd, bwd)  (nnet/bilstm.py:199-200). */
 int lcb_add_f16(void* y, const void* x, size_t n, void* stream);
+/* y[r,c] += mask * x[r,c] / keep_prob on 16-bit 2-D tensors (dtype 1 bf16, 2 fp16; row strides ldy, ldx in elements), mask =
+ * element (mask_base + r*ldm + c) of the (seed) stream lcb_gemm16_dropout applies to the same output.  The residual connection of
+ * DropoutWrapper(ResidualWrapper(LSTMCell)), out = dropout(x + cell(x))  (nnet/lstm.py:236-260): forward adds the masked layer
+ * input to the projected output, backward adds the masked output gradient to the input gradient. */
+int lcb_masked_add16(void* y, int ldy, const void* x, int ldx, long long rows, int cols, int dtype, float keep_prob,
+                     unsigned long long seed, unsigned long long mask_base, int ldm, void* stream);
 /* label-smoothing regulariser (nnet/bilstm.py:254-269) over `rows` rows of logits [rows,V]:
  *   *loss_out += weight * sum p (log p - q),  dlogits (nullable) += its gradient;  q = log(1/V) when log_prior is
  *   NULL (uniform_label_sm) else log_prior[V] (prior_label_sm, nnet/class_prior.py).  All rows, padding included. */

@@ -1,6 +1,6 @@
 """lstm_ctc_b200 -- B200-native (sm_100a) BiLSTM / mixture-output / CTC training hot path behind the
 reference's `nnet` Python API (/root/reference/nnet/__init__.py:15-26: the same eleven names, minus the
-broken beam-search decoding graph)."""
+broken beam-search decoding graph).  nnet_type 'blstm' (nnet/bilstm.py) and 'lstm' (functional core of nnet/lstm.py)."""
 __version__ = "0.1.0"
 
 from .config import parse_config  # noqa: F401

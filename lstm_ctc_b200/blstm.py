@@ -57,6 +57,12 @@ class ModelConfig:
         self.prior_label_sm = c.get("prior_label_sm")
         self.prior_label_path = c.get("prior_label_path")
         self.forget_bias = 5.0                                            # bilstm.py:133,154
+        # nnet_type 'lstm': the uni-directional residual stack of create_logits_lstm (nnet/lstm.py:125-368) -- run on the same
+        # kernels with the backward cells and every weight that reads their output pinned at zero (see lstm.py of this package)
+        self.uni = (c.get("nnet_type") == "lstm")
+        if self.uni:
+            self.use_peepholes = True                                     # lstm.py:241,252 (hard-coded)
+            self.forget_bias = 1.0                                        # LSTMCell default (lstm.py:238-244 passes none)
         # device layout
         self.Hp = _ceil(self.H, 64)
         if self.Hp > 512:
@@ -64,7 +70,11 @@ class ModelConfig:
         if self.P % 8:
             raise _lib.LcbError(-3, "num_projects must be a multiple of 8")
         self.Dp0 = _ceil(self.input_dim, 8)
-        self.residual0 = (self.input_dim == 2 * self.P)                   # bilstm.py:199-200
+        self.residual0 = (not self.uni) and (self.input_dim == 2 * self.P)   # bilstm.py:199-200
+
+    def uni_residual(self, i):
+        """ResidualWrapper on every cell except layer 0 when input_dim != num_projects (lstm.py:236-260)."""
+        return self.uni and (i > 0 or self.input_dim == self.P)
 
     def din(self, i):
         return self.input_dim if i == 0 else 2 * self.P
@@ -490,6 +500,13 @@ class BLSTMEncoder:
                     main.wait_event(hp_done)
                 else:
                     hproj(0, T)
+            if c.uni_residual(i):
+                # DropoutWrapper(ResidualWrapper(cell)): out = dropout(x + h) -- the GEMM epilogue wrote dropout(h); add dropout(x)
+                # with the same mask (forward half of the columns only; the other half is identically zero in this mode)
+                src = ws["X0"] if i == 0 else ws["Hout"][i - 1]
+                keep = c.keep_prob if training else 1.0
+                _lib.check(L.lcb_masked_add16(_lib.ptr(Hout), 2 * c.P, _lib.ptr(src), src.stride(0), T * B, c.P, 2, keep,
+                                              self.dropout_seed(i), 0, 2 * c.P, st), "lcb_masked_add16")
             if i == 0 and c.residual0:              # finput = finput + concat(...)  iff input_dim == 2*num_projects (bilstm.py:199-200)
                 _lib.check(L.lcb_add_f16(_lib.ptr(Hout), _lib.ptr(ws["X0"]), Hout.numel(), st), "lcb_add_f16")
             X = Hout
@@ -652,13 +669,19 @@ class BLSTMEncoder:
             for d in range(2):
                 gemm(dH_[r0:r1, d * c.P:(d + 1) * c.P], self._bf[("WpT", i)][d], 0, 1, out=ws["dM"][r0:r1, d * c.Hp:(d + 1) * c.Hp])
 
-        def dx_rows(i, dG_, dXn_, r0, r1):
+        def dx_rows(i, dG_, dXn_, r0, r1, dHcur=None):
             """dX[r0:r1] = dG[r0:r1] * W_x of layer i, with the mask of layer i-1's output dropout (same seed and element indices as
             the forward pass) in the epilogue"""
             if r1 <= r0:
                 return
             gemm(dG_[r0:r1], self._bf[("Wx", i)], 0, 1, out=dXn_[r0:r1],
                  dropout=(c.keep_prob, self.dropout_seed(i - 1), r0 * 2 * c.P) if c.keep_prob < 1.0 else None)
+            if c.uni_residual(i):
+                # residual path of layer i: d loss / d x_i += d loss / d (x_i + h_i) = this layer's (already masked) output gradient,
+                # then through layer i-1's output dropout like the GEMM result
+                _lib.check(L.lcb_masked_add16(_lib.ptr(dXn_[r0:r1]), 2 * c.P, _lib.ptr(dHcur[r0:r1]), dHcur.stride(0), r1 - r0, c.P, 1,
+                                              c.keep_prob, self.dropout_seed(i - 1), r0 * 2 * c.P, 2 * c.P, _lib.stream_ptr()),
+                           "lcb_masked_add16")
 
         # "Early rows": scan step s of BPTT visits frame T-1-s in the forward and frame s in the backward direction, so after the
         # scan steps [0, Tb) with Tb > T/2 the frames [T-Tb, Tb) have their final dG in BOTH directions.  Their rows of dX -- and of
@@ -724,7 +747,7 @@ class BLSTMEncoder:
                         self.xstream.wait_event(launched)
                         old_cap = L.lcb_gemm_set_max_ctas(self.early_cap)
                         for (t0, t1) in blocks:
-                            dx_rows(i, dG, dXn, t0 * B, t1 * B)
+                            dx_rows(i, dG, dXn, t0 * B, t1 * B, dH)
                             dm_rows(i - 1, dXn, t0 * B, t1 * B)
                         L.lcb_gemm_set_max_ctas(old_cap)
                         ev = torch.cuda.Event()
@@ -736,10 +759,10 @@ class BLSTMEncoder:
             if i > 0:
                 # dX = dG * W_x (layer i+1's wgrad reads ITS dH from another of the three buffers)
                 if early is None:
-                    dx_rows(i, dG, dXn, 0, N)
+                    dx_rows(i, dG, dXn, 0, N, dH)
                 else:
-                    dx_rows(i, dG, dXn, 0, early[0])
-                    dx_rows(i, dG, dXn, early[1], N)
+                    dx_rows(i, dG, dXn, 0, early[0], dH)
+                    dx_rows(i, dG, dXn, early[1], N, dH)
                 dH = dXn
             pending = (i, dH_this)
         wgrad(pending[0], pending[1], mark(), released0)

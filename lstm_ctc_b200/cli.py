@@ -66,7 +66,7 @@ def _build(args, is_training, training_graph):
     if args.objective != "ctc":
         _fatal("unsupported objective: %s" % args.objective)
         sys.exit(1)
-    if nnet_type != "blstm":            # the reference's 'lstm' / 'cudnnlstm' builders do not run as shipped
+    if nnet.get_create_logits(nnet_type) is None:      # 'blstm', 'lstm'; the reference's 'cudnnlstm' builder does not run as shipped
         _fatal("unsupported nnet_type: %s" % nnet_type)
         sys.exit(1)
     init, pipeline = nnet.create_pipeline_sequence_batch(dataset=tfrecord, input_dim=input_dim, batch_size=args.batch_size,

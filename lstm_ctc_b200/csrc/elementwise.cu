@@ -89,6 +89,33 @@ __global__ void add_f16_kernel(__half2* __restrict__ y, const __half2* __restric
     }
 }
 
+// y[r, c] += mask * x[r, c] / keep on 16-bit 2-D tensors, mask = element (mask_base + r*ldm + c) of the (seed) stream that
+// lcb_gemm16_dropout uses for the same output: the residual connection of ResidualWrapper under a DropoutWrapper
+// (nnet/lstm.py:236-260: out = dropout(x + cell(x))) -- the GEMM epilogue already wrote dropout(cell(x)), this adds dropout(x)
+// with the SAME mask; in backward it adds the masked output gradient to the input gradient.
+template <bool F16>
+__global__ void masked_add16_kernel(uint16_t* __restrict__ y, int ldy, const uint16_t* __restrict__ x, int ldx, long long rows, int cols,
+                                    float inv_keep, uint32_t thr16, uint64_t seed, unsigned long long mask_base, int ldm) {
+    const long long total = rows * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cols;
+        const int c = (int)(i - r * cols);
+        const unsigned long long k = mask_base + (unsigned long long)r * ldm + c;
+        const bool keep = thr16 >= 65536u || rng_keep16(rng_u64(seed, k >> 2), (int)(k & 3), thr16);
+        if (!keep) continue;
+        float a, b;
+        if constexpr (F16) {
+            a = __half2float(reinterpret_cast<const __half*>(y)[r * ldy + c]);
+            b = __half2float(reinterpret_cast<const __half*>(x)[r * ldx + c]);
+            reinterpret_cast<__half*>(y)[r * ldy + c] = __float2half_rn(sat_f16(a + b * inv_keep));
+        } else {
+            a = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(y)[r * ldy + c]);
+            b = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[r * ldx + c]);
+            reinterpret_cast<__nv_bfloat16*>(y)[r * ldy + c] = __float2bfloat16(a + b * inv_keep);
+        }
+    }
+}
+
 // label-smoothing regulariser (nnet/bilstm.py:254-269): per row p = softmax(logits),
 //   loss += w * sum_v p_v (log p_v - q_v),   q = log(1/V) (uniform) or the given log prior;
 //   dlogits_v += w * p_v * ((log p_v - q_v) - sum_u p_u (log p_u - q_u)).   Over ALL B*T rows, padding included,
@@ -233,6 +260,18 @@ extern "C" int lcb_add_f16(void* y, const void* x, size_t n, void* stream) {
     if (n == 0) return LCB_OK;
     g_launches += 1;
     add_f16_kernel<<<grid_for(n / 2, 1, 256), 256, 0, (cudaStream_t)stream>>>((__half2*)y, (const __half2*)x, n / 2);
+    return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
+}
+
+extern "C" int lcb_masked_add16(void* y, int ldy, const void* x, int ldx, long long rows, int cols, int dtype, float keep_prob,
+                                unsigned long long seed, unsigned long long mask_base, int ldm, void* stream) {
+    if (!y || !x) return LCB_ERR_NULL_POINTER;
+    if ((dtype != 1 && dtype != 2) || !(keep_prob > 0.f) || keep_prob > 1.f || rows < 0 || cols < 0 || ldy < cols || ldx < cols) return LCB_ERR_BAD_SHAPE;
+    if (rows == 0 || cols == 0) return LCB_OK;
+    g_launches += 1;
+    const int grid = grid_for((size_t)rows * cols, 1, 256);
+    if (dtype == 2) masked_add16_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((uint16_t*)y, ldy, (const uint16_t*)x, ldx, rows, cols, 1.f / keep_prob, keep_threshold16(keep_prob), seed, mask_base, ldm);
+    else masked_add16_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((uint16_t*)y, ldy, (const uint16_t*)x, ldx, rows, cols, 1.f / keep_prob, keep_threshold16(keep_prob), seed, mask_base, ldm);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }
 

@@ -64,12 +64,16 @@ class Saver:
 
 
 def get_create_logits(string):
-    """graph.py:24-34.  Only 'blstm' is functional in the reference (the other two builders are stale)."""
+    """graph.py:24-34.  'blstm' is the builder both recipes use; 'lstm' is the functional core of the reference's stale
+    uni-directional builder (lstm.py of this package); 'cudnnlstm' (a cuDNN wrapper returning a bare tensor) is not offered."""
     if not string:
         return None
     if string == "blstm":
         from .bilstm import create_logits_blstm
         return create_logits_blstm
+    if string == "lstm":
+        from .lstm import create_logits_lstm
+        return create_logits_lstm
     return None
 
 

@@ -10,6 +10,7 @@ import torch
 
 from . import _lib
 from .blstm import BF16, F16, F32, BLSTMEncoder, ModelConfig, ParamSpec, _cast16, _ceil, _to_bf16
+from .lstm import embed_uni_variables, extract_uni_variables, random_uni_variables, uni_prefix
 from .ctc import ctc_loss_grad
 from .gemm import gemm
 
@@ -98,11 +99,13 @@ class AcousticModel:
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._gnorm = torch.zeros(1, dtype=F32, device=self.device)
         if init:
-            self.from_tf_dict(random_tf_variables(c, seed))
+            self.from_tf_dict(random_uni_variables(c, seed) if c.uni else random_tf_variables(c, seed))
 
     # ------------------------------------------------------------------ variables
     def from_tf_dict(self, tf: Dict[str, torch.Tensor]):
         c = self.cfg
+        if c.uni and (uni_prefix(0) + "/kernel") in tf:      # nnet_type 'lstm': uni-directional variables, embedded (lstm.py)
+            tf = embed_uni_variables(c, {k: v.detach().cpu() for k, v in tf.items()})
         self.enc.from_tf_dict(tf)
         Wall, ball = self.params.w("out/Wall"), self.params.w("out/ball")
         dev = self.device
@@ -121,8 +124,11 @@ class AcousticModel:
             ball.copy_(tf["Variable_1"].to(dev, F32))
         self.mark_stale()
 
-    def to_tf_dict(self, grads=False) -> Dict[str, torch.Tensor]:
+    def to_tf_dict(self, grads=False, embedded=False) -> Dict[str, torch.Tensor]:
+        """Reference-layout variables (or their gradients).  nnet_type 'lstm': the uni-directional set unless embedded=True."""
         c = self.cfg
+        if c.uni and not embedded:
+            return extract_uni_variables(c, self.to_tf_dict(grads, embedded=True))
         out = self.enc.to_tf_dict(grads)
         get = self.params.g if grads else self.params.w
         Wall, ball = get("out/Wall"), get("out/ball")

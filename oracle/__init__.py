@@ -22,4 +22,5 @@ from .model import (  # noqa: F401
     OracleConfig, init_params, blstm_forward, create_moe, output_layer, ctc_loss_sum,
     training_loss, clip_by_global_norm, adam_step, sgd_step, momentum_step, l2_loss,
     greedy_decode, edit_distance, param_order,
+    lstm_param_order, init_lstm_params, lstm_forward, lstm_training_loss,
 )

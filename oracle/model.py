@@ -7,6 +7,7 @@ Follows, line by line:
   /root/reference/nnet/bilstm.py:104-273   create_logits_blstm
   /root/reference/nnet/moe.py:29-72        create_moe
   /root/reference/nnet/graph.py:51-209     loss / training graph
+  /root/reference/nnet/lstm.py:125-368     create_logits_lstm -- its functional core only (lstm_* functions at the end)
 and the TF r1.8 semantics those call into (third-party, restated from the published sources):
   rnn_cell_impl.LSTMCell.call  (gate order i,j,f,o; peepholes; forget_bias; num_proj)
   rnn.dynamic_rnn / _rnn_step  (zero output + state copy-through past sequence_length)
@@ -133,7 +134,7 @@ def lstm_cell(x_t, c, h, kernel, bias, w_f, w_i, w_o, proj, forget_bias):
     return c_new, h_new
 
 
-def dynamic_rnn(x, seq_len, cellp, forget_bias, keep_prob=1.0, masks=None):
+def dynamic_rnn(x, seq_len, cellp, forget_bias, keep_prob=1.0, masks=None, residual=False):
     """tf.nn.dynamic_rnn over a DropoutWrapper(LSTMCell) (bilstm.py:127-137,171-188):
     zero output and state copy-through for t >= seq_len[b]; dropout on the emitted output only.
     masks: optional [B,T,P] 0/1 tensor standing in for TF's (unmatchable) RNG stream."""
@@ -147,7 +148,7 @@ def dynamic_rnn(x, seq_len, cellp, forget_bias, keep_prob=1.0, masks=None):
     for t in range(T):
         c_new, h_new = lstm_cell(x[:, t], c, h, kernel, bias, w_f, w_i, w_o, proj, forget_bias)
         live = (t < seq_len).to(x.dtype).unsqueeze(1)
-        out = h_new
+        out = h_new + x[:, t] if residual else h_new        # ResidualWrapper sits INSIDE the DropoutWrapper (lstm.py:247-259)
         if keep_prob < 1.0 and masks is not None:
             out = out * masks[:, t] / keep_prob
         outs.append(out * live)
@@ -310,3 +311,63 @@ def edit_distance(a, b):
             d[j] = min(d[j] + 1, d[j - 1] + 1, prev + (a[i - 1] != b[j - 1]))
             prev = cur
     return d[m]
+
+
+
+# ------------------------------------------------------------------------------------------------
+# create_logits_lstm (nnet/lstm.py:125-368), functional core: uni-directional stack of
+# DropoutWrapper([ResidualWrapper](LSTMCell(use_peepholes=True, num_proj))) run by dynamic_rnn(scope="drnn{i}"), default
+# forget_bias 1.0, no ResidualWrapper on layer 0 when input_dim != num_projects (lstm.py:236-260), then the affine /
+# mixture output layer over [N, num_projects] (lstm.py:318-345).  The builder's feature projection, ornn and
+# orthogonality terms call helpers that do not exist in the reference and are not restated.
+def lstm_param_order(cfg: OracleConfig) -> List[str]:
+    names = []
+    for i in range(cfg.num_layers):
+        p = "drnn%d/lstm_cell" % i
+        names += [p + "/kernel", p + "/bias", p + "/w_f_diag", p + "/w_i_diag", p + "/w_o_diag", p + "/projection/kernel"]
+    return names + (["Variable", "Variable_1", "Variable_2", "Variable_3"] if cfg.num_experts > 0 else ["Variable", "Variable_1"])
+
+
+def init_lstm_params(cfg: OracleConfig, seed=0, dtype=torch.float64, bias_scale=0.0) -> Dict[str, torch.Tensor]:
+    g = torch.Generator().manual_seed(seed)
+    H, P = cfg.num_neurons, cfg.num_projects
+    p: Dict[str, torch.Tensor] = {}
+    for i in range(cfg.num_layers):
+        din = cfg.input_dim if i == 0 else P
+        pre = "drnn%d/lstm_cell" % i
+        p[pre + "/kernel"] = _glorot((din + P, 4 * H), g, dtype)
+        p[pre + "/bias"] = (torch.randn(4 * H, generator=g, dtype=torch.float64) * bias_scale).to(dtype)
+        for w in ("w_f_diag", "w_i_diag", "w_o_diag"):
+            p[pre + "/" + w] = _glorot((H,), g, dtype)
+        p[pre + "/projection/kernel"] = _glorot((H, P), g, dtype)
+    std = 1.0 / math.sqrt(P)                                               # lstm.py:331
+    if cfg.num_experts > 0:
+        K, V = cfg.num_experts, cfg.num_targets
+        p["Variable"] = _trunc_normal((P, K), std, g, dtype)
+        p["Variable_1"] = (torch.randn(K, generator=g, dtype=torch.float64) * bias_scale).to(dtype)
+        p["Variable_2"] = _trunc_normal((P, K * V), std, g, dtype)
+        p["Variable_3"] = (torch.randn(K * V, generator=g, dtype=torch.float64) * bias_scale).to(dtype)
+    else:
+        p["Variable"] = _trunc_normal((P, cfg.num_targets), std, g, dtype)
+        p["Variable_1"] = (torch.randn(cfg.num_targets, generator=g, dtype=torch.float64) * bias_scale).to(dtype)
+    assert list(p.keys()) == lstm_param_order(cfg)
+    return p
+
+
+def lstm_forward(p, cfg: OracleConfig, nnet_input, seq_len, keep_prob=1.0, masks=None):
+    """Returns the last layer's output [B,T,P].  masks: optional {layer: [B,T,P]} 0/1 tensors."""
+    x = nnet_input
+    for i in range(cfg.num_layers):
+        pre = "drnn%d/lstm_cell" % i
+        cellp = (p[pre + "/kernel"], p[pre + "/bias"], p[pre + "/w_f_diag"], p[pre + "/w_i_diag"], p[pre + "/w_o_diag"],
+                 p[pre + "/projection/kernel"])
+        residual = not (i == 0 and cfg.input_dim != cfg.num_projects)      # lstm.py:236
+        x, _ = dynamic_rnn(x, seq_len, cellp, 1.0, keep_prob, None if masks is None else masks.get(i), residual=residual)
+    return x
+
+
+def lstm_training_loss(p, cfg, nnet_input, seq_len, labels, l2_decay_weight=1e-5, keep_prob=1.0, masks=None):
+    enc = lstm_forward(p, cfg, nnet_input, seq_len, keep_prob, masks)
+    logits = output_layer(p, cfg, enc)
+    ctc = ctc_loss_sum(logits, labels, seq_len)
+    return ctc, ctc + l2_loss(p, l2_decay_weight), logits

@@ -93,7 +93,8 @@ def test_validate_logs_cv_lines_and_nan_exits(capsys):
 
 def test_unsupported_optimizer_and_nnet_type():
     assert nnet.get_optimizer("adagrad", 0.1) is None and nnet.get_optimizer("adam", 0.1)["name"] == "adam"
-    assert nnet.get_create_logits("lstm") is None and nnet.get_create_logits(None) is None
+    assert nnet.get_create_logits("cudnnlstm") is None and nnet.get_create_logits(None) is None
+    assert nnet.get_create_logits("blstm") is not None and nnet.get_create_logits("lstm") is not None
 
 
 def test_param_store_bucket_order_matches_backward():
