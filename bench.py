@@ -137,8 +137,9 @@ def run_reference(args, w, emit):
     torch.set_num_threads(cores)
     cfg = oracle.OracleConfig(input_dim=w["D"], num_layers=w["num_layers"], num_neurons=w["H"], num_projects=w["P"],
                               num_targets=w["V"], use_peepholes=True, num_experts=w["K"], moe_temp=10.0)
-    # bounded sample of the same workload: a few utterances, a prefix of the frames
-    Bs, Ts = (2, 200) if w["T"] >= 1000 else (2, min(w["T"], 200))
+    # bounded sample of the same workload: the workload's batch width (the per-step matmuls of the reference's while-loop are
+    # [B, .] x [., 4H]: two utterances would leave the host cores idle -- 86 vs 670 frames/s on 8 cores), a prefix of the frames
+    Bs, Ts = min(w["B"], 64), min(w["T"], 60)
     ws = dict(w); ws["B"], ws["T"] = Bs, Ts
     x, lens, y = synth_batch(ws, 777)
     p = oracle.init_params(cfg, seed=0, dtype=torch.float32)
@@ -174,7 +175,7 @@ def cpu_baseline_sample(w, budget_s=20.0):
     torch.set_num_threads(cores)
     cfg = oracle.OracleConfig(input_dim=w["D"], num_layers=w["num_layers"], num_neurons=w["H"], num_projects=w["P"],
                               num_targets=w["V"], use_peepholes=True, num_experts=w["K"], moe_temp=10.0)
-    ws = dict(w); ws["B"], ws["T"] = 2, min(w["T"], 120)
+    ws = dict(w); ws["B"], ws["T"] = min(w["B"], 64), min(w["T"], 60)      # full batch width, a prefix of the frames (see run_reference)
     x, lens, y = synth_batch(ws, 777)
     p = oracle.init_params(cfg, seed=0, dtype=torch.float32)
     t_tot, frames, n = 0.0, 0, 0
