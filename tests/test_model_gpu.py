@@ -249,3 +249,53 @@ def test_layer0_residual(cuda_dev):
     bad = {k: ((v - p64[k].grad).norm() / (p64[k].grad.norm() + 1e-12)).item() for k, v in grads.items()}
     bad = {k: r for k, r in bad.items() if r > 5e-2}
     assert not bad, bad
+
+
+@pytest.mark.parametrize("T", [1, 9])
+def test_edge_lengths_through_the_whole_path(cuda_dev, T):
+    """Ragged edge cases in ONE batch, through BiLSTM -> mixture -> CTC -> gradients: an empty utterance (sequence_length 0: zero
+    output rows, skipped by CTC, loss 0 -- SURVEY 8c), a one-frame utterance, an utterance with no labels, one whose labels are
+    longer than its frames (ignore_longer_outputs_than_inputs=True, graph.py:113: loss 0, gradient 0) and a full one; T = 1 is
+    the shortest batch the kernels can be handed."""
+    from lstm_ctc_b200 import _lib
+    from lstm_ctc_b200.model import AcousticModel
+    cfg = oracle.OracleConfig(**CASES["mos_k4"])
+    cfg.num_layers = 2
+    params = oracle.init_params(cfg, seed=61, bias_scale=0.1)
+    B = 5
+    g = torch.Generator().manual_seed(62)
+    x = torch.randn(B, T, cfg.input_dim, generator=g, dtype=torch.float64)
+    lens = torch.tensor([0, 1, T, max(1, T // 2), T], dtype=torch.int32)
+    labels = torch.tensor([[1, -1, -1, -1, -1, -1], [2, -1, -1, -1, -1, -1], [-1, -1, -1, -1, -1, -1],
+                           [3, 4, 5, 6, 7, 8], [1, 2, -1, -1, -1, -1]])
+    if T == 1:
+        labels[4, 1] = -1
+    for b in range(B):
+        x[b, lens[b]:] = 0
+    p64 = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    ctc, _, ref_logits = oracle.training_loss(p64, cfg, x, lens, labels, l2_decay_weight=0.0)
+    ctc.backward()
+    m = AcousticModel(nnet_config(cfg), cuda_dev, init=False)
+    m.from_tf_dict(params)
+    loss_sum, loss = m.loss_and_grad(x.float().to(cuda_dev), lens.to(cuda_dev), labels.to(cuda_dev))
+    torch.cuda.synchronize()
+    assert _lib.lib().lcb_device_error(1) == 0
+    loss = loss.cpu()
+    assert loss[0].item() == 0.0                                   # empty utterance
+    if T > 1:
+        assert loss[3].item() == 0.0                               # 6 labels, T // 2 frames: ignored
+    assert abs(loss_sum.item() - ctc.item()) < 2e-3 * max(abs(ctc.item()), 1.0), (loss_sum.item(), ctc.item())
+    enc = m.enc._workspace(T, B, True)["Hout"][-1].float().view(T, B, -1)
+    assert enc[:, 0].abs().max().item() == 0.0                     # sequence_length 0: every output row exactly zero
+    assert enc[1:, 1].abs().max().item() == 0.0 if T > 1 else True
+    grads = {k: v.cpu().double() for k, v in m.to_tf_dict(grads=True).items()}
+    bad = {}
+    for k, v in grads.items():
+        rg = p64[k].grad
+        if rg.norm().item() < 1e-9:
+            assert v.norm().item() < 1e-6, k
+            continue
+        rel = ((v - rg).norm() / rg.norm()).item()
+        if rel > 5e-2:
+            bad[k] = rel
+    assert not bad, bad
