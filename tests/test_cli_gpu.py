@@ -87,3 +87,41 @@ def test_cli_init_train_validate_forward(cuda_dev, tmp_path, capfd):
     with pytest.raises(SystemExit) as e:
         cli.nnet_validate([scp, cfg, n1, "--batch-size", "4"])
     assert e.value.code == 1 and "unsupported objective: xent" in capfd.readouterr().err
+
+
+def test_cli_with_nnet_type_lstm(cuda_dev, tmp_path, capfd):
+    """The same four CLIs on the uni-directional stack (nnet_type lstm): the bundle holds the uni-directional
+    variables under TF's names, training lowers cv_loss, posteriors are normalised, cudnnlstm is refused like the reference's
+    unsupported types (nnet-train.py:70-77)."""
+    from lstm_ctc_b200 import cli, tf_bundle
+    tmp = str(tmp_path)
+    D, V = 8, 11
+    scp, lens = _write_corpus(tmp, 8, D, V, 1)
+    cfg = os.path.join(tmp, "nnet.config")
+    with open(cfg, "w") as fh:
+        fh.write("nnet_type lstm\ninput_dim %d\nleft_context 1\nright_context 1\nsubsample 3\nnum_layers 3\n"
+                 "num_neurons 64\nnum_projects 24\nnum_targets %d\nnum_experts 0\ndropout_rate 0.9\n" % (D, V))   # 3 * 8 = 24 = P: residual on layer 0 too
+    n0, n1 = os.path.join(tmp, "nnet.0"), os.path.join(tmp, "nnet.1")
+    cli.nnet_init([scp, cfg, n0, "--objective", "ctc", "--batch-size", "4"])
+    err = capfd.readouterr().err
+    cv0 = float(err.split("cv_loss = ")[1].split()[0])
+    names = sorted(tf_bundle.read_bundle(n0))
+    assert "drnn0/lstm_cell/kernel" in names and "drnn2/lstm_cell/projection/kernel" in names and not any(k.startswith(("fd", "bd")) for k in names)
+    assert tf_bundle.read_bundle(n0)["drnn1/lstm_cell/kernel"].shape == (24 + 24, 4 * 64)
+    for it in range(3):
+        cli.nnet_train([scp, cfg, n0 if it == 0 else n1, n1, "--objective", "ctc", "--optimizer", "adam", "--learn-rate", "0.004",
+                        "--batch-size", "4", "--shuffle", "false"])
+    capfd.readouterr()
+    cli.nnet_validate([scp, cfg, n1, "--objective", "ctc", "--batch-size", "4"])
+    cv1 = float(capfd.readouterr().err.split("cv_loss = ")[1].split()[0])
+    assert np.isfinite(cv0) and np.isfinite(cv1) and cv1 < cv0
+    ark = os.path.join(tmp, "post.ark")
+    cli.nnet_forward([scp, cfg, n1, "ark:" + ark])
+    capfd.readouterr()
+    for (k, a), n in zip(kaldi_io.read_float_matrix_ark(ark), lens):
+        assert a.shape == (n // 3, V) and np.allclose(np.exp(a).sum(1), 1.0, atol=1e-4)
+    with open(cfg, "w") as fh:
+        fh.write("nnet_type cudnnlstm\ninput_dim %d\nleft_context 1\nright_context 1\nsubsample 3\nnum_layers 1\nnum_neurons 64\nnum_projects 24\nnum_targets %d\ndropout_rate 1.0\n" % (D, V))
+    with pytest.raises(SystemExit) as e:
+        cli.nnet_validate([scp, cfg, n1, "--objective", "ctc", "--batch-size", "4"])
+    assert e.value.code == 1 and "unsupported nnet_type: cudnnlstm" in capfd.readouterr().err
