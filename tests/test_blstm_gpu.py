@@ -181,8 +181,9 @@ def test_split_bptt_equals_whole(cuda_dev, B, T, frac):
     assert g0.abs().max().item() > 0
 
 
-@pytest.mark.parametrize("B,T,fracs,keep", [(40, 96, [0.75], 0.8), (64, 80, [0.6], 1.0), (24, 130, [0.65, 0.85], 0.9)])
-def test_early_rows_schedule_equals_serial(cuda_dev, B, T, fracs, keep):
+@pytest.mark.parametrize("B,T,fracs,keep,layers", [(40, 96, [0.75], 0.8, 3), (64, 80, [0.6], 1.0, 3), (24, 130, [0.65, 0.85], 0.9, 3),
+                                                   (16, 96, [0.67, 0.85], 0.9, 1), (33, 70, [0.67, 0.85], 1.0, 2)])
+def test_early_rows_schedule_equals_serial(cuda_dev, B, T, fracs, keep, layers):
     """backward() with bwd_early_fracs: BPTT of layers 1.. in two or three launches, the rows of dX (fused dropout mask addressed by
     absolute element index) and of the next layer's dM whose dG is final after the first launch computed on a side stream
     beside the second -- three layers so that the three dX buffers rotate.  Same dz bit for bit in every layer that is still
@@ -191,7 +192,7 @@ def test_early_rows_schedule_equals_serial(cuda_dev, B, T, fracs, keep):
     from lstm_ctc_b200.blstm import BLSTMEncoder, ModelConfig
     H = 512
     assert _lib.lib().lcb_lstm_rec_bwd_can_split(H) == 1
-    cfg, params, x, lens = make_case(H, H, 24, 3, B, T, True, seed=21)
+    cfg, params, x, lens = make_case(H, H, 24, layers, B, T, True, seed=21)      # one layer: only layer 0's released frames
     lens[1] = 5
     x[1, 5:] = 0
     dev = torch.device("cuda:0")
@@ -212,8 +213,9 @@ def test_early_rows_schedule_equals_serial(cuda_dev, B, T, fracs, keep):
         res.append(([d.clone() for d in ws["dG"]], enc.params.gflat.clone(), ws["dX"][1].clone()))
     assert _lib.lib().lcb_device_error(1) == 0
     (dg0, g0, dx0), (dg1, g1, dx1) = res
-    assert torch.equal(dx0, dx1)                   # layer 1's dX (= layer 0's dH), all rows
-    for a, b in zip(dg0, dg1):
+    if layers > 1:
+        assert torch.equal(dx0, dx1)               # layer 1's dX (= layer 0's dH), all rows
+    for a, b in list(zip(dg0, dg1))[:min(layers, 2)]:      # (a one-layer stack never writes the second dz buffer)
         assert torch.equal(a, b)
     assert (g0 - g1).abs().max().item() <= 1e-5 * g0.abs().max().item()
     assert g0.abs().max().item() > 0
