@@ -13,9 +13,10 @@ PARITY PINNING.  The reference holds no tests, fixtures or golden vectors, and i
 lives in TensorFlow 1.8 (third-party, py2.7, not installable here).  The oracle is therefore
 pinned by (1) the two known-answer vectors of upstream TF's ctc_loss_op_test.py
 (tests/golden/ctc_tf_kat.json), (2) agreement with torch.nn.functional.ctc_loss and brute-force
-path enumeration, (3) agreement of the LSTM restatement with torch.nn.LSTM in the
-no-peephole/no-projection special case, and (4) torch.autograd.gradcheck.  Beyond that:
-"parity unpinned" against the TF binary itself.
+path enumeration, (3) agreement of the BiLSTM restatement (stacked, projected, ragged lengths, final states,
+input gradient) with torch.nn.LSTM(bidirectional, proj_size) on packed sequences and of the optimizers with
+torch.optim / clip_grad_norm_ (tests/test_oracle_model_cpu.py), and (4) the closed form of one peephole step plus
+torch.autograd.gradcheck.  Beyond that: "parity unpinned" against the TF binary itself.
 """
 from .ctc import ctc_loss_grad, build_ctc_oracle  # noqa: F401
 from .model import (  # noqa: F401
