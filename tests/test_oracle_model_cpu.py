@@ -174,3 +174,33 @@ def test_greedy_decode_and_edit_distance_known_answers():
     assert list(oracle.greedy_decode(logits, torch.tensor([4], dtype=torch.int32))[0]) == [0, 0]
     assert oracle.edit_distance([0, 0, 1, 2], [0, 1, 2]) == 1 and oracle.edit_distance([], [1, 2]) == 2
     assert oracle.edit_distance([1, 2, 3], [1, 2, 3]) == 0 and oracle.edit_distance([1, 2, 3], [3, 2, 1]) == 2
+
+
+def test_mixture_output_layer_against_explicit_loops():
+    """create_moe (moe.py:29-72): y[n,v] = sum_k softmax_k(x Wp + bp)[n,k] * tau * tanh(x W + b)[n, k*V + v]  -- the expert
+    logits are k-major columns (moe.py:60), the mixture is over tanh-bounded LOGITS; dropout acts on the mixture
+    weights and on the expert logits with keep-probability semantics (moe.py:46,61)."""
+    g = torch.Generator().manual_seed(11)
+    N, D, K, V, tau = 3, 5, 4, 6, 10.0
+    r = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)
+    x, Wp, bp, W, b = r(N, D), r(D, K), r(K), r(D, K * V), r(K * V)
+    y = oracle.create_moe(x, Wp, bp, W, b, V, K, tau)
+    ref = torch.zeros(N, V, dtype=torch.float64)
+    for n in range(N):
+        a = [sum(x[n, d] * Wp[d, k] for d in range(D)) + bp[k] for k in range(K)]
+        mx = max(a)
+        e = [math.exp(float(v - mx)) for v in a]
+        pi = [v / sum(e) for v in e]
+        for v in range(V):
+            for k in range(K):
+                z = sum(x[n, d] * W[d, k * V + v] for d in range(D)) + b[k * V + v]
+                ref[n, v] += pi[k] * tau * math.tanh(float(z))
+    assert torch.allclose(y, ref, atol=1e-12)
+    assert y.abs().max().item() <= tau + 1e-9                         # |y| <= tau * sum_k pi_k = tau
+    keep = 0.5
+    mp = (torch.rand(N, K, 1, generator=g) < keep).double()
+    md = (torch.rand(N, K, V, generator=g) < keep).double()
+    yd = oracle.create_moe(x, Wp, bp, W, b, V, K, tau, keep_prob=keep, mask_prior=mp, mask_dec=md)
+    pi = torch.softmax(x @ Wp + bp, 1).unsqueeze(2) * mp / keep
+    dec = (tau * torch.tanh(x @ W + b)).reshape(N, K, V) * md / keep
+    assert torch.allclose(yd, (pi * dec).sum(1), atol=1e-12)
