@@ -9,7 +9,8 @@ import re
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+_pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+peak = json.load(open(_pk)) if os.path.exists(_pk) else {}          # driver-written per pod; fallback below
 
 
 def find(d, *keys):
