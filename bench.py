@@ -126,66 +126,85 @@ def synth_batch(w, seed, device=None):
 
 
 # ------------------------------------------------------------------------------------------------
+def _oracle_step(oracle, cfg, p, state, x, lens, y):
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    ctc, total, _ = oracle.training_loss(pr, cfg, x, lens, y, l2_decay_weight=1e-5)
+    total.backward()
+    clipped, _ = oracle.clip_by_global_norm({k: v.grad for k, v in pr.items()}, 5.0)
+    return oracle.adam_step({k: v.detach() for k, v in pr.items()}, clipped, state, 4e-4)
+
+
+def _oracle_cfg(oracle, w):
+    return oracle.OracleConfig(input_dim=w["D"], num_layers=w["num_layers"], num_neurons=w["H"], num_projects=w["P"],
+                               num_targets=w["V"], use_peepholes=True, num_experts=w["K"], moe_temp=10.0)
+
+
 def run_reference(args, w, emit):
     """The reference's own CPU path: TF 1.8 cannot be installed offline, so (north_star fallback) the
-    PyTorch-CPU transcription of the same ops in oracle/ is timed on the host cores, all threads."""
+    PyTorch-CPU transcription of the same ops in oracle/ is timed on the host cores, all threads.
+
+    Sample: the workload's full batch width (the per-step matmuls of the reference's while-loop are [B, .] x [., 4H]; fewer
+    utterances would leave the host cores idle) x a PREFIX of the frames.  The prefix is as long as the run-time budget allows
+    (<= 300 frames): one probe step on 60 frames gives the cost per frame, and the per-frame cost of the per-time-step cell does not
+    depend on the prefix length, so frames/s of the prefix is the full-length figure; only the CTC lattice (a few % of the CPU
+    step) scales differently."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = oracle.OracleConfig(input_dim=w["D"], num_layers=w["num_layers"], num_neurons=w["H"], num_projects=w["P"],
-                              num_targets=w["V"], use_peepholes=True, num_experts=w["K"], moe_temp=10.0)
-    # bounded sample of the same workload: the workload's batch width (the per-step matmuls of the reference's while-loop are
-    # [B, .] x [., 4H]: two utterances would leave the host cores idle -- 86 vs 670 frames/s on 8 cores), a prefix of the frames
-    Bs, Ts = min(w["B"], 64), min(w["T"], 60)
+    cfg = _oracle_cfg(oracle, w)
+    Bs = min(w["B"], 64)
+    p = oracle.init_params(cfg, seed=0, dtype=torch.float32)
+    # probe: one step on a 60-frame prefix (also pages the libraries in)
+    wp = dict(w); wp["B"], wp["T"] = Bs, min(w["T"], 60)
+    xp, lp, yp = synth_batch(wp, 777)
+    t0 = time.perf_counter()
+    _oracle_step(oracle, cfg, p, {}, xp, lp, yp)
+    per_frame = (time.perf_counter() - t0) / wp["T"]
+    budget_s = 240.0
+    Ts = int(budget_s / ((args.steps + args.warmup) * per_frame))
+    Ts = max(min(Ts, 300, w["T"]), min(w["T"], 60)) // 20 * 20 or min(w["T"], 60)
     ws = dict(w); ws["B"], ws["T"] = Bs, Ts
     x, lens, y = synth_batch(ws, 777)
-    p = oracle.init_params(cfg, seed=0, dtype=torch.float32)
     state = {}
     times = []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
-        ctc, total, _ = oracle.training_loss(pr, cfg, x, lens, y, l2_decay_weight=1e-5)
-        total.backward()
-        clipped, _ = oracle.clip_by_global_norm({k: v.grad for k, v in pr.items()}, 5.0)
-        p = oracle.adam_step({k: v.detach() for k, v in pr.items()}, clipped, state, 4e-4)
+        p = _oracle_step(oracle, cfg, p, state, x, lens, y)
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     frames = int(lens.sum())
     val = frames / (ms / 1e3)
-    sample = "%d utts x %d frames of workload %s per step (oracle port, torch CPU fp32, per-time-step cell)" % (Bs, Ts, args.workload)
+    sample = "%d utts x %d-frame prefix of workload %s per step (oracle port, torch CPU fp32, per-time-step cell)" % (Bs, Ts, args.workload)
     line = {"metric": "train_frames_per_sec", "value": val, "unit": "frames/s", "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"], "sample": sample},
+            "config": {"workload": w["desc"], "sample": sample, "same_config": Ts == w["T"],
+                       "same_config_note": "same model, batch width, optimizer and metric; frames per utterance cut to a %d-frame "
+                                           "prefix so that %d CPU steps end within minutes (frames/s of the per-time-step cell does "
+                                           "not depend on the prefix length)" % (Ts, args.steps + args.warmup)},
             "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
-def cpu_baseline_sample(w, budget_s=20.0):
-    """Oracle port timed on the host cores on a bounded sample (rank 0, N=1 only)."""
+def cpu_baseline_sample(w, budget_s=25.0):
+    """Oracle port timed on the host cores on a bounded sample (rank 0, N=1 only): full batch width x a 150-frame prefix."""
     import oracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = oracle.OracleConfig(input_dim=w["D"], num_layers=w["num_layers"], num_neurons=w["H"], num_projects=w["P"],
-                              num_targets=w["V"], use_peepholes=True, num_experts=w["K"], moe_temp=10.0)
-    ws = dict(w); ws["B"], ws["T"] = min(w["B"], 64), min(w["T"], 60)      # full batch width, a prefix of the frames (see run_reference)
+    cfg = _oracle_cfg(oracle, w)
+    ws = dict(w); ws["B"], ws["T"] = min(w["B"], 64), min(w["T"], 150)      # full batch width, a prefix of the frames (see run_reference)
     x, lens, y = synth_batch(ws, 777)
     p = oracle.init_params(cfg, seed=0, dtype=torch.float32)
     t_tot, frames, n = 0.0, 0, 0
-    while t_tot < budget_s and n < 3:
+    while t_tot < budget_s and n < 4:
         t0 = time.perf_counter()
-        pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
-        ctc, total, _ = oracle.training_loss(pr, cfg, x, lens, y, l2_decay_weight=1e-5)
-        total.backward()
-        clipped, _ = oracle.clip_by_global_norm({k: v.grad for k, v in pr.items()}, 5.0)
-        oracle.adam_step({k: v.detach() for k, v in pr.items()}, clipped, {}, 4e-4)
+        _oracle_step(oracle, cfg, p, {}, x, lens, y)
         dt = time.perf_counter() - t0
         if n > 0 or dt > budget_s / 2:          # first pass doubles as warm-up unless it is already long
             t_tot += dt; frames += int(lens.sum())
@@ -193,7 +212,7 @@ def cpu_baseline_sample(w, budget_s=20.0):
     if frames == 0:
         t_tot, frames = dt, int(lens.sum())
     return {"value": frames / t_tot, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": "%d utts x %d frames of the workload, full training step, torch CPU fp32 oracle" % (ws["B"], ws["T"])}
+            "sample": "%d utts x %d-frame prefix of the workload, full training step, torch CPU fp32 oracle" % (ws["B"], ws["T"])}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -214,6 +233,7 @@ def main():
     ap.add_argument("--keep-prob", type=float, default=0.9)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ctc", action="store_true")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -288,7 +308,15 @@ def main():
     if not args.no_e2e:
         e2e = run_e2e(nnet, cfg, w, x_h, lens_h, y_h, args, world, device, frames_global)
 
+    # ---- the metric's second half: CTC loss+grad utts/s (C4 points), rank 0 ----
+    ctc_rec = ctc_microbench(device) if (rank == 0 and not args.no_ctc) else None
+
+    # ---- N > 1: the reduced gradient equals the 1-GPU gradient of the concatenated batch, and the strong-scaling figure ----
+    dp = dp_check_and_strong_scaling(model, reducer, w, args, rank, world, device) if world > 1 else None
+
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     out = {"metric": "train_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -300,7 +328,13 @@ def main():
            "clocks": clocks, "gpu_launches": launches, "e2e": e2e}
     if kt is not None:
         out["roofline"] = kt["roofline"]
+        out["rooflines_other"] = kt["others"]
         out["kernels"] = kt["kernels"]
+    if ctc_rec is not None:
+        out["ctc"] = ctc_rec
+    if dp is not None:
+        out["dp_check"] = dp["dp_check"]
+        out["strong_scaling"] = dp["strong_scaling"]
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_sample(w)
     emit(out)
@@ -321,6 +355,7 @@ def kernel_breakdown(model, x, lens, y, w, frames):
     instrumented step after the timed region; the un-instrumented timed region above is the headline)."""
     from lstm_ctc_b200 import _lib, gemm as gemm_mod, blstm as blstm_mod, model as model_mod, ctc as ctc_mod
     L = _lib.lib()
+    nsm = L.lcb_device_sm_count()
     spans = {}
 
     gemm_calls = []                 # (class, flops, start, end) of every bulk GEMM launch of the instrumented step
@@ -340,9 +375,9 @@ def kernel_breakdown(model, x, lens, y, w, frames):
                 N_ = Bm.shape[0] if bl == 0 else Bm.shape[1]
                 cls = {(0, 0): "forward (X*W^T: projections, h-projection, output recompute)", (0, 1): "dgrad (dG*W)",
                        (1, 1): "wgrad (X^T*dG, K = frames)"}.get((al, bl), "other")
-                cap = L.lcb_gemm_set_max_ctas(148)          # read the persistent-grid cap this launch ran under (host-side setting)
-                L.lcb_gemm_set_max_ctas(cap)
-                gemm_calls.append((cls, 2.0 * M_ * N_ * K_, s, e, min(max(int(cap), 1), 148) / 148.0))
+                cap = k.get("max_ctas")                     # the persistent-grid cap this launch ran under (per-call argument)
+                cap = gemm_mod.current_cap() if cap is None else cap
+                gemm_calls.append((cls, 2.0 * M_ * N_ * K_, s, e, (min(int(cap), nsm) if cap and cap > 0 else nsm) / float(nsm)))
             return r
         return wrap
 
@@ -379,39 +414,78 @@ def kernel_breakdown(model, x, lens, y, w, frames):
     for v in kernels.values():
         v["share"] = v["ms_total"] / tot if tot else 0.0
     hbm, tf_burst, tf_sus, how = _peaks()
-    # dominant kernel family by time
-    dom = max(kernels, key=lambda k: kernels[k]["ms_total"])
     B, T, H, Ltot = w["B"], w["T"], w["H"], w["num_layers"]
     Hp = (H + 63) // 64 * 64
-    roof = None
-    if dom in ("lstm_rec_fwd", "lstm_rec_bwd"):
-        # algorithmic flops of the family per step: the folded recurrent product m_{t-1} W' (or its dgrad W' dz_t), both
-        # directions, all layers, VALID frames only (padded frames are not algorithmic work)
-        flops = recurrent_flops_per_frame(w) * frames
-        ms_all = kernels[dom]["ms_total"]
-        ach = flops / (ms_all * 1e-3) / 1e12
-        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus,
-                "traffic": None, "peak_source": how + " sustained (kernel timed inside a long step)",
-                "note": "serial recurrence: latency-bound, not tensor- or HBM-bound (2 x T dependent steps per layer, 64 of 148 SMs); "
-                        "us_per_time_step = %.3f" % (ms_all * 1e3 / (Ltot * T))}
-    elif dom == "gemm":
+    traffic = {}
+    try:        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+        traffic = tr.get(w.get("desc", ""), {})
+    except Exception:
+        pass
+
+    def ms_of(*names):
+        return sum(kernels[n]["ms_total"] for n in names if n in kernels)
+
+    def launches_of(*names):
+        return sum(kernels[n]["launches"] for n in names if n in kernels)
+
+    roofs = {}
+    # (1) the recurrence family: forward recurrence + BPTT (cluster-persistent kernels).  Neither tensor- nor HBM-bound: 2 x T
+    # dependent steps per layer on 64 of the SMs -- the figure of merit is microseconds per time step against the floor of the
+    # decomposition; achieved / peak are kept in the contract's units (algorithmic flops of the recurrent product and
+    # its dgrad over VALID frames).
+    ms_f, ms_b = ms_of("lstm_rec_fwd"), ms_of("lstm_rec_bwd")
+    if ms_f + ms_b > 0:
+        flops = 2.0 * recurrent_flops_per_frame(w) * frames          # forward product + its dgrad in BPTT
+        ach = flops / ((ms_f + ms_b) * 1e-3) / 1e12
+        # algorithmic HBM bytes per time step and utterance: forward reads G (8Hp f32) and writes m (2Hp f16), gates (2Hp x 8 B),
+        # c (2Hp f32); BPTT reads gates, c (twice: c_t and c_{t-1}), dM (2Hp f32) and writes dG (8Hp bf16)
+        by_f = (8 * Hp * 4 + 2 * Hp * (2 + 8 + 4)) * float(frames) * Ltot
+        by_b = (2 * Hp * (8 + 4 + 4 + 4) + 8 * Hp * 2) * float(frames) * Ltot
+        tr_f, tr_b = traffic.get("lstm_rec_fwd"), traffic.get("lstm_rec_bwd")
+        clk = 1.965e9
+        roofs["lstm_rec"] = {
+            "kernel": "lstm_rec (lstm_rec_fwd2 + lstm_rec_bwd3: forward recurrence and BPTT, all layers, both directions)",
+            "bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus,
+            "traffic": ({"lstm_rec_fwd": tr_f["dram_bytes_per_launch"], "lstm_rec_bwd": tr_b["dram_bytes_per_launch"],
+                         "source": tr_f.get("source", "")} if (tr_f and tr_b) else None),
+            "peak_source": how + " sustained (kernels timed inside a long step)",
+            "latency_bound": True,
+            "us_per_time_step": {"fwd": ms_f * 1e3 / (Ltot * T), "bwd": ms_b * 1e3 / (Ltot * T)},
+            "floor_us_per_time_step": {"fwd": 1800.0 / clk * 1e6, "bwd": 2400.0 / clk * 1e6,
+                                       "how": "cycles of the serial chain this decomposition cannot shed, at 1.965 GHz: one weight pass "
+                                              "out of tensor memory (128 KB per CTA and step, ~250 B/clk measured = 526) + two L2 trips "
+                                              "of the m_t exchange (bulk store 500 + multicast 670, probes) + the dependent MUFU chain "
+                                              "of the gate math (~100); BPTT adds the 4-way reduce-scatter over DSMEM (~600)"},
+            "algorithmic_hbm_bytes": {"fwd": by_f, "bwd": by_b},
+            "hbm_gbs": {"fwd": by_f / (ms_f * 1e-3) / 1e9 if ms_f else None, "bwd": by_b / (ms_b * 1e-3) / 1e9 if ms_b else None,
+                        "peak": hbm},
+            "launches": launches_of("lstm_rec_fwd", "lstm_rec_bwd"), "ms_total": ms_f + ms_b,
+            "note": "share of the step: see kernels[*].share; achieved = 2 x recurrent_flops_per_frame x valid frames / summed launch time"}
+    # (2) bulk GEMM family
+    if "gemm" in kernels:
         flops = gemm_family_flops_per_frame(w) * frames
-        ms1 = kernels[dom]["ms_total"]
+        ms1 = kernels["gemm"]["ms_total"]
         ach = flops / (ms1 * 1e-3) / 1e12
-        roof = {"kernel": "gemm16 (all bulk GEMMs of the step: projections, dgrad, wgrad, output layer)", "bound": "tensor",
-                "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": None,
-                "peak_source": how + " sustained",
-                "note": "algorithmic flops over VALID frames / summed GEMM launch time (weight-gradient GEMMs run on a capped grid "
-                        "beside the BPTT clusters, so their launch time overlaps other kernels)"}
-    else:
+        roofs["gemm"] = {"kernel": "gemm16 (all bulk GEMMs of the step: projections, dgrad, wgrad, output layer)", "bound": "tensor",
+                         "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus,
+                         "traffic": (traffic.get("gemm") or {}).get("dram_bytes_per_launch"),
+                         "peak_source": how + " sustained (MEASURED_PEAKS.json, unscaled: the whole chip's cuBLAS bf16 peak)",
+                         "launches": kernels["gemm"]["launches"], "ms_total": ms1,
+                         "note": "algorithmic flops over VALID frames / summed GEMM launch time; many launches run on a capped "
+                                 "persistent grid beside the recurrence clusters (sm_share_* keys), so frac understates what the "
+                                 "kernel does on the SMs it is given"}
+    # (3) CTC (in-step shape)
+    if "ctc_loss_grad" in kernels:
         bytes_ = 8.0 * T * B * w["V"]
-        ms1 = kernels.get("ctc_loss_grad", {"ms_total": 1.0, "launches": 1})
-        ach = bytes_ / (ms1["ms_total"] / ms1["launches"] * 1e-3) / 1e9
-        roof = {"kernel": "ctc_loss_grad", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                "traffic": None, "peak_source": how}
+        k_ = kernels["ctc_loss_grad"]
+        ach = bytes_ / (k_["ms_total"] / k_["launches"] * 1e-3) / 1e9
+        roofs["ctc_loss_grad"] = {"kernel": "ctc_loss_grad (in-step shape B=%d T=%d V=%d)" % (B, T, w["V"]), "bound": "hbm",
+                                  "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                                  "traffic": (traffic.get("ctc_loss_grad") or {}).get("dram_bytes_per_launch"),
+                                  "peak_source": how, "ms_per_launch": k_["ms_total"] / k_["launches"]}
     # per-class GEMM throughput of the same instrumented step (launched flops incl. padded frames / launch time); launches of
-    # >= 20 GFLOP only, so the tiny weight-folding GEMMs do not blur the classes.  The forward projections' tails and all
-    # weight gradients run on a CAPPED grid (84 / 80 of 148 SMs) beside the recurrence, by design.
+    # >= 20 GFLOP only, so the tiny weight-folding GEMMs do not blur the classes.
     classes = {}
     share_ms = 0.0                      # sum over GEMM launches of duration x fraction of the SMs the launch was granted
     all_ms = 0.0
@@ -428,33 +502,108 @@ def kernel_breakdown(model, x, lens, y, w, frames):
         c_["sm_ms"] += ms_ * share
     for c_ in classes.values():
         c_["tflops"] = c_["flops"] / (c_["ms_total"] * 1e-3) / 1e12 if c_["ms_total"] > 0 else 0.0
+        c_["frac"] = c_["tflops"] / tf_sus
         c_["mean_sm_share"] = c_["sm_ms"] / c_["ms_total"] if c_["ms_total"] > 0 else 1.0
         c_["frac_of_sustained_peak_of_sms_granted"] = c_["tflops"] / (tf_sus * c_["mean_sm_share"])
         del c_["flops"], c_["sm_ms"]
-    if roof is not None and classes:
-        roof["gemm_classes"] = classes
-    if roof is not None and dom == "gemm" and all_ms > 0:
-        # Many launches of this family run on a CAPPED persistent grid (84 / 80 of 148 SMs) beside the recurrence clusters, by
-        # design; the roofline of such a launch is the peak of the SMs it was granted.  `peak` is therefore the measured
-        # sustained peak x the duration-weighted mean SM share of the family's launches; the whole-chip figures stay beside it.
-        mean_share = share_ms / all_ms
-        roof["peak_whole_chip"] = roof["peak"]
-        roof["frac_whole_chip"] = roof["frac"]
-        roof["mean_sm_share"] = mean_share
-        roof["peak"] = roof["peak_whole_chip"] * mean_share
-        roof["frac"] = roof["achieved"] / roof["peak"]
-        roof["note"] += "; peak = measured sustained peak x duration-weighted mean fraction of the 148 SMs the launches were granted"
-    # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed `ncu --set full`
-    # capture of this same command (profiles/r01_ncu_traffic.json; null if the capture does not cover this workload)
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
-        ent = tr.get(w.get("desc", ""), {}).get(dom if dom != "gemm" else "gemm")
-        if ent is not None:
-            roof["traffic"] = ent["dram_bytes_per_launch"]
-            roof["traffic_source"] = ent["source"]
-    except Exception:
-        pass
-    return {"kernels": kernels, "roofline": roof}
+    if "gemm" in roofs and all_ms > 0:
+        roofs["gemm"]["gemm_classes"] = classes
+        roofs["gemm"]["sm_share_mean"] = share_ms / all_ms
+        roofs["gemm"]["sm_share_frac"] = roofs["gemm"]["achieved"] / (tf_sus * share_ms / all_ms)
+    # dominant family by summed launch time (forward recurrence and BPTT count as ONE family)
+    fam_ms = {"lstm_rec": ms_f + ms_b, "gemm": ms_of("gemm"), "ctc_loss_grad": ms_of("ctc_loss_grad")}
+    dom = max((k for k in fam_ms if k in roofs), key=lambda k: fam_ms[k])
+    roof = roofs.pop(dom)
+    roof["dominant_by"] = "summed launch time of the instrumented step (ms): " + json.dumps({k: round(v, 3) for k, v in fam_ms.items()})
+    return {"kernels": kernels, "roofline": roof, "others": roofs}
+
+
+def ctc_microbench(device, B=256, T=700, Llab=100, Vs=(72, 5000), iters=5):
+    """CTC loss+grad utts/s (the second half of BASELINE.json's metric) on two points of the C4 sweep, timed with CUDA events.
+    Inputs are rotated over enough distinct buffers that consecutive launches never find their logits in the 126 MB L2."""
+    from lstm_ctc_b200.ctc import ctc_loss_grad
+    hbm = _peaks()[0]
+    out = []
+    for V in Vs:
+        g = torch.Generator().manual_seed(0)
+        bytes_one = 4.0 * B * T * V
+        nbuf = 1 if bytes_one > 512e6 else int(min(8, max(2, 300e6 // bytes_one + 1)))
+        xs = [(torch.randn(B, T, V, generator=g) * 3).to(device) for _ in range(nbuf)]
+        sl = torch.randint(int(0.8 * T), T + 1, (B,), generator=g).to(torch.int32).to(device)
+        lab = torch.randint(0, V - 1, (B, Llab), generator=g).to(device)
+        for k in range(3):
+            ctc_loss_grad(xs[k % nbuf], lab, sl, check_labels=False)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for k in range(iters):
+            ctc_loss_grad(xs[k % nbuf], lab, sl, check_labels=False)
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / iters
+        gb = 8.0 * T * B * V / 1e9
+        out.append({"T": T, "L": Llab, "V": V, "B": B, "ms": ms, "utts_per_s": B / ms * 1e3, "gbs": gb / ms * 1e3,
+                    "peak_gbs": hbm, "frac": gb / ms * 1e3 / hbm, "input_buffers_rotated": nbuf})
+        del xs
+    return {"metric": "ctc_loss_grad_utts_per_sec", "unit": "utts/s", "algorithmic_bytes": "8*T*B*V", "points": out}
+
+
+def dp_check_and_strong_scaling(model, reducer, w, args, rank, world, device):
+    """(a) dp_check: the SUM all-reduced gradient of a global batch of w['B'] utterances dealt round-robin over the ranks equals the
+    gradient rank 0 computes alone on the whole batch (summed loss graph.py:116, global norm graph.py:190) -- with keep_prob 1
+    (dropout masks are indexed by the element's position in the local batch, so they differ between the two runs by design).
+    (b) strong scaling: the same global batch, training steps timed like the headline (max over ranks)."""
+    import torch.distributed as dist
+    xg, lg, yg = synth_batch(w, 777)
+    idx = list(range(rank, w["B"], world))
+    xs, ls, ys = xg[idx].to(device), lg[idx].to(device), yg[idx].to(device)
+    keep = model.cfg.keep_prob
+    model.cfg.keep_prob = 1.0
+    reducer.broadcast_weights()
+    reducer.begin_step()
+    loss_s, _ = model.loss_and_grad(xs, ls, ys, bucket_ready=reducer.bucket_ready, check_labels=False)
+    reducer.finish()
+    lsum = loss_s.double().reshape(1).clone()
+    dist.all_reduce(lsum)
+    torch.cuda.synchronize()
+    res = None
+    if rank == 0:
+        g_dp = model.params.gflat.double().clone()
+        loss_1, _ = model.loss_and_grad(xg.to(device), lg.to(device), yg.to(device), check_labels=False)
+        g_1 = model.params.gflat.double()
+        n1, ndp = float(g_1.norm()), float(g_dp.norm())
+        rel = float((g_dp - g_1).norm()) / max(n1, 1e-30)
+        l1, ldp = float(loss_1.double()), float(lsum)
+        res = {"global_batch": w["B"], "ranks": world, "keep_prob": 1.0, "grad_rel_err": rel, "global_norm_dp": ndp,
+               "global_norm_1gpu": n1, "loss_sum_dp": ldp, "loss_sum_1gpu": l1,
+               "tolerance": {"grad_rel_err": 1e-4, "norm_rel": 1e-5, "loss_rel": 1e-5},
+               "ok": bool(rel < 1e-4 and abs(ndp - n1) <= 1e-5 * n1 and abs(ldp - l1) <= 1e-5 * abs(l1))}
+    model.cfg.keep_prob = keep
+    dist.barrier()
+    torch.cuda.synchronize()
+
+    def step():
+        reducer.begin_step()
+        model.loss_and_grad(xs, ls, ys, bucket_ready=reducer.bucket_ready, check_labels=False)
+        reducer.finish()
+        model.optimizer_step("adam", 4e-4, clip_norm=5.0, l2_decay_weight=1e-5)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms.item()) / args.steps
+    frames = float(lg.sum())
+    strong = {"scaling": "strong", "global_batch": w["B"], "per_gpu_batch": len(idx), "ms_per_step": ms_step,
+              "value": frames / (ms_step / 1e3), "unit": "frames/s", "n_gpus": world}
+    return {"dp_check": res, "strong_scaling": strong}
 
 
 def run_e2e(nnet, cfg, w, x_h, lens_h, y_h, args, world, device, frames_global):

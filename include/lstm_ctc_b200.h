@@ -74,12 +74,14 @@ int lcb_ctc_status(const void* workspace, void* stream);
  *   dtype codes: 0 = fp32 (C only), 1 = bf16, 2 = fp16.  A and B must share one 16-bit type (the
  *   hardware rejects mixed kind::f16 operands): forward GEMMs are fp16 x fp16, gradient GEMMs bf16 x bf16.
  * lda/ldb multiples of 8 elements, A/B base pointers 16-byte aligned.
- * accumulate != 0 adds into the existing fp32 C (c_dtype must be 0). */
+ * accumulate != 0 adds into the existing fp32 C (c_dtype must be 0).
+ * max_ctas caps the persistent grid of THIS launch (0 = one CTA per SM of the device): a GEMM that runs on a side
+ * stream next to a cluster kernel owning part of the SMs is launched with as many CTAs as there are free SMs. */
 int lcb_gemm16(int M, int N, int K,
                const void* A, int lda, int a_layout, int a_dtype,
                const void* B, int ldb, int b_layout, int b_dtype,
                void* C, int ldc, int c_dtype,
-               const float* bias, int accumulate, void* stream);
+               const float* bias, int accumulate, int max_ctas, void* stream);
 /* Same, with inverted dropout fused into the epilogue: C = dropout(op(A)*op(B) + bias), where element (row, col) of C uses
  * element mask_base + row*ldc + col of the counter-based mask stream of lcb_dropout16 / lcb_dropout_mask (seed).  Replaces
  * DropoutWrapper(output_keep_prob) on the layer output h = m*W_proj (nnet/bilstm.py:128,137) and, with the same seed, the
@@ -87,11 +89,10 @@ int lcb_gemm16(int M, int N, int K,
 int lcb_gemm16_dropout(int M, int N, int K, const void* A, int lda, int a_layout, int a_dtype,
                        const void* B, int ldb, int b_layout, int b_dtype,
                        void* C, int ldc, int c_dtype, const float* bias, int accumulate,
-                       float keep_prob, unsigned long long seed, unsigned long long mask_base, void* stream);
-/* caps the persistent grid of subsequent lcb_gemm16 launches (1..148 CTAs); returns the previous cap.  Used when a
- * GEMM runs on a side stream next to a cluster kernel that owns part of the SMs. */
-int lcb_gemm_set_max_ctas(int n);
-/* bf16 x bf16 shorthand of the above. */
+                       float keep_prob, unsigned long long seed, unsigned long long mask_base, int max_ctas, void* stream);
+/* number of SMs of the current device (what max_ctas = 0 means; grids of every kernel are sized from it). */
+int lcb_device_sm_count(void);
+/* bf16 x bf16 shorthand of the above (max_ctas = 0). */
 int lcb_gemm_bf16(int M, int N, int K,
                   const void* A, int lda, int a_layout,
                   const void* B, int ldb, int b_layout,
@@ -128,22 +129,30 @@ int lcb_gemm_bf16_simt_check(int M, int N, int K,
 int lcb_lstm_rec_config(int Hp, int* units_per_cta_div32, int* cluster_size);
 /* clusters of the forward (which=0) / BPTT (which=1) kernel the device keeps resident at once (<0: error) */
 int lcb_lstm_rec_max_clusters(int Hp, int which);
+/* SMs (one CTA each) a forward (which=0) / BPTT (which=1) launch over B utterances occupies -- what a GEMM overlapped with it
+ * on another stream must leave free: its max_ctas = lcb_device_sm_count() - lcb_lstm_rec_grid(...). */
+int lcb_lstm_rec_grid(int B, int Hp, int num_dirs, int which);
 /* debug probe: the next lcb_lstm_rec_fwd launches write steps*16 clock64 samples of CTA 0 into buf (NULL: off). */
 int lcb_debug_rec_profile(long long* buf, int steps);
-/* workspace: device scratch of lcb_lstm_rec_workspace_bytes(B, Hp) bytes (16-byte aligned, caller-owned, one per
+/* workspace (required): device scratch of lcb_lstm_rec_workspace_bytes(B, Hp) bytes (16-byte aligned, caller-owned, one per
  * concurrently running launch): the per-step exchange of m_t goes  shared memory -> bulk store -> this L2-resident
- * scratch -> ONE multicast bulk load into all CTAs of the cluster.  NULL keeps the exchange on unicast DSMEM copies. */
+ * scratch -> ONE multicast bulk load into all CTAs of the cluster.
+ * num_dirs: 2 = BiLSTM layer, clusters alternate between the "fd" and "bd" direction and both run concurrently;
+ *           1 = uni-directional layer (nnet/lstm.py:236-260, dynamic_rnn scope "drnn{i}"): only direction-0 clusters are
+ *               launched; the direction-1 column halves of G / Mout / gates / cst / dG / dbias / dpeep are neither read nor
+ *               written (tensor shapes stay those of the two-direction layout). */
 size_t lcb_lstm_rec_workspace_bytes(int B, int Hp);
 int lcb_lstm_rec_fwd(const float* G, const void* WfoldT, const float* peep, const int32_t* lens,
                      void* Mout, void* gates, float* cst, float* cfin, float* mfin,
-                     int T, int B, int Hp, float forget_bias, void* workspace, size_t workspace_bytes, void* stream);
+                     int T, int B, int Hp, int num_dirs, float forget_bias,
+                     void* workspace, size_t workspace_bytes, void* stream);
 /* Same, for scan steps [s_begin, s_end) only (scan step s is frame s of the forward direction and frame T-1-s of the
  * backward direction).  A launch with s_begin > 0 resumes from the saved cst / Mout rows of scan step s_begin-1 (so gates
  * and cst must be given); launches over consecutive ranges in stream order equal one launch over [0, T).  This lets the
  * caller start the recurrence when only the first frames' pre-activations G exist and compute the rest beside it. */
 int lcb_lstm_rec_fwd_range(const float* G, const void* WfoldT, const float* peep, const int32_t* lens,
                            void* Mout, void* gates, float* cst, float* cfin, float* mfin,
-                           int T, int B, int Hp, float forget_bias, int s_begin, int s_end,
+                           int T, int B, int Hp, int num_dirs, float forget_bias, int s_begin, int s_end,
                            void* workspace, size_t workspace_bytes, void* stream);
 /* BPTT of the above (replaces tf.gradients through the while_loop, nnet/graph.py:190-191).
  *   dM    [T*B, 2Hp] f32   d loss / d m_t arriving from the output projection
@@ -152,7 +161,7 @@ int lcb_lstm_rec_fwd_range(const float* G, const void* WfoldT, const float* peep
  *   dbias [2*4Hp] f32 +=,  dpeep [2,3,Hp] f32 += (NULL iff peep NULL) */
 int lcb_lstm_rec_bwd(const float* dM, const void* gates, const float* cst, const void* Wfold, const float* peep,
                      const int32_t* lens, void* dG, float* dbias, float* dpeep,
-                     int T, int B, int Hp, void* workspace, size_t workspace_bytes, void* stream);
+                     int T, int B, int Hp, int num_dirs, void* workspace, size_t workspace_bytes, void* stream);
 /* The same over scan steps [s_begin, s_end) only (scan step s visits frame T-1-s in the forward, s in the backward direction --
  * the reverse of the forward pass).  A launch with s_end < T leaves, per cell, the recurrent part of d loss / d m of the next
  * step and the carried d loss / d c in `carry` ([B,2,Hp,2] f32); a launch with s_begin > 0 resumes from them.  Launches over
@@ -161,7 +170,7 @@ int lcb_lstm_rec_bwd(const float* dM, const void* gates, const float* cst, const
  * unless lcb_lstm_rec_bwd_can_split(Hp). */
 int lcb_lstm_rec_bwd_range(const float* dM, const void* gates, const float* cst, const void* Wfold, const float* peep,
                            const int32_t* lens, void* dG, float* dbias, float* dpeep,
-                           int T, int B, int Hp, int s_begin, int s_end, float* carry,
+                           int T, int B, int Hp, int num_dirs, int s_begin, int s_end, float* carry,
                            void* workspace, size_t workspace_bytes, void* stream);
 int lcb_lstm_rec_bwd_can_split(int Hp);
 

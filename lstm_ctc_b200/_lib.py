@@ -70,18 +70,19 @@ _SIGS = {
     "lcb_lstm_rec_max_clusters": (c_int, [c_int, c_int]),
     "lcb_debug_rec_profile": (c_int, [c_void_p, c_int]),
     "lcb_lstm_rec_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "lcb_lstm_rec_fwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
-    "lcb_lstm_rec_fwd_range": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_size_t, c_void_p]),
-    "lcb_lstm_rec_bwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
-    "lcb_lstm_rec_bwd_range": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "lcb_lstm_rec_grid": (c_int, [c_int, c_int, c_int, c_int]),
+    "lcb_lstm_rec_fwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
+    "lcb_lstm_rec_fwd_range": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "lcb_lstm_rec_bwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "lcb_lstm_rec_bwd_range": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "lcb_lstm_rec_bwd_can_split": (c_int, [c_int]),
     "lcb_pack_input": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "lcb_cast_f32_16": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p]),
-    "lcb_gemm_set_max_ctas": (c_int, [c_int]),
+    "lcb_device_sm_count": (c_int, []),
     "lcb_gemm16": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
-                           c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+                           c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "lcb_gemm16_dropout": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
-                                   c_void_p, c_int, c_int, c_void_p, c_int, c_float, ctypes.c_ulonglong, ctypes.c_ulonglong, c_void_p]),
+                                   c_void_p, c_int, c_int, c_void_p, c_int, c_float, ctypes.c_ulonglong, ctypes.c_ulonglong, c_int, c_void_p]),
     "lcb_gemm16_simt_check": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                       c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "lcb_split_f32_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -16,4 +16,9 @@ def create_logits_blstm(nnet_input, sequence_length, nnet_config, model=None):
     training = True if training is None else bool(training)
     logits = m.forward_logits(nnet_input, sequence_length, training=training)
     encoder = m.enc.encoder_state()
-    return logits, encoder, []
+    # reg_loss (bilstm.py:254-273): [(label-smoothing loss tensor, its weight)] when uniform_label_sm / prior_label_sm > 0 -- the
+    # reference appends the UNWEIGHTED loss and graph.py:120-133 multiplies by the weight; empty otherwise
+    reg_loss = []
+    if m.sm_weight > 0:
+        reg_loss.append((m.label_smoothing(logits) / m.sm_weight, m.sm_weight))
+    return logits, encoder, reg_loss

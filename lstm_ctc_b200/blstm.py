@@ -13,13 +13,12 @@ flat fp32 buffer; `to_tf_dict` / `from_tf_dict` convert to/from the reference's 
 shapes (fd{i}/frnn{i}/kernel, .../bias, .../w_{f,i,o}_diag, .../projection/kernel; bilstm.py:125-165).
 """
 import math
-import os
 from typing import Dict, List, Optional
 
 import torch
 
 from . import _lib
-from .gemm import gemm
+from .gemm import gemm, grid_cap
 
 F32 = torch.float32
 BF16 = torch.bfloat16      # gradient operands (range-safe without loss scaling)
@@ -148,6 +147,39 @@ def _split_bf16(src, hi=None, lo=None):
     return hi, lo
 
 
+class Arena:
+    """Grow-only named device buffers.  A minibatch of (T, B) gets VIEWS of the first T*B rows of each buffer, so a stream of
+    batches with different T (every real epoch: `_BatchSource` pads to the batch's own longest utterance) reuses one allocation
+    sized for the largest batch seen, instead of one full activation set per distinct T.  Growing frees the old buffer first
+    (after a device synchronisation, since side streams may still be reading it) and over-allocates by 1/8 so that a
+    length-sorted epoch triggers O(log) regrowths."""
+
+    def __init__(self, device, zero=False):
+        self.device, self.zero = device, zero
+        self.bufs = {}
+        self.generation = 0           # bumped whenever a buffer moves (cached views become stale)
+
+    def flat(self, name, numel, dtype, zero=None):
+        buf = self.bufs.get(name)
+        if buf is None or buf.numel() < numel or buf.dtype != dtype:
+            if buf is not None:
+                if buf.is_cuda:
+                    torch.cuda.synchronize()
+                self.bufs[name] = buf = None
+            cap = int(numel + numel // 8) if name in self.bufs else int(numel)
+            alloc = torch.zeros if (self.zero if zero is None else zero) else torch.empty
+            buf = alloc(max(cap, 1), dtype=dtype, device=self.device)
+            self.bufs[name] = buf
+            self.generation += 1
+        return buf[:numel]
+
+    def rows(self, name, rows, cols, dtype, zero=None):
+        return self.flat(name, rows * cols, dtype, zero).view(rows, cols)
+
+    def bytes_allocated(self):
+        return sum(b.numel() * b.element_size() for b in self.bufs.values() if b is not None)
+
+
 class BLSTMEncoder:
     """Weights + forward/backward of the L-layer BiLSTM stack."""
 
@@ -164,37 +196,55 @@ class BLSTMEncoder:
                       ParamSpec("L%d/Wx" % i, (8 * c.Hp, c.dinp(i)), True)]
         self.params = ParamStore(specs, device)
         self._bf = {}            # bf16 operand copies, refreshed by refresh_operands()
-        self._ws = {}            # activation workspaces keyed by (T, B)
         self._stale = True
         self.wstream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None   # wgrad side stream
         self.overlap_wgrad = True
         self.rstream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None   # operand-refresh side stream
         self.use_graphs = True
         self.pstream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None   # projection of the later frames
-        # fraction of the scan steps whose pre-activations are projected before the recurrence starts (LCB_HEAD_FRAC overrides)
-        self.head_fracs = [float(v) for v in os.environ.get("LCB_HEAD_FRACS", "0.36").split(",") if v]
-        self.overlap_hproj = os.environ.get("LCB_OVERLAP_HPROJ", "0") != "0"   # output projection of finished chunks on the side stream (c3: +-0, c2: 15 % slower -> off)
-        self.bwd_split_frac = float(os.environ.get("LCB_BWD_SPLIT_FRAC", "0"))   # > 0: BPTT as two launches (lcb_lstm_rec_bwd_range)
+        # ---- schedule options (explicit attributes; defaults = what measured best on the C3 step) ----
+        # fractions of the scan steps at which the forward recurrence is cut into launches: the pre-activations of the first chunk
+        # are projected before the recurrence starts, the later chunks' beside it on a side stream
+        self.head_fracs = [0.36]
+        self.overlap_hproj = False     # output projection of finished chunks on the side stream (c3: +-0, c2: 15 % slower)
+        self.bwd_split_frac = 0.0      # > 0: BPTT as two launches at this fraction (lcb_lstm_rec_bwd_range; tests)
         # increasing fractions > 0.5 of the scan at which BPTT of layers 1.. is cut into consecutive launches; the rows of dX (and of
         # the next layer's dM) whose dG is final in BOTH directions after a launch are computed beside the next one (backward(),
         # "early rows").  Empty: one launch.
-        self.bwd_early_fracs = [float(v) for v in os.environ.get("LCB_BWD_EARLY_FRACS", "0.67,0.85").split(",") if v]
-        self.l0_released = os.environ.get("LCB_L0_RELEASED", "1") != "0"   # layer 0's frame-sum gradients over released frames
-        self.xstream = (torch.cuda.Stream(device=device, priority=int(os.environ.get("LCB_XSTREAM_PRIO", "0")))
-                        if torch.cuda.is_available() else None)   # early rows of dX / dM
-        self.early_cap = int(os.environ.get("LCB_EARLY_CAP", "84"))   # persistent-grid cap of those GEMMs (84 SMs idle beside BPTT)
+        self.bwd_early_fracs = [0.67, 0.85]
+        self.l0_released = True        # layer 0's frame-sum gradients over released frames
+        self.xstream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None   # early rows of dX / dM
+        self.ndir = 1 if cfg.uni else 2          # nnet_type 'lstm': only direction-0 clusters / column halves run (lstm.py)
+        self.num_sms = _lib.lib().lcb_device_sm_count() if torch.cuda.is_available() else 0
+        self._arena = Arena(device, zero=cfg.uni)   # uni: the never-written direction-1 halves must read as 0, not as garbage
+        self._ws_key = None
+        self._ws_views = None
         self._refresh_graphs = None
         self._refresh_done = None
-        self.seed_base = 777           # reference default --seed (nnet-train.py:141-142)
+        self.seed_base = 777           # reference default --seed (nnet-train.py:141-142); set_dropout_seed() overrides
+        self.seed_rank = 0
         self.step_id = 0
         mt = _lib.ctypes.c_int()
         nc = _lib.ctypes.c_int()
         _lib.check(_lib.lib().lcb_lstm_rec_config(c.Hp, _lib.ctypes.byref(mt), _lib.ctypes.byref(nc)), "lcb_lstm_rec_config")
         self.rec_mt, self.rec_nc = mt.value, nc.value
 
+    def set_dropout_seed(self, seed, rank=0):
+        """`--seed` of nnet-train.py:141-142 (tf.set_random_seed) seeds the dropout streams as well; data-parallel ranks mix their
+        rank in so that shards do not share masks."""
+        self.seed_base = int(seed) & 0xffffff
+        self.seed_rank = int(rank) & 0xff
+
     def dropout_seed(self, layer):
-        """One mask stream per (training step, layer); layer 255 = mixture output layer."""
-        return ((self.seed_base & 0xffffffff) << 32) ^ ((self.step_id & 0xffffff) << 8) ^ (layer & 0xff)
+        """One mask stream per (seed, rank, training step, layer); layer 255 = mixture output layer."""
+        return (((self.seed_base & 0xffffff) << 40) ^ ((self.seed_rank & 0xff) << 32) ^ ((self.step_id & 0xffffff) << 8)
+                ^ (layer & 0xff))
+
+    def idle_sms(self, B, which):
+        """SMs a forward (which=0) / BPTT (which=1) recurrence launch over B utterances leaves free: the persistent-grid cap of
+        the GEMMs that run beside it on a side stream."""
+        used = _lib.lib().lcb_lstm_rec_grid(B, self.cfg.Hp, self.ndir, which)
+        return max(8, self.num_sms - max(used, 0))
 
     def _dropout(self, x, layer):
         dt = 2 if x.dtype == F16 else 1
@@ -354,33 +404,44 @@ class BLSTMEncoder:
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, T, B, training):
-        key = (T, B, training)
-        ws = self._ws.get(key)
-        if ws is None:
-            c = self.cfg
-            N = T * B
-            dev = self.device
-            ws = {"X0": torch.empty(N, c.Dp0, dtype=F16, device=dev),
-                  "G": torch.empty(N, 8 * c.Hp, dtype=F32, device=dev),
-                  "M": [torch.empty(N, 2 * c.Hp, dtype=F16, device=dev) for _ in range(c.num_layers)],
-                  "Hout": [torch.empty(N, 2 * c.P, dtype=F16, device=dev) for _ in range(c.num_layers)],
-                  "rec_ws": torch.zeros(max(16, _lib.lib().lcb_lstm_rec_workspace_bytes(B, c.Hp)), dtype=torch.uint8, device=dev),
-                  "cfin": torch.zeros(B, 2, c.Hp, dtype=F32, device=dev),
-                  "mfin": torch.zeros(B, 2, c.Hp, dtype=F32, device=dev)}
-            if training:
-                ws["gates"] = [torch.empty(N, 2 * c.Hp, dtype=torch.int64, device=dev) for _ in range(c.num_layers)]   # 4 x fp16
-                ws["cst"] = [torch.empty(N, 2 * c.Hp, dtype=F32, device=dev) for _ in range(c.num_layers)]
-                ws["dM"] = torch.empty(N, 2 * c.Hp, dtype=F32, device=dev)
-                # double-buffered by layer parity: the wgrad GEMMs of layer i run on a side stream while the main
-                # stream already produces layer i-1's tensors
-                ws["dG"] = [torch.empty(N, 8 * c.Hp, dtype=BF16, device=dev) for _ in range(2)]
-                # three, by layer % 3: layer i's dX is written (early rows) while layer i+1's wgrad still reads ITS dH = layer i+2's dX
-                ws["dX"] = [torch.empty(N, 2 * c.P, dtype=BF16, device=dev) for _ in range(3)]
-                ws["dfold"] = [torch.empty(4 * c.Hp, c.Hp, dtype=F32, device=dev) for _ in range(2)]
-                ws["Xbf"] = [torch.empty(N * max(c.Dp0, 2 * c.P), dtype=BF16, device=dev) for _ in range(2)]   # bf16 copies for wgrad
-                ws["Mbf"] = [torch.empty(N, 2 * c.Hp, dtype=BF16, device=dev) for _ in range(2)]
-            self._ws[key] = ws
+        """Views of the arena for a (T, B) minibatch.  Inference keeps ONE m buffer and two ping-pong layer outputs; training
+        keeps every layer's m / gates / c for BPTT."""
+        key = (T, B, training, self._arena.generation)
+        if self._ws_key == key:
+            return self._ws_views
+        c, a = self.cfg, self._arena
+        N, nl = T * B, c.num_layers
+        ws = {"X0": a.rows("X0", N, c.Dp0, F16),
+              "G": a.rows("G", N, 8 * c.Hp, F32),
+              "rec_ws": a.flat("rec_ws", max(16, _lib.lib().lcb_lstm_rec_workspace_bytes(B, c.Hp)), torch.uint8),
+              "cfin": a.flat("cfin", B * 2 * c.Hp, F32).view(B, 2, c.Hp),
+              "mfin": a.flat("mfin", B * 2 * c.Hp, F32).view(B, 2, c.Hp)}
+        if training:
+            ws["M"] = [a.rows("M%d" % i, N, 2 * c.Hp, F16) for i in range(nl)]
+            ws["Hout"] = [a.rows("Hout%d" % i, N, 2 * c.P, F16) for i in range(nl)]
+            ws["gates"] = [a.rows("gates%d" % i, N, 2 * c.Hp, torch.int64) for i in range(nl)]   # 4 x fp16
+            ws["cst"] = [a.rows("cst%d" % i, N, 2 * c.Hp, F32) for i in range(nl)]
+            ws["dM"] = a.rows("dM", N, 2 * c.Hp, F32)
+            # double-buffered by layer parity: the wgrad GEMMs of layer i run on a side stream while the main
+            # stream already produces layer i-1's tensors
+            ws["dG"] = [a.rows("dG%d" % k, N, 8 * c.Hp, BF16) for k in range(2)]
+            # three, by layer % 3: layer i's dX is written (early rows) while layer i+1's wgrad still reads ITS dH = layer i+2's dX
+            ws["dX"] = [a.rows("dX%d" % k, N, 2 * c.P, BF16) for k in range(3)]
+            ws["dfold"] = [a.rows("dfold%d" % k, 4 * c.Hp, c.Hp, F32) for k in range(2)]
+            ws["Xbf"] = [a.flat("Xbf%d" % k, N * max(c.Dp0, 2 * c.P), BF16) for k in range(2)]   # bf16 copies for wgrad
+            ws["Mbf"] = [a.rows("Mbf%d" % k, N, 2 * c.Hp, BF16) for k in range(2)]
+            ws["bwd_carry"] = a.flat("bwd_carry", B * 2 * c.Hp * 2, F32)
+        else:
+            m1 = a.rows("M0", N, 2 * c.Hp, F16)
+            ho = [a.rows("Hout%d" % k, N, 2 * c.P, F16) for k in range(min(2, nl))]
+            ws["M"] = [m1] * nl
+            ws["Hout"] = [ho[i % len(ho)] for i in range(nl)]
+        key = (T, B, training, a.generation)          # (allocation above may have bumped the generation)
+        self._ws_key, self._ws_views = key, ws
         return ws
+
+    def workspace_bytes(self):
+        return self._arena.bytes_allocated()
 
     # ------------------------------------------------------------------ forward
     @property
@@ -407,7 +468,12 @@ class BLSTMEncoder:
         nnet_input = nnet_input.contiguous()
         seq_len = seq_len.to(device=self.device, dtype=torch.int32).contiguous()
         _lib.check(L.lcb_pack_input(_lib.ptr(nnet_input), _lib.ptr(ws["X0"]), B, T, D, c.Dp0, st), "lcb_pack_input")
+        ws["cfin"].zero_()                          # utterances of length 0 keep the zero initial state (bilstm.py:140-144)
+        ws["mfin"].zero_()
         X = ws["X0"]
+        nd = self.ndir
+        H4n = nd * 4 * c.Hp                         # gate columns that exist: both directions' or direction 0's
+        side_cap = self.idle_sms(B, 0)              # SMs the forward recurrence clusters leave free
         for i in range(c.num_layers):
             if i == 1:
                 self._await_refresh()               # layers 1.. were refreshed on the side stream during layer 0's recurrence
@@ -416,12 +482,13 @@ class BLSTMEncoder:
             cst = ws["cst"][i] if training else None
             last = (i == c.num_layers - 1)
             W16, bias, G = self._bf[("Wx16", i)], self.params.w("L%d/bias" % i), ws["G"]
+            kin = X.shape[1] if (i == 0 or nd == 2) else c.P     # uni: layers 1.. read the forward half of the layer below only
 
             def rec(s0, s1):
                 _lib.check(L.lcb_lstm_rec_fwd_range(_lib.ptr(G), _lib.ptr(self._bf[("fold16", i)]), _lib.ptr(peep), _lib.ptr(seq_len),
                                                     _lib.ptr(ws["M"][i]), _lib.ptr(gates), _lib.ptr(cst),
                                                     _lib.ptr(ws["cfin"]) if last else None, _lib.ptr(ws["mfin"]) if last else None,
-                                                    T, B, c.Hp, c.forget_bias, s0, s1, _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(),
+                                                    T, B, c.Hp, nd, c.forget_bias, s0, s1, _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(),
                                                     _lib.stream_ptr()), "lcb_lstm_rec_fwd_range")
 
             Hout = ws["Hout"][i]
@@ -432,7 +499,7 @@ class BLSTMEncoder:
             def hproj(s0, s1):
                 """Output projection of the frames scan steps [s0, s1) visited: rows [s0,s1) of the forward, [T-s1,T-s0) of the
                 backward direction's column half."""
-                for d, (r0, r1) in enumerate(((s0 * B, s1 * B), ((T - s1) * B, (T - s0) * B))):
+                for d, (r0, r1) in enumerate(((s0 * B, s1 * B), ((T - s1) * B, (T - s0) * B))[:nd]):
                     gemm(ws["M"][i][r0:r1, d * c.Hp:(d + 1) * c.Hp], self._bf[("WpT16", i)][d], 0, 0,
                          out=Hout[r0:r1, d * c.P:(d + 1) * c.P],
                          dropout=(drop + (r0 * 2 * c.P + d * c.P,)) if drop else None)
@@ -445,7 +512,7 @@ class BLSTMEncoder:
                     if b_ >= 16 and b_ <= T - 16 and (not bounds or b_ >= bounds[-1] + 16):
                         bounds.append(b_)
             if not bounds:
-                gemm(X, W16, 0, 0, out=G, bias=bias)
+                gemm(X[:, :kin], W16[:H4n, :kin], 0, 0, out=G[:, :H4n], bias=bias[:H4n])
                 rec(0, T)
                 hproj(0, T)
             else:
@@ -462,23 +529,22 @@ class BLSTMEncoder:
 
                 def proj(s0, s1):
                     r0, r1 = s0 * B, s1 * B
-                    gemm(X[r0:r1], W16[:H4], 0, 0, out=G[r0:r1, :H4], bias=bias[:H4])
-                    r0, r1 = (T - s1) * B, (T - s0) * B
-                    gemm(X[r0:r1], W16[H4:], 0, 0, out=G[r0:r1, H4:], bias=bias[H4:])
+                    gemm(X[r0:r1, :kin], W16[:H4, :kin], 0, 0, out=G[r0:r1, :H4], bias=bias[:H4])
+                    if nd == 2:
+                        r0, r1 = (T - s1) * B, (T - s0) * B
+                        gemm(X[r0:r1], W16[H4:], 0, 0, out=G[r0:r1, H4:], bias=bias[H4:])
 
                 proj(0, bounds[0])
                 head_done = torch.cuda.Event()
                 head_done.record(main)
                 chunk_ready = []
-                with torch.cuda.stream(self.pstream):
+                with torch.cuda.stream(self.pstream), grid_cap(side_cap):
                     self.pstream.wait_event(head_done)
-                    old_cap = L.lcb_gemm_set_max_ctas(84)
                     for k in range(1, len(bounds)):
                         proj(bounds[k - 1], bounds[k])
                         ev = torch.cuda.Event()
                         ev.record(self.pstream)
                         chunk_ready.append(ev)
-                    L.lcb_gemm_set_max_ctas(old_cap)
                 prev = 0
                 for k, b_ in enumerate(bounds):
                     if k > 0:
@@ -487,11 +553,9 @@ class BLSTMEncoder:
                     if k + 1 < len(bounds) and self.overlap_hproj:
                         rec_done = torch.cuda.Event()
                         rec_done.record(main)
-                        with torch.cuda.stream(self.pstream):
+                        with torch.cuda.stream(self.pstream), grid_cap(side_cap):
                             self.pstream.wait_event(rec_done)
-                            old_cap = L.lcb_gemm_set_max_ctas(84)
                             hproj(prev, b_)
-                            L.lcb_gemm_set_max_ctas(old_cap)
                     prev = b_
                 if self.overlap_hproj:
                     hproj(bounds[-2], T)
@@ -541,6 +605,9 @@ class BLSTMEncoder:
         ws = self._workspace(T, B, True)
         N = T * B
         ps = self.params
+        nd = self.ndir
+        H4n = nd * 4 * c.Hp
+        bwd_cap = self.idle_sms(B, 1)        # SMs the BPTT clusters leave free: grid cap of everything that runs beside them
         main = torch.cuda.current_stream()
         side = self.wstream if (self.overlap_wgrad and self.wstream is not None) else main
         overlap = side is not main
@@ -583,25 +650,27 @@ class BLSTMEncoder:
                 M = _to_bf16(ws["M"][i], ws["Mbf"][k])
                 if split:
                     # dW_p^T = dH^T * M needs nothing from layer 0's BPTT: both directions run beside it (capped grid)
-                    cap0 = L.lcb_gemm_set_max_ctas(80)
-                    for d in range(2):
-                        gemm(dH_this[:, d * c.P:(d + 1) * c.P], M[:, d * c.Hp:(d + 1) * c.Hp], 1, 1, out=gWpT[d])
-                    done_blocks = []
-                    for blocks, ev in released:
-                        side.wait_event(ev)
-                        for (t0, t1) in blocks:
-                            for d in range(2):
-                                dfold_rows(d, t0 * B, t1 * B, M, dG, bool(done_blocks))
-                            gemm(dG[t0 * B:t1 * B], X[t0 * B:t1 * B], 1, 1, out=gWx, accumulate=bool(done_blocks))
-                            done_blocks.append((t0, t1))
-                    L.lcb_gemm_set_max_ctas(cap0)
+                    with grid_cap(max(8, bwd_cap - 4)):
+                        for d in range(nd):
+                            gemm(dH_this[:, d * c.P:(d + 1) * c.P], M[:, d * c.Hp:(d + 1) * c.Hp], 1, 1, out=gWpT[d])
+                        done_blocks = []
+                        for blocks, ev in released:
+                            side.wait_event(ev)
+                            for (t0, t1) in blocks:
+                                for d in range(nd):
+                                    dfold_rows(d, t0 * B, t1 * B, M, dG, bool(done_blocks))
+                                gemm(dG[t0 * B:t1 * B, :H4n], X[t0 * B:t1 * B], 1, 1, out=gWx[:H4n], accumulate=bool(done_blocks))
+                                done_blocks.append((t0, t1))
                     converted = torch.cuda.Event()
                     converted.record(side)
                     side.wait_event(after)
                     # frames not covered yet: the two outer bands (or everything)
                     rest = [(0, T)] if not done_blocks else [(0, min(b[0] for b in done_blocks)), (max(b[1] for b in done_blocks), T)]
-                if overlap:
-                    old_cap = L.lcb_gemm_set_max_ctas(80 if i > 0 else 148)
+                # layers 1..: beside the BPTT of the layer below (capped grid); layer 0's tail runs alone on the whole chip
+                cap_ctx = grid_cap(max(8, bwd_cap - 4) if (overlap and i > 0) else 0)
+                cap_ctx.__enter__()
+                xin = X if (i == 0 or nd == 2) else X[:, :c.P]      # uni: layers 1.. read the forward half of the layer below only
+
                 def direction(d):
                     dHd = dH_this[:, d * c.P:(d + 1) * c.P]
                     Md = M[:, d * c.Hp:(d + 1) * c.Hp]
@@ -629,25 +698,26 @@ class BLSTMEncoder:
                         gemm(self._bf[("Wh", i)][rows], df_lo, 1, 1, out=gWpT[d], accumulate=True)
 
                 direction(0)
-                if split:
-                    with torch.cuda.stream(main):
-                        main.wait_event(converted)
+                if nd == 2:
+                    if split:
+                        with torch.cuda.stream(main), grid_cap(0):
+                            main.wait_event(converted)
+                            direction(1)
+                            dir1_done = torch.cuda.Event()
+                            dir1_done.record(main)
+                    else:
                         direction(1)
-                        dir1_done = torch.cuda.Event()
-                        dir1_done.record(main)
-                else:
-                    direction(1)
                 # dW_x[g,k] = sum_n dz_n[g] * x_n[k]   (both directions at once)
+                gWxn = gWx[:H4n, :xin.shape[1]]
                 if split and done_blocks:
                     for (t0, t1) in rest:
                         if t1 > t0:
-                            gemm(dG[t0 * B:t1 * B], X[t0 * B:t1 * B], 1, 1, out=gWx, accumulate=True)
+                            gemm(dG[t0 * B:t1 * B, :H4n], xin[t0 * B:t1 * B], 1, 1, out=gWxn, accumulate=True)
                 else:
-                    gemm(dG, X, 1, 1, out=gWx)
-                if split:
+                    gemm(dG[:, :H4n], xin, 1, 1, out=gWxn)
+                if split and nd == 2:
                     side.wait_event(dir1_done)
-                if overlap:
-                    L.lcb_gemm_set_max_ctas(old_cap)
+                cap_ctx.__exit__(None, None, None)
                 if bucket_ready is not None:
                     bucket_ready(["L%d/WpT" % i, "L%d/Wh" % i, "L%d/peep" % i, "L%d/bias" % i, "L%d/Wx" % i])
                 if overlap:
@@ -666,7 +736,7 @@ class BLSTMEncoder:
             """dM[r0:r1] = dH[r0:r1] * W_p^T of layer i, both directions"""
             if r1 <= r0:
                 return
-            for d in range(2):
+            for d in range(nd):
                 gemm(dH_[r0:r1, d * c.P:(d + 1) * c.P], self._bf[("WpT", i)][d], 0, 1, out=ws["dM"][r0:r1, d * c.Hp:(d + 1) * c.Hp])
 
         def dx_rows(i, dG_, dXn_, r0, r1, dHcur=None):
@@ -674,7 +744,8 @@ class BLSTMEncoder:
             the forward pass) in the epilogue"""
             if r1 <= r0:
                 return
-            gemm(dG_[r0:r1], self._bf[("Wx", i)], 0, 1, out=dXn_[r0:r1],
+            pw = 2 * c.P if nd == 2 else c.P         # uni: only the forward half of the layer below exists (the other half stays 0)
+            gemm(dG_[r0:r1, :H4n], self._bf[("Wx", i)][:H4n, :pw], 0, 1, out=dXn_[r0:r1, :pw],
                  dropout=(c.keep_prob, self.dropout_seed(i - 1), r0 * 2 * c.P) if c.keep_prob < 1.0 else None)
             if c.uni_residual(i):
                 # residual path of layer i: d loss / d x_i += d loss / d (x_i + h_i) = this layer's (already masked) output gradient,
@@ -723,15 +794,13 @@ class BLSTMEncoder:
             else:
                 Ts = int(math.ceil(self.bwd_split_frac * T)) if self.bwd_split_frac > 0 and L.lcb_lstm_rec_bwd_can_split(c.Hp) else 0
                 ranges = [(0, T)] if (Ts < 1 or Ts >= T) else [(0, Ts), (Ts, T)]
-            if len(ranges) > 1 and "bwd_carry" not in ws:
-                ws["bwd_carry"] = torch.empty(B * 2 * c.Hp * 2, dtype=F32, device=self.device)
             dXn = ws["dX"][i % 3] if i > 0 else None
             prev_cut = None
             for (s0, s1) in ranges:
                 _lib.check(L.lcb_lstm_rec_bwd_range(_lib.ptr(dM), _lib.ptr(ws["gates"][i]), _lib.ptr(ws["cst"][i]),
                                                     _lib.ptr(self._bf[("fold", i)]), _lib.ptr(peep),
                                                     _lib.ptr(seq_len), _lib.ptr(dG), _lib.ptr(ps.g("L%d/bias" % i)), _lib.ptr(gpeep),
-                                                    T, B, c.Hp, s0, s1, _lib.ptr(ws.get("bwd_carry")),
+                                                    T, B, c.Hp, nd, s0, s1, _lib.ptr(ws["bwd_carry"]),
                                                     _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(), _lib.stream_ptr()), "lcb_lstm_rec_bwd_range")
                 if cuts and s1 < T:
                     # frames final in both directions now: [T-s1, s1), minus those the previous cut already released
@@ -743,13 +812,11 @@ class BLSTMEncoder:
                         if self.l0_released:
                             released0.append((blocks, launched))      # layer 0 has no dX: its weight gradients use the released frames
                         continue
-                    with torch.cuda.stream(self.xstream):
+                    with torch.cuda.stream(self.xstream), grid_cap(bwd_cap):
                         self.xstream.wait_event(launched)
-                        old_cap = L.lcb_gemm_set_max_ctas(self.early_cap)
                         for (t0, t1) in blocks:
                             dx_rows(i, dG, dXn, t0 * B, t1 * B, dH)
                             dm_rows(i - 1, dXn, t0 * B, t1 * B)
-                        L.lcb_gemm_set_max_ctas(old_cap)
                         ev = torch.cuda.Event()
                         ev.record(self.xstream)
                     early = ((T - s1) * B, s1 * B, ev)

@@ -513,7 +513,7 @@ static void launch_softmax(const float* logits, float* grad, int B, int T, int V
     const long long rows = (long long)B * T;
     const int gpc = 256 / GROUP;
     long long want = (rows + gpc - 1) / gpc;
-    int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+    int grid = (int)(want < num_sms() * 8 ? want : num_sms() * 8);
     if (grid < 1) grid = 1;
     ctc_softmax_kernel<GROUP, VEC, NCH><<<grid, 256, 0, st>>>(logits, grad, B, T, V, meta, lab, LABP, lpb, lpl, LPP);
 }
@@ -540,7 +540,7 @@ static void dispatch_softmax(const float* logits, float* grad, int B, int T, int
     const int nch_cta = (nvec + 255) / 256;
     if (nch_cta <= 8) { dispatch_nch<256, VEC>(nch_cta, logits, grad, B, T, V, meta, lab, LABP, lpb, lpl, LPP, st); return; }
     const long long rows = (long long)B * T;
-    int grid = (int)(rows < 148 * 8 ? rows : 148 * 8);
+    int grid = (int)(rows < num_sms() * 8 ? rows : num_sms() * 8);
     ctc_softmax_bigrow_kernel<<<grid, 256, 0, st>>>(logits, grad, B, T, V, meta, lab, LABP, lpb, lpl, LPP);
 }
 
@@ -553,7 +553,7 @@ static cudaError_t launch_ab(const CtcPlan& p, int B, int T, int V, const CtcMet
     ctc_alpha_beta_kernel<NW, SPT><<<2 * B, NW * 32, p.smem, st>>>(meta, lab, p.LABP, lpb, lpl, p.LPP, alpha, beta, logp, loss, T, V, p.TC);
     const long long rows = (long long)B * T;
     long long want = (rows + 7) / 8;
-    const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+    const int grid = (int)(want < num_sms() * 8 ? want : num_sms() * 8);
     ctc_gamma_kernel<<<grid, 256, 0, st>>>(meta, lab, p.LABP, alpha, beta, logp, grad, B, T, V, NW * 32 * SPT);
     return cudaGetLastError();
 }

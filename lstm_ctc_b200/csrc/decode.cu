@@ -77,7 +77,7 @@ extern "C" int lcb_posterior(const float* logits, float* out, long long rows, in
 {
     if (!logits || !out) return LCB_ERR_NULL_POINTER;
     if (rows <= 0 || V <= 0) return LCB_ERR_BAD_SHAPE;
-    long long blocks = (rows + 7) / 8; if (blocks > 148 * 8) blocks = 148 * 8;
+    long long blocks = (rows + 7) / 8; if (blocks > num_sms() * 8) blocks = num_sms() * 8;
     g_launches += 1;
     posterior_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(logits, out, rows, V, smooth_factor, apply_log, log_prior);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;

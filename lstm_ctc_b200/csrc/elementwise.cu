@@ -205,7 +205,7 @@ __global__ void colsum_kernel(const TIn* __restrict__ src, int rows, int cols, i
 static inline int grid_for(size_t n, int per_thread, int threads) {
     size_t b = (n + (size_t)per_thread * threads - 1) / ((size_t)per_thread * threads);
     if (b < 1) b = 1;
-    if (b > 148 * 16) b = 148 * 16;
+    if (b > num_sms() * 16) b = num_sms() * 16;
     return (int)b;
 }
 
@@ -280,7 +280,7 @@ extern "C" int lcb_label_smooth(const float* logits, float* dlogits, long long r
                                 const float* log_prior, float* loss_out, void* stream) {
     if (!logits) return LCB_ERR_NULL_POINTER;
     if (rows <= 0 || V <= 0) return LCB_ERR_BAD_SHAPE;
-    long long blocks = (rows + 7) / 8; if (blocks > 148 * 8) blocks = 148 * 8;
+    long long blocks = (rows + 7) / 8; if (blocks > num_sms() * 8) blocks = num_sms() * 8;
     g_launches += 1;
     label_smooth_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(logits, dlogits, rows, V, weight, log_prior, loss_out);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;

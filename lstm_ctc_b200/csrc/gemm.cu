@@ -22,9 +22,10 @@
 namespace lcb {
 
 
-// upper bound on the persistent grid (host-side knob): GEMMs that are overlapped with a cluster kernel on another
-// stream are launched with only as many CTAs as there are free SMs, so no CTA sits waiting with its share of tiles
-static int g_gemm_max_ctas = 148;
+// Upper bound on the persistent grid: a per-call argument (max_ctas, 0 = every SM of the device).  GEMMs that are overlapped
+// with a cluster kernel on another stream are launched with only as many CTAs as there are free SMs, so no CTA sits waiting
+// with its share of tiles.  (Per call, not process state: calls stay re-entrant across streams.)
+static inline int gemm_cta_cap(int max_ctas) { const int n = num_sms(); return (max_ctas <= 0 || max_ctas > n) ? n : max_ctas; }
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;          // 64 bf16 = 128 B = one swizzle row
@@ -358,7 +359,7 @@ __global__ void gemm_simt_check_kernel(int M, int N, int K, const void* A, int a
 
 template <int BN, bool A_MN, bool B_MN, int CT>
 static int launch_gemm(int M, int N, int K, const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc,
-                       const float* bias, int accumulate, uint32_t fmt_bits, cudaStream_t st, const GemmDropout& drop)
+                       const float* bias, int accumulate, uint32_t fmt_bits, cudaStream_t st, const GemmDropout& drop, int max_ctas)
 {
     // output through TMA stores when the tensor is addressable by a tensor map (16-byte aligned base and pitch)
     const size_t es = CT == 0 ? 4 : 2;
@@ -373,7 +374,7 @@ static int launch_gemm(int M, int N, int K, const CUtensorMap& ta, const CUtenso
     // (tile, K split), all of equal cost and dealt round-robin, so the run time is ceil(tiles*s / ctas) rounds of K/s.
     // Pick the s that minimises rounds/s, with a small charge per extra split for its fp32 reduce-add traffic.
     int splits = 1;
-    const int ctas = g_gemm_max_ctas;
+    const int ctas = gemm_cta_cap(max_ctas);
     if (CT == 0 && tiles0 < 2 * ctas && nkb0 >= 64 && drop.thr16 >= 65536u) {
         int smax = nkb0 / 16; if (smax > 48) smax = 48;
         double best = 1e30;
@@ -395,7 +396,7 @@ static int launch_gemm(int M, int N, int K, const CUtensorMap& ta, const CUtenso
         attr_done = true;
     }
     const int tiles = tiles0 * splits;
-    int nsm = g_gemm_max_ctas;
+    int nsm = ctas;
     int grid = tiles < nsm ? tiles : nsm;
     g_launches += 1; kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tma_out, C, ldc, bias, accumulate, M, N, K, idesc, splits, drop);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
@@ -403,20 +404,20 @@ static int launch_gemm(int M, int N, int K, const CUtensorMap& ta, const CUtenso
 
 template <int BN, int CT>
 static int dispatch_layout(int a_layout, int b_layout, int M, int N, int K, const CUtensorMap& ta, const CUtensorMap& tb,
-                           void* C, int ldc, const float* bias, int accumulate, uint32_t fmt, cudaStream_t st, const GemmDropout& drop)
+                           void* C, int ldc, const float* bias, int accumulate, uint32_t fmt, cudaStream_t st, const GemmDropout& drop, int max_ctas)
 {
-    if (!a_layout && !b_layout) return launch_gemm<BN, false, false, CT>(M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop);
-    if (!a_layout && b_layout) return launch_gemm<BN, false, true, CT>(M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop);
-    if (a_layout && !b_layout) return launch_gemm<BN, true, false, CT>(M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop);
-    return launch_gemm<BN, true, true, CT>(M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop);
+    if (!a_layout && !b_layout) return launch_gemm<BN, false, false, CT>(M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop, max_ctas);
+    if (!a_layout && b_layout) return launch_gemm<BN, false, true, CT>(M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop, max_ctas);
+    if (a_layout && !b_layout) return launch_gemm<BN, true, false, CT>(M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop, max_ctas);
+    return launch_gemm<BN, true, true, CT>(M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop, max_ctas);
 }
 template <int BN>
 static int dispatch_ct(int c_dtype, int a_layout, int b_layout, int M, int N, int K, const CUtensorMap& ta, const CUtensorMap& tb,
-                       void* C, int ldc, const float* bias, int accumulate, uint32_t fmt, cudaStream_t st, const GemmDropout& drop)
+                       void* C, int ldc, const float* bias, int accumulate, uint32_t fmt, cudaStream_t st, const GemmDropout& drop, int max_ctas)
 {
-    if (c_dtype == 0) return dispatch_layout<BN, 0>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop);
-    if (c_dtype == 1) return dispatch_layout<BN, 1>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop);
-    return dispatch_layout<BN, 2>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop);
+    if (c_dtype == 0) return dispatch_layout<BN, 0>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop, max_ctas);
+    if (c_dtype == 1) return dispatch_layout<BN, 1>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop, max_ctas);
+    return dispatch_layout<BN, 2>(a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop, max_ctas);
 }
 
 }  // namespace lcb
@@ -438,16 +439,16 @@ static int gemm_check_args(int M, int N, int K, const void* A, int lda, int a_la
 
 extern "C" int lcb_gemm16(int M, int N, int K, const void* A, int lda, int a_layout, int a_dtype,
                           const void* B, int ldb, int b_layout, int b_dtype,
-                          void* C, int ldc, int c_dtype, const float* bias, int accumulate, void* stream)
+                          void* C, int ldc, int c_dtype, const float* bias, int accumulate, int max_ctas, void* stream)
 {
     return lcb_gemm16_dropout(M, N, K, A, lda, a_layout, a_dtype, B, ldb, b_layout, b_dtype, C, ldc, c_dtype, bias, accumulate,
-                              1.0f, 0ull, 0ull, stream);
+                              1.0f, 0ull, 0ull, max_ctas, stream);
 }
 
 extern "C" int lcb_gemm16_dropout(int M, int N, int K, const void* A, int lda, int a_layout, int a_dtype,
                                   const void* B, int ldb, int b_layout, int b_dtype,
                                   void* C, int ldc, int c_dtype, const float* bias, int accumulate,
-                                  float keep_prob, unsigned long long seed, unsigned long long mask_base, void* stream)
+                                  float keep_prob, unsigned long long seed, unsigned long long mask_base, int max_ctas, void* stream)
 {
     if (!(keep_prob > 0.f) || keep_prob > 1.f) return LCB_ERR_BAD_SHAPE;
     if (keep_prob < 1.f && accumulate) return LCB_ERR_UNSUPPORTED;
@@ -472,14 +473,14 @@ extern "C" int lcb_gemm16_dropout(int M, int N, int K, const void* A, int lda, i
     if (!ok) return LCB_ERR_CUDA;
     // instruction-descriptor operand formats: 0 = F16, 1 = BF16 (a: bits 7-9, b: bits 10-12)
     const uint32_t fmt = ((a_dtype == 1 ? 1u : 0u) << 7) | ((b_dtype == 1 ? 1u : 0u) << 10);
-    if (bn256) return dispatch_ct<256>(c_dtype, a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop);
-    return dispatch_ct<128>(c_dtype, a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop);
+    if (bn256) return dispatch_ct<256>(c_dtype, a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop, max_ctas);
+    return dispatch_ct<128>(c_dtype, a_layout, b_layout, M, N, K, ta, tb, C, ldc, bias, accumulate, fmt, st, drop, max_ctas);
 }
 
 extern "C" int lcb_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_layout, const void* B, int ldb,
                              int b_layout, void* C, int ldc, int c_dtype, const float* bias, int accumulate, void* stream)
 {
-    return lcb_gemm16(M, N, K, A, lda, a_layout, 1, B, ldb, b_layout, 1, C, ldc, c_dtype, bias, accumulate, stream);
+    return lcb_gemm16(M, N, K, A, lda, a_layout, 1, B, ldb, b_layout, 1, C, ldc, c_dtype, bias, accumulate, 0, stream);
 }
 
 extern "C" int lcb_gemm16_simt_check(int M, int N, int K, const void* A, int lda, int a_layout, int a_dtype,
@@ -503,12 +504,7 @@ extern "C" int lcb_gemm_bf16_simt_check(int M, int N, int K, const void* A, int 
     return lcb_gemm16_simt_check(M, N, K, A, lda, a_layout, 1, B, ldb, b_layout, 1, C, ldc, c_dtype, bias, accumulate, stream);
 }
 
-extern "C" int lcb_gemm_set_max_ctas(int n)
-{
-    const int old = lcb::g_gemm_max_ctas;
-    lcb::g_gemm_max_ctas = (n < 1) ? 1 : (n > 148 ? 148 : n);
-    return old;
-}
+extern "C" int lcb_device_sm_count(void) { return lcb::num_sms(); }
 
 extern "C" int lcb_version(void) { return 100; }
 

@@ -42,7 +42,6 @@ __global__ void splice_subsample_kernel(const float* __restrict__ in, const int*
 }
 
 static uint32_t g_crc_tab[8][256];
-static bool g_crc_init = false;
 static void crc32c_init() {
     for (uint32_t n = 0; n < 256; ++n) {
         uint32_t c = n;
@@ -53,7 +52,6 @@ static void crc32c_init() {
         uint32_t c = g_crc_tab[0][n];
         for (int k = 1; k < 8; ++k) { c = g_crc_tab[0][c & 0xffu] ^ (c >> 8); g_crc_tab[k][n] = c; }
     }
-    g_crc_init = true;
 }
 
 }  // namespace lcb
@@ -75,7 +73,8 @@ extern "C" int lcb_splice_subsample(const float* in, const int32_t* lens, float*
 
 extern "C" uint32_t lcb_crc32c(const void* data, size_t n, uint32_t crc)
 {
-    if (!g_crc_init) crc32c_init();
+    static const bool ready = (crc32c_init(), true);      // C++11 static: initialised once, thread-safe (prefetch thread + main thread)
+    (void)ready;
     const unsigned char* p = (const unsigned char*)data;
     uint32_t c = crc ^ 0xffffffffu;
     while (n && ((uintptr_t)p & 7)) { c = g_crc_tab[0][(c ^ *p++) & 0xffu] ^ (c >> 8); --n; }

@@ -432,7 +432,7 @@ extern "C" int lcb_output_fwd(const void* X, int ldx, const void* Wall, const fl
         smem_set = smem;
     }
     const int tiles_m = (p.N + OUT_BM - 1) / OUT_BM;
-    const int grid = tiles_m < 148 ? tiles_m : 148;
+    const int grid = tiles_m < num_sms() ? tiles_m : num_sms();
     g_launches += 1; out_fwd_kernel<<<grid, OUT_THREADS, smem, (cudaStream_t)stream>>>(tx, tw, twp, p);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }
@@ -443,7 +443,7 @@ extern "C" int lcb_mos_bwd_dz(const float* Z, const float* dlogits, void* dZ, in
     if (!(keep_prob > 0.f) || keep_prob > 1.f) return LCB_ERR_BAD_SHAPE;
     if (!Z || !dlogits || !dZ) return LCB_ERR_NULL_POINTER;
     if (R <= 0 || K <= 0 || V <= 0 || ldz < K * V + K) return LCB_ERR_BAD_SHAPE;
-    int grid = (R + 7) / 8; if (grid > 148 * 8) grid = 148 * 8;
+    int grid = (R + 7) / 8; if (grid > num_sms() * 8) grid = num_sms() * 8;
     const float inv_keep = 1.f / keep_prob;
     const uint32_t thr = keep_threshold16(keep_prob);
     const unsigned long long seed_d = seed ^ 0xD1B54A32D192ED03ull;
@@ -470,7 +470,7 @@ extern "C" int lcb_pack_dlogits(const float* dlogits, void* out, int T, int B, i
     if (!dlogits || !out) return LCB_ERR_NULL_POINTER;
     if (T <= 0 || B <= 0 || V <= 0 || ldo < V) return LCB_ERR_BAD_SHAPE;
     const size_t total = (size_t)T * B * ldo;
-    size_t blocks = (total + 255) / 256; if (blocks > 148 * 16) blocks = 148 * 16;
+    size_t blocks = (total + 255) / 256; if (blocks > num_sms() * 16) blocks = num_sms() * 16;
     g_launches += 1; pack_dlogits_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(dlogits, (__nv_bfloat16*)out, T, B, V, ldo);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }

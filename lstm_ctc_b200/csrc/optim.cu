@@ -84,7 +84,7 @@ extern "C" int lcb_optimizer_step(float* w, float* g, float* s1, float* s2, long
     for (int k = 0; k < n_ranges; ++k) { nd.lo[k] = nodecay_ranges_host[2 * k]; nd.hi[k] = nodecay_ranges_host[2 * k + 1]; }
     cudaStream_t st = (cudaStream_t)stream;
     long long blocks = (n + 256 * 8 - 1) / (256 * 8);
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
     if (blocks < 1) blocks = 1;
     cudaMemsetAsync(sumsq_scratch, 0, sizeof(double), st);
     g_launches += 2; l2_sumsq_kernel<<<(int)blocks, 256, 0, st>>>(w, g, n, l2, nd, sumsq_scratch);

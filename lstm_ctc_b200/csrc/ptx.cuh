@@ -11,6 +11,19 @@ namespace lcb {
 // host-side count of kernels launched by this library (bench.py reports it as gpu_launches)
 static long long g_launches = 0;
 
+// SM count of the current device (queried once per device, never a literal): grids are sized in multiples of it
+static inline int num_sms() {
+    static int cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (cache[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 1;
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+
 // ----------------------------------------------------------------------------------------
 // device-side error word: a kernel that times out on a barrier records a code here and bails
 // out instead of hanging the GPU.  Host reads it through lcb_device_error().

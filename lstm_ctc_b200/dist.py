@@ -29,6 +29,10 @@ def init_from_env(backend=None):
     return rank, world, device
 
 
+def rank():
+    return dist.get_rank() if dist.is_initialized() else 0
+
+
 def shard_utterances(num_utts, rank, world):
     """Length-sorted utterances are dealt round-robin so every rank sees the same length profile."""
     return list(range(rank, num_utts, world))

@@ -57,7 +57,7 @@ class Saver:
         if tf_bundle.bundle_exists(path):
             sd = {k: torch.from_numpy(v) for k, v in tf_bundle.read_bundle(path).items()}
         elif os.path.isfile(path):
-            sd = torch.load(path, map_location="cpu")
+            sd = torch.load(path, map_location="cpu", weights_only=True)
         else:
             raise tf_bundle.BundleError("no checkpoint at %r (neither %s.index nor a state-dict file)" % (path, path))
         self.model.load_state_dict(sd)
@@ -106,11 +106,13 @@ class _Graph:
             raise ValueError("unsupported nnet_type: %s" % nnet_type)
         self.model = AcousticModel(self.nnet_config, seed=seed)
         _default_model[0] = self.model
+        if seed is not None:                 # --seed (nnet-train.py:141-142, tf.set_random_seed) seeds dropout too; ranks differ
+            self.model.enc.set_dropout_seed(seed, _dist.rank())
         self.train_cfg = None
         self.smooth_factor = 1.0
         self.reducer = _dist.GradientAllReducer(self.model.params)
         self.reducer.broadcast_weights()
-        self._scal = torch.zeros(2, dtype=torch.float64, device=self.model.device)
+        self._scal = torch.zeros(4, dtype=torch.float64, device=self.model.device)
         self._staged = None            # (batch, device tensors, copy-done event) of the NEXT step, or the OutOfRangeError to raise
         self._copy_stream = None
         self._staged_epoch = 0
@@ -176,21 +178,27 @@ class _Graph:
             logits = m.forward_logits(x, lens, training=False)
             loss, _ = m.ctc(logits, y, lens)
             loss_sum = loss.sum()
+        reg = m.reg_loss if "train" in wanted else m.label_smoothing(logits)
+        ev = self._greedy_edit_distance(logits, batch) if "eval" in wanted else 0.0
         if self.reducer.world > 1:
+            # every reported scalar is a sum over the GLOBAL batch (graph.py:105-106,116,120-136,150): CTC loss, token count,
+            # label-smoothing term and edit distance travel in one all-reduce
             self._scal[0] = loss_sum.double()
             self._scal[1] = float(size)
+            self._scal[2] = reg.double().sum() if reg is not None else 0.0
+            self._scal[3] = float(ev)
             self.reducer.all_reduce_scalars(self._scal)
             vals = self._scal.tolist()
-            out["eval_loss"], out["size"] = vals[0], int(round(vals[1]))
+            out["eval_loss"], out["size"], regv, ev = vals[0], int(round(vals[1])), vals[2], vals[3]
         else:
             out["eval_loss"] = float(loss_sum.item())                 # D2H read of the step's result
-        reg = m.reg_loss if "train" in wanted else m.label_smoothing(logits)
-        out["loss"] = out["eval_loss"] + (float(reg.item()) if reg is not None else 0.0)   # graph.py:120-136
+            regv = float(reg.item()) if reg is not None else 0.0
+        out["loss"] = out["eval_loss"] + regv                         # graph.py:120-136
         out["global_step"] = m.global_step
         if "logits" in wanted:
             out["logits"] = logits.cpu().numpy()
         if "eval" in wanted:
-            out["eval"] = self._greedy_edit_distance(logits, batch)
+            out["eval"] = ev
         return out
 
     def _greedy_edit_distance(self, logits, batch):

@@ -91,11 +91,12 @@ class AcousticModel:
         self._out16 = None
         self._outbf = None
         self._out_stale = True
-        self._ows = {}
         self.opt_state = None
         self.reg_loss = None
         self.global_step = 0
         self._nodecay = self.params.nodecay_ranges()
+        if len(self._nodecay) > 24:
+            raise _lib.LcbError(-3, "num_layers = %d: lcb_optimizer_step takes at most 24 no-decay (LSTM bias) ranges" % c.num_layers)
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._gnorm = torch.zeros(1, dtype=F32, device=self.device)
         if init:
@@ -158,19 +159,17 @@ class AcousticModel:
 
     # ------------------------------------------------------------------ forward
     def _out_ws(self, T, B):
-        key = (T, B)
-        ws = self._ows.get(key)
-        if ws is None:
-            c = self.cfg
-            N = T * B
-            R = min(self.MOS_BWD_ROWS, N)
-            ws = {"logits": torch.empty(B, T, c.V, dtype=F32, device=self.device),
-                  "Xbf": torch.empty(N, 2 * c.P, dtype=BF16, device=self.device),
-                  "dXtop": torch.empty(N, 2 * c.P, dtype=BF16, device=self.device),
-                  "dZ": torch.empty(R if c.K > 0 else N, self.ldz, dtype=BF16, device=self.device)}
-            if c.K > 0:
-                ws["Z"] = torch.empty(R, self.ldz, dtype=F32, device=self.device)
-            self._ows[key] = ws
+        """Output-layer buffers of a (T, B) minibatch: views of the encoder's grow-only arena (one allocation for the largest
+        batch seen, whatever sequence of T the data brings)."""
+        c, a = self.cfg, self.enc._arena
+        N = T * B
+        R = min(self.MOS_BWD_ROWS, N)
+        ws = {"logits": a.flat("logits", N * c.V, F32).view(B, T, c.V),
+              "Xbf": a.rows("outXbf", N, 2 * c.P, BF16),
+              "dXtop": a.rows("dXtop", N, 2 * c.P, BF16),
+              "dZ": a.rows("dZ", R if c.K > 0 else N, self.ldz, BF16)}
+        if c.K > 0:
+            ws["Z"] = a.rows("Z", R, self.ldz, F32)
         return ws
 
     def forward_logits(self, nnet_input, seq_len, training=True):

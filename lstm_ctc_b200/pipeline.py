@@ -41,32 +41,59 @@ class _BatchSource:
     def initialize(self):
         """(Re)start the epoch.  Batches are assembled into pinned memory by a background thread, two ahead
         (the reference's tf.data pipeline prefetches on host threads as well, tfrecord.py:122-123)."""
+        self._stop_producer()                                 # a previous epoch's thread may be blocked on its full queue
         self.epoch_id = getattr(self, "epoch_id", 0) + 1      # consumers drop anything they staged from the previous epoch
         self._it = iter(self.dataset)
         self._q = queue.Queue(maxsize=2)
-        self._thread = threading.Thread(target=self._producer, args=(self._it, self._q), daemon=True)
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._producer, args=(self._it, self._q, self._stop), daemon=True)
         self._thread.start()
 
-    def _producer(self, it, q):
-        while True:
+    def _stop_producer(self):
+        """Ends the producer of the previous epoch: signal it, drain its queue so a blocked put() returns, join it -- so
+        re-initialising never leaks a thread holding pinned batches."""
+        th = getattr(self, "_thread", None)
+        if th is None:
+            return
+        self._stop.set()
+        while th.is_alive():
+            try:
+                self._q.get_nowait()
+            except queue.Empty:
+                pass
+            th.join(timeout=0.01)
+        self._thread = None
+
+    def _producer(self, it, q, stop):
+        def put(item):
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.05)
+                    return True
+                except queue.Full:
+                    continue
+            return False
+
+        while not stop.is_set():
             try:
                 item = self._assemble(it)
             except OutOfRangeError:
-                q.put(None)
+                put(None)
                 return
             except Exception as e:          # surface data errors on the consumer side
-                q.put(e)
+                put(e)
                 return
-            q.put(item)
+            if not put(item):
+                return
 
     def next(self):
         if self._it is None:
             raise RuntimeError("pipeline not initialised: sess.run(pipeline_initializer) first")
         item = self._q.get()
-        if item is None:
-            self._q.put(None)               # stay exhausted
-            raise OutOfRangeError()
-        if isinstance(item, Exception):
+        if item is None or isinstance(item, Exception):
+            self._q.put(item)               # the producer has exited: stay exhausted / keep failing, never block
+            if item is None:
+                raise OutOfRangeError()
             raise item
         return item
 
