@@ -219,6 +219,7 @@ class BLSTMEncoder:
         self._arena = Arena(device, zero=cfg.uni)   # uni: the never-written direction-1 halves must read as 0, not as garbage
         self._ws_key = None
         self._ws_views = None
+        self.debug_dz = None           # tests: a dict here receives {layer: copy of dz [T*B, 8Hp] bf16} from backward()
         self._refresh_graphs = None
         self._refresh_done = None
         self.seed_base = 777           # reference default --seed (nnet-train.py:141-142); set_dropout_seed() overrides
@@ -820,6 +821,8 @@ class BLSTMEncoder:
                         ev = torch.cuda.Event()
                         ev.record(self.xstream)
                     early = ((T - s1) * B, s1 * B, ev)
+            if self.debug_dz is not None:
+                self.debug_dz[i] = dG.clone()
             if pending is not None:
                 wgrad(pending[0], pending[1], chain_issued)   # layer i+1's weight gradients run beside this BPTT
             dH_this = dH

@@ -120,9 +120,14 @@ def reverse_sequence(x, seq_len):
     return torch.gather(x, 1, idx.unsqueeze(-1).expand_as(x))
 
 
-def lstm_cell(x_t, c, h, kernel, bias, w_f, w_i, w_o, proj, forget_bias):
-    """TF r1.8 rnn_cell_impl.LSTMCell.call."""
+def lstm_cell(x_t, c, h, kernel, bias, w_f, w_i, w_o, proj, forget_bias, zs=None):
+    """TF r1.8 rnn_cell_impl.LSTMCell.call.  zs: optional list that receives the pre-activation z_t (with its gradient
+    retained), so tests can compare d loss / d z_t -- what the BPTT kernel emits -- layer by layer."""
     z = torch.cat([x_t, h], 1) @ kernel + bias
+    if zs is not None:
+        if z.requires_grad:
+            z.retain_grad()
+        zs.append(z)
     i, j, f, o = torch.chunk(z, 4, dim=1)
     if w_f is not None:
         c_new = torch.sigmoid(f + forget_bias + w_f * c) * c + torch.sigmoid(i + w_i * c) * torch.tanh(j)
@@ -134,7 +139,7 @@ def lstm_cell(x_t, c, h, kernel, bias, w_f, w_i, w_o, proj, forget_bias):
     return c_new, h_new
 
 
-def dynamic_rnn(x, seq_len, cellp, forget_bias, keep_prob=1.0, masks=None, residual=False):
+def dynamic_rnn(x, seq_len, cellp, forget_bias, keep_prob=1.0, masks=None, residual=False, zs=None):
     """tf.nn.dynamic_rnn over a DropoutWrapper(LSTMCell) (bilstm.py:127-137,171-188):
     zero output and state copy-through for t >= seq_len[b]; dropout on the emitted output only.
     masks: optional [B,T,P] 0/1 tensor standing in for TF's (unmatchable) RNG stream."""
@@ -146,7 +151,7 @@ def dynamic_rnn(x, seq_len, cellp, forget_bias, keep_prob=1.0, masks=None, resid
     h = x.new_zeros(B, P)
     outs = []
     for t in range(T):
-        c_new, h_new = lstm_cell(x[:, t], c, h, kernel, bias, w_f, w_i, w_o, proj, forget_bias)
+        c_new, h_new = lstm_cell(x[:, t], c, h, kernel, bias, w_f, w_i, w_o, proj, forget_bias, zs)
         live = (t < seq_len).to(x.dtype).unsqueeze(1)
         out = h_new + x[:, t] if residual else h_new        # ResidualWrapper sits INSIDE the DropoutWrapper (lstm.py:247-259)
         if keep_prob < 1.0 and masks is not None:
@@ -165,18 +170,22 @@ def _cell_params(p, cfg, i, d, c):
             p[pre + "/w_o_diag"] if pe else None, p[pre + "/projection/kernel"])
 
 
-def blstm_forward(p, cfg: OracleConfig, nnet_input, seq_len, keep_prob=1.0, masks=None):
+def blstm_forward(p, cfg: OracleConfig, nnet_input, seq_len, keep_prob=1.0, masks=None, trace=None):
     """create_logits_blstm up to the encoder output (bilstm.py:104-211).
     Returns (output [B,T,2P], encoder [B,2(H+P)]).
-    masks: optional dict {(layer, 'f'|'b'): [B,T,P]} in each direction's OWN time order."""
+    masks: optional dict {(layer, 'f'|'b'): [B,T,P]} in each direction's OWN time order.
+    trace: optional dict that receives {(layer, 'f'|'b'): [z_0 .. z_{T-1}]}, the cells' pre-activations in each direction's own
+    time order (see lstm_cell)."""
     finput = nnet_input
     binput = reverse_sequence(nnet_input, seq_len)
     fw_state = bw_state = None
     for i in range(cfg.num_layers):
         fo, fw_state = dynamic_rnn(finput, seq_len, _cell_params(p, cfg, i, "fd", "frnn"),
-                                   cfg.forget_bias, keep_prob, None if masks is None else masks.get((i, "f")))
+                                   cfg.forget_bias, keep_prob, None if masks is None else masks.get((i, "f")),
+                                   zs=None if trace is None else trace.setdefault((i, "f"), []))
         bo, bw_state = dynamic_rnn(binput, seq_len, _cell_params(p, cfg, i, "bd", "brnn"),
-                                   cfg.forget_bias, keep_prob, None if masks is None else masks.get((i, "b")))
+                                   cfg.forget_bias, keep_prob, None if masks is None else masks.get((i, "b")),
+                                   zs=None if trace is None else trace.setdefault((i, "b"), []))
         rbo = reverse_sequence(bo, seq_len)
         cat = torch.cat([fo, rbo], 2)
         if i == 0 and cfg.input_dim == 2 * cfg.num_projects:      # bilstm.py:199-200
