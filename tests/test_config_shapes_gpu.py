@@ -10,7 +10,10 @@ with a ragged last group; 64 -> two paired sub-groups per cluster (`lstm_rec_fwd
 H = 512, the 1-D `lstm_rec_bwd2_kernel` BPTT at H = 320).
 
 Stated tolerances (the observed errors are written to gpurun_out/r02_parity_config_shapes.json and committed under profiles/):
-  logits   max |err| over live frames  <= 1e-2 * max |logit|          (fp16 operands, fp32 accumulate, T <= 128 steps)
+  logits   max |err| over live frames  <= 2.5e-2 * max |logit|, rms <= 5e-3 * max |logit|
+           (fp16 operands, fp32 accumulate.  The rounding of each layer's 16-bit output is amplified ~2x by every layer above it
+           -- tools/parity_diag.py, profiles/r02_parity_diag_c3.txt: rms error of h 2.5e-4 / 5.4e-4 / 1.0e-3 / 1.9e-3 / 3.7e-3 in
+           layers 0..4 -- so a 5-layer stack sits at 1.5e-2 max / 2.7e-3 rms where the 2-layer cases of test_model_gpu.py hold 1e-2.)
   loss     |sum - sum_ref|             <= 2e-3 * |sum_ref|
   grads    ||g - g_ref|| / ||g_ref||   <= 5e-2 per variable             (bf16 gradient operands)
   dz       ||dz - dz_ref|| / ||dz_ref|| <= 5e-2 per layer               (bf16 storage)
@@ -22,6 +25,7 @@ import pytest
 import torch
 
 import oracle
+from oracle import twin
 
 pytestmark = pytest.mark.gpu
 
@@ -30,9 +34,15 @@ DIMS = {
     "c2": dict(input_dim=120, num_layers=4, num_neurons=320, num_projects=320, num_targets=72, use_peepholes=True, num_experts=8),
     "c3": dict(input_dim=120, num_layers=5, num_neurons=512, num_projects=512, num_targets=72, use_peepholes=True, num_experts=8),
 }
-# (dims, B, T, keep_prob)
-CASES = [("c3", 33, 64, 1.0), ("c3", 64, 128, 0.9), ("c2", 64, 64, 0.9), ("c1", 33, 128, 1.0), ("c1", 64, 64, 0.9)]
-TOL = {"logits": 1e-2, "loss": 2e-3, "grad": 5e-2, "dz": 5e-2}
+# (dims, B, T, keep_prob, forget-gate bias variable).  fb = 0: TF's default initialisation (zero biases; with LSTMCell's forget_bias = 5
+# the cell is an integrator and the stack's gradients explode with T).  fb = -4: the same weights with the forget-gate block of
+# every `bias` variable set to -4, i.e. an effective forget bias of 1 -- a stable model, where the exact oracle pins long sequences.
+CASES = [("c3", 33, 64, 1.0, 0.0), ("c2", 64, 64, 0.9, 0.0), ("c1", 64, 64, 0.9, 0.0),
+         ("c3", 64, 128, 0.9, -4.0), ("c1", 33, 128, 1.0, -4.0), ("c2", 49, 192, 0.9, -4.0),
+         ("c3", 64, 128, 0.9, 0.0), ("c1", 33, 128, 1.0, 0.0)]
+TOL_TWIN = {"logits": 1e-2, "logits_rms": 2e-3, "loss": 1e-3, "grad": 3e-2, "dz": 3e-2}      # provisional: set from the first measured run
+TOL_STABLE = {"logits": 1e-2, "logits_rms": 2e-3, "loss": 1e-3, "grad": 3e-2, "dz": 3e-2}    # provisional
+TOL = {"logits": 2.5e-2, "logits_rms": 5e-3, "loss": 2e-3, "grad": 5e-2, "dz": 5e-2}
 REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "r02_parity_config_shapes.json")
 
 
@@ -71,8 +81,8 @@ def _unpack_dz(dG, T, B, H, Hp):
     return d.reshape(2, B, T, 4 * H)
 
 
-@pytest.mark.parametrize("dims,B,T,keep", CASES, ids=["%s-B%d-T%d-keep%.1f" % c for c in CASES])
-def test_whole_path_vs_oracle_at_config_shapes(cuda_dev, dims, B, T, keep):
+@pytest.mark.parametrize("dims,B,T,keep,fb", CASES, ids=["%s-B%d-T%d-keep%.1f-fb%g" % c for c in CASES])
+def test_whole_path_vs_oracle_at_config_shapes(cuda_dev, dims, B, T, keep, fb):
     from lstm_ctc_b200 import _lib
     from lstm_ctc_b200.model import AcousticModel
     torch.set_num_threads(os.cpu_count() or 1)
@@ -80,6 +90,11 @@ def test_whole_path_vs_oracle_at_config_shapes(cuda_dev, dims, B, T, keep):
     params = oracle.init_params(cfg, seed=101, bias_scale=0.1)
     x, lens, labels = make_batch(cfg, B, T, seed=202)
     H, P, K, V, nl = cfg.num_neurons, cfg.num_projects, cfg.num_experts, cfg.num_targets, cfg.num_layers
+    if fb:
+        for k in params:
+            if k.endswith("/bias"):
+                params[k][2 * H:3 * H] += fb                          # gate blocks i, j, f, o (rnn_cell_impl.LSTMCell)
+    stable = fb < 0
 
     # ---- CUDA path ----
     m = AcousticModel(nnet_config(cfg, keep), cuda_dev, init=False)
@@ -104,43 +119,62 @@ def test_whole_path_vs_oracle_at_config_shapes(cuda_dev, dims, B, T, keep):
             seed = m._out_seed
             mp = _mask(N * K, keep, seed, cuda_dev).view(T, B, K).permute(1, 0, 2).reshape(B * T, K, 1)
             md = _mask(N * K * V, keep, seed ^ 0xD1B54A32D192ED03, cuda_dev).view(T, B, V, K).permute(1, 0, 3, 2).reshape(B * T, K, V)
-    p64 = {k: v.clone().requires_grad_(True) for k, v in params.items()}
-    trace = {}
-    enc, _ = oracle.blstm_forward(p64, cfg, x, lens, keep_prob=keep, masks=masks, trace=trace)
-    if K > 0:
-        y = oracle.create_moe(enc.reshape(-1, 2 * P), p64["Variable"], p64["Variable_1"], p64["Variable_2"], p64["Variable_3"],
-                              V, K, cfg.moe_temp, keep_prob=keep, mask_prior=mp, mask_dec=md).reshape(B, T, V)
-    else:
-        y = oracle.output_layer(p64, cfg, enc)
-    ctc = oracle.ctc_loss_sum(y, labels, lens)
-    ctc.backward()
-
-    # ---- compare ----
-    rep = {"case": "%s B=%d T=%d keep=%.1f" % (dims, B, T, keep), "tolerance": TOL}
     live = (torch.arange(T).unsqueeze(0) < lens.unsqueeze(1))
-    scale = y.detach().abs().max().item()
-    rep["logits_max_err_over_scale"] = (logits - y.detach())[live].abs().max().item() / scale
-    rep["loss_rel_err"] = abs(loss_sum.item() - ctc.item()) / abs(ctc.item())
-    rep["grad_rel_err"] = {k: ((v - p64[k].grad).norm() / (p64[k].grad.norm() + 1e-30)).item() for k, v in grads.items()}
-    rep["grad_rel_err_max"] = max(rep["grad_rel_err"].values())
-    rep["dz_rel_err"] = {}
     Hp = m.cfg.Hp
-    for i in range(nl):
-        ours = _unpack_dz(m.enc.debug_dz[i], T, B, H, Hp)
-        zf = torch.stack([z.grad if z.grad is not None else torch.zeros_like(z) for z in trace[(i, "f")]], 1)      # [B,T,4H]
-        zb = torch.stack([z.grad if z.grad is not None else torch.zeros_like(z) for z in trace[(i, "b")]], 1)
-        zb = oracle.model.reverse_sequence(zb, lens)                  # the backward cell's own time order -> absolute time
-        for d, ref in enumerate((zf, zb)):
-            ref = ref * live.unsqueeze(-1)                            # (padded steps carry no gradient)
-            rep["dz_rel_err"]["L%d/%s" % (i, "fd" if d == 0 else "bd")] = ((ours[d] - ref).norm() / (ref.norm() + 1e-30)).item()
-            assert ours[d][~live].abs().max().item() == 0.0 if (~live).any() else True       # exact masking
-    rep["dz_rel_err_max"] = max(rep["dz_rel_err"].values())
+    dz_ours = [_unpack_dz(m.enc.debug_dz[i], T, B, H, Hp) for i in range(nl)]
+    for d4 in dz_ours:
+        if (~live).any():
+            assert d4[:, ~live].abs().max().item() == 0.0                # exact length masking of dz
+
+    def reference(kind):
+        """(logits, loss, grads, dz[layer][dir]) of the exact fp64 oracle or of its precision twin"""
+        p64 = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        trace = {}
+        if kind == "exact":
+            enc, _ = oracle.blstm_forward(p64, cfg, x, lens, keep_prob=keep, masks=masks, trace=trace)
+            if K > 0:
+                y = oracle.create_moe(enc.reshape(-1, 2 * P), p64["Variable"], p64["Variable_1"], p64["Variable_2"], p64["Variable_3"],
+                                      V, K, cfg.moe_temp, keep_prob=keep, mask_prior=mp, mask_dec=md).reshape(B, T, V)
+            else:
+                y = oracle.output_layer(p64, cfg, enc)
+        else:
+            enc = twin.blstm_forward_twin(p64, cfg, x, lens, keep_prob=keep, masks=masks, trace=trace)
+            y = twin.output_layer_twin(p64, cfg, enc, keep_prob=keep, mask_prior=mp, mask_dec=md)
+        ctc = oracle.ctc_loss_sum(y, labels, lens)
+        ctc.backward()
+        dz = []
+        for i in range(nl):
+            key_f, key_b = ((i, "f"), (i, "b"))
+            zf = torch.stack([z.grad if z.grad is not None else torch.zeros_like(z) for z in trace[key_f]], 1)      # [B,T,4H]
+            zb = torch.stack([z.grad if z.grad is not None else torch.zeros_like(z) for z in trace[key_b]], 1)
+            zb = oracle.model.reverse_sequence(zb, lens)              # the backward cell's own time order -> absolute time
+            dz.append([zf * live.unsqueeze(-1), zb * live.unsqueeze(-1)])       # (padded steps carry no gradient)
+        return y.detach(), ctc.item(), {k: v.grad for k, v in p64.items()}, dz
+
+    def compare(a, b_):
+        """errors of a = (logits, loss, grads, dz) against the reference b_"""
+        (la, ca, ga, za), (lb, cb, gb, zb) = a, b_
+        scale = lb.abs().max().item()
+        e = (la - lb)[live]
+        r = {"logits_max_err_over_scale": e.abs().max().item() / scale, "logits_rms_err_over_scale": e.pow(2).mean().sqrt().item() / scale,
+             "loss_rel_err": abs(ca - cb) / abs(cb),
+             "grad_rel_err": {k: ((ga[k] - gb[k]).norm() / (gb[k].norm() + 1e-30)).item() for k in gb},
+             "dz_rel_err": {"L%d/%s" % (i, "fd" if d == 0 else "bd"): ((za[i][d] - zb[i][d]).norm() / (zb[i][d].norm() + 1e-30)).item()
+                            for i in range(nl) for d in range(2)}}
+        r["grad_rel_err_max"] = max(r["grad_rel_err"].values())
+        r["dz_rel_err_max"] = max(r["dz_rel_err"].values())
+        return r
+
+    ours = (logits, loss_sum.item(), grads, dz_ours)
+    ref_twin, ref_exact = reference("twin"), reference("exact")
+    rep = {"case": "%s B=%d T=%d keep=%.1f forget-bias-variable=%g" % (dims, B, T, keep, fb), "tolerance_vs_twin": TOL_TWIN, "tolerance_vs_exact_T<=64": TOL,
+           "cuda_vs_twin": compare(ours, ref_twin), "cuda_vs_exact": compare(ours, ref_exact),
+           "twin_vs_exact": compare(ref_twin, ref_exact)}
     # padded frames: the output layer applied to a zero encoder row (bilstm.py:237-250 quirk Q5) -- identical rows, bit for bit
-    if (~live).any():
+    if (~live).any() and keep >= 1.0:
         pad_rows = m._out_ws(T, B)["logits"][(~live).to(cuda_dev)]
-        rep["padded_rows_identical"] = bool((pad_rows == pad_rows[0]).all()) if keep >= 1.0 else None
-        if keep >= 1.0:
-            assert rep["padded_rows_identical"]
+        rep["padded_rows_identical"] = bool((pad_rows == pad_rows[0]).all())
+        assert rep["padded_rows_identical"]
     try:
         os.makedirs(os.path.dirname(REPORT), exist_ok=True)
         allr = json.load(open(REPORT)) if os.path.exists(REPORT) else {}
@@ -148,11 +182,40 @@ def test_whole_path_vs_oracle_at_config_shapes(cuda_dev, dims, B, T, keep):
         json.dump(allr, open(REPORT, "w"), indent=1)
     except OSError:
         pass
-    print(json.dumps({k: v for k, v in rep.items() if not isinstance(v, dict) or k == "tolerance"}))
-    assert rep["logits_max_err_over_scale"] < TOL["logits"], rep
-    assert rep["loss_rel_err"] < TOL["loss"], rep
-    assert rep["grad_rel_err_max"] < TOL["grad"], rep["grad_rel_err"]
-    assert rep["dz_rel_err_max"] < TOL["dz"], rep["dz_rel_err"]
+    short = lambda r: {k: (round(v, 6) if isinstance(v, float) else v) for k, v in r.items() if not isinstance(v, dict)}
+    print(json.dumps({"case": rep["case"], "cuda_vs_twin": short(rep["cuda_vs_twin"]), "cuda_vs_exact": short(rep["cuda_vs_exact"]),
+                      "twin_vs_exact": short(rep["twin_vs_exact"])}))
+    # (1) arithmetic agreement, any length: CUDA path vs the precision twin
+    ct = rep["cuda_vs_twin"]
+    if stable or T <= 64:
+        assert ct["logits_max_err_over_scale"] < TOL_TWIN["logits"], ct
+        assert ct["logits_rms_err_over_scale"] < TOL_TWIN["logits_rms"], ct
+        assert ct["loss_rel_err"] < TOL_TWIN["loss"], ct
+        assert ct["grad_rel_err_max"] < TOL_TWIN["grad"], ct["grad_rel_err"]
+        assert ct["dz_rel_err_max"] < TOL_TWIN["dz"], ct["dz_rel_err"]
+    else:       # default initialisation beyond T = 64: even fp32-level differences are amplified ~1e4-fold; the CUDA path must sit
+        #         much closer to the twin than the twin sits to the exact oracle
+        te_ = rep["twin_vs_exact"]
+        assert ct["loss_rel_err"] < TOL_TWIN["loss"], ct
+        assert ct["grad_rel_err_max"] < 0.5 * te_["grad_rel_err_max"], (ct["grad_rel_err_max"], te_["grad_rel_err_max"])
+        assert ct["logits_rms_err_over_scale"] < 0.5 * te_["logits_rms_err_over_scale"], (ct, te_)
+    # (2) against the exact fp64 oracle: asserted where the model's own sensitivity to 16-bit operands is still small (T <= 64);
+    #     beyond that the CUDA path must stay as close to the exact oracle as the twin does (same dynamical amplification)
+    ce, te = rep["cuda_vs_exact"], rep["twin_vs_exact"]
+    if stable:
+        for key, tk in (("logits_max_err_over_scale", "logits"), ("logits_rms_err_over_scale", "logits_rms"), ("loss_rel_err", "loss"),
+                        ("grad_rel_err_max", "grad"), ("dz_rel_err_max", "dz")):
+            assert ce[key] < TOL_STABLE[tk], (key, ce[key], ce["grad_rel_err"], ce["dz_rel_err"])
+    elif T <= 64:
+        assert ce["logits_max_err_over_scale"] < TOL["logits"], ce
+        assert ce["logits_rms_err_over_scale"] < TOL["logits_rms"], ce
+        assert ce["loss_rel_err"] < TOL["loss"], ce
+        assert ce["grad_rel_err_max"] < TOL["grad"], ce["grad_rel_err"]
+        assert ce["dz_rel_err_max"] < TOL["dz"], ce["dz_rel_err"]
+    else:
+        assert ce["loss_rel_err"] < 2 * TOL["loss"], ce
+        assert ce["grad_rel_err_max"] < 1.5 * te["grad_rel_err_max"] + TOL_TWIN["grad"], (ce["grad_rel_err_max"], te["grad_rel_err_max"])
+        assert ce["logits_rms_err_over_scale"] < 1.5 * te["logits_rms_err_over_scale"] + TOL_TWIN["logits_rms"], (ce, te)
 
 
 def test_workspace_stays_bounded_over_varying_lengths(cuda_dev):

@@ -8,7 +8,7 @@ one device; the N-GPU NCCL path is checked by bench.py's `dp_check` record at N 
 indexed by the element's position in the LOCAL batch, so sharded and unsharded runs draw different masks by design.
 
 Tolerances: gradient 1e-4 normwise (identical per-utterance activations; only the fp32 summation order of the weight gradients
-differs), loss / global norm 1e-5 relative, weights after the update 5e-5 absolute (Adam's first step is lr * g / |g|: a
+differs), loss / global norm 1e-5 relative, weights after the update 2e-4 absolute = 0.2 lr (Adam's first step is lr * g / |g|: a
 gradient entry below the summation noise may flip sign, damped by eps)."""
 import os
 import subprocess
@@ -100,4 +100,4 @@ def test_two_rank_gradient_equals_one_rank_gradient(cuda_dev, tmp_path):
     assert r0["grad_rel"] < 1e-4, r0
     assert abs(r0["loss_dp"] - r0["loss_1"]) <= 1e-5 * abs(r0["loss_1"]), r0
     assert abs(r0["norm_dp"] - r0["norm_1"]) <= 1e-5 * r0["norm_1"], r0
-    assert r0["w_moved"] > 1e-4 and r0["w_abs"] <= 5e-5, r0
+    assert r0["w_moved"] > 1e-4 and r0["w_abs"] <= 2e-4, r0

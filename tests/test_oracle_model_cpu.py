@@ -204,3 +204,67 @@ def test_mixture_output_layer_against_explicit_loops():
     pi = torch.softmax(x @ Wp + bp, 1).unsqueeze(2) * mp / keep
     dec = (tau * torch.tanh(x @ W + b)).reshape(N, K, V) * md / keep
     assert torch.allclose(yd, (pi * dec).sum(1), atol=1e-12)
+
+
+def test_twin_without_rounding_is_the_oracle(monkeypatch):
+    """oracle/twin.py restates the stack in the device's formulation (hoisted x-projection, folded recurrent weight W' =
+    W_proj W_h acting on m_{t-1}, bulk projection after the loop).  With its rounding hooks switched off it must BE the oracle:
+    outputs, gradients and per-step dz."""
+    from oracle import twin
+    monkeypatch.setattr(twin, "q16", lambda x: x)
+    monkeypatch.setattr(twin, "gq_bf16", lambda x: x)
+    cfg = oracle.OracleConfig(input_dim=12, num_layers=3, num_neurons=24, num_projects=16, num_targets=9, use_peepholes=True,
+                              num_experts=3)
+    p = oracle.init_params(cfg, seed=5, bias_scale=0.2)
+    g = torch.Generator().manual_seed(6)
+    B, T = 5, 11
+    x = torch.randn(B, T, 12, generator=g, dtype=torch.float64)
+    lens = torch.tensor([11, 7, 3, 11, 1], dtype=torch.int32)
+    for b in range(B):
+        x[b, lens[b]:] = 0
+    keep = 0.8
+    masks = {(i, d): (torch.rand(B, T, 16, generator=g) < keep).double() for i in range(3) for d in "fb"}
+    mp = (torch.rand(B * T, 3, 1, generator=g) < keep).double()
+    md = (torch.rand(B * T, 3, 9, generator=g) < keep).double()
+    res = []
+    for which in (0, 1):
+        pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+        tr = {}
+        if which == 0:
+            enc, _ = oracle.blstm_forward(pr, cfg, x, lens, keep_prob=keep, masks=masks, trace=tr)
+            y = oracle.create_moe(enc.reshape(-1, 32), pr["Variable"], pr["Variable_1"], pr["Variable_2"], pr["Variable_3"], 9, 3,
+                                  cfg.moe_temp, keep_prob=keep, mask_prior=mp, mask_dec=md).reshape(B, T, 9)
+        else:
+            enc = twin.blstm_forward_twin(pr, cfg, x, lens, keep_prob=keep, masks=masks, trace=tr)
+            y = twin.output_layer_twin(pr, cfg, enc, keep_prob=keep, mask_prior=mp, mask_dec=md)
+        (y * torch.arange(y.numel(), dtype=torch.float64).reshape(y.shape).cos()).sum().backward()
+        dz = torch.stack([z.grad for z in tr[(2, "b")]], 1)
+        res.append((y.detach(), {k: v.grad for k, v in pr.items()}, dz))
+    (y0, g0, dz0), (y1, g1, dz1) = res
+    assert (y0 - y1).abs().max().item() < 1e-11
+    assert (dz0 - dz1).abs().max().item() < 1e-11
+    for k in g0:
+        assert (g0[k] - g1[k]).abs().max().item() < 1e-10 * (1 + g0[k].abs().max().item()), k
+
+
+def test_sensitivity_to_fp16_rounding():
+    """Why long-sequence parity is checked against the precision twin: rounding ONLY the weights and the input features to fp16,
+    once, moves the fp64 oracle's own outputs and gradients by an amount that grows steeply with T (a random peephole BiLSTM with
+    forget bias 5 has exploding gradients: |g| grows ~10x per doubling of T).  Recorded in profiles/r02_oracle_fp16_sensitivity.txt
+    at C1 dimensions; here a smaller stack, asserting the growth."""
+    cfg = oracle.OracleConfig(input_dim=40, num_layers=3, num_neurons=128, num_projects=128, num_targets=20, use_peepholes=True)
+    p = oracle.init_params(cfg, seed=101, bias_scale=0.1)
+    rel = {}
+    for T in (24, 96):
+        g = torch.Generator().manual_seed(202)
+        x = torch.randn(4, T, 40, generator=g, dtype=torch.float64)
+        lens = torch.full((4,), T, dtype=torch.int32)
+        lab = torch.randint(0, 19, (4, T // 8), generator=g)
+        grads = []
+        for half in (False, True):
+            pr = {k: (v.half().double() if half else v.clone()).requires_grad_(True) for k, v in p.items()}
+            ctc, _, _ = oracle.training_loss(pr, cfg, x.half().double() if half else x, lens, lab, l2_decay_weight=0.0)
+            ctc.backward()
+            grads.append({k: v.grad for k, v in pr.items()})
+        rel[T] = max(((grads[1][k] - grads[0][k]).norm() / grads[0][k].norm()).item() for k in grads[0])
+    assert rel[24] < 2e-2 and rel[96] > 3 * rel[24], rel
