@@ -243,11 +243,13 @@ int lcb_optimizer_step(float* w, float* g, float* s1, float* s2, long long n, in
  * lcb_greedy_decode replaces tf.nn.ctc_greedy_decoder(merge_repeated=True) (nnet/graph.py:138-142):
  *   out [B,T] int32 receives the collapsed label sequence of each utterance, out_len [B] its length.
  * lcb_posterior replaces tf.nn.softmax(smooth_factor*logits) (nnet/graph.py:236) and the numpy.log /
- *   class-prior subtraction of bin/nnet-forward.py:87-91 (log_prior nullable, [V]). */
+ *   class-prior subtraction of bin/nnet-forward.py:87-91 (log_prior nullable, [V]); blank_to_front != 0 also moves
+ *   column V-1 to column 0 (the `select-feats` reorder of scripts/decode_ctc_lat.sh:161-163).  out must not alias logits
+ *   when blank_to_front is set. */
 int lcb_greedy_decode(const float* logits, const int32_t* seq_len, int32_t* out, int32_t* out_len,
                       int B, int T, int V, void* stream);
 int lcb_posterior(const float* logits, float* out, long long rows, int V, float smooth_factor,
-                  int apply_log, const float* log_prior, void* stream);
+                  int apply_log, const float* log_prior, int blank_to_front, void* stream);
 
 /* ---- data formats either side of the path ------------------------------------
  * replaces: _splice / _subsample of nnet/tfrecord.py:28-51 (edge-replicated +-context splicing, then every

@@ -98,7 +98,7 @@ _SIGS = {
                                    c_float, c_float, c_float, c_float, c_float, c_float, ctypes.POINTER(ctypes.c_longlong), c_int,
                                    c_void_p, c_void_p, c_void_p]),
     "lcb_greedy_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "lcb_posterior": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_float, c_int, c_void_p, c_void_p]),
+    "lcb_posterior": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_float, c_int, c_void_p, c_int, c_void_p]),
     "lcb_add_f16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "lcb_masked_add16": (c_int, [c_void_p, c_int, c_void_p, c_int, ctypes.c_longlong, c_int, c_int, c_float, ctypes.c_ulonglong, ctypes.c_ulonglong, c_int, c_void_p]),
     "lcb_label_smooth": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_float, c_void_p, c_void_p, c_void_p]),

@@ -138,7 +138,11 @@ def nnet_validate(argv=None):
 
 def nnet_forward(argv=None):
     """bin/nnet-forward.py <tfrecords-scp> <nnet-config> <nnet-in> <nnet-output-wspecifier>: per utterance
-    softmax(smooth * logits) [-> log] [- class prior] as a Kaldi float matrix (nnet-forward.py:77-96)."""
+    softmax(smooth * logits) [-> log] [- class prior] as a Kaldi float matrix (nnet-forward.py:77-96).
+
+    --batch-size 1 (default) is the reference's mode, one utterance per forward pass; larger values run length-bucketed
+    minibatches through the same kernels (forward.py) -- identical matrices, in the same order.  --blank-to-front applies the
+    `select-feats $[ntargets-1],0-$[ntargets-2]` reorder of scripts/decode_ctc_lat.sh:161-163 on the device."""
     p = argparse.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter)
     p.add_argument("tfrecords_scp", metavar="<tfrecords-scp>", type=str)
     p.add_argument("nnet_config", metavar="<nnet-config>", type=str)
@@ -150,42 +154,41 @@ def nnet_forward(argv=None):
     p.add_argument("--class-prior", type=str, default=None)
     p.add_argument("--smooth-factor", type=float, default=1.0)
     p.add_argument("--device-splice", type=str2bool, default="false")
+    p.add_argument("--batch-size", type=int, default=1)
+    p.add_argument("--blank-to-front", type=str2bool, default="false")
+    p.add_argument("--io-threads", type=int, default=4)
     args = p.parse_args(argv)
     _info(" ".join(sys.argv))
+    from .forward import BatchedForward, read_scp
+    from .model import AcousticModel
     writer = nnet.BaseFloatMatrixWriter(args.nnet_output)
     nnet_config = nnet.parse_config(args.nnet_config)
     nnet_config["is_training"] = False
+    if nnet.get_create_logits(nnet_config.get("nnet_type")) is None:
+        _fatal("unsupported nnet_type: %s" % nnet_config.get("nnet_type"))
+        sys.exit(1)
     if args.apply_log:
         args.apply_softmax = True
     class_prior = None if args.class_prior is None else nnet.get_class_prior(args.class_prior)
-    filename, tfrecord, _ = nnet.dataset_from_tfrecords(
-        tfrecords_scp=args.tfrecords_scp, left_context=nnet_config.get("left_context"),
-        right_context=nnet_config.get("right_context"), subsample=nnet_config.get("subsample"), shuffle=False,
-        device_splice=args.device_splice)
-    init, pipeline = nnet.create_pipeline_sequential(filename=filename, tfrecord=tfrecord)
-    graph = nnet.create_graph_for_inference(pipeline=pipeline, nnet_config=nnet_config, smooth_factor=args.smooth_factor)
-    sess = nnet.Session()
-    sess.run(init)
-    nnet.Saver(nnet.trainable_variables()).restore(sess, args.nnet_in)
-    nodes = {"filename": graph["filename"], "nnet_output": graph["nnet_output"] if args.apply_softmax else graph["logits"]}
+    model = AcousticModel(nnet_config)
+    from . import graph as _graph
+    _graph._default_model[0] = model
+    nnet.Saver(model).restore(None, args.nnet_in)
+    engine = BatchedForward(model, read_scp(args.tfrecords_scp), left_context=nnet_config.get("left_context"),
+                            right_context=nnet_config.get("right_context"), subsample=nnet_config.get("subsample"),
+                            device_splice=args.device_splice, batch_size=args.batch_size, smooth_factor=args.smooth_factor,
+                            apply_softmax=args.apply_softmax, apply_log=args.apply_log, class_prior=class_prior,
+                            blank_to_front=args.blank_to_front, io_threads=args.io_threads)
+
+    def report(n):
+        if args.report_interval and n % args.report_interval == 0:
+            _info("processed = %d" % n)
+
     try:
-        processed = 0
-        while True:
-            values = sess.run(nodes)
-            out = values["nnet_output"]
-            if args.apply_log:
-                with numpy.errstate(divide="ignore"):
-                    out = numpy.log(out)
-            if class_prior is not None:
-                out = out - class_prior
-            key, _ = os.path.splitext(os.path.basename(values["filename"]))
-            writer.Write(key, out)
-            processed += 1
-            if args.report_interval and processed % args.report_interval == 0:
-                _info("processed = %d" % processed)
-    except nnet.OutOfRangeError:
+        engine.run(writer.Write, report)
         _info("done")
     except KeyboardInterrupt:
         _fatal("interrupted by user")
         sys.exit(1)
     writer.Close()
+    return engine

@@ -33,7 +33,7 @@ __global__ void greedy_decode_kernel(const float* __restrict__ logits, const int
 }
 
 __global__ void posterior_kernel(const float* __restrict__ logits, float* __restrict__ out, long long rows, int V,
-                                 float smooth, int apply_log, const float* __restrict__ log_prior)
+                                 float smooth, int apply_log, const float* __restrict__ log_prior, int blank_to_front)
 {
     const int lane = threadIdx.x & 31;
     for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows;
@@ -53,7 +53,9 @@ __global__ void posterior_kernel(const float* __restrict__ logits, float* __rest
             float y = smooth * x[v] - lse;
             if (!apply_log) y = __expf(y);
             if (log_prior) y -= log_prior[v];
-            o[v] = y;
+            // blank_to_front: column V-1 (<blk>) moves to column 0, the others shift up by one -- the order EESEN's latgen-faster
+            // expects (`select-feats $[ntargets-1],0-$[ntargets-2]`, scripts/decode_ctc_lat.sh:163)
+            o[blank_to_front ? (v == V - 1 ? 0 : v + 1) : v] = y;
         }
     }
 }
@@ -73,12 +75,12 @@ extern "C" int lcb_greedy_decode(const float* logits, const int32_t* seq_len, in
 }
 
 extern "C" int lcb_posterior(const float* logits, float* out, long long rows, int V, float smooth_factor,
-                             int apply_log, const float* log_prior, void* stream)
+                             int apply_log, const float* log_prior, int blank_to_front, void* stream)
 {
     if (!logits || !out) return LCB_ERR_NULL_POINTER;
     if (rows <= 0 || V <= 0) return LCB_ERR_BAD_SHAPE;
     long long blocks = (rows + 7) / 8; if (blocks > num_sms() * 8) blocks = num_sms() * 8;
     g_launches += 1;
-    posterior_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(logits, out, rows, V, smooth_factor, apply_log, log_prior);
+    posterior_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(logits, out, rows, V, smooth_factor, apply_log, log_prior, blank_to_front);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }

@@ -17,15 +17,18 @@ def greedy_decode(logits, seq_len):
     return [out_h[b, :int(n_h[b])].tolist() for b in range(B)]
 
 
-def softmax_rows(logits, smooth_factor=1.0, apply_log=False, log_prior=None):
-    """softmax(smooth_factor * logits) over the last axis; optional log and log-prior subtraction."""
+def softmax_rows(logits, smooth_factor=1.0, apply_log=False, log_prior=None, blank_to_front=False, out=None):
+    """softmax(smooth_factor * logits) over the last axis; optional log, log-prior subtraction and blank -> column 0 reorder
+    (scripts/decode_ctc_lat.sh:161-163)."""
     x = logits.contiguous()
     V = x.shape[-1]
     rows = x.numel() // V
-    out = torch.empty_like(x)
+    if out is None:
+        out = torch.empty_like(x)
+    assert out.is_contiguous() and out.shape == x.shape and out.data_ptr() != x.data_ptr()
     lp = None
     if log_prior is not None:
         lp = torch.as_tensor(log_prior, dtype=torch.float32).to(x.device).contiguous()
     _lib.check(_lib.lib().lcb_posterior(_lib.ptr(x), _lib.ptr(out), rows, V, float(smooth_factor), 1 if apply_log else 0,
-                                        _lib.ptr(lp), _lib.stream_ptr()), "lcb_posterior")
+                                        _lib.ptr(lp), 1 if blank_to_front else 0, _lib.stream_ptr()), "lcb_posterior")
     return out

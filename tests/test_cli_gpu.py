@@ -125,3 +125,61 @@ def test_cli_with_nnet_type_lstm(cuda_dev, tmp_path, capfd):
     with pytest.raises(SystemExit) as e:
         cli.nnet_validate([scp, cfg, n1, "--objective", "ctc", "--batch-size", "4"])
     assert e.value.code == 1 and "unsupported nnet_type: cudnnlstm" in capfd.readouterr().err
+
+
+def test_cli_forward_batched_equals_one_by_one(cuda_dev, tmp_path, capfd):
+    """nnet-forward --batch-size N (length-bucketed minibatches, forward.py) writes the SAME archive as the reference's
+    one-utterance-per-run mode: same keys in scp order, matrices bit for bit; --blank-to-front is the select-feats reorder of
+    scripts/decode_ctc_lat.sh:161-163; the graph-API path (create_graph_for_inference + Session.run, what the reference's script
+    calls) gives the same posteriors."""
+    import lstm_ctc_b200 as nnet
+    from lstm_ctc_b200 import cli
+    tmp = str(tmp_path)
+    D, V = 8, 11
+    scp, lens = _write_corpus(tmp, 37, D, V, 3)
+    # scp order != length order
+    lines = open(scp).read().splitlines()
+    rng = np.random.RandomState(0)
+    perm = rng.permutation(len(lines))
+    with open(scp, "w") as fh:
+        fh.write("\n".join(lines[i] for i in perm) + "\n")
+    lens = [lens[i] for i in perm]
+    cfg = os.path.join(tmp, "nnet.config")
+    with open(cfg, "w") as fh:
+        fh.write("nnet_type blstm\ninput_dim %d\nleft_context 1\nright_context 1\nsubsample 3\nnum_layers 2\n"
+                 "num_neurons 64\nnum_projects 64\nnum_targets %d\nuse_peepholes true\nnum_experts 4\nmoe_temp 10.0\n"
+                 "dropout_rate 0.9\n" % (D, V))
+    n0 = os.path.join(tmp, "nnet.0")
+    cli.nnet_init([scp, cfg, n0, "--objective", "ctc", "--batch-size", "4"])
+    prior = os.path.join(tmp, "prior.txt")
+    with open(prior, "w") as fh:
+        fh.write(" ".join("%d" % c for c in rng.randint(1, 100, size=V)) + "\n")
+    arks = {}
+    for name, extra in (("b1", []), ("b5", ["--batch-size", "5"]), ("b64", ["--batch-size", "64", "--device-splice", "true"]),
+                        ("front", ["--batch-size", "16", "--blank-to-front", "true"])):
+        ark = os.path.join(tmp, "post_%s.ark" % name)
+        cli.nnet_forward([scp, cfg, n0, "ark,scp:%s,%s.scp" % (ark, ark), "--class-prior", prior] + extra)
+        arks[name] = kaldi_io.read_float_matrix_ark(ark)
+    capfd.readouterr()
+    keys = [os.path.splitext(os.path.basename(l.split()[4]))[0] for l in open(scp)]
+    for name in arks:
+        assert [k for k, _ in arks[name]] == keys, name                       # scp order
+    for (k, a), (_, b), (_, c), (_, f), n in zip(arks["b1"], arks["b5"], arks["b64"], arks["front"], lens):
+        assert a.shape == (n // 3, V)
+        assert np.array_equal(a, b) and np.array_equal(a, c), k               # independent of the batch an utterance travels in
+        assert np.array_equal(f[:, 0], a[:, V - 1]) and np.array_equal(f[:, 1:], a[:, :V - 1])
+    # the reference's own call sequence (nnet-forward.py:60-96)
+    nc = nnet.parse_config(cfg)
+    nc["is_training"] = False
+    filename, tfrecord, _ = nnet.dataset_from_tfrecords(tfrecords_scp=scp, left_context=1, right_context=1, subsample=3, shuffle=False)
+    init, pipeline = nnet.create_pipeline_sequential(filename=filename, tfrecord=tfrecord)
+    graph = nnet.create_graph_for_inference(pipeline=pipeline, nnet_config=nc, smooth_factor=1.0)
+    sess = nnet.Session()
+    sess.run(init)
+    nnet.Saver(nnet.trainable_variables()).restore(sess, n0)
+    log_prior = nnet.get_class_prior(prior)
+    for k, a in arks["b1"][:5]:
+        v = sess.run({"filename": graph["filename"], "nnet_output": graph["nnet_output"]})
+        ref = np.log(v["nnet_output"]) - log_prior
+        assert os.path.splitext(os.path.basename(v["filename"]))[0] == k
+        assert np.abs(ref - a).max() < 1e-5
