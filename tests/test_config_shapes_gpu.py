@@ -9,14 +9,23 @@ the BPTT kernel emits, bf16).  Batch sizes 33 and 64 select both recurrence mapp
 with a ragged last group; 64 -> two paired sub-groups per cluster (`lstm_rec_fwd2_kernel<16,2>` / `lstm_rec_bwd3_kernel<16,2>` at
 H = 512, the 1-D `lstm_rec_bwd2_kernel` BPTT at H = 320).
 
-Stated tolerances (the observed errors are written to gpurun_out/r02_parity_config_shapes.json and committed under profiles/):
-  logits   max |err| over live frames  <= 2.5e-2 * max |logit|, rms <= 5e-3 * max |logit|
-           (fp16 operands, fp32 accumulate.  The rounding of each layer's 16-bit output is amplified ~2x by every layer above it
-           -- tools/parity_diag.py, profiles/r02_parity_diag_c3.txt: rms error of h 2.5e-4 / 5.4e-4 / 1.0e-3 / 1.9e-3 / 3.7e-3 in
-           layers 0..4 -- so a 5-layer stack sits at 1.5e-2 max / 2.7e-3 rms where the 2-layer cases of test_model_gpu.py hold 1e-2.)
-  loss     |sum - sum_ref|             <= 2e-3 * |sum_ref|
-  grads    ||g - g_ref|| / ||g_ref||   <= 5e-2 per variable             (bf16 gradient operands)
-  dz       ||dz - dz_ref|| / ||dz_ref|| <= 5e-2 per layer               (bf16 storage)
+Three comparisons per case, all written to gpurun_out/r02_parity_config_shapes.json (committed under profiles/):
+  cuda_vs_exact   CUDA path vs the fp64 oracle (oracle/model.py)
+  cuda_vs_twin    CUDA path vs the oracle's precision twin (oracle/twin.py: same maths, rounded to 16 bits where the device rounds)
+  twin_vs_exact   what the mandated 16-bit operands alone do to the exact model
+and two weight regimes:
+  default init (forget-gate bias variable 0; with LSTMCell's forget_bias = 5 the cell integrates and the stack's gradient norm
+      explodes with T -- rounding ONLY weights and inputs to fp16 moves the oracle's own gradients by 4 % at T = 64 and 45 % at
+      T = 128, profiles/r02_oracle_fp16_sensitivity.txt).  Asserted vs the exact oracle at T = 64:
+        logits max |err| <= 2.5e-2 * max |logit|, rms <= 5e-3 (observed 1.5e-2 / 2.7e-3 at 5 layers: the 16-bit rounding of each
+        layer's output is amplified ~2x per layer above it, profiles/r02_parity_diag_c3.txt), loss 2e-3, per-variable gradients and
+        per-layer dz 5e-2 normwise (observed 4.3e-2 / 3.9e-2); and vs the twin: 1e-2 / 2e-3 / 1e-3 / 3e-2 / 3e-2.
+      At T = 128 the comparison is reported and bounded RELATIVELY: the CUDA path must sit at least twice as close to the twin as
+      the twin sits to the exact oracle (observed 5x), i.e. the deviation is the dynamical amplification of the operand precision,
+      not arithmetic disagreement.
+  stable (the same weights with every forget-gate bias variable at -4, i.e. an effective forget bias of 1): no amplification, so
+      the exact oracle pins LONG sequences at full config dimensions -- C3 B=64 T=128 keep 0.9, C1 B=33 T=128, C2 B=49 T=192:
+        logits max <= 2e-3 (observed 6.5e-4), rms <= 5e-4 (1.2e-4), loss <= 2e-4 (1.8e-5), gradients / dz <= 1.5e-2 (7.3e-3 / 6.3e-3).
 Length masking is exact: logits rows of padded frames equal the zero-input output row bit for bit, dz rows of padded frames are 0."""
 import json
 import os
@@ -40,8 +49,8 @@ DIMS = {
 CASES = [("c3", 33, 64, 1.0, 0.0), ("c2", 64, 64, 0.9, 0.0), ("c1", 64, 64, 0.9, 0.0),
          ("c3", 64, 128, 0.9, -4.0), ("c1", 33, 128, 1.0, -4.0), ("c2", 49, 192, 0.9, -4.0),
          ("c3", 64, 128, 0.9, 0.0), ("c1", 33, 128, 1.0, 0.0)]
-TOL_TWIN = {"logits": 1e-2, "logits_rms": 2e-3, "loss": 1e-3, "grad": 3e-2, "dz": 3e-2}      # provisional: set from the first measured run
-TOL_STABLE = {"logits": 1e-2, "logits_rms": 2e-3, "loss": 1e-3, "grad": 3e-2, "dz": 3e-2}    # provisional
+TOL_TWIN = {"logits": 1e-2, "logits_rms": 2e-3, "loss": 1e-3, "grad": 3e-2, "dz": 3e-2}      # observed <= 3.6e-3 / 6e-4 / 6e-5 / 1.3e-2 / 1.2e-2
+TOL_STABLE = {"logits": 2e-3, "logits_rms": 5e-4, "loss": 2e-4, "grad": 1.5e-2, "dz": 1.5e-2}  # observed <= 6.5e-4 / 1.2e-4 / 1.8e-5 / 7.3e-3 / 6.3e-3
 TOL = {"logits": 2.5e-2, "logits_rms": 5e-3, "loss": 2e-3, "grad": 5e-2, "dz": 5e-2}
 REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "r02_parity_config_shapes.json")
 
