@@ -261,6 +261,13 @@ int lcb_splice_subsample(const float* in, const int32_t* lens, float* out, int32
 /* CRC-32C (Castagnoli, reflected 0x82F63B78) of a HOST buffer, continuing from `crc` (0 to start): the checksum of the
  * TFRecord framing written by tf.python_io.TFRecordWriter (nnet/tfrecord.py:132) -- masked as ((c >> 15 | c << 17) + 0xa282ead8). */
 uint32_t lcb_crc32c(const void* data, size_t n, uint32_t crc);
+/* tf.train.SequenceExample decoder on HOST buffers: what tf.parse_single_sequence_example yields for the FixedLenSequenceFeature
+ * specs of nnet/tfrecord.py:96-106 -- feature_lists "nnet_input" (one float_list Feature per frame) -> x_out [rows, cols] f32,
+ * "nnet_target" (int64_list) -> y_out [num_labels].  Two calls: with x_out = y_out = NULL it only sizes (rows, cols,
+ * num_labels -- -1 when the record has no "nnet_target" list); the fill call passes the buffers, their capacities in elements, and *cols as returned by the sizing call.
+ * LCB_ERR_BAD_SHAPE: malformed message or frames of unequal width. */
+int lcb_parse_sequence_example(const void* buf, size_t n, float* x_out, size_t x_cap, int64_t* y_out, size_t y_cap,
+                               long long* rows, long long* cols, long long* num_labels);
 
 #ifdef __cplusplus
 }

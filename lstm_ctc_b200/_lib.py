@@ -104,6 +104,9 @@ _SIGS = {
     "lcb_label_smooth": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "lcb_splice_subsample": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "lcb_crc32c": (ctypes.c_uint32, [c_void_p, c_size_t, ctypes.c_uint32]),
+    "lcb_parse_sequence_example": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_size_t,
+                                           ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong),
+                                           ctypes.POINTER(ctypes.c_longlong)]),
     "lcb_colsum": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 

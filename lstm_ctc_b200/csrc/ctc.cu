@@ -725,6 +725,15 @@ static cudaError_t launch_lattice(const CtcPlan& p, int B, int T, int V, const f
     return cudaGetLastError();
 }
 
+// one non-blocking helper stream per device for the two-half overlap of large-vocabulary calls (created on first use)
+static cudaStream_t ctc_helper_stream() {
+    static cudaStream_t streams[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) streams[dev] = nullptr;
+    return streams[dev];
+}
+
 }  // namespace lcb
 
 using namespace lcb;
@@ -756,21 +765,58 @@ extern "C" int lcb_ctc_loss_grad_f32(const float* logits, const int64_t* labels,
     int2* spill = (int2*)(ws + p.off_spill);
 
     cudaMemsetAsync(status, 0, 16, st);
-    g_launches += 3; ctc_prep_kernel<<<(B + 3) / 4, 128, 0, st>>>(labels, Lmax, seq_len, B, T, V, meta, lab, p.LABP, status);
-    if ((V & 3) == 0 && ((uintptr_t)logits & 15) == 0 && ((uintptr_t)grad & 15) == 0)
-        dispatch_softmax<4>(logits, grad, B, T, V, meta, frame, st);
-    else if ((V & 1) == 0 && ((uintptr_t)logits & 7) == 0 && ((uintptr_t)grad & 7) == 0)
-        dispatch_softmax<2>(logits, grad, B, T, V, meta, frame, st);
-    else
-        dispatch_softmax<1>(logits, grad, B, T, V, meta, frame, st);
-    cudaError_t e = cudaSuccess;
-    const int nt = 2 * p.NW * 32;
-#define LCB_CTC_LAUNCH(SPT_, MAXT_) e = launch_lattice<SPT_, MAXT_>(p, B, T, V, logits, meta, lab, frame, spill, grad, loss, st)
-    if (p.SPT == 2) { if (nt <= 256) LCB_CTC_LAUNCH(2, 256); else if (nt <= 512) LCB_CTC_LAUNCH(2, 512); else LCB_CTC_LAUNCH(2, 1024); }
-    else if (p.SPT == 4) LCB_CTC_LAUNCH(4, 1024);
-    else if (p.SPT == 8) LCB_CTC_LAUNCH(8, 1024);
-    else LCB_CTC_LAUNCH(16, 1024);
+    g_launches += 1; ctc_prep_kernel<<<(B + 3) / 4, 128, 0, st>>>(labels, Lmax, seq_len, B, T, V, meta, lab, p.LABP, status);
+    const int NSP = p.NW * 32 * p.SPT;
+    // the two passes over utterances [b0, b0 + nb)
+    auto softmax_pass = [&](int b0, int nb, cudaStream_t s) {
+        const float* x = logits + (size_t)b0 * T * V;
+        float* g = grad + (size_t)b0 * T * V;
+        g_launches += 1;
+        if ((V & 3) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)g & 15) == 0)
+            dispatch_softmax<4>(x, g, nb, T, V, meta + b0, frame + (size_t)b0 * T, s);
+        else if ((V & 1) == 0 && ((uintptr_t)x & 7) == 0 && ((uintptr_t)g & 7) == 0)
+            dispatch_softmax<2>(x, g, nb, T, V, meta + b0, frame + (size_t)b0 * T, s);
+        else
+            dispatch_softmax<1>(x, g, nb, T, V, meta + b0, frame + (size_t)b0 * T, s);
+    };
+    auto lattice_pass = [&](int b0, int nb, cudaStream_t s) -> cudaError_t {
+        const float* x = logits + (size_t)b0 * T * V;
+        float* g = grad + (size_t)b0 * T * V;
+        const int nt = 2 * p.NW * 32;
+        cudaError_t e = cudaSuccess;
+        g_launches += 1;
+#define LCB_CTC_LAUNCH(SPT_, MAXT_) e = launch_lattice<SPT_, MAXT_>(p, nb, T, V, x, meta + b0, lab + (size_t)b0 * p.LABP, frame + (size_t)b0 * T, \
+                                                                     spill + (size_t)b0 * T * NSP, g, loss + b0, s)
+        if (p.SPT == 2) { if (nt <= 256) LCB_CTC_LAUNCH(2, 256); else if (nt <= 512) LCB_CTC_LAUNCH(2, 512); else LCB_CTC_LAUNCH(2, 1024); }
+        else if (p.SPT == 4) LCB_CTC_LAUNCH(4, 1024);
+        else if (p.SPT == 8) LCB_CTC_LAUNCH(8, 1024);
+        else LCB_CTC_LAUNCH(16, 1024);
 #undef LCB_CTC_LAUNCH
+        return e;
+    };
+    cudaError_t e = cudaSuccess;
+    // Large vocabularies: the softmax pass streams 8*T*B*V bytes (HBM-bound) while the lattice pass is a latency-bound chain on a
+    // few warps per SM -- run the lattice of the first half of the batch on a helper stream BESIDE the softmax pass of the second.
+    cudaStream_t helper = (V >= 1024 && B >= 32) ? ctc_helper_stream() : nullptr;
+    if (helper) {
+        const int h0 = B / 2;
+        cudaEvent_t ev_s0, ev_l0;
+        if (cudaEventCreateWithFlags(&ev_s0, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_l0, cudaEventDisableTiming) != cudaSuccess) return LCB_ERR_CUDA;
+        softmax_pass(0, h0, st);
+        cudaEventRecord(ev_s0, st);
+        cudaStreamWaitEvent(helper, ev_s0, 0);
+        e = lattice_pass(0, h0, helper);
+        cudaEventRecord(ev_l0, helper);
+        softmax_pass(h0, B - h0, st);
+        if (e == cudaSuccess) e = lattice_pass(h0, B - h0, st);
+        cudaStreamWaitEvent(st, ev_l0, 0);
+        cudaEventDestroy(ev_s0);
+        cudaEventDestroy(ev_l0);
+    } else {
+        softmax_pass(0, B, st);
+        e = lattice_pass(0, B, st);
+    }
     if (e != cudaSuccess) return LCB_ERR_CUDA;
     e = cudaGetLastError();
     return e == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;

@@ -162,8 +162,30 @@ def _parse_int64_feature(buf, lo, hi):
 
 
 def parse_sequence_example(buf):
-    """-> {'nnet_input': [T, D] float32, 'nnet_target': [L] int64 (if present)} (tf.parse_single_sequence_example with the
-    FixedLenSequenceFeature specs of tfrecord.py:96-106)."""
+    """-> {'nnet_input': [T, D] float32, 'nnet_target': [L] int64} (tf.parse_single_sequence_example with the
+    FixedLenSequenceFeature specs of tfrecord.py:96-106), decoded by the library's native parser (`lcb_parse_sequence_example`,
+    host code that runs without the GIL on the pipeline's decoding threads).  `parse_sequence_example_py` below is the
+    interpreter-level statement of the same decoding that the tests compare it with."""
+    import ctypes
+    from . import _lib
+    L = _lib.lib()
+    buf = bytes(buf)
+    rows, cols, ny = ctypes.c_longlong(0), ctypes.c_longlong(0), ctypes.c_longlong(0)
+    st = L.lcb_parse_sequence_example(buf, len(buf), None, 0, None, 0, ctypes.byref(rows), ctypes.byref(cols), ctypes.byref(ny))
+    if st != 0:
+        raise ValueError("malformed SequenceExample (status %d)" % st)
+    has_y = ny.value >= 0
+    x = np.empty((rows.value, cols.value), dtype=np.float32)
+    y = np.empty(max(ny.value, 0), dtype=np.int64)
+    st = L.lcb_parse_sequence_example(buf, len(buf), x.ctypes.data_as(ctypes.c_void_p), x.size, y.ctypes.data_as(ctypes.c_void_p),
+                                      y.size, ctypes.byref(rows), ctypes.byref(cols), ctypes.byref(ny))
+    if st != 0:
+        raise ValueError("malformed SequenceExample (status %d)" % st)
+    return {"nnet_input": x, "nnet_target": y} if has_y else {"nnet_input": x}
+
+
+def parse_sequence_example_py(buf):
+    """The same decoding in Python (test cross-check of the native parser)."""
     buf = bytes(buf)
     out = {}
     for f, wt, v in _fields(buf, 0, len(buf)):

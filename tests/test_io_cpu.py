@@ -138,3 +138,29 @@ def test_kaldi_float_matrix_archive(tmp_path):
     w = kaldi_io.BaseFloatMatrixWriter("ark,t:%s" % t)
     w.Write("k", np.array([[1.0, 2.5]], np.float32)); w.Close()
     assert open(t).read() == "k  [\n  1.000000 2.500000 ]\n"
+
+
+def test_native_sequence_example_parser_equals_python_statement():
+    """lcb_parse_sequence_example (host C++ in the library, GIL-free) vs the interpreter-level decoder on packed and
+    unpacked float encodings, negative / 64-bit labels, empty label lists, and malformed input."""
+    rng = np.random.RandomState(3)
+    for T, D, L in ((1, 1, 0), (5, 3, 2), (64, 120, 9), (7, 40, 1)):
+        x = rng.randn(T, D).astype(np.float32)
+        y = rng.randint(-5, 2 ** 40, size=L).astype(np.int64) if L else None
+        buf = tfr.serialize_sequence_example(x, y)
+        a, b = tfr.parse_sequence_example(buf), tfr.parse_sequence_example_py(buf)
+        assert np.array_equal(a["nnet_input"], b["nnet_input"]) and np.array_equal(a["nnet_input"], x)
+        assert ("nnet_target" in a) == ("nnet_target" in b)
+        if y is not None:
+            assert np.array_equal(a["nnet_target"], y)
+    # unpacked floats (wire type 5, one value per tag): Feature{float_list{value: 1.5, value: -2.0}}
+    fl = b"".join(b"\x0d" + struct.pack("<f", v) for v in (1.5, -2.0))
+    feat = b"\x12" + bytes([len(fl)]) + fl
+    flist = b"\x0a" + bytes([len(feat)]) + feat
+    entry = b"\x0a\x0anet_input"[:0] + b"\x0a" + bytes([10]) + b"nnet_input" + b"\x12" + bytes([len(flist)]) + flist
+    fls = b"\x0a" + bytes([len(entry)]) + entry
+    msg = b"\x12" + bytes([len(fls)]) + fls
+    a, b = tfr.parse_sequence_example(msg), tfr.parse_sequence_example_py(msg)
+    assert np.array_equal(a["nnet_input"], np.array([[1.5, -2.0]], np.float32)) and np.array_equal(a["nnet_input"], b["nnet_input"])
+    with pytest.raises(ValueError):
+        tfr.parse_sequence_example(msg[:-3])                       # truncated
