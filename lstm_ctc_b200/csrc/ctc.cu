@@ -677,6 +677,8 @@ static bool ctc_make_plan(int B, int T, int V, int Lmax, CtcPlan& p) {
     return true;
 }
 
+constexpr int g_ctc_softmax_ctas_per_sm = 8;      // resident CTAs per SM of the (persistent, grid-stride) softmax pass
+
 template <int GROUP, int VEC, int NCH>
 static void launch_softmax(const float* logits, float* grad, int B, int T, int V, const CtcMeta* meta,
                            float4* frame, cudaStream_t st)
@@ -684,7 +686,7 @@ static void launch_softmax(const float* logits, float* grad, int B, int T, int V
     const long long rows = (long long)B * T;
     const int gpc = 256 / GROUP;
     long long want = (rows + gpc - 1) / gpc;
-    int grid = (int)(want < num_sms() * 8 ? want : num_sms() * 8);
+    int grid = (int)(want < num_sms() * g_ctc_softmax_ctas_per_sm ? want : num_sms() * g_ctc_softmax_ctas_per_sm);
     if (grid < 1) grid = 1;
     ctc_softmax_kernel<GROUP, VEC, NCH><<<grid, 256, 0, st>>>(logits, grad, B, T, V, meta, frame);
 }
@@ -711,7 +713,7 @@ static void dispatch_softmax(const float* logits, float* grad, int B, int T, int
     const int nch_cta = (nvec + 255) / 256;
     if (nch_cta <= 8) { dispatch_nch<256, VEC>(nch_cta, logits, grad, B, T, V, meta, frame, st); return; }
     const long long rows = (long long)B * T;
-    int grid = (int)(rows < num_sms() * 8 ? rows : num_sms() * 8);
+    int grid = (int)(rows < num_sms() * g_ctc_softmax_ctas_per_sm ? rows : num_sms() * g_ctc_softmax_ctas_per_sm);
     ctc_softmax_bigrow_kernel<<<grid, 256, 0, st>>>(logits, grad, B, T, V, meta, frame);
 }
 
@@ -723,15 +725,6 @@ static cudaError_t launch_lattice(const CtcPlan& p, int B, int T, int V, const f
         return cudaErrorInvalidValue;
     ctc_lattice_kernel<SPT, MAXT><<<B, 2 * p.NW * 32, p.smem, st>>>(logits, meta, lab, p.LABP, frame, spill, loss, grad, T, V, p.NW);
     return cudaGetLastError();
-}
-
-// one non-blocking helper stream per device for the two-half overlap of large-vocabulary calls (created on first use)
-static cudaStream_t ctc_helper_stream() {
-    static cudaStream_t streams[64];
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) streams[dev] = nullptr;
-    return streams[dev];
 }
 
 }  // namespace lcb
@@ -795,28 +788,11 @@ extern "C" int lcb_ctc_loss_grad_f32(const float* logits, const int64_t* labels,
         return e;
     };
     cudaError_t e = cudaSuccess;
-    // Large vocabularies: the softmax pass streams 8*T*B*V bytes (HBM-bound) while the lattice pass is a latency-bound chain on a
-    // few warps per SM -- run the lattice of the first half of the batch on a helper stream BESIDE the softmax pass of the second.
-    cudaStream_t helper = (V >= 1024 && B >= 32) ? ctc_helper_stream() : nullptr;
-    if (helper) {
-        const int h0 = B / 2;
-        cudaEvent_t ev_s0, ev_l0;
-        if (cudaEventCreateWithFlags(&ev_s0, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ev_l0, cudaEventDisableTiming) != cudaSuccess) return LCB_ERR_CUDA;
-        softmax_pass(0, h0, st);
-        cudaEventRecord(ev_s0, st);
-        cudaStreamWaitEvent(helper, ev_s0, 0);
-        e = lattice_pass(0, h0, helper);
-        cudaEventRecord(ev_l0, helper);
-        softmax_pass(h0, B - h0, st);
-        if (e == cudaSuccess) e = lattice_pass(h0, B - h0, st);
-        cudaStreamWaitEvent(st, ev_l0, 0);
-        cudaEventDestroy(ev_s0);
-        cudaEventDestroy(ev_l0);
-    } else {
-        softmax_pass(0, B, st);
-        e = lattice_pass(0, B, st);
-    }
+    // (Tried and dropped, profiles/r02_ctc_notes.txt: running the lattice of one half of the batch on a helper stream beside the
+    // softmax pass of the other half at large V -- the persistent softmax CTAs and the 640-thread / 41 K-register lattice CTAs do
+    // not co-reside, and a softmax grid thin enough to leave room no longer saturates HBM: 2.54 -> 2.55 / 2.74 ms at V = 5000.)
+    softmax_pass(0, B, st);
+    e = lattice_pass(0, B, st);
     if (e != cudaSuccess) return LCB_ERR_CUDA;
     e = cudaGetLastError();
     return e == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;

@@ -64,7 +64,6 @@ class BatchedForward:
         self.windows = plan_batches([e[1] for e in entries], self.batch_size, window_batches)
         self.io_threads = max(1, int(io_threads))
         self.timing = {"device_s": 0.0, "batches": 0, "frames": 0, "padded_frames": 0}
-        self._host = None               # grow-only pinned staging buffer for the device -> host copy
 
     # ---- host side: decode one utterance ----
     def _load(self, i):
@@ -111,10 +110,14 @@ class BatchedForward:
         q.put(None)
 
     # ---- device side ----
-    def _forward(self, xb, lens):
-        """-> host array [B, T', V] of the requested output, and the per-utterance frame counts after subsampling"""
+    def _forward(self, xb, lens, host):
+        """Enqueues one minibatch: H2D, forward, posterior, D2H into `host` (pinned).  Returns (view of host, frame counts, event that
+        completes when the copy has landed, timing events) WITHOUT synchronising: the next minibatch is enqueued while this one
+        is written out."""
         m = self.model
         dev = m.device
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         x = xb.to(dev, non_blocking=True)
         ln = lens.to(dev, non_blocking=True)
         lens_out = lens
@@ -133,50 +136,83 @@ class BatchedForward:
                 out = torch.cat([out[..., -1:], out[..., :-1]], -1)
         else:
             out = logits
-        n = out.numel()
-        if self._host is None or self._host.numel() < n:
-            self._host = torch.empty(int(n * 1.25) + 1, dtype=torch.float32, pin_memory=True)
-        host = self._host[:n].view(out.shape)
-        host.copy_(out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return host.numpy(), lens_out
+        view = host[:out.numel()].view(out.shape)
+        view.copy_(out, non_blocking=True)
+        e1.record()
+        return view, lens_out, e0, e1
 
     def run(self, write, report=None):
-        """write(key, matrix) is called once per utterance, in scp order; report(n) after every utterance."""
+        """write(key, matrix) is called once per utterance, in scp order; report(n) after every utterance.
+        Three stages run concurrently: TFRecord decoding + pinned batch assembly (producer thread and its pool), the device
+        (this thread only enqueues), and slicing + archive writing (writer thread, fed through two pinned staging buffers)."""
         q = queue.Queue(maxsize=3)
         stop = threading.Event()
         th = threading.Thread(target=self._producer, args=(q, stop), daemon=True)
         th.start()
-        pending = {}
-        done = 0
+        wq = queue.Queue(maxsize=4)
+        free = queue.Queue()
+        err = []
+        done = [0]
+
+        def writer():
+            pending = {}
+            try:
+                while True:
+                    item = wq.get()
+                    if item is None:
+                        return
+                    if item[0] == "window_end":
+                        for i in sorted(item[1]):
+                            key, _ = os.path.splitext(os.path.basename(self.entries[i][0]))
+                            write(key, pending.pop(i))
+                            done[0] += 1
+                            if report:
+                                report(done[0])
+                        continue
+                    _, batch, view, lens_out, e0, e1, buf = item
+                    e1.synchronize()
+                    self.timing["device_s"] += e0.elapsed_time(e1) * 1e-3
+                    self.timing["batches"] += 1
+                    self.timing["frames"] += int(lens_out.sum())
+                    self.timing["padded_frames"] += int(view.shape[0] * view.shape[1])
+                    arr = view.numpy()
+                    for b, i in enumerate(batch):
+                        pending[i] = arr[b, :int(lens_out[b])].copy()      # (the pinned staging buffer is reused)
+                    free.put(buf)
+            except Exception as e:              # surfaced by the main thread
+                err.append(e)
+                free.put(None)
+
+        wt = threading.Thread(target=writer, daemon=True)
+        wt.start()
+        bufs = 0
         try:
-            while True:
+            while not err:
                 item = q.get()
                 if item is None:
                     break
                 if isinstance(item, Exception):
                     raise item
                 if item[0] == "window_end":
-                    for i in sorted(item[1]):
-                        key, _ = os.path.splitext(os.path.basename(self.entries[i][0]))
-                        write(key, pending.pop(i))
-                        done += 1
-                        if report:
-                            report(done)
+                    wq.put(item)
                     continue
                 batch, xb, lens = item
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                out, lens_out = self._forward(xb, lens)
-                e1.record()
-                e1.synchronize()
-                self.timing["device_s"] += e0.elapsed_time(e1) * 1e-3
-                self.timing["batches"] += 1
-                self.timing["frames"] += int(lens_out.sum())
-                self.timing["padded_frames"] += int(out.shape[0] * out.shape[1])
-                for b, i in enumerate(batch):
-                    pending[i] = out[b, :int(lens_out[b])].copy()      # (the pinned staging buffer is reused by the next batch)
+                need = xb.shape[0] * xb.shape[1] * self.model.cfg.V
+                buf = None
+                if bufs >= 2:
+                    buf = free.get()
+                    if buf is None:
+                        break
+                if buf is None or buf.numel() < need:
+                    buf = torch.empty(int(need * 1.25) + 1, dtype=torch.float32, pin_memory=True)
+                    bufs += 1 if bufs < 2 else 0
+                view, lens_out, e0, e1 = self._forward(xb, lens, buf)
+                wq.put(("batch", batch, view, lens_out, e0, e1, buf))
         finally:
             stop.set()
+            wq.put(None)
+            wt.join()
             th.join(timeout=5)
-        return done
+        if err:
+            raise err[0]
+        return done[0]
