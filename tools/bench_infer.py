@@ -110,5 +110,5 @@ if __name__ == "__main__":
             res["B%d_%s" % (B, "e2e" if e2e else "device")] = {"ms_per_batch": ms, "frames_per_s": frames / ms * 1e3, "utts_per_s": B / ms * 1e3}
         torch.cuda.empty_cache()
     if "--cli" in sys.argv:
-        res["cli_nnet_forward"] = run_cli(2048, 700, (1, 64, 512))
+        res["cli_nnet_forward"] = run_cli(4096, 700, (1, 64, 512))
     print(json.dumps(res))
