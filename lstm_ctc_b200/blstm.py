@@ -214,6 +214,9 @@ class BLSTMEncoder:
         self.bwd_early_fracs = [0.67, 0.85]
         self.l0_released = True        # layer 0's frame-sum gradients over released frames
         self.xstream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None   # early rows of dX / dM
+        # share of the SMs a recurrence launch leaves idle that the GEMMs beside it may occupy (forward, BPTT): < 1 trades GEMM
+        # time (hidden under the recurrence) for power and L2 headroom of the latency-bound clusters (tools/gpu_side_cap.py)
+        self.side_sm_scale = [1.0, 1.0]
         self.ndir = 1 if cfg.uni else 2          # nnet_type 'lstm': only direction-0 clusters / column halves run (lstm.py)
         self.num_sms = _lib.lib().lcb_device_sm_count() if torch.cuda.is_available() else 0
         self._arena = Arena(device, zero=cfg.uni)   # uni: the never-written direction-1 halves must read as 0, not as garbage
@@ -245,7 +248,7 @@ class BLSTMEncoder:
         """SMs a forward (which=0) / BPTT (which=1) recurrence launch over B utterances leaves free: the persistent-grid cap of
         the GEMMs that run beside it on a side stream."""
         used = _lib.lib().lcb_lstm_rec_grid(B, self.cfg.Hp, self.ndir, which)
-        return max(8, self.num_sms - max(used, 0))
+        return max(8, int((self.num_sms - max(used, 0)) * self.side_sm_scale[which]))
 
     def _dropout(self, x, layer):
         dt = 2 if x.dtype == F16 else 1

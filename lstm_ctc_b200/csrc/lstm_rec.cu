@@ -49,7 +49,7 @@ __device__ int g_rec_prof_steps = 0;
 #define LCB_REC_NIW 2             // issuer warps of the v2 forward / v3 BPTT kernels (measured: 1 issuer = 657-cycle passes, 2 = 526)
 #endif
 constexpr int REC_BG = 16;        // utterances per cluster
-constexpr int REC_GROW = 132;     // padded fp32 row of a staged G tile: 2*132 = 8 (mod 32) -> conflict-free gate reads
+constexpr int REC_GCOLS = 128;    // fp32 row of a staged G tile (dense TMA box: the 4-way bank conflict of its 8 reads per thread and step is off the chain)
 constexpr int REC_SG = 8;         // G prefetch ring depth
 constexpr int REC_TMEM_ACC = 256; // first accumulator column (weights occupy [0, Hp/2) forward, [0, 64*MB) backward)
 
@@ -152,14 +152,14 @@ template <int BG, int NSG = 1> struct RecFwd2Cfg {
     static constexpr int SLICE = 512 * NUB;                // bytes of one CTA's m_t slice: 32 units x BG utterances, fp16
     static constexpr int BARS = 1 + 2 * REC_SG + 2 + 2 + 1; // mma g[SG] gfree[SG] op[2] slice[2] acc
     __host__ __device__ static size_t op_bytes(int KB) { return (size_t)KB * 8 * NUB * 128; }    // one operand buffer (all K blocks)
-    __host__ __device__ static size_t g_bytes() { return (size_t)REC_SG * BG * REC_GROW * 4; }
+    __host__ __device__ static size_t g_bytes() { return (size_t)REC_SG * BG * REC_GCOLS * 4; }
     __host__ __device__ static size_t sg_bytes(int KB) { return (2 * op_bytes(KB) + g_bytes() + 2 * SLICE + BARS * 8 + 1023) & ~(size_t)1023; }
     static size_t smem_bytes(int KB) { return 1024 + NSG * sg_bytes(KB) + 64; }
 };
 
 template <int BG, int NSG>
 __global__ void __launch_bounds__(RecFwd2Cfg<BG, NSG>::THREADS, 1)
-lstm_rec_fwd2_kernel(const RecFwdParams p)
+lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap tmG)
 {
     using Cfg = RecFwd2Cfg<BG, NSG>;
     constexpr int SG = REC_SG, NUB = Cfg::NUB, NCW = Cfg::NCW, NIW = Cfg::NIW, SLICE = Cfg::SLICE;
@@ -179,7 +179,7 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
     // operand m_{t-1}: no-swizzle K-major core matrices (8 utterances x 8 units = 128 B), index (unit/8)*NUB + utt/8
     unsigned char* Bsm = smem;                                                   // [2][KB*8][NUB][128 B]
     float* Gsm = reinterpret_cast<float*>(Bsm + 2 * (size_t)OPB);               // [SG][BG][132]
-    unsigned char* Msm = reinterpret_cast<unsigned char*>(Gsm + (size_t)SG * BG * REC_GROW);   // [2 step parities][SLICE]
+    unsigned char* Msm = reinterpret_cast<unsigned char*>(Gsm + (size_t)SG * BG * REC_GCOLS);   // [2 step parities][SLICE]
     uint64_t* bars = reinterpret_cast<uint64_t*>(Msm + 2 * SLICE);
     uint64_t* mbar_mma = bars;                         //      this step's accumulator is complete
     uint64_t* mbar_g = bars + 1;                       // [SG] G tile landed (bulk-copy tx)
@@ -266,7 +266,11 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
 
     bool ok = true;
     if (role == 2) {
-        // ============================ loader warp: G tile prefetch, one 512-byte bulk copy per lane ============================
+        // ============================ loader warp: G tile prefetch ============================
+        // ONE TMA tensor load per tile (box = 128 packed gate columns x BG utterances of frame t).  The first version issued one
+        // 512-byte bulk copy per utterance: 16 (paired: 32) operations per step in the SM's TMA queue, in a burst right when the
+        // exchange warp issues the bulk store + multicast of m_t that the serial chain waits for -- measured 1.36 -> 1.27 us per
+        // step (paired groups), 1.15 -> 1.09 (a group alone), profiles/r02_rec_g_tile_tma.txt
         for (int s = 0; s < S; ++s) {
             const int stage = s % SG;
             if (s >= SG) {              // wait until the compute warps drained this stage (step s - SG)
@@ -275,12 +279,8 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
                 if (!ok) break;
             }
             const int t = dir ? (T - 1 - (S0 + s)) : (S0 + s);
-            if (lane == 0) mbar_arrive_expect_tx(&mbar_g[stage], (uint32_t)(nvalid * 512));
-            __syncwarp();
-            for (int u = lane; u < nvalid; u += 32)
-                bulk_load_1d(Gsm + ((size_t)stage * BG + u) * REC_GROW,
-                             p.G + ((size_t)t * B + b0 + u) * 8 * Hp + (size_t)dir * 4 * Hp + (size_t)cta * 128,
-                             512, &mbar_g[stage]);
+            if (lane == 0) mbar_arrive_expect_tx(&mbar_g[stage], (uint32_t)(BG * 512));     // the whole box counts (rows past B are zero-filled)
+            if (lane == 0) tma_load_3d(Gsm + (size_t)stage * BG * REC_GCOLS, &tmG, &mbar_g[stage], dir * 4 * Hp + (int)cta * 128, b0, t);
         }
     } else if (role == 3) {
         // ============================ exchange warp: slice -> L2 scratch -> multicast into every CTA of the cluster ============================
@@ -326,18 +326,19 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
             const uint32_t par = (uint32_t)(s & 1);
             if (leader && iw == 0 && s + 1 < S) mbar_arrive_expect_tx(&mbar_op[(s + 1) & 1], (uint32_t)(NC * SLICE));   // the buffer that step s fills
             ok = mbar_wait(mbar_acc, (uint32_t)(s & 1));                 // accumulator = G tile of step s
-            if (ok && s > 0) ok = mbar_wait(&mbar_op[par], (uint32_t)(((s - 1) >> 1) & 1));
-            if (!ok) break;
-            REC_PROBE(1);
             // Two sub-groups: the weight passes take strict turns.  Issued at the same time they share the tensor pipe, both
             // finish late and the sub-groups fall into phase; one after the other, each pass runs at full rate under the other
             // sub-group's exchange and gate math (without turns: forward equal, BPTT 3330 -> 3560 cycles per step,
-            // profiles/r01_rec_experiments_lock_stasync.txt).
-            if (paired) {                                                     // pass n of sub-group 0 follows pass n-1 of sub-group 1,
+            // profiles/r01_rec_experiments_lock_stasync.txt).  The turn is awaited BEFORE the operand: in steady state the other
+            // sub-group's pass ran while this one's exchange was in flight, and a try_wait on an already completed phase still
+            // costs ~100 cycles -- behind the operand wait they sat on the serial chain of every step.
+            if (ok && paired) {                                               // pass n of sub-group 0 follows pass n-1 of sub-group 1,
                 if (sg == 1 || s > 0) ok = mbar_wait(&mbar_turn[sg], (uint32_t)((sg ? s : s - 1) & 1));   // pass n of sub-group 1 follows pass n of sub-group 0
-                if (!ok) break;
             }
             REC_PROBE(4);
+            if (ok && s > 0) ok = mbar_wait(&mbar_op[par], (uint32_t)(((s - 1) >> 1) & 1));
+            if (!ok) break;
+            REC_PROBE(1);
             tc_fence_after();
             const uint32_t b_lo_s = b_lo0 + ((par * OPB) >> 4);
             if (S0 + s > 0) {                                            // m_{-1} = 0: scan step 0 is the x-part alone
@@ -387,11 +388,11 @@ lstm_rec_fwd2_kernel(const RecFwdParams p)
         auto load_acc = [&](int s2) {
             const int stage = s2 % SG;
             if (ok) ok = mbar_wait(&mbar_g[stage], (uint32_t)((s2 / SG) & 1));
-            const float* gt = Gsm + (size_t)stage * BG * REC_GROW + q * 32 + up;
+            const float* gt = Gsm + (size_t)stage * BG * REC_GCOLS + q * 32 + up;
             uint32_t a0[4], a1[4];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const float* gr = gt + (ub * 8 + 2 * g + j) * REC_GROW;
+                const float* gr = gt + (ub * 8 + 2 * g + j) * REC_GCOLS;
                 a0[j] = pad_j[j] ? 0u : __float_as_uint(gr[0]);
                 a0[2 + j] = pad_j[j] ? 0u : __float_as_uint(gr[8]);
                 a1[j] = pad_j[j] ? 0u : __float_as_uint(gr[16] + fbias);
@@ -978,17 +979,13 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
             REC_PROBE(0);
             if (leader && iw == 0) mbar_arrive_expect_tx(&mbar_op[s & 1], 4u * SLICE);
             ok = mbar_wait(mbar_acc, (uint32_t)(s & 1));                      // accumulator zeroed
+            if (ok && paired) {                                               // strict turns, awaited before the operand (see lstm_rec_fwd2_kernel)
+                if (sg == 1 || s > 0) ok = mbar_wait(&mbar_turn[sg], (uint32_t)((sg ? s : s - 1) & 1));   // pass n of sub-group 1 follows pass n of sub-group 0
+            }
+            REC_PROBE(4);
             if (ok) ok = mbar_wait(&mbar_op[s & 1], (uint32_t)((s >> 1) & 1)); // dz_t of the whole K block landed
             if (!ok) break;
             REC_PROBE(1);
-            // the reduce buffer the NEXT step's partials go to: its previous contents were consumed in phase A of
-            // this step (our own dz slice, part of the operand just awaited, was staged after reading them)
-            if (leader && iw == 0 && s + 1 < S && S0 + s + 2 < T) mbar_arrive_expect_tx(&mbar_red[(s + 1) & 1], 4u * PT);
-            if (paired) {                                                     // strict turns (see lstm_rec_fwd2_kernel)                 
-                if (sg == 1 || s > 0) ok = mbar_wait(&mbar_turn[sg], (uint32_t)((sg ? s : s - 1) & 1));   // pass n of sub-group 1 follows pass n of sub-group 0
-                if (!ok) break;
-            }
-            REC_PROBE(4);
             tc_fence_after();
             const uint32_t b_lo_s = b_lo0 + (uint32_t)(((s & 1) * 4 * SLICE) >> 4);
 #pragma unroll 4
@@ -1002,6 +999,10 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
                 umma_commit(mbar_mma);
                 if (paired) mbar_arrive(&mbar_turn[sg ^ 1]);
             }
+            // the reduce buffer the NEXT step's partials go to: its previous contents were consumed in phase A of
+            // this step (our own dz slice, part of the operand awaited above, was staged after reading them), and nobody can
+            // send step s+1's partials before our dz of step s+1 exists
+            if (leader && iw == 0 && s + 1 < S && S0 + s + 2 < T) mbar_arrive_expect_tx(&mbar_red[(s + 1) & 1], 4u * PT);
             REC_PROBE(2);
         }
         __syncwarp();
@@ -1359,10 +1360,14 @@ extern "C" int lcb_lstm_rec_fwd_range(const float* G, const void* WfoldT, const 
     const int bgs = choose_bg(B, nc, num_dirs, 0);
     const int ncl = num_dirs * ((B + bgs - 1) / bgs);
     cudaStream_t st = (cudaStream_t)stream;
+    // G as a 3-D tensor [T][B][8Hp] fp32, box = 128 packed gate columns x 16 utterances of one frame (dense, no swizzle)
+    CUtensorMap tm;
+    if (!make_tmap_3d(&tm, true, G, (uint64_t)8 * Hp, (uint64_t)B, (uint64_t)T, (uint64_t)8 * Hp * 4, (uint64_t)B * 8 * Hp * 4,
+                      128, 16u, 1, false)) return LCB_ERR_CUDA;
     if (bgs == 16)
-        return launch_cluster(lstm_rec_fwd2_kernel<16, 1>, ncl * nc, RecFwd2Cfg<16>::THREADS, RecFwd2Cfg<16>::smem_bytes(Hp / 64), nc, st, p);
+        return launch_cluster(lstm_rec_fwd2_kernel<16, 1>, ncl * nc, RecFwd2Cfg<16>::THREADS, RecFwd2Cfg<16>::smem_bytes(Hp / 64), nc, st, p, tm);
     // too many 16-utterance groups for one wave of clusters: two of them per cluster, stepping independently
-    return launch_cluster(lstm_rec_fwd2_kernel<16, 2>, ncl * nc, RecFwd2Cfg<16, 2>::THREADS, RecFwd2Cfg<16, 2>::smem_bytes(Hp / 64), nc, st, p);
+    return launch_cluster(lstm_rec_fwd2_kernel<16, 2>, ncl * nc, RecFwd2Cfg<16, 2>::THREADS, RecFwd2Cfg<16, 2>::smem_bytes(Hp / 64), nc, st, p, tm);
 }
 
 extern "C" int lcb_lstm_rec_bwd(const float* dM, const void* gates, const float* cst, const void* Wfold, const float* peep,
