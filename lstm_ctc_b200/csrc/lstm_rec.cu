@@ -342,8 +342,11 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
             tc_fence_after();
             const uint32_t b_lo_s = b_lo0 + ((par * OPB) >> 4);
             if (S0 + s > 0) {                                            // m_{-1} = 0: scan step 0 is the x-part alone
+                // issuer 0 accumulates onto the G tile; the others start their accumulator with a non-accumulating MMA
+                if (iw > 0) umma_f16_ts_elect<false>(d_tmem, tmem_base + 8 * iw, b_lo_s + (2 * NUB * 128 / 16) * iw, b_hi, idesc, leader);
+                else umma_f16_ts_elect<true>(d_tmem, tmem_base, b_lo_s, b_hi, idesc, leader);
 #pragma unroll 4
-                for (int kk = iw; kk < nk; kk += NIW)
+                for (int kk = iw + NIW; kk < nk; kk += NIW)
                     umma_f16_ts_elect(d_tmem, tmem_base + 8 * kk, b_lo_s + (2 * NUB * 128 / 16) * kk, b_hi, idesc, leader);
             }
             REC_PROBE(7);
@@ -382,34 +385,49 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
         }
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + REC_TMEM_ACC + sg * NIW * BG + ub * 8;
         const float fbias = p.forget_bias;
-        const size_t out0 = (size_t)dir * Hp + unit;
+        // running output pointers of utterance j = 0 at this launch's first frame (utterance j = 1 is the next row, + ld2 elements;
+        // a scan step moves them by one frame = B rows, backwards for the backward direction)
+        const int bj0 = b0 + ub * 8 + 2 * g;
+        const long long tstep = (dir ? -1LL : 1LL) * (long long)B * (long long)ld2;
+        const size_t idx0 = ((size_t)(dir ? (T - 1 - S0) : S0) * B + bj0) * ld2 + (size_t)dir * Hp + unit;
+        const bool save = p.gates != nullptr;
+        __half* mo_p = p.Mout + idx0;
+        uint2* ga_p = (save ? p.gates : reinterpret_cast<uint2*>(p.Mout)) + idx0;        // (never dereferenced unless save)
+        float* cs_p = (save ? p.cst : reinterpret_cast<float*>(p.Mout)) + idx0;
+        // frame at which an utterance's final state is emitted: its last live step in this direction's own order (-1: never)
+        const int t_last[2] = {dir ? (len_j[0] > 0 ? 0 : -1) : len_j[0] - 1, dir ? (len_j[1] > 0 ? 0 : -1) : len_j[1] - 1};
         // accumulator := hoisted x-part of step s2's pre-activations (G tile, forget bias folded in; padding utterances 0),
         // then release the G stage and tell the issuers that they may accumulate onto it
+        // shared-space addresses (32-bit, explicit ld/st.shared: the generic-address forms cost an address-space check per access)
+        const uint32_t g_addr = smem_u32(Gsm) + (uint32_t)(((ub * 8 + 2 * g) * REC_GCOLS + q * 32 + up) * 4);     // row of utterance j = 0
+        const uint32_t ms_addr = smem_u32(Msm) + (uint32_t)((q * NUB + ub) * 128 + (2 * g) * 16 + up * 2);        // staged m_t, utterance j = 0
         auto load_acc = [&](int s2) {
             const int stage = s2 % SG;
             if (ok) ok = mbar_wait(&mbar_g[stage], (uint32_t)((s2 / SG) & 1));
-            const float* gt = Gsm + (size_t)stage * BG * REC_GCOLS + q * 32 + up;
+            const uint32_t ga = g_addr + (uint32_t)(stage * BG * REC_GCOLS * 4);
             uint32_t a0[4], a1[4];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const float* gr = gt + (ub * 8 + 2 * g + j) * REC_GCOLS;
-                a0[j] = pad_j[j] ? 0u : __float_as_uint(gr[0]);
-                a0[2 + j] = pad_j[j] ? 0u : __float_as_uint(gr[8]);
-                a1[j] = pad_j[j] ? 0u : __float_as_uint(gr[16] + fbias);
-                a1[2 + j] = pad_j[j] ? 0u : __float_as_uint(gr[24]);
+                const uint32_t gr = ga + (uint32_t)(j * REC_GCOLS * 4);
+                a0[j] = pad_j[j] ? 0u : lds_b32(gr);
+                a0[2 + j] = pad_j[j] ? 0u : lds_b32(gr + 32);
+                a1[j] = pad_j[j] ? 0u : __float_as_uint(__uint_as_float(lds_b32(gr + 64)) + fbias);
+                a1[2 + j] = pad_j[j] ? 0u : lds_b32(gr + 96);
             }
             tmem_st_16x256b_x1(t_addr, a0);
             tmem_st_16x256b_x1(t_addr + (16u << 16), a1);
-            if (NIW > 1) {
-                const uint32_t zz[4] = {0u, 0u, 0u, 0u};               // the second issuer's accumulator starts from zero
-                tmem_st_16x256b_x1(t_addr + BG, zz);
-                tmem_st_16x256b_x1(t_addr + BG + (16u << 16), zz);
-            }
+            // (the second issuer's accumulator needs no zero fill: its first MMA of a step overwrites it; before scan step 0,
+            // which issues no MMAs, it is zeroed once below)
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(&mbar_gfree[stage]); mbar_arrive(mbar_acc); }
         };
+        if (NIW > 1) {
+            const uint32_t zz[4] = {0u, 0u, 0u, 0u};
+            tmem_st_16x256b_x1(t_addr + BG, zz);
+            tmem_st_16x256b_x1(t_addr + BG + (16u << 16), zz);
+        }
         load_acc(0);
 
         for (int s = 0; s < S; ++s) {
@@ -450,13 +468,14 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
                 mo[j] = live[j] ? og[j] * tc[j] : 0.f;
             }
             const __half2 mh = __floats2half2_rn(mo[0], mo[1]);
+            const uint32_t mhb = *reinterpret_cast<const uint32_t*>(&mh);
             REC_PROBE(15);
             if (s + 1 < S) {
                 // stage the warp's [8 utts][8 units] fp16 block = core matrix (q, ub) of this CTA's operand slice (double-
                 // buffered by step parity) and hand it to the exchange warp
-                __half* ms16 = reinterpret_cast<__half*>(Msm + (s & 1) * SLICE + (q * NUB + ub) * 128);
-                ms16[(2 * g) * 8 + up] = __low2half(mh);
-                ms16[(2 * g + 1) * 8 + up] = __high2half(mh);
+                const uint32_t ma = ms_addr + (uint32_t)((s & 1) * SLICE);
+                sts_b16(ma, (uint16_t)(mhb & 0xffffu));
+                sts_b16(ma + 16, (uint16_t)(mhb >> 16));
                 fence_proxy_async_smem();                              // generic-proxy stores -> visible to the bulk (async-proxy) store
                 __syncwarp();
                 REC_PROBE(12);
@@ -464,26 +483,32 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
                 load_acc(s + 1);                                       // off the chain: the operand is >= 1000 cycles away
             }
             REC_PROBE(13);
-            // ---- off the critical path: outputs and saved activations ----
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int b = b0 + ub * 8 + 2 * g + j;
-                if (!pad_j[j]) {
-                    const size_t idx = ((size_t)t * B + b) * ld2 + out0;
-                    p.Mout[idx] = j ? __high2half(mh) : __low2half(mh);
-                    if (p.gates) {
-                        const __half2 g01 = __floats2half2_rn(ig[j], jt[j]), g23 = __floats2half2_rn(fg[j], og[j]);
-                        p.gates[idx] = make_uint2(*reinterpret_cast<const uint32_t*>(&g01), *reinterpret_cast<const uint32_t*>(&g23));
-                        p.cst[idx] = cn[j];
-                    }
-                    // final state = state at the last live step in this direction's own order
-                    const bool last = dir ? (t == 0 && live[j]) : (t == len_j[j] - 1);
-                    if (last && p.cfin) {
-                        p.cfin[((size_t)b * 2 + dir) * Hp + unit] = cn[j];
-                        p.mfin[((size_t)b * 2 + dir) * Hp + unit] = og[j] * tc[j];
-                    }
+            // ---- off the critical path: outputs and saved activations (running pointers: one add per array and step) ----
+            if (!pad_j[0]) {
+                *mo_p = __low2half(mh);
+                if (save) {
+                    const __half2 g01 = __floats2half2_rn(ig[0], jt[0]), g23 = __floats2half2_rn(fg[0], og[0]);
+                    *ga_p = make_uint2(*reinterpret_cast<const uint32_t*>(&g01), *reinterpret_cast<const uint32_t*>(&g23));
+                    *cs_p = cn[0];
+                }
+                if (t == t_last[0] && p.cfin) {          // final state = state at the last live step in this direction's own order
+                    p.cfin[((size_t)bj0 * 2 + dir) * Hp + unit] = cn[0];
+                    p.mfin[((size_t)bj0 * 2 + dir) * Hp + unit] = mo[0];
                 }
             }
+            if (!pad_j[1]) {
+                mo_p[ld2] = __high2half(mh);
+                if (save) {
+                    const __half2 g01 = __floats2half2_rn(ig[1], jt[1]), g23 = __floats2half2_rn(fg[1], og[1]);
+                    ga_p[ld2] = make_uint2(*reinterpret_cast<const uint32_t*>(&g01), *reinterpret_cast<const uint32_t*>(&g23));
+                    cs_p[ld2] = cn[1];
+                }
+                if (t == t_last[1] && p.cfin) {
+                    p.cfin[((size_t)(bj0 + 1) * 2 + dir) * Hp + unit] = cn[1];
+                    p.mfin[((size_t)(bj0 + 1) * 2 + dir) * Hp + unit] = mo[1];
+                }
+            }
+            mo_p += tstep; ga_p += tstep; cs_p += tstep;
             REC_PROBE(14);
         }
     }
