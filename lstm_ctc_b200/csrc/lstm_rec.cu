@@ -1013,8 +1013,10 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
             REC_PROBE(1);
             tc_fence_after();
             const uint32_t b_lo_s = b_lo0 + (uint32_t)(((s & 1) * 4 * SLICE) >> 4);
+            // idx = src * 8 + kk; the first MMA of a step overwrites this issuer's accumulator, the others accumulate
+            umma_f16_ts_elect<false>(d_tmem, tmem_base + 8 * iw, b_lo_s + (uint32_t)(iw * 2), b_hi, idesc, leader);      // (src 0, kk = iw < 4)
 #pragma unroll 4
-            for (int idx = iw; idx < 32; idx += NIW) {                        // idx = src * 8 + kk
+            for (int idx = iw + NIW; idx < 32; idx += NIW) {
                 const int src = idx >> 3, kk = idx & 7;
                 umma_f16_ts_elect(d_tmem, tmem_base + 8 * idx,
                                   b_lo_s + (uint32_t)((src * SLICE + (kk >> 2) * (BG * 128)) / 16 + (kk & 3) * 2), b_hi, idesc, leader);
@@ -1192,11 +1194,8 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
                                   pw, (uint32_t)PT, mapa_shared(smem_u32(&mbar_red[s & 1]), owner));
                 }
                 REC_PROBE(14);
-                // off the chain: zero our part of the accumulator for the next step's MMAs
-                const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-                tmem_st_32x32b_x8(acc_addr, z);
-                if (NIW > 1) tmem_st_32x32b_x8(acc_addr + BG, z);
-                tmem_st_wait();
+                // the accumulators are read: the next pass may overwrite them (each issuer's first MMA of a step does not
+                // accumulate, so there is no zero fill)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(mbar_acc);
