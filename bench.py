@@ -234,6 +234,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ctc", action="store_true")
+    ap.add_argument("--no-flow-control", action="store_true",
+                    help="forward recurrence as consecutive range launches instead of one launch that waits in-kernel for the "
+                         "projection chunks (needed when kernels cannot run concurrently, e.g. under ncu; detected automatically "
+                         "from CUDA_INJECTION64_PATH / CUDA_LAUNCH_BLOCKING)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -251,6 +255,8 @@ def main():
     L = _lib.lib()
     cfg = nnet_config(w, args.keep_prob)
     model = AcousticModel(cfg, device, seed=1234)
+    if args.no_flow_control:
+        model.enc.fwd_flow_control = False
     reducer = lcb_dist.GradientAllReducer(model.params)
     reducer.broadcast_weights()
     x_h, lens_h, y_h = synth_batch(w, 777 + rank)
@@ -265,7 +271,9 @@ def main():
 
     def step(instrument=False):
         reducer.begin_step()
-        loss_sum, _ = model.loss_and_grad(x, lens, y, bucket_ready=reducer.bucket_ready, check_labels=False)
+        # (the lengths are also handed over on the host, as every batch assembler has them: the forward recurrence then skips the
+        # scan steps in which a whole 16-utterance group is past its last frame)
+        loss_sum, _ = model.loss_and_grad(x, lens, y, bucket_ready=reducer.bucket_ready, check_labels=False, seq_len_host=lens_h)
         reducer.finish()
         model.optimizer_step("adam", 4e-4, clip_norm=5.0, l2_decay_weight=1e-5)
         return loss_sum
@@ -324,6 +332,7 @@ def main():
            "config": {"workload": w["desc"], "name": args.workload, "per_gpu_batch": w["B"], "frames_per_step_global": frames_global,
                       "optimizer": "adam", "keep_prob": args.keep_prob, "l2": 1e-5, "clip_norm": 5.0,
                       "l2_cache": "inputs_exceed_l2 (per-step activations >> 126 MB)", "parallelism": "dp%d" % world,
+                      "fwd_flow_control": bool(model.enc.fwd_flow_control), "fwd_rec_sms": int(L.lcb_lstm_rec_grid(w["B"], model.cfg.Hp, 2, 0)),
                       "final_loss": last_loss, "device_error": dev_err},
            "clocks": clocks, "gpu_launches": launches, "e2e": e2e}
     if kt is not None:
@@ -389,7 +398,7 @@ def kernel_breakdown(model, x, lens, y, w, frames):
             self._lib = lib
         def __getattr__(self, k):
             f = getattr(self._lib, k)
-            m = {"lcb_lstm_rec_fwd": "lstm_rec_fwd", "lcb_lstm_rec_fwd_range": "lstm_rec_fwd", "lcb_lstm_rec_bwd": "lstm_rec_bwd", "lcb_lstm_rec_bwd_range": "lstm_rec_bwd", "lcb_output_fwd": "output_fwd",
+            m = {"lcb_lstm_rec_fwd": "lstm_rec_fwd", "lcb_lstm_rec_fwd_range": "lstm_rec_fwd", "lcb_lstm_rec_fwd_range_hl": "lstm_rec_fwd", "lcb_lstm_rec_bwd": "lstm_rec_bwd", "lcb_lstm_rec_bwd_range": "lstm_rec_bwd", "lcb_output_fwd": "output_fwd",
                  "lcb_mos_bwd_dz": "mos_bwd_dz", "lcb_optimizer_step": "optimizer"}.get(k)
             return timed(m, f) if m else f
 
@@ -403,7 +412,7 @@ def kernel_breakdown(model, x, lens, y, w, frames):
         for _ in range(2):
             spans.clear()
             del gemm_calls[:]
-            model.loss_and_grad(x, lens, y, check_labels=False)
+            model.loss_and_grad(x, lens, y, check_labels=False, seq_len_host=lens.cpu())
             model.optimizer_step("adam", 4e-4)
             torch.cuda.synchronize()
     finally:

@@ -134,6 +134,9 @@ int lcb_lstm_rec_max_clusters(int Hp, int which);
 int lcb_lstm_rec_grid(int B, int Hp, int num_dirs, int which);
 /* debug probe: the next lcb_lstm_rec_fwd launches write steps*16 clock64 samples of CTA 0 into buf (NULL: off). */
 int lcb_debug_rec_profile(long long* buf, int steps);
+/* debug: forward cluster layout (0 = automatic: as many clusters as stay resident, the surplus 16-utterance groups paired into
+ * the first clusters; 1 = two groups in every cluster, the round-1 layout).  Results are identical, only the timing differs. */
+int lcb_debug_fwd_layout(int mode);
 /* workspace (required): device scratch of lcb_lstm_rec_workspace_bytes(B, Hp) bytes (16-byte aligned, caller-owned, one per
  * concurrently running launch): the per-step exchange of m_t goes  shared memory -> bulk store -> this L2-resident
  * scratch -> ONE multicast bulk load into all CTAs of the cluster.
@@ -154,6 +157,24 @@ int lcb_lstm_rec_fwd_range(const float* G, const void* WfoldT, const float* peep
                            void* Mout, void* gates, float* cst, float* cfin, float* mfin,
                            int T, int B, int Hp, int num_dirs, float forget_bias, int s_begin, int s_end,
                            void* workspace, size_t workspace_bytes, void* stream);
+/* *dst = value on `stream` (one thread): advances the ready_steps counter below behind a projected chunk of G. */
+int lcb_store_i32(int32_t* dst, int32_t value, void* stream);
+/* Same, with the utterance lengths ALSO given on the host (lens_host [B], as every batch assembler has them; NULL = as above).
+ * The kernel then skips, per 16-utterance group, the scan steps in which no utterance of the group is live (behind the group's
+ * longest utterance in the forward direction, before it starts in the backward direction): those steps cost no weight pass and
+ * no exchange, only the zero rows of m are written.  The group maxima travel in the kernel parameters -- control flow around
+ * the tcgen05.mma issue must be provably warp-uniform, which a value loaded from device memory is not.  Results are identical
+ * to lcb_lstm_rec_fwd_range except that gates / cst rows of the skipped steps (never read by BPTT) are left unwritten.
+ * ready_steps (device word, NULL = everything is there): the number of leading scan steps whose G rows exist -- frames [0, n) of
+ * the forward and [T-n, T) of the backward direction.  The caller projects G chunk by chunk on ANOTHER stream, on the SMs this
+ * launch leaves idle (lcb_lstm_rec_grid), and advances the word with lcb_store_i32 behind every chunk; the kernel's prefetch warp
+ * waits for it (bounded: LCB_WAIT_TIMEOUT_NS, then lcb_device_error).  One launch covers the scan; the chunks must already be
+ * enqueued when it is launched, and the two streams must be able to run concurrently (not under a serialising profiler). */
+int lcb_lstm_rec_fwd_range_hl(const float* G, const void* WfoldT, const float* peep, const int32_t* lens, const int32_t* lens_host,
+                              const int32_t* ready_steps,
+                              void* Mout, void* gates, float* cst, float* cfin, float* mfin,
+                              int T, int B, int Hp, int num_dirs, float forget_bias, int s_begin, int s_end,
+                              void* workspace, size_t workspace_bytes, void* stream);
 /* BPTT of the above (replaces tf.gradients through the while_loop, nnet/graph.py:190-191).
  *   dM    [T*B, 2Hp] f32   d loss / d m_t arriving from the output projection
  *   Wfold [2*Hp, 4Hp] bf16 W' = W_proj*W_h per direction: rows = units, cols = packed gate columns

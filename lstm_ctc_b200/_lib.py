@@ -69,10 +69,13 @@ _SIGS = {
     "lcb_lstm_rec_config": (c_int, [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "lcb_lstm_rec_max_clusters": (c_int, [c_int, c_int]),
     "lcb_debug_rec_profile": (c_int, [c_void_p, c_int]),
+    "lcb_debug_fwd_layout": (c_int, [c_int]),
     "lcb_lstm_rec_workspace_bytes": (c_size_t, [c_int, c_int]),
     "lcb_lstm_rec_grid": (c_int, [c_int, c_int, c_int, c_int]),
     "lcb_lstm_rec_fwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
     "lcb_lstm_rec_fwd_range": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "lcb_store_i32": (c_int, [c_void_p, c_int, c_void_p]),
+    "lcb_lstm_rec_fwd_range_hl": (c_int, [c_void_p] * 11 + [c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "lcb_lstm_rec_bwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "lcb_lstm_rec_bwd_range": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "lcb_lstm_rec_bwd_can_split": (c_int, [c_int]),

@@ -29,6 +29,15 @@ def _ceil(x, m):
     return (x + m - 1) // m * m
 
 
+def _kernels_serialised():
+    """True when the process runs under a tool that executes one kernel at a time (Nsight Compute / Systems and
+    compute-sanitizer inject through CUDA_INJECTION64_PATH; CUDA_LAUNCH_BLOCKING=1 serialises launches): a recurrence launch that
+    waits in-kernel for GEMMs of another stream (BLSTMEncoder.fwd_flow_control) could never be fed there, so the encoder falls
+    back to consecutive range launches -- same results, ~0.7 ms slower per C3 step."""
+    import os
+    return bool(os.environ.get("CUDA_INJECTION64_PATH")) or os.environ.get("CUDA_LAUNCH_BLOCKING", "0") not in ("", "0")
+
+
 class ModelConfig:
     """The nnet_config keys consumed by create_logits_blstm (bilstm.py:39-99)."""
 
@@ -206,6 +215,18 @@ class BLSTMEncoder:
         # fractions of the scan steps at which the forward recurrence is cut into launches: the pre-activations of the first chunk
         # are projected before the recurrence starts, the later chunks' beside it on a side stream
         self.head_fracs = [0.36]
+        # ... when the forward recurrence occupies more clusters (B = 64: 96 SMs) and leaves the projection GEMMs beside it fewer
+        # SMs than this: more, smaller chunks, so that each chunk's capped GEMM still fits under the recurrence of the one before
+        self.head_fracs_tight = [0.34, 0.62, 0.85]
+        self.tight_side_sms = 56
+        # One recurrence launch per layer with in-kernel flow control (lcb_lstm_rec_fwd_range_hl, ready_steps): the first
+        # flow_fracs[0] of the scan is projected before the launch, the chunks up to each following fraction beside it on the side
+        # stream, each followed by lcb_store_i32 on the counter the kernel's prefetch warps wait on.  Clusters are then not
+        # re-synchronised at chunk boundaries (which costs ~0.2 ms per layer once 16-utterance groups of different length run at
+        # different speeds) and the chunks can be small.  False: consecutive range launches at head_fracs (e.g. under a profiler
+        # that serialises kernels -- the waiting launch and the GEMM it waits for must be able to run concurrently).
+        self.fwd_flow_control = not _kernels_serialised()
+        self.flow_fracs = [0.3, 0.55, 0.8]
         self.overlap_hproj = False     # output projection of finished chunks on the side stream (c3: +-0, c2: 15 % slower)
         self.bwd_split_frac = 0.0      # > 0: BPTT as two launches at this fraction (lcb_lstm_rec_bwd_range; tests)
         # increasing fractions > 0.5 of the scan at which BPTT of layers 1.. is cut into consecutive launches; the rows of dX (and of
@@ -418,6 +439,7 @@ class BLSTMEncoder:
         ws = {"X0": a.rows("X0", N, c.Dp0, F16),
               "G": a.rows("G", N, 8 * c.Hp, F32),
               "rec_ws": a.flat("rec_ws", max(16, _lib.lib().lcb_lstm_rec_workspace_bytes(B, c.Hp)), torch.uint8),
+              "ready": a.flat("ready", max(c.num_layers, 1), torch.int32),
               "cfin": a.flat("cfin", B * 2 * c.Hp, F32).view(B, 2, c.Hp),
               "mfin": a.flat("mfin", B * 2 * c.Hp, F32).view(B, 2, c.Hp)}
         if training:
@@ -457,8 +479,11 @@ class BLSTMEncoder:
     def head_frac(self, v):
         self.head_fracs = [float(v)] if v and v > 0 else []
 
-    def forward(self, nnet_input, seq_len, training=True):
+    def forward(self, nnet_input, seq_len, training=True, seq_len_host=None):
         """nnet_input [B,T,D] f32 cuda (zero padded), seq_len [B] int32 cuda.
+        seq_len_host: the same lengths on the host (numpy / CPU tensor / sequence; every batch assembler has them) -- lets the
+        recurrence skip, per 16-utterance group, the scan steps in which no utterance of the group is live
+        (lcb_lstm_rec_fwd_range_hl); None = every group runs all T steps.  The result is the same either way.
         Returns the encoder output [T*B, 2P] fp16 (time-major rows n = t*B + b)."""
         L = _lib.lib()
         c = self.cfg
@@ -472,10 +497,14 @@ class BLSTMEncoder:
         nnet_input = nnet_input.contiguous()
         seq_len = seq_len.to(device=self.device, dtype=torch.int32).contiguous()
         _lib.check(L.lcb_pack_input(_lib.ptr(nnet_input), _lib.ptr(ws["X0"]), B, T, D, c.Dp0, st), "lcb_pack_input")
+        ws["ready"].zero_()                         # flow-control counters (one per layer) of this pass
         ws["cfin"].zero_()                          # utterances of length 0 keep the zero initial state (bilstm.py:140-144)
         ws["mfin"].zero_()
         X = ws["X0"]
         nd = self.ndir
+        lens_host = None
+        if seq_len_host is not None:
+            lens_host = (_lib.ctypes.c_int32 * B)(*[int(v) for v in (seq_len_host.tolist() if hasattr(seq_len_host, "tolist") else seq_len_host)])
         H4n = nd * 4 * c.Hp                         # gate columns that exist: both directions' or direction 0's
         side_cap = self.idle_sms(B, 0)              # SMs the forward recurrence clusters leave free
         for i in range(c.num_layers):
@@ -488,12 +517,12 @@ class BLSTMEncoder:
             W16, bias, G = self._bf[("Wx16", i)], self.params.w("L%d/bias" % i), ws["G"]
             kin = X.shape[1] if (i == 0 or nd == 2) else c.P     # uni: layers 1.. read the forward half of the layer below only
 
-            def rec(s0, s1):
-                _lib.check(L.lcb_lstm_rec_fwd_range(_lib.ptr(G), _lib.ptr(self._bf[("fold16", i)]), _lib.ptr(peep), _lib.ptr(seq_len),
-                                                    _lib.ptr(ws["M"][i]), _lib.ptr(gates), _lib.ptr(cst),
-                                                    _lib.ptr(ws["cfin"]) if last else None, _lib.ptr(ws["mfin"]) if last else None,
-                                                    T, B, c.Hp, nd, c.forget_bias, s0, s1, _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(),
-                                                    _lib.stream_ptr()), "lcb_lstm_rec_fwd_range")
+            def rec(s0, s1, ready=None):
+                _lib.check(L.lcb_lstm_rec_fwd_range_hl(_lib.ptr(G), _lib.ptr(self._bf[("fold16", i)]), _lib.ptr(peep), _lib.ptr(seq_len),
+                                                       lens_host, _lib.ptr(ready), _lib.ptr(ws["M"][i]), _lib.ptr(gates), _lib.ptr(cst),
+                                                       _lib.ptr(ws["cfin"]) if last else None, _lib.ptr(ws["mfin"]) if last else None,
+                                                       T, B, c.Hp, nd, c.forget_bias, s0, s1, _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(),
+                                                       _lib.stream_ptr()), "lcb_lstm_rec_fwd_range_hl")
 
             Hout = ws["Hout"][i]
             # h = m * W_proj with DropoutWrapper(output_keep_prob) (bilstm.py:128,137) applied in the GEMM epilogue: element
@@ -508,10 +537,12 @@ class BLSTMEncoder:
                          out=Hout[r0:r1, d * c.P:(d + 1) * c.P],
                          dropout=(drop + (r0 * 2 * c.P + d * c.P,)) if drop else None)
 
-            # scan-step boundaries of the recurrence launches (training, side stream available, long enough sequences)
+            # scan-step boundaries of the recurrence launches / projection chunks (training, side stream available, long enough
+            # sequences)
             bounds = []
+            flow = training and self.pstream is not None and self.fwd_flow_control
             if training and self.pstream is not None:
-                for fr in self.head_fracs:
+                for fr in (self.flow_fracs if flow else (self.head_fracs_tight if side_cap <= self.tight_side_sms else self.head_fracs)):
                     b_ = int(math.ceil(fr * T))
                     if b_ >= 16 and b_ <= T - 16 and (not bounds or b_ >= bounds[-1] + 16):
                         bounds.append(b_)
@@ -539,6 +570,9 @@ class BLSTMEncoder:
                         gemm(X[r0:r1], W16[H4:], 0, 0, out=G[r0:r1, H4:], bias=bias[H4:])
 
                 proj(0, bounds[0])
+                ready = ws["ready"][i:i + 1] if flow else None
+                if flow:
+                    _lib.check(L.lcb_store_i32(_lib.ptr(ready), bounds[0], _lib.stream_ptr()), "lcb_store_i32")
                 head_done = torch.cuda.Event()
                 head_done.record(main)
                 chunk_ready = []
@@ -546,11 +580,18 @@ class BLSTMEncoder:
                     self.pstream.wait_event(head_done)
                     for k in range(1, len(bounds)):
                         proj(bounds[k - 1], bounds[k])
+                        if flow:
+                            _lib.check(L.lcb_store_i32(_lib.ptr(ready), bounds[k], _lib.stream_ptr()), "lcb_store_i32")
                         ev = torch.cuda.Event()
                         ev.record(self.pstream)
                         chunk_ready.append(ev)
                 prev = 0
-                for k, b_ in enumerate(bounds):
+                if flow:
+                    # every chunk is enqueued: ONE launch over the whole scan, its prefetch warps wait for the counter
+                    rec(0, T, ready)
+                    main.wait_event(chunk_ready[-1])
+                    hproj(0, T)
+                for k, b_ in enumerate(bounds if not flow else []):
                     if k > 0:
                         main.wait_event(chunk_ready[k - 1])
                     rec(prev, b_)
@@ -561,7 +602,9 @@ class BLSTMEncoder:
                             self.pstream.wait_event(rec_done)
                             hproj(prev, b_)
                     prev = b_
-                if self.overlap_hproj:
+                if flow:
+                    pass
+                elif self.overlap_hproj:
                     hproj(bounds[-2], T)
                     hp_done = torch.cuda.Event()
                     hp_done.record(self.pstream)

@@ -51,6 +51,7 @@ __device__ int g_rec_prof_steps = 0;
 constexpr int REC_BG = 16;        // utterances per cluster
 constexpr int REC_GCOLS = 128;    // fp32 row of a staged G tile (dense TMA box: the 4-way bank conflict of its 8 reads per thread and step is off the chain)
 constexpr int REC_SG = 8;         // G prefetch ring depth
+constexpr int REC_MAXGRP = 32;    // 16-utterance groups whose longest utterance travels in the kernel parameters (B <= 512; beyond: no early exit)
 constexpr int REC_TMEM_ACC = 256; // first accumulator column (weights occupy [0, Hp/2) forward, [0, 64*MB) backward)
 
 struct RecFwdParams {
@@ -69,6 +70,10 @@ struct RecFwdParams {
     unsigned char* xch;           // v2: L2 exchange scratch [clusters][2][NC][slice] (nullptr: DSMEM copies)
     int s_begin, s_end;           // v2: scan steps [s_begin, s_end) of this launch (t = s forward, T-1-s backward direction);
                                   // a launch with s_begin > 0 resumes from the saved cst / Mout of step s_begin - 1
+    int n_paired;                 // clusters (per direction) that hold TWO 16-utterance groups: cluster c < n_paired holds groups
+                                  // 2c and 2c+1, cluster c >= n_paired holds group n_paired + c alone (fwd_layout())
+    int gmax[REC_MAXGRP];         // longest utterance of each 16-utterance group (T when the caller gave no host-side lengths)
+    const int* ready;             // nullable: device word = number of leading scan steps whose G rows exist (see the loader warp)
 };
 
 struct RecBwdParams {
@@ -194,11 +199,43 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
     uint64_t* mbar_turn = reinterpret_cast<uint64_t*>(tmem_slot + 2);           // [2]
 
     const uint32_t cta = cluster_ctarank();
-    const int cid = (int)cluster_id_x();
+    // cluster index from blockIdx (NOT %clusterid: the output of an asm statement is not provably warp-uniform, and dir / cg feed
+    // the control flow around the MMA issue through the active ranges below)
+    const int cid = (int)(blockIdx.x / (unsigned)NC);
     const int dir = p.ndir == 2 ? (cid & 1) : 0, cg = p.ndir == 2 ? (cid >> 1) : cid;   // direction, utterance group of the cluster
-    const int bg = cg * NSG + sg;
-    const int b0 = bg * BG;                            // first utterance of this sub-group
+    // utterance groups of this cluster (fwd_layout(): the first n_paired clusters of a direction hold two groups, the others one)
+    const int npair = NSG == 2 ? p.n_paired : 0;
+    auto group_of = [&](int g2) { return cg < npair ? 2 * cg + g2 : (g2 == 0 ? npair + cg : -1); };
+    const int bg = group_of(sg);
+    const int b0 = bg >= 0 ? bg * BG : B;              // first utterance of this sub-group (B: none)
     const size_t ld2 = (size_t)2 * Hp;
+    // Scan steps this launch covers, and the part of them in which a group has a live utterance at all: the forward direction of
+    // a group whose longest utterance has Lm frames is finished after scan step Lm - 1, its backward direction (descending t,
+    // mask t < len) only starts at scan step T - Lm.  Outside that range every role of the sub-group skips the step -- no weight
+    // pass, no exchange -- and the compute warps just write the zero rows of m; the roles below run the LOCAL range [S0, S0 + S).
+    const int LS0 = p.s_begin, LS = p.s_end - p.s_begin;
+    // (the issue loop below must stay PROVABLY warp-uniform, or the compiler wraps every tcgen05.mma in an ELECT / R2UR waterfall
+    // again -- 86 instead of 29 cycles per MMA, measured)
+    auto active_range = [&](int g2, int& a0, int& a1) {      // active steps of sub-group g2, as offsets into [LS0, LS0 + LS)
+        const int gr = group_of(g2);
+        // the group's longest utterance comes from the KERNEL PARAMETERS (host-computed, lcb_lstm_rec_fwd_range_hl): a value
+        // loaded from memory -- even from a uniform address, even laundered through a shuffle -- is not provably warp-uniform,
+        // and every range below feeds the control flow around the MMA issue
+        // (static indices only: a dynamically indexed by-value parameter array is copied to local memory first)
+        int Lm = gr < 0 ? 0 : T;
+#pragma unroll
+        for (int k = 0; k < REC_MAXGRP; ++k)
+            if (k == gr) Lm = min(max(p.gmax[k], 0), T);
+        const int lo = dir ? T - Lm : 0, hi = dir ? T : Lm;
+        a0 = min(max(lo - LS0, 0), LS);
+        a1 = max(min(max(hi - LS0, 0), LS), a0);
+    };
+    int actA0, actA1, actB0 = 0, actB1 = 0;                  // sub-group 0, sub-group 1
+    active_range(0, actA0, actA1);
+    if (NSG == 2) active_range(1, actB0, actB1);
+    const int act0_me = sg == 0 ? actA0 : actB0, act1_me = sg == 0 ? actA1 : actB1;
+    const int S0 = LS0 + act0_me, S = act1_me - act0_me;     // this sub-group runs scan steps S0 .. S0+S-1 (local index s = 0..S-1)
+    const int Koth = NSG == 2 ? (sg == 0 ? actB1 - actB0 : actA1 - actA0) : 0;   // weight passes of the other sub-group (turn taking)
 
     if (role == 0 && rw == 0 && lane == 0) {
         mbar_init(mbar_mma, NIW);
@@ -210,7 +247,6 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
         fence_mbar_init();
     }
     if (warp == NSG * NCW) tmem_alloc<512>(tmem_slot);
-    const int S0 = p.s_begin, S = p.s_end - p.s_begin;      // this launch runs scan steps S0 .. S0+S-1 (local index s = 0..S-1)
     {   // operand buffer 0 := m of the step before S0 (0 for a fresh start; a padded frame's saved m is 0 as well); the
         // whole block fills the buffers of every sub-group
         const int n16 = (int)(2 * OPB / 16);
@@ -218,20 +254,22 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
             uint4* bz = reinterpret_cast<uint4*>(smem_all + (size_t)g2 * Cfg::sg_bytes(KB));
             for (int i = threadIdx.x; i < n16; i += blockDim.x) bz[i] = make_uint4(0u, 0u, 0u, 0u);
         }
-        if (S0 > 0) {
-            __syncthreads();
-            const int tp = dir ? (T - S0) : (S0 - 1);
-            const int pieces = (Hp >> 3) * BG;               // 16-byte pieces: (unit chunk of 8, utterance)
-            for (int g2 = 0; g2 < NSG; ++g2) {
-                unsigned char* Bs2 = smem_all + (size_t)g2 * Cfg::sg_bytes(KB);
-                const int b02 = (cg * NSG + g2) * BG;
-                for (int i = threadIdx.x; i < pieces; i += blockDim.x) {
-                    const int u = i % BG, ch = i / BG;
-                    if (b02 + u < B) {
-                        const uint4 v = *reinterpret_cast<const uint4*>(p.Mout + ((size_t)tp * B + b02 + u) * ld2 + (size_t)dir * Hp + ch * 8);
-                        *reinterpret_cast<uint4*>(Bs2 + ((size_t)ch * NUB + (u >> 3)) * 128 + (u & 7) * 16) = v;
-                    }
-                }
+        __syncthreads();
+        const int pieces = (Hp >> 3) * BG;               // 16-byte pieces: (unit chunk of 8, utterance)
+        // (one flat, predicated loop: branches on the computed ranges around this thread-divergent loop cost the compiler its
+        // proof that the issuer warps below are converged)
+        for (int i = threadIdx.x; i < NSG * pieces; i += blockDim.x) {
+            const int g2 = i / pieces, i2 = i - g2 * pieces;
+            const int u = i2 % BG, ch = i2 / BG;
+            const int S02 = LS0 + (g2 == 0 ? actA0 : actB0), n2 = g2 == 0 ? actA1 - actA0 : actB1 - actB0;
+            const int tp = dir ? (T - S02) : (S02 - 1);
+            const int gr2 = group_of(g2), b2 = gr2 * BG + u;
+            // only a frame that was live for the utterance carries state (a row past its end is zero -- and may be one this
+            // very launch is still zero-filling)
+            const bool have = S02 > 0 && n2 > 0 && gr2 >= 0 && b2 < B && tp < __ldg(p.lens + (gr2 >= 0 && b2 < B ? b2 : 0));
+            if (have) {
+                const uint4 v = *reinterpret_cast<const uint4*>(p.Mout + ((size_t)tp * B + b2) * ld2 + (size_t)dir * Hp + ch * 8);
+                *reinterpret_cast<uint4*>(smem_all + (size_t)g2 * Cfg::sg_bytes(KB) + ((size_t)ch * NUB + (u >> 3)) * 128 + (u & 7) * 16) = v;
             }
         }
     }
@@ -262,7 +300,6 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
     const int prof_steps = g_rec_prof_steps & 0xffff;
     const int nvalid = (B - b0) < BG ? (B - b0) : BG;           // utterances of this group that exist
     if (nvalid <= 0) role = 4;                                  // an empty second sub-group (in every CTA of the cluster alike) idles
-    const bool paired = NSG == 2 && cg * NSG * BG + BG < B;   // both sub-groups of this cluster hold utterances
 
     bool ok = true;
     if (role == 2) {
@@ -271,6 +308,7 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
         // 512-byte bulk copy per utterance: 16 (paired: 32) operations per step in the SM's TMA queue, in a burst right when the
         // exchange warp issues the bulk store + multicast of m_t that the serial chain waits for -- measured 1.36 -> 1.27 us per
         // step (paired groups), 1.15 -> 1.09 (a group alone), profiles/r02_rec_g_tile_tma.txt
+        int ready_seen = 0;
         for (int s = 0; s < S; ++s) {
             const int stage = s % SG;
             if (s >= SG) {              // wait until the compute warps drained this stage (step s - SG)
@@ -279,6 +317,30 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
                 if (!ok) break;
             }
             const int t = dir ? (T - 1 - (S0 + s)) : (S0 + s);
+            // Flow control against the projection GEMMs that still run beside this launch (another stream, the SMs the clusters
+            // leave idle): *ready = number of leading scan steps whose G rows are written (frames [0, n) of the forward, [T-n, T)
+            // of the backward direction), advanced by lcb_store_i32 behind every projected chunk.  ONE launch then covers the
+            // whole scan -- clusters are not re-synchronised at chunk boundaries, which matters once groups of different
+            // length run at different speeds -- and only this prefetch warp, 8 steps ahead of the chain, ever waits.
+            if (p.ready && S0 + s >= ready_seen) {
+                if (lane == 0) {
+                    uint64_t t0 = 0; uint32_t spins = 0;
+                    int v;
+                    while ((v = ld_acquire_gpu_s32(p.ready)) <= S0 + s) {
+                        __nanosleep(100);
+                        if ((++spins & 0xff) == 0) {
+                            const uint64_t now = globaltimer_ns();
+                            if (t0 == 0) t0 = now;
+                            if (now - t0 > LCB_WAIT_TIMEOUT_NS || dev_has_error()) { dev_set_error(DEV_ERR_MBAR_TIMEOUT); ok = false; break; }
+                        }
+                    }
+                    ready_seen = v;
+                    fence_proxy_async_all();              // generic-proxy acquire -> the async-proxy (TMA) read below
+                }
+                ready_seen = __shfl_sync(0xffffffffu, ready_seen, 0);
+                ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+                if (!ok) break;
+            }
             if (lane == 0) mbar_arrive_expect_tx(&mbar_g[stage], (uint32_t)(BG * 512));     // the whole box counts (rows past B are zero-filled)
             if (lane == 0) tma_load_3d(Gsm + (size_t)stage * BG * REC_GCOLS, &tmG, &mbar_g[stage], dir * 4 * Hp + (int)cta * 128, b0, t);
         }
@@ -332,8 +394,11 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
             // profiles/r01_rec_experiments_lock_stasync.txt).  The turn is awaited BEFORE the operand: in steady state the other
             // sub-group's pass ran while this one's exchange was in flight, and a try_wait on an already completed phase still
             // costs ~100 cycles -- behind the operand wait they sat on the serial chain of every step.
-            if (ok && paired) {                                               // pass n of sub-group 0 follows pass n-1 of sub-group 1,
-                if (sg == 1 || s > 0) ok = mbar_wait(&mbar_turn[sg], (uint32_t)((sg ? s : s - 1) & 1));   // pass n of sub-group 1 follows pass n of sub-group 0
+            // Passes are counted per sub-group from its own first step: pass n of sub-group 0 follows pass n-1 of sub-group 1,
+            // pass n of sub-group 1 follows pass n of sub-group 0 -- as long as the other sub-group HAS that pass (a group with
+            // shorter utterances retires early and its partner then runs alone).  Waits and arrivals pair up one to one.
+            if (NSG == 2 && ok) {
+                if (sg == 0 ? (s >= 1 && s - 1 < Koth) : (s < Koth)) ok = mbar_wait(&mbar_turn[sg], (uint32_t)((sg ? s : s - 1) & 1));
             }
             REC_PROBE(4);
             if (ok && s > 0) ok = mbar_wait(&mbar_op[par], (uint32_t)(((s - 1) >> 1) & 1));
@@ -341,18 +406,18 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
             REC_PROBE(1);
             tc_fence_after();
             const uint32_t b_lo_s = b_lo0 + ((par * OPB) >> 4);
-            if (S0 + s > 0) {                                            // m_{-1} = 0: scan step 0 is the x-part alone
-                // issuer 0 accumulates onto the G tile; the others start their accumulator with a non-accumulating MMA
-                if (iw > 0) umma_f16_ts_elect<false>(d_tmem, tmem_base + 8 * iw, b_lo_s + (2 * NUB * 128 / 16) * iw, b_hi, idesc, leader);
-                else umma_f16_ts_elect<true>(d_tmem, tmem_base, b_lo_s, b_hi, idesc, leader);
+            // (no special case for scan step 0, whose m_{-1} = 0: operand buffer 0 starts zero-filled, so the pass adds W' * 0 --
+            // and a data-dependent branch around the issue would cost the warp-uniformity proof again)
+            // issuer 0 accumulates onto the G tile; the others start their accumulator with a non-accumulating MMA
+            if (iw > 0) umma_f16_ts_elect<false>(d_tmem, tmem_base + 8 * iw, b_lo_s + (2 * NUB * 128 / 16) * iw, b_hi, idesc, leader);
+            else umma_f16_ts_elect<true>(d_tmem, tmem_base, b_lo_s, b_hi, idesc, leader);
 #pragma unroll 4
-                for (int kk = iw + NIW; kk < nk; kk += NIW)
-                    umma_f16_ts_elect(d_tmem, tmem_base + 8 * kk, b_lo_s + (2 * NUB * 128 / 16) * kk, b_hi, idesc, leader);
-            }
+            for (int kk = iw + NIW; kk < nk; kk += NIW)
+                umma_f16_ts_elect(d_tmem, tmem_base + 8 * kk, b_lo_s + (2 * NUB * 128 / 16) * kk, b_hi, idesc, leader);
             REC_PROBE(7);
             if (leader) {
                 umma_commit(mbar_mma);
-                if (paired) mbar_arrive(&mbar_turn[sg ^ 1]);
+                if (NSG == 2 && (sg == 0 ? (s < Koth) : (s + 1 < Koth))) mbar_arrive(&mbar_turn[sg ^ 1]);
             }
             REC_PROBE(2);
         }
@@ -389,7 +454,7 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
         // a scan step moves them by one frame = B rows, backwards for the backward direction)
         const int bj0 = b0 + ub * 8 + 2 * g;
         const long long tstep = (dir ? -1LL : 1LL) * (long long)B * (long long)ld2;
-        const size_t idx0 = ((size_t)(dir ? (T - 1 - S0) : S0) * B + bj0) * ld2 + (size_t)dir * Hp + unit;
+        const size_t idx0 = ((size_t)(dir ? (T - 1 - LS0) : LS0) * B + bj0) * ld2 + (size_t)dir * Hp + unit;
         const bool save = p.gates != nullptr;
         __half* mo_p = p.Mout + idx0;
         uint2* ga_p = (save ? p.gates : reinterpret_cast<uint2*>(p.Mout)) + idx0;        // (never dereferenced unless save)
@@ -428,7 +493,17 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
             tmem_st_16x256b_x1(t_addr + BG, zz);
             tmem_st_16x256b_x1(t_addr + BG + (16u << 16), zz);
         }
-        load_acc(0);
+        // steps of this launch before the group's first live frame (backward direction of a group of short utterances): m = 0
+        auto zero_steps = [&](int n) {
+            for (int i = 0; i < n; ++i) {
+                if (!pad_j[0]) *mo_p = __float2half_rn(0.f);
+                if (!pad_j[1]) mo_p[ld2] = __float2half_rn(0.f);
+                mo_p += tstep;
+            }
+            ga_p += (long long)n * tstep; cs_p += (long long)n * tstep;
+        };
+        zero_steps(act0_me);
+        if (S > 0) load_acc(0);
 
         for (int s = 0; s < S; ++s) {
             const int t = dir ? (T - 1 - (S0 + s)) : (S0 + s);
@@ -511,6 +586,7 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
             mo_p += tstep; ga_p += tstep; cs_p += tstep;
             REC_PROBE(14);
         }
+        zero_steps(LS - act1_me);                 // ... and behind its last one (forward direction)
     }
     tc_fence_before();
     cluster_sync_all();          // nobody leaves while multicast traffic addressed to it may still be in flight
@@ -1287,13 +1363,29 @@ static int max_clusters(K kern, int threads, size_t smem, int nc) {
 
 // clusters of one 16-utterance group each that the device keeps resident at once (queried once per cluster size)
 static int resident_clusters(int nc, int which) {
-    static int cap[2][17];
+    static int cap[3][17];
     if (cap[which][nc] == 0) {
-        int n = which ? max_clusters(lstm_rec_bwd2_kernel<16>, RecBwd2Cfg<16>::THREADS, RecBwd2Cfg<16>::smem_bytes(nc), nc)
+        int n = which == 2 ? max_clusters(lstm_rec_fwd2_kernel<16, 2>, RecFwd2Cfg<16, 2>::THREADS, RecFwd2Cfg<16, 2>::smem_bytes(nc * 32 / 64), nc)
+              : which ? max_clusters(lstm_rec_bwd2_kernel<16>, RecBwd2Cfg<16>::THREADS, RecBwd2Cfg<16>::smem_bytes(nc), nc)
                       : max_clusters(lstm_rec_fwd2_kernel<16, 1>, RecFwd2Cfg<16>::THREADS, RecFwd2Cfg<16>::smem_bytes(nc * 32 / 64), nc);
         cap[which][nc] = n > 0 ? n : 1;
     }
     return cap[which][nc];
+}
+
+// Forward layout: ncd clusters per direction, the first n_paired of them hold two 16-utterance groups (stepping independently,
+// sharing the resident weights: ~1.24 us per scan step), the others one group alone (~1.08 us).  As many clusters as the device
+// keeps resident are used (7 of 16 CTAs on a B200: 3 per direction); with length-sorted batches the paired clusters get the
+// lowest group indices = the shortest utterances, whose sub-groups retire early (see the kernel), so the cluster that carries
+// two groups and the one that carries the longest group alone finish about together (profiles/r02_rec_fwd_layout.txt).
+static int g_fwd_layout_mode = 0;         // debug (lcb_debug_fwd_layout): 1 = pair everything as the round-1 kernels did
+static void fwd_layout(int B, int nc, int ndir, int& ncd, int& n_paired) {
+    const int groups = (B + 15) / 16;
+    if (g_fwd_layout_mode == 1 && ndir * groups > resident_clusters(nc, 0)) { ncd = (groups + 1) / 2; n_paired = groups - ncd; return; }
+    const int cap = resident_clusters(nc, 0) / ndir > 0 ? resident_clusters(nc, 0) / ndir : 1;   // resident clusters per direction
+    if (groups <= cap) { ncd = groups; n_paired = 0; }
+    else if (groups <= 2 * cap) { ncd = cap; n_paired = groups - cap; }
+    else { ncd = (groups + 1) / 2; n_paired = groups - ncd; }                                   // several waves: pair everything
 }
 
 // Utterances per cluster: 16 while every 16-utterance group gets its own resident cluster (shortest per-step chain), 32
@@ -1316,13 +1408,26 @@ extern "C" int lcb_debug_rec_profile(long long* buf, int steps)
     return LCB_OK;
 }
 
+// one-word store on a stream (the "frames projected so far" counter of lcb_lstm_rec_fwd_range_hl)
+__global__ void store_i32_kernel(int* dst, int v) { *dst = v; __threadfence(); }
+extern "C" int lcb_store_i32(int32_t* dst, int32_t value, void* stream)
+{
+    if (!dst) return LCB_ERR_NULL_POINTER;
+    store_i32_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dst, value);
+    lcb::g_launches += 1;
+    return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
+}
+
+// debug: forward cluster layout override (0 = automatic, 1 = two groups in every cluster whenever one group per cluster does not fit)
+extern "C" int lcb_debug_fwd_layout(int mode) { lcb::g_fwd_layout_mode = mode; return LCB_OK; }
+
 // how many clusters of the forward (which = 0) / backward (which = 1) kernel (one 16-utterance group per cluster) the
 // device can keep resident at once
 extern "C" int lcb_lstm_rec_max_clusters(int Hp, int which)
 {
     int nc;
     if (!rec_plan(Hp, nc)) return LCB_ERR_UNSUPPORTED;
-    return resident_clusters(nc, which ? 1 : 0);
+    return resident_clusters(nc, which == 2 ? 2 : (which ? 1 : 0));        // 2: the forward kernel with two sub-groups per cluster
 }
 
 extern "C" int lcb_lstm_rec_config(int Hp, int* units_per_cta_div32, int* cluster_size)
@@ -1340,7 +1445,12 @@ extern "C" int lcb_lstm_rec_grid(int B, int Hp, int num_dirs, int which)
 {
     int nc;
     if (!rec_plan(Hp, nc) || B <= 0 || num_dirs < 1 || num_dirs > 2) return LCB_ERR_UNSUPPORTED;
-    const int bgs = choose_bg(B, nc, num_dirs, which ? 1 : 0);
+    if (!which) {
+        int ncd, npair;
+        fwd_layout(B, nc, num_dirs, ncd, npair);
+        return num_dirs * ncd * nc;
+    }
+    const int bgs = choose_bg(B, nc, num_dirs, 1);
     return num_dirs * ((B + bgs - 1) / bgs) * nc;
 }
 
@@ -1367,6 +1477,16 @@ extern "C" int lcb_lstm_rec_fwd_range(const float* G, const void* WfoldT, const 
                                       int T, int B, int Hp, int num_dirs, float forget_bias, int s_begin, int s_end,
                                       void* workspace, size_t workspace_bytes, void* stream)
 {
+    return lcb_lstm_rec_fwd_range_hl(G, WfoldT, peep, lens, nullptr, nullptr, Mout, gates, cst, cfin, mfin, T, B, Hp, num_dirs, forget_bias,
+                                     s_begin, s_end, workspace, workspace_bytes, stream);
+}
+
+extern "C" int lcb_lstm_rec_fwd_range_hl(const float* G, const void* WfoldT, const float* peep, const int32_t* lens,
+                                         const int32_t* lens_host, const int32_t* ready_steps,
+                                         void* Mout, void* gates, float* cst, float* cfin, float* mfin,
+                                         int T, int B, int Hp, int num_dirs, float forget_bias, int s_begin, int s_end,
+                                         void* workspace, size_t workspace_bytes, void* stream)
+{
     if (!G || !WfoldT || !lens || !Mout || !workspace) return LCB_ERR_NULL_POINTER;
     if (T <= 0 || B <= 0 || num_dirs < 1 || num_dirs > 2) return LCB_ERR_BAD_SHAPE;
     if (s_begin < 0 || s_end > T || s_begin >= s_end) return LCB_ERR_BAD_SHAPE;
@@ -1381,16 +1501,27 @@ extern "C" int lcb_lstm_rec_fwd_range(const float* G, const void* WfoldT, const 
     p.gates = (uint2*)gates; p.cst = cst; p.cfin = cfin; p.mfin = mfin;
     p.T = T; p.B = B; p.Hp = Hp; p.NC = nc; p.ndir = num_dirs; p.forget_bias = forget_bias; p.s_begin = s_begin; p.s_end = s_end;
     p.xch = (unsigned char*)workspace;
-    const int bgs = choose_bg(B, nc, num_dirs, 0);
-    const int ncl = num_dirs * ((B + bgs - 1) / bgs);
+    int ncd, npair;
+    fwd_layout(B, nc, num_dirs, ncd, npair);
+    p.n_paired = npair;
+    p.ready = ready_steps;
+    for (int g = 0; g < REC_MAXGRP; ++g) {
+        int m = T;
+        if (lens_host && g * 16 < B) {
+            m = 0;
+            for (int u = g * 16; u < B && u < g * 16 + 16; ++u) m = lens_host[u] > m ? lens_host[u] : m;
+        }
+        p.gmax[g] = m;
+    }
+    const int ncl = num_dirs * ncd;
     cudaStream_t st = (cudaStream_t)stream;
     // G as a 3-D tensor [T][B][8Hp] fp32, box = 128 packed gate columns x 16 utterances of one frame (dense, no swizzle)
     CUtensorMap tm;
     if (!make_tmap_3d(&tm, true, G, (uint64_t)8 * Hp, (uint64_t)B, (uint64_t)T, (uint64_t)8 * Hp * 4, (uint64_t)B * 8 * Hp * 4,
                       128, 16u, 1, false)) return LCB_ERR_CUDA;
-    if (bgs == 16)
+    if (npair == 0)
         return launch_cluster(lstm_rec_fwd2_kernel<16, 1>, ncl * nc, RecFwd2Cfg<16>::THREADS, RecFwd2Cfg<16>::smem_bytes(Hp / 64), nc, st, p, tm);
-    // too many 16-utterance groups for one wave of clusters: two of them per cluster, stepping independently
+    // too many 16-utterance groups for one wave of clusters: two of them in some (or all) clusters, stepping independently
     return launch_cluster(lstm_rec_fwd2_kernel<16, 2>, ncl * nc, RecFwd2Cfg<16, 2>::THREADS, RecFwd2Cfg<16, 2>::smem_bytes(Hp / 64), nc, st, p, tm);
 }
 

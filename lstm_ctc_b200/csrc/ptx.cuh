@@ -48,6 +48,11 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+__device__ __forceinline__ int ld_acquire_gpu_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile(

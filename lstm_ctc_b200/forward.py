@@ -125,7 +125,7 @@ class BatchedForward:
             lc, rc, sub = self.ctx
             x, ln = splice_subsample_device(x, ln, lc, rc, sub)
             lens_out = lens // max(sub, 1)
-        logits = m.forward_logits(x, ln, training=False)
+        logits = m.forward_logits(x, ln, training=False, seq_len_host=lens_out)
         if self.apply_softmax:
             out = m.enc._arena.flat("posterior", logits.numel(), torch.float32).view(logits.shape)
             softmax_rows(logits, self.smooth, apply_log=self.apply_log, log_prior=self.prior,

@@ -169,13 +169,13 @@ class _Graph:
         if "train" in wanted:
             tc = self.train_cfg
             self.reducer.begin_step()
-            loss_sum, _ = m.loss_and_grad(x, lens, y, bucket_ready=self.reducer.bucket_ready)
+            loss_sum, _ = m.loss_and_grad(x, lens, y, bucket_ready=self.reducer.bucket_ready, seq_len_host=seq_len_host)
             self.reducer.finish()
             m.optimizer_step(tc["optimizer"], tc["learn_rate"], tc["clip_norm"], tc["l2_decay_weight"])
             out["train"] = None
             logits = m._out_ws(x.shape[1], x.shape[0])["logits"]
         else:
-            logits = m.forward_logits(x, lens, training=False)
+            logits = m.forward_logits(x, lens, training=False, seq_len_host=seq_len_host)
             loss, _ = m.ctc(logits, y, lens)
             loss_sum = loss.sum()
         reg = m.reg_loss if "train" in wanted else m.label_smoothing(logits)
@@ -222,7 +222,7 @@ class _Graph:
             x, lens = splice_subsample_device(x, lens, lc, rc, sub)
             batch = dict(batch, sequence_length=int(batch["sequence_length"]) // max(sub, 1))
         T = x.shape[1]
-        logits = m.forward_logits(x, lens, training=False)[0]                       # squeeze, graph.py:234
+        logits = m.forward_logits(x, lens, training=False, seq_len_host=[int(batch["sequence_length"])])[0]   # squeeze, graph.py:234
         out = {"filename": batch["filename"], "sequence_length": batch["sequence_length"]}
         if "logits" in wanted:
             out["logits"] = logits.cpu().numpy()

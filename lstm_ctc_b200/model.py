@@ -172,13 +172,13 @@ class AcousticModel:
             ws["Z"] = a.rows("Z", R, self.ldz, F32)
         return ws
 
-    def forward_logits(self, nnet_input, seq_len, training=True):
+    def forward_logits(self, nnet_input, seq_len, training=True, seq_len_host=None):
         """create_logits_blstm: returns logits [B,T,V] f32 (batch-major).  Rows past seq_len hold the
         output layer applied to a zero encoder row (bias-only / MoE(0)), like the reference."""
         L = _lib.lib()
         c = self.cfg
         self._refresh()
-        X = self.enc.forward(nnet_input, seq_len, training)
+        X = self.enc.forward(nnet_input, seq_len, training, seq_len_host=seq_len_host)
         B, T = nnet_input.shape[0], nnet_input.shape[1]
         ws = self._out_ws(T, B)
         keep = c.keep_prob if training else 1.0
@@ -245,11 +245,11 @@ class AcousticModel:
         """tf.nn.ctc_loss(..., ignore_longer_outputs_than_inputs=True) + its gradient (graph.py:109-114)."""
         return ctc_loss_grad(logits, labels, seq_len, check_labels=check_labels)
 
-    def loss_and_grad(self, nnet_input, seq_len, labels, bucket_ready=None, check_labels=True):
+    def loss_and_grad(self, nnet_input, seq_len, labels, bucket_ready=None, check_labels=True, seq_len_host=None):
         """Forward + CTC + backward for one minibatch.  Returns (sum of per-utt CTC losses as a device
         scalar, per-utt losses).  Gradients are left in params.gflat (un-clipped, no L2 yet)."""
         self.params.gflat.zero_()
-        logits = self.forward_logits(nnet_input, seq_len, training=True)
+        logits = self.forward_logits(nnet_input, seq_len, training=True, seq_len_host=seq_len_host)
         loss, dlogits = self.ctc(logits, labels, seq_len, check_labels)
         self.reg_loss = self.label_smoothing(logits, dlogits)
         self.backward(dlogits, bucket_ready)

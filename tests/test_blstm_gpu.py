@@ -121,7 +121,9 @@ def test_split_recurrence_equals_whole(cuda_dev, H, B, T):
     for fracs in ([], [0.3], [0.25, 0.5, 0.75]):
         enc = BLSTMEncoder(ModelConfig(nnet_config(cfg)), dev)
         enc.from_tf_dict(params)
+        enc.fwd_flow_control = False               # consecutive range launches (the flow-controlled single launch: next test)
         enc.head_fracs = fracs
+        enc.head_fracs_tight = fracs
         out = enc.forward(x.float().to(dev), lens.to(dev), training=True).float().clone()
         ws = enc._workspace(T, B, True)
         outs.append((out, [m.float().clone() for m in ws["M"]], [c.clone() for c in ws["cst"]], enc.encoder_state().clone()))
@@ -141,6 +143,65 @@ def test_split_recurrence_equals_whole(cuda_dev, H, B, T):
     assert torch.equal(e0, e1)
     ref, _ = oracle.blstm_forward(params, cfg, x, lens)
     out_bt = o1.view(T, B, -1).permute(1, 0, 2).cpu().double()
+    assert (out_bt - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("H,B,T,order", [(512, 64, 96, "sorted"), (512, 64, 70, "shuffled"), (512, 80, 64, "sorted"), (512, 33, 50, "shuffled"),
+                                         (320, 52, 60, "sorted"), (512, 128, 40, "sorted")])
+def test_host_lengths_skip_dead_steps(cuda_dev, H, B, T, order):
+    """lcb_lstm_rec_fwd_range_hl: with the lengths given on the host, a 16-utterance group skips the scan steps in which none of
+    its utterances is live (and B = 64 / 80 run on 2 x 3 clusters, the surplus groups paired into the first ones).  Activations,
+    zero rows past sequence_length, saved states of live frames, final states and the gradients BPTT forms from them are
+    bit-identical to the path without host lengths -- in one launch and in several, with groups that retire early, start
+    late, or are not live at all in a launch's range."""
+    from lstm_ctc_b200.blstm import BLSTMEncoder, ModelConfig
+    cfg, params, x, lens = make_case(H, H, 24, 2, B, T, True, seed=23)
+    g = torch.Generator().manual_seed(5)
+    lens = torch.randint(max(1, T // 4), T + 1, (B,), generator=g, dtype=torch.int32)
+    lens[0] = 2                                    # a whole group of very short utterances: not live in most launch ranges
+    lens[1:16] = torch.randint(1, 6, (15,), generator=g, dtype=torch.int32)
+    if order == "sorted":
+        lens = torch.sort(lens).values
+    lens[-1] = T
+    for b in range(B):
+        x[b, int(lens[b]):] = 0
+    dev = torch.device("cuda:0")
+    dX = torch.randn(T * B, 2 * H, generator=g).to(dev).bfloat16()
+    outs = []
+    # (launch structure, host lengths, flow control): range launches vs ONE launch whose prefetch warps wait for the projection
+    # chunks still running beside it (ready_steps)
+    for fracs, host, flow in (([], None, False), ([], lens, False), ([0.3, 0.6], None, False), ([0.3, 0.6], lens.numpy(), False),
+                              ([0.5], lens.tolist(), False), ([0.25, 0.5, 0.8], lens, True), ([0.2], None, True)):
+        enc = BLSTMEncoder(ModelConfig(nnet_config(cfg)), dev)
+        enc.from_tf_dict(params)
+        enc.fwd_flow_control = flow
+        enc.flow_fracs = fracs
+        enc.head_fracs = fracs
+        enc.head_fracs_tight = fracs
+        out = enc.forward(x.float().to(dev), lens.to(dev), training=True, seq_len_host=host).float().clone()
+        ws = enc._workspace(T, B, True)
+        saved = ([m.clone() for m in ws["M"]], [c.clone() for c in ws["cst"]], [q.clone() for q in ws["gates"]])
+        enc.params.gflat.zero_()
+        enc.backward(dX.clone())
+        outs.append((out, saved, enc.encoder_state().clone(), enc.params.gflat.clone()))
+    torch.cuda.synchronize()
+    from lstm_ctc_b200 import _lib
+    assert _lib.lib().lcb_device_error(1) == 0
+    valid = (torch.arange(T).unsqueeze(1) < lens.unsqueeze(0)).reshape(T * B).to(dev)      # rows n = t*B + b of live frames
+    o0, (m0, c0, q0), e0, g0 = outs[0]
+    assert o0[~valid].abs().max().item() == 0.0
+    for o, (m, c, q), e, gr in outs[1:]:
+        assert torch.equal(o, o0) and torch.equal(e, e0)
+        for a, b in zip(m, m0):
+            assert torch.equal(a, b)                                   # m: every row (zeros past the end)
+        for a, b in zip(c, c0):
+            assert torch.equal(a[valid], b[valid])
+        for a, b in zip(q, q0):
+            assert torch.equal(a[valid], b[valid])
+        # BPTT reads saved activations of live frames only; its sums run in one fixed order per launch structure
+        assert (gr - g0).abs().max().item() <= 1e-5 * g0.abs().max().item()
+    ref, _ = oracle.blstm_forward(params, cfg, x, lens)
+    out_bt = o0.view(T, B, -1).permute(1, 0, 2).cpu().double()
     assert (out_bt - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
 
 

@@ -13,7 +13,7 @@ T = int(sys.argv[1]) if len(sys.argv) > 1 else 1500
 g = torch.Generator(device="cpu").manual_seed(0)
 
 
-def run(B, lens_mode):
+def run(B, lens_mode, host_lens=False):
     N = T * B
     G = (torch.randn(N, 8 * Hp, generator=g) * 0.5).to(dev)
     fold16 = (torch.randn(8 * Hp, Hp, generator=g) * 0.03).to(dev).half()
@@ -36,16 +36,19 @@ def run(B, lens_mode):
     carry = torch.zeros(B * 2 * Hp * 2, device=dev)
     st = _lib.stream_ptr()
 
+    lens_host = (_lib.ctypes.c_int32 * B)(*[int(v) for v in lens.cpu().tolist()]) if host_lens else None
+
     def fwd():
-        _lib.check(L.lcb_lstm_rec_fwd_range(_lib.ptr(G), _lib.ptr(fold16), _lib.ptr(peep), _lib.ptr(lens), _lib.ptr(M), _lib.ptr(gates),
-                                            _lib.ptr(cst), None, None, T, B, Hp, 2, 5.0, 0, T, _lib.ptr(ws), ws.numel(), st), "fwd")
+        _lib.check(L.lcb_lstm_rec_fwd_range_hl(_lib.ptr(G), _lib.ptr(fold16), _lib.ptr(peep), _lib.ptr(lens), lens_host, _lib.ptr(M),
+                                               _lib.ptr(gates), _lib.ptr(cst), None, None, T, B, Hp, 2, 5.0, 0, T, _lib.ptr(ws), ws.numel(),
+                                               st), "fwd")
 
     def bwd():
         _lib.check(L.lcb_lstm_rec_bwd_range(_lib.ptr(dM), _lib.ptr(gates), _lib.ptr(cst), _lib.ptr(foldb), _lib.ptr(peep), _lib.ptr(lens),
                                             _lib.ptr(dG), _lib.ptr(dbias), _lib.ptr(dpeep), T, B, Hp, 2, 0, T, _lib.ptr(carry),
                                             _lib.ptr(ws), ws.numel(), st), "bwd")
 
-    out = {"B": B, "T": T, "lens": lens_mode, "grid_fwd": L.lcb_lstm_rec_grid(B, Hp, 2, 0), "grid_bwd": L.lcb_lstm_rec_grid(B, Hp, 2, 1)}
+    out = {"B": B, "T": T, "lens": lens_mode, "host_lens": host_lens, "grid_fwd": L.lcb_lstm_rec_grid(B, Hp, 2, 0), "grid_bwd": L.lcb_lstm_rec_grid(B, Hp, 2, 1)}
     for name, fn in (("fwd", fwd), ("bwd", bwd)):
         fn(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -60,6 +63,13 @@ def run(B, lens_mode):
     print(json.dumps(out), flush=True)
 
 
-for B in (16, 32, 48, 64):
+for B in (16, 48, 64):
     run(B, "full")
 run(64, "sorted_0.8T..T")
+run(64, "sorted_0.8T..T", host_lens=True)
+if hasattr(L, "lcb_debug_fwd_layout"):
+    L.lcb_debug_fwd_layout(1)
+    print("# forward layout forced to two groups per cluster (round-1 layout)")
+    run(64, "full")
+    run(64, "sorted_0.8T..T", host_lens=True)
+    L.lcb_debug_fwd_layout(0)

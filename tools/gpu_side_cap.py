@@ -1,4 +1,5 @@
-"""C3 training step time against the share of the idle SMs the side-stream GEMMs may use (power / L2 headroom of the recurrence)."""
+"""C3 training step time against the share of the idle SMs the side-stream GEMMs may use and the forward launch boundaries
+(what a forward recurrence on 96 instead of 64 SMs would leave to the projection GEMMs beside it)."""
 import sys
 import json
 import torch
@@ -14,7 +15,7 @@ x, lens, y = x_h.to(dev), lens_h.to(dev), y_h.to(dev)
 
 
 def step():
-    model.loss_and_grad(x, lens, y, check_labels=False)
+    model.loss_and_grad(x, lens, y, check_labels=False, seq_len_host=HOST[0])
     model.optimizer_step("adam", 4e-4, clip_norm=5.0, l2_decay_weight=1e-5)
 
 
@@ -30,7 +31,14 @@ def timed(n=12):
     return e0.elapsed_time(e1) / n
 
 
-combos = [(1.0, 1.0), (0.85, 0.85), (0.7, 0.7), (1.0, 0.8), (0.7, 1.0), (0.55, 0.9), (1.0, 1.0)]
-for sf, sb in combos:
-    model.enc.side_sm_scale = [sf, sb]
-    print(json.dumps({"side_sm_scale_fwd": sf, "side_sm_scale_bwd": sb, "ms_per_step": round(timed(), 3)}), flush=True)
+HOST = [lens_h]
+from lstm_ctc_b200 import _lib
+L = _lib.lib()
+combos = [("auto", 1.0), ("auto", 0.75), ("auto", 0.55), ("paired", 1.0), ("paired", 0.75), ("paired", 0.55), ("paired", 0.4), ("auto", 1.0), ("paired", 1.0)]
+for layout, sc in combos:
+    L.lcb_debug_fwd_layout(1 if layout == "paired" else 0)
+    HOST[0] = lens_h
+    model.enc.fwd_flow_control = True
+    model.enc.flow_fracs = [0.3, 0.55, 0.8]
+    model.enc.side_sm_scale = [sc, 1.0]
+    print(json.dumps({"fwd_layout": layout, "side_sm_scale_fwd": sc, "ms_per_step": round(timed(), 3), "device_error": L.lcb_device_error(0)}), flush=True)

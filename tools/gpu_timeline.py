@@ -15,7 +15,7 @@ x, lens, y = [t.to(dev) for t in bench.synth_batch(w, 777)]
 
 
 def step():
-    model.loss_and_grad(x, lens, y, check_labels=False)
+    model.loss_and_grad(x, lens, y, check_labels=False, seq_len_host=lens.cpu())
     model.optimizer_step("adam", 4e-4, clip_norm=5.0, l2_decay_weight=1e-5)
 
 
