@@ -12,8 +12,9 @@ How it runs: on the SAME cluster-persistent kernels as the BiLSTM, as a BiLSTM w
 reads their output -- are zero.  That state is exactly invariant under training: a zero backward cell emits h = m * 0 = 0, every
 gradient that reaches it is multiplied by a zero weight, and the gradients of the zero weights are products with the zero
 activations, so L2, clipping and SGD / Momentum / Adam all leave them at 0.0 (asserted by tests/test_lstm_uni_gpu.py).  The
-price is the bidirectional step time for a uni-directional model; the variables, checkpoints and gradients the caller sees are
-the uni-directional ones, under the names TF gives them (drnn{i}/lstm_cell/{kernel,bias,w_*_diag,projection/kernel})."""
+recurrence kernels run in their native uni-directional mode (num_dirs = 1: only direction-0 clusters and column halves), so the
+zero cells cost no recurrence time; the variables, checkpoints and gradients the caller sees are the uni-directional ones, under
+the names TF gives them (drnn{i}/lstm_cell/{kernel,bias,w_*_diag,projection/kernel})."""
 import math
 from typing import Dict
 

@@ -1,6 +1,4 @@
 mkdir -p gpurun_out
-timeout 1700 python -m pytest tests -x -q -m gpu 2>&1 | tail -5 > gpurun_out/r02_pytest_gpu.txt; cat gpurun_out/r02_pytest_gpu.txt
-python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_c3_1gpu.json 2> gpurun_out/r02_bench_c3_1gpu.err; python -c "
-import json; d=json.load(open('gpurun_out/r02_bench_c3_1gpu.json')); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['clocks'], {k:(v['ms_total']) for k,v in d['kernels'].items()}); print(d['roofline']['us_per_time_step'], d['config'])"; tail -3 gpurun_out/r02_bench_c3_1gpu.err
-python __graft_entry__.py 2>&1 | tail -2; python -c "
-import __graft_entry__ as g; g.smoke(); print('smoke ok')"
+python tools/bench_infer.py > gpurun_out/r02_bench_c5_infer.json 2> gpurun_out/r02_bench_c5_infer.err; tail -c 1500 gpurun_out/r02_bench_c5_infer.json; tail -3 gpurun_out/r02_bench_c5_infer.err
+for wl in c1 c2; do python bench.py --workload $wl --steps 20 --warmup 5 --no-cpu-baseline --no-ctc > gpurun_out/r02_bench_$wl.json 2> gpurun_out/r02_bench_$wl.err; python -c "
+import json; d=json.load(open('gpurun_out/r02_bench_$wl.json')); print('$wl', d['ms_per_step'], d['value'], d['e2e']['value'])"; done
