@@ -193,6 +193,17 @@ int lcb_lstm_rec_bwd_range(const float* dM, const void* gates, const float* cst,
                            const int32_t* lens, void* dG, float* dbias, float* dpeep,
                            int T, int B, int Hp, int num_dirs, int s_begin, int s_end, float* carry,
                            void* workspace, size_t workspace_bytes, void* stream);
+/* Same, publishing its progress: word (cluster, sub-group, CTA) of `progress` (lcb_lstm_rec_bwd_progress_words words, zeroed by the
+ * caller before the launch; Hp = 512 only) = number of leading scan steps whose dG rows that CTA has written.  A caller that wants
+ * the rows of frames final in both directions after scan step s -- [T-s, s) -- while the launch is still running enqueues
+ * lcb_wait_progress(progress, words, s, other_stream) in front of the GEMMs that read them: ONE BPTT launch per layer instead of
+ * one per release point.  The launch itself never waits on anything, so a serialised execution order cannot deadlock. */
+int lcb_lstm_rec_bwd_range_pg(const float* dM, const void* gates, const float* cst, const void* Wfold, const float* peep,
+                              const int32_t* lens, void* dG, float* dbias, float* dpeep,
+                              int T, int B, int Hp, int num_dirs, int s_begin, int s_end, float* carry, int32_t* progress,
+                              void* workspace, size_t workspace_bytes, void* stream);
+int lcb_lstm_rec_bwd_progress_words(int B, int Hp, int num_dirs);
+int lcb_wait_progress(const int32_t* progress, int n, int target, void* stream);
 int lcb_lstm_rec_bwd_can_split(int Hp);
 
 /* ---- HBM-bound helpers -----------------------------------------------------------------

@@ -78,6 +78,9 @@ _SIGS = {
     "lcb_lstm_rec_fwd_range_hl": (c_int, [c_void_p] * 11 + [c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "lcb_lstm_rec_bwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "lcb_lstm_rec_bwd_range": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "lcb_lstm_rec_bwd_range_pg": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "lcb_lstm_rec_bwd_progress_words": (c_int, [c_int, c_int, c_int]),
+    "lcb_wait_progress": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "lcb_lstm_rec_bwd_can_split": (c_int, [c_int]),
     "lcb_pack_input": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "lcb_cast_f32_16": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p]),

@@ -234,6 +234,10 @@ class BLSTMEncoder:
         # "early rows").  Empty: one launch.
         self.bwd_early_fracs = [0.67, 0.85]
         self.l0_released = True        # layer 0's frame-sum gradients over released frames
+        # BPTT as ONE launch per layer that publishes its progress (lcb_lstm_rec_bwd_range_pg); the early-rows GEMMs wait for the
+        # release points on their own stream (lcb_wait_progress) instead of following a launch boundary.  False: one launch per
+        # range, as in round 1 (bit-identical results either way)
+        self.bwd_progress = True
         self.xstream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None   # early rows of dX / dM
         # share of the SMs a recurrence launch leaves idle that the GEMMs beside it may occupy (forward, BPTT): < 1 trades GEMM
         # time (hidden under the recurrence) for power and L2 headroom of the latency-bound clusters (tools/gpu_side_cap.py)
@@ -457,6 +461,8 @@ class BLSTMEncoder:
             ws["Xbf"] = [a.flat("Xbf%d" % k, N * max(c.Dp0, 2 * c.P), BF16) for k in range(2)]   # bf16 copies for wgrad
             ws["Mbf"] = [a.rows("Mbf%d" % k, N, 2 * c.Hp, BF16) for k in range(2)]
             ws["bwd_carry"] = a.flat("bwd_carry", B * 2 * c.Hp * 2, F32)
+            ws["bwd_prog_words"] = _lib.lib().lcb_lstm_rec_bwd_progress_words(B, c.Hp, self.ndir)
+            ws["bwd_prog"] = a.flat("bwd_prog", max(1, nl * ws["bwd_prog_words"]), torch.int32)
         else:
             m1 = a.rows("M0", N, 2 * c.Hp, F16)
             ho = [a.rows("Hout%d" % k, N, 2 * c.P, F16) for k in range(min(2, nl))]
@@ -702,7 +708,11 @@ class BLSTMEncoder:
                             gemm(dH_this[:, d * c.P:(d + 1) * c.P], M[:, d * c.Hp:(d + 1) * c.Hp], 1, 1, out=gWpT[d])
                         done_blocks = []
                         for blocks, ev in released:
-                            side.wait_event(ev)
+                            if isinstance(ev, tuple):          # (event before the launch, progress words, count, scan step)
+                                side.wait_event(ev[0])
+                                _lib.check(L.lcb_wait_progress(_lib.ptr(ev[1]), ev[2], ev[3], _lib.stream_ptr()), "lcb_wait_progress")
+                            else:
+                                side.wait_event(ev)
                             for (t0, t1) in blocks:
                                 for d in range(nd):
                                     dfold_rows(d, t0 * B, t1 * B, M, dG, bool(done_blocks))
@@ -814,6 +824,10 @@ class BLSTMEncoder:
                 if fr > 0.5 and Tb >= lo and T - Tb >= 16:
                     cuts.append(Tb)
         released0 = []
+        pwords = ws["bwd_prog_words"]
+        use_pg = bool(cuts) and self.bwd_progress and pwords > 0
+        if use_pg:
+            ws["bwd_prog"].zero_()
         early = None                         # (first row, end row, event): rows of dH and of this layer's dM made on xstream
         pending = None                       # (layer, its dH): weight gradients not yet enqueued
         for i in reversed(range(c.num_layers)):
@@ -843,24 +857,42 @@ class BLSTMEncoder:
                 ranges = [(0, T)] if (Ts < 1 or Ts >= T) else [(0, Ts), (Ts, T)]
             dXn = ws["dX"][i % 3] if i > 0 else None
             prev_cut = None
+            prog = ws["bwd_prog"][i * pwords:(i + 1) * pwords] if use_pg else None
+            if use_pg:
+                # one launch over the whole scan; the release points below are waited for on the consumers' stream
+                pre = torch.cuda.Event()
+                pre.record(main)
+                _lib.check(L.lcb_lstm_rec_bwd_range_pg(_lib.ptr(dM), _lib.ptr(ws["gates"][i]), _lib.ptr(ws["cst"][i]),
+                                                       _lib.ptr(self._bf[("fold", i)]), _lib.ptr(peep),
+                                                       _lib.ptr(seq_len), _lib.ptr(dG), _lib.ptr(ps.g("L%d/bias" % i)), _lib.ptr(gpeep),
+                                                       T, B, c.Hp, nd, 0, T, _lib.ptr(ws["bwd_carry"]), _lib.ptr(prog),
+                                                       _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(), _lib.stream_ptr()), "lcb_lstm_rec_bwd_range_pg")
             for (s0, s1) in ranges:
-                _lib.check(L.lcb_lstm_rec_bwd_range(_lib.ptr(dM), _lib.ptr(ws["gates"][i]), _lib.ptr(ws["cst"][i]),
-                                                    _lib.ptr(self._bf[("fold", i)]), _lib.ptr(peep),
-                                                    _lib.ptr(seq_len), _lib.ptr(dG), _lib.ptr(ps.g("L%d/bias" % i)), _lib.ptr(gpeep),
-                                                    T, B, c.Hp, nd, s0, s1, _lib.ptr(ws["bwd_carry"]),
-                                                    _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(), _lib.stream_ptr()), "lcb_lstm_rec_bwd_range")
+                if not use_pg:
+                    _lib.check(L.lcb_lstm_rec_bwd_range(_lib.ptr(dM), _lib.ptr(ws["gates"][i]), _lib.ptr(ws["cst"][i]),
+                                                        _lib.ptr(self._bf[("fold", i)]), _lib.ptr(peep),
+                                                        _lib.ptr(seq_len), _lib.ptr(dG), _lib.ptr(ps.g("L%d/bias" % i)), _lib.ptr(gpeep),
+                                                        T, B, c.Hp, nd, s0, s1, _lib.ptr(ws["bwd_carry"]),
+                                                        _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(), _lib.stream_ptr()), "lcb_lstm_rec_bwd_range")
                 if cuts and s1 < T:
                     # frames final in both directions now: [T-s1, s1), minus those the previous cut already released
                     blocks = [(T - s1, s1)] if prev_cut is None else [(T - s1, T - prev_cut), (prev_cut, s1)]
                     prev_cut = s1
-                    launched = torch.cuda.Event()
-                    launched.record(main)
+                    if use_pg:
+                        launched = (pre, prog, pwords, s1)
+                    else:
+                        launched = torch.cuda.Event()
+                        launched.record(main)
                     if i == 0:
                         if self.l0_released:
                             released0.append((blocks, launched))      # layer 0 has no dX: its weight gradients use the released frames
                         continue
                     with torch.cuda.stream(self.xstream), grid_cap(bwd_cap):
-                        self.xstream.wait_event(launched)
+                        if use_pg:
+                            self.xstream.wait_event(pre)
+                            _lib.check(L.lcb_wait_progress(_lib.ptr(prog), pwords, s1, _lib.stream_ptr()), "lcb_wait_progress")
+                        else:
+                            self.xstream.wait_event(launched)
                         for (t0, t1) in blocks:
                             dx_rows(i, dG, dXn, t0 * B, t1 * B, dH)
                             dm_rows(i - 1, dXn, t0 * B, t1 * B)

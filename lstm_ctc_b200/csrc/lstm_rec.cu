@@ -92,6 +92,8 @@ struct RecBwdParams {
     int s_begin, s_end;           // v3: scan steps [s_begin, s_end) of this launch (t = T-1-s forward, s backward direction)
     float* carry;                 // v3: [B][2][Hp][2] (recurrent dm, carried dc) handed from one launch to the next (nullable
                                   //     when the launch covers [0, T))
+    int* progress;                // v3, nullable: [clusters * NSG * 16] words; word (cluster, sub-group, CTA) = number of leading scan
+                                  //     steps whose dG rows this CTA has written (lcb_lstm_rec_bwd_range_pg)
 };
 
 __device__ __forceinline__ unsigned char* align_1024(unsigned char* p) {
@@ -1033,7 +1035,10 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
     long long* prof = (blockIdx.x == 0 && lane == 0 && rw == 0 && role < 2 && sg == (g_rec_prof_steps >> 16)) ? g_rec_prof : nullptr;
     const int prof_steps = g_rec_prof_steps & 0xffff;
     bool ok = true;
-    if (b0 >= B) role = 3;                             // an empty second sub-group (in every CTA of the cluster alike) idles
+    if (b0 >= B) {                                     // an empty second sub-group (in every CTA of the cluster alike) idles
+        if (role == 2 && lane == 0 && p.progress) st_release_gpu_s32(p.progress + (size_t)(cid * NSG + sg) * NC + cta, T);
+        role = 3;
+    }
     if (role == 2) {
         // ============================ exchange warp: own dz slice -> L2 scratch -> multicast into the 4 CTAs of the group ============================
         // The staged slice is also the layer output dG[t, b0.., own 128 packed gate columns]: two 128B-swizzled TMA tensor
@@ -1042,6 +1047,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
             unsigned char* scr = p.xch + (size_t)(cid * NSG + sg) * 2 * NC * SLICE;
             const uint16_t mask = (uint16_t)(0xFu << (4 * kc));
             const int col0 = dir * 4 * Hp + (int)cta * 128;
+            int* prog = p.progress ? p.progress + (size_t)(cid * NSG + sg) * NC + cta : nullptr;
             for (int s = 0; s < S && ok; ++s) {
                 ok = mbar_wait(&mbar_slice[s & 1], (uint32_t)((s >> 1) & 1));
                 if (!ok) break;
@@ -1056,6 +1062,9 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
                     tma_store_3d(&tmDG, src, col0, b0, t);                     // behind the multicast: off the chain; read out of
                     tma_store_3d(&tmDG, src + BG * 128, col0 + 64, b0, t);     // Stg[s&1] before step s+1's wait_group returns
                     bulk_commit_group();
+                    // progress for the GEMMs that consume released dG rows beside this launch: the wait_group above also
+                    // covered the dG stores of every earlier step (published here, behind the multicast: off the chain)
+                    if (prog) { fence_proxy_async_all(); st_release_gpu_s32(prog, S0 + s); }
                 } else {
                     tma_store_3d(&tmDG, src, col0, b0, t);
                     tma_store_3d(&tmDG, src + BG * 128, col0 + 64, b0, t);
@@ -1063,6 +1072,7 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
                 }
             }
             bulk_wait_group_all();                          // dG of the last steps is written before the kernel ends
+            if (prog && ok) { fence_proxy_async_all(); st_release_gpu_s32(prog, S0 + S); }
         }
         __syncwarp();
     } else if (role == 1) {
@@ -1533,6 +1543,40 @@ extern "C" int lcb_lstm_rec_bwd(const float* dM, const void* gates, const float*
                                   workspace, workspace_bytes, stream);
 }
 
+// words of the progress array of lcb_lstm_rec_bwd_range_pg for a batch of B utterances (0: this cell size has no progress output)
+extern "C" int lcb_lstm_rec_bwd_progress_words(int B, int Hp, int num_dirs)
+{
+    int nc;
+    if (!rec_plan(Hp, nc) || B <= 0 || Hp != 512) return 0;
+    const int bgs0 = choose_bg(B, nc, num_dirs, 1);
+    return num_dirs * ((B + bgs0 - 1) / bgs0) * (bgs0 == 32 ? 2 : 1) * nc;
+}
+
+// Spin (one thread per word, nanosleep back-off, bounded) until every word of `progress` has reached `target`: enqueued on the
+// stream of the GEMMs that consume the dG rows a running lcb_lstm_rec_bwd_range_pg launch has released.  The BPTT launch never
+// waits for anything here, so this cannot deadlock -- serialised, it finds the final values.
+__global__ void wait_progress_kernel(const int* progress, int n, int target)
+{
+    const int i = threadIdx.x + blockIdx.x * blockDim.x;
+    if (i >= n) return;
+    uint64_t t0 = 0; uint32_t spins = 0;
+    while (ld_acquire_gpu_s32(progress + i) < target) {
+        __nanosleep(200);
+        if ((++spins & 0xff) == 0) {
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > LCB_WAIT_TIMEOUT_NS || dev_has_error()) { dev_set_error(DEV_ERR_MBAR_TIMEOUT); return; }
+        }
+    }
+}
+extern "C" int lcb_wait_progress(const int32_t* progress, int n, int target, void* stream)
+{
+    if (!progress || n <= 0) return LCB_ERR_NULL_POINTER;
+    wait_progress_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(progress, n, target);
+    lcb::g_launches += 1;
+    return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
+}
+
 // 1 when lcb_lstm_rec_bwd_range accepts partial ranges for this cell size (the 4 x 4 kernel, Hp = 512)
 extern "C" int lcb_lstm_rec_bwd_can_split(int Hp)
 {
@@ -1544,6 +1588,16 @@ extern "C" int lcb_lstm_rec_bwd_range(const float* dM, const void* gates, const 
                                       int T, int B, int Hp, int num_dirs, int s_begin, int s_end, float* carry,
                                       void* workspace, size_t workspace_bytes, void* stream)
 {
+    return lcb_lstm_rec_bwd_range_pg(dM, gates, cst, Wfold, peep, lens, dG, dbias, dpeep, T, B, Hp, num_dirs, s_begin, s_end, carry,
+                                     nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int lcb_lstm_rec_bwd_range_pg(const float* dM, const void* gates, const float* cst, const void* Wfold, const float* peep,
+                                         const int32_t* lens, void* dG, float* dbias, float* dpeep,
+                                         int T, int B, int Hp, int num_dirs, int s_begin, int s_end, float* carry, int32_t* progress,
+                                         void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (progress && Hp != 512) return LCB_ERR_UNSUPPORTED;
     if (!dM || !gates || !cst || !Wfold || !lens || !dG || !dbias || !workspace) return LCB_ERR_NULL_POINTER;
     if (T <= 0 || B <= 0 || num_dirs < 1 || num_dirs > 2) return LCB_ERR_BAD_SHAPE;
     if (s_begin < 0 || s_end > T || s_begin >= s_end) return LCB_ERR_BAD_SHAPE;
@@ -1560,6 +1614,7 @@ extern "C" int lcb_lstm_rec_bwd_range(const float* dM, const void* gates, const 
     p.dM = dM; p.gates = (const uint2*)gates; p.cst = cst; p.W = (const __nv_bfloat16*)Wfold; p.peep = peep; p.lens = lens;
     p.dG = (__nv_bfloat16*)dG; p.dbias = dbias; p.dpeep = dpeep;
     p.T = T; p.B = B; p.Hp = Hp; p.NC = nc; p.ndir = num_dirs; p.s_begin = s_begin; p.s_end = s_end; p.carry = carry;
+    p.progress = progress;
     p.xch = (unsigned char*)workspace;
     cudaStream_t st = (cudaStream_t)stream;
     const int bgs0 = choose_bg(B, nc, num_dirs, 1);

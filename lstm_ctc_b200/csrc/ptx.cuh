@@ -53,6 +53,9 @@ __device__ __forceinline__ int ld_acquire_gpu_s32(const int* p) {
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_release_gpu_s32(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile(

@@ -262,10 +262,12 @@ def test_early_rows_schedule_equals_serial(cuda_dev, B, T, fracs, keep, layers):
     nc = nnet_config(cfg)
     nc["dropout_rate"] = keep
     res = []
-    for f in ([], fracs):
+    # serial | range launches at the release points (round 1) | ONE launch publishing its progress, consumers wait on their stream
+    for f, pg in (([], False), (fracs, False), (fracs, True)):
         enc = BLSTMEncoder(ModelConfig(nc), dev)
         enc.from_tf_dict(params)
         enc.bwd_early_fracs = f
+        enc.bwd_progress = pg
         enc.forward(x.float().to(dev), lens.to(dev), training=True)
         enc.params.gflat.zero_()
         enc.backward(dtop.clone())
@@ -273,10 +275,11 @@ def test_early_rows_schedule_equals_serial(cuda_dev, B, T, fracs, keep, layers):
         torch.cuda.synchronize()
         res.append(([d.clone() for d in ws["dG"]], enc.params.gflat.clone(), ws["dX"][1].clone()))
     assert _lib.lib().lcb_device_error(1) == 0
-    (dg0, g0, dx0), (dg1, g1, dx1) = res
-    if layers > 1:
-        assert torch.equal(dx0, dx1)               # layer 1's dX (= layer 0's dH), all rows
-    for a, b in list(zip(dg0, dg1))[:min(layers, 2)]:      # (a one-layer stack never writes the second dz buffer)
-        assert torch.equal(a, b)
-    assert (g0 - g1).abs().max().item() <= 1e-5 * g0.abs().max().item()
+    dg0, g0, dx0 = res[0]
+    for dg1, g1, dx1 in res[1:]:
+        if layers > 1:
+            assert torch.equal(dx0, dx1)               # layer 1's dX (= layer 0's dH), all rows
+        for a, b in list(zip(dg0, dg1))[:min(layers, 2)]:      # (a one-layer stack never writes the second dz buffer)
+            assert torch.equal(a, b)
+        assert (g0 - g1).abs().max().item() <= 1e-5 * g0.abs().max().item()
     assert g0.abs().max().item() > 0

@@ -19,8 +19,8 @@ def step():
     model.optimizer_step("adam", 4e-4, clip_norm=5.0, l2_decay_weight=1e-5)
 
 
-def timed(n=12):
-    for _ in range(3):
+def timed(n=12, warm=2):
+    for _ in range(warm):
         step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -34,11 +34,27 @@ def timed(n=12):
 HOST = [lens_h]
 from lstm_ctc_b200 import _lib
 L = _lib.lib()
-combos = [("auto", 1.0), ("auto", 0.75), ("auto", 0.55), ("paired", 1.0), ("paired", 0.75), ("paired", 0.55), ("paired", 0.4), ("auto", 1.0), ("paired", 1.0)]
-for layout, sc in combos:
-    L.lcb_debug_fwd_layout(1 if layout == "paired" else 0)
-    HOST[0] = lens_h
-    model.enc.fwd_flow_control = True
-    model.enc.flow_fracs = [0.3, 0.55, 0.8]
-    model.enc.side_sm_scale = [sc, 1.0]
-    print(json.dumps({"fwd_layout": layout, "side_sm_scale_fwd": sc, "ms_per_step": round(timed(), 3), "device_error": L.lcb_device_error(0)}), flush=True)
+import statistics
+HOST[0] = lens_h
+
+
+def apply(cfg):
+    L.lcb_debug_fwd_layout(1 if cfg.get("layout") == "paired" else 0)
+    HOST[0] = lens_h if cfg.get("host", True) else None
+    model.enc.fwd_flow_control = cfg.get("flow", True)
+    model.enc.bwd_progress = cfg.get("pg", True)
+    model.enc.bwd_early_fracs = cfg.get("early", [0.67, 0.85])
+    model.enc.flow_fracs = cfg.get("fracs", [0.3, 0.55, 0.8])
+
+
+configs = {"default": {}, "bwd_range_launches": {"pg": False}, "fwd_range_launches": {"flow": False}, "fwd_paired_layout": {"layout": "paired"},
+           "no_host_lens": {"host": False}, "round1_schedule": {"pg": False, "flow": False, "layout": "paired", "host": False},
+           "early_0.6_0.75_0.9": {"early": [0.6, 0.75, 0.9]}}
+samples = {k: [] for k in configs}
+for rnd in range(7):                      # interleaved rounds: the power-capped clock drifts by more than the effects compared
+    for k, cfg in configs.items():
+        apply(cfg)
+        samples[k].append(timed(6))
+for k, v in samples.items():
+    print(json.dumps({"config": k, "settings": configs[k], "ms_per_step_median": round(statistics.median(v), 3), "min": round(min(v), 3),
+                      "max": round(max(v), 3), "rounds": len(v), "device_error": L.lcb_device_error(0)}), flush=True)
