@@ -643,10 +643,14 @@ class BLSTMEncoder:
         return torch.cat(out, 1)
 
     # ------------------------------------------------------------------ backward
-    def backward(self, dXtop, bucket_ready=None, top_dropped=False):
+    def backward(self, dXtop, bucket_ready=None, top_dropped=False, top_ready=None):
         """dXtop [T*B, 2P] bf16 = d loss / d encoder output.  Accumulates parameter gradients into
         params.gflat (which the caller zeroed).  bucket_ready(name_list) is called as soon as the
         gradients of a layer are final (data-parallel all-reduce hook).
+
+        top_ready: [(scan step s_k, event)] with increasing s_k, the last one T -- the rows of dXtop for the frames BPTT visits
+        in scan steps < s_k (frames [0, s_k) and [T - s_k, T)) are final once the event has fired.  The top layer's BPTT then runs
+        as consecutive range launches [s_{k-1}, s_k), each started as soon as its rows exist (AcousticModel.backward).
 
         Stream structure: the serial chain (dM GEMM -> BPTT -> dX GEMM) stays on the current stream; the
         weight-gradient GEMMs of layer i are enqueued on a side stream and execute on the SMs the next layer's
@@ -838,7 +842,27 @@ class BLSTMEncoder:
                 self._dropout(dH, i)                # same (seed, index) mask as the forward pass, on the gradient
             dM, dG = ws["dM"], ws["dG"][k]
             # dM = dH * W_p^T
-            if early is None:
+            top_s0 = 0                       # scan steps of the top layer already run by the launches below
+            if top_ready and i == c.num_layers - 1 and early is None and L.lcb_lstm_rec_bwd_can_split(c.Hp):
+                peep_t = ps.w("L%d/peep" % i) if c.use_peepholes else None
+                gpeep_t = ps.g("L%d/peep" % i) if c.use_peepholes else None
+                for kk, (sk, ev) in enumerate(top_ready):
+                    main.wait_event(ev)
+                    a0, a1 = top_s0, min(sk, T)
+                    if a1 >= T - a1:                                 # the bands have met: one block of rows
+                        dm_rows(i, dH, a0 * B, (T - a0) * B)
+                    else:
+                        dm_rows(i, dH, a0 * B, a1 * B)
+                        dm_rows(i, dH, (T - a1) * B, (T - a0) * B)
+                    if kk + 1 < len(top_ready):
+                        _lib.check(L.lcb_lstm_rec_bwd_range(_lib.ptr(dM), _lib.ptr(ws["gates"][i]), _lib.ptr(ws["cst"][i]),
+                                                            _lib.ptr(self._bf[("fold", i)]), _lib.ptr(peep_t), _lib.ptr(seq_len),
+                                                            _lib.ptr(dG), _lib.ptr(ps.g("L%d/bias" % i)), _lib.ptr(gpeep_t),
+                                                            T, B, c.Hp, nd, a0, a1, _lib.ptr(ws["bwd_carry"]),
+                                                            _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(), _lib.stream_ptr()),
+                                   "lcb_lstm_rec_bwd_range")
+                        top_s0 = a1
+            elif early is None:
                 dm_rows(i, dH, 0, N)
             else:
                 dm_rows(i, dH, 0, early[0])
@@ -850,8 +874,10 @@ class BLSTMEncoder:
             gpeep = ps.g("L%d/peep" % i) if c.use_peepholes else None
             # BPTT in one launch, or as two launches over consecutive scan ranges joined by the carry buffer -- bit-identical
             # (lcb_lstm_rec_bwd_range): at Tb for the early rows above (layers 1..), or at bwd_split_frac (experiments)
-            if cuts:
-                ranges = list(zip([0] + cuts, cuts + [T]))
+            if cuts and all(cc > top_s0 for cc in cuts):
+                ranges = list(zip([top_s0] + cuts, cuts + [T]))
+            elif top_s0 > 0:
+                ranges = [(top_s0, T)]
             else:
                 Ts = int(math.ceil(self.bwd_split_frac * T)) if self.bwd_split_frac > 0 and L.lcb_lstm_rec_bwd_can_split(c.Hp) else 0
                 ranges = [(0, T)] if (Ts < 1 or Ts >= T) else [(0, Ts), (Ts, T)]
@@ -865,7 +891,7 @@ class BLSTMEncoder:
                 _lib.check(L.lcb_lstm_rec_bwd_range_pg(_lib.ptr(dM), _lib.ptr(ws["gates"][i]), _lib.ptr(ws["cst"][i]),
                                                        _lib.ptr(self._bf[("fold", i)]), _lib.ptr(peep),
                                                        _lib.ptr(seq_len), _lib.ptr(dG), _lib.ptr(ps.g("L%d/bias" % i)), _lib.ptr(gpeep),
-                                                       T, B, c.Hp, nd, 0, T, _lib.ptr(ws["bwd_carry"]), _lib.ptr(prog),
+                                                       T, B, c.Hp, nd, top_s0, T, _lib.ptr(ws["bwd_carry"]), _lib.ptr(prog),
                                                        _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(), _lib.stream_ptr()), "lcb_lstm_rec_bwd_range_pg")
             for (s0, s1) in ranges:
                 if not use_pg:

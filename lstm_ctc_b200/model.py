@@ -12,7 +12,7 @@ from . import _lib
 from .blstm import BF16, F16, F32, BLSTMEncoder, ModelConfig, ParamSpec, _cast16, _ceil, _to_bf16
 from .lstm import embed_uni_variables, extract_uni_variables, random_uni_variables, uni_prefix
 from .ctc import ctc_loss_grad
-from .gemm import gemm
+from .gemm import gemm, grid_cap
 
 OPT_CODES = {"sgd": 0, "momentum": 1, "adam": 2}
 
@@ -88,6 +88,10 @@ class AcousticModel:
         specs = [ParamSpec("out/Wall", (self.rows_out, 2 * c.P), True), ParamSpec("out/ball", (self.rows_out,), True)]
         self.enc = BLSTMEncoder(c, self.device, extra_specs=specs)
         self.params = self.enc.params
+        # mixture-layer backward in three bands of frames, outermost first: the top layer's BPTT visits frames T-1-s and s at scan
+        # step s, so it starts on the outer band while the inner ones are still being processed beside it (backward())
+        self.top_overlap = True
+        self.ostream = torch.cuda.Stream(device=self.device) if torch.cuda.is_available() else None
         self._out16 = None
         self._outbf = None
         self._out_stale = True
@@ -227,15 +231,45 @@ class AcousticModel:
             _lib.check(L.lcb_colsum(_lib.ptr(dZ), 1, N, ro, self.ldz, _lib.ptr(gb), st), "lcb_colsum")
         else:
             R = ws["Z"].shape[0]
-            for ci, n0 in enumerate(range(0, N, R)):
-                r = min(R, N - n0)
-                Z, dZ = ws["Z"][:r], ws["dZ"][:r]
-                gemm(X16[n0:n0 + r], self._out16, 0, 0, out=Z[:, :ro], bias=self.params.w("out/ball"))   # recompute z
-                _lib.check(L.lcb_mos_bwd_dz(_lib.ptr(Z), _lib.ptr(dlogits), _lib.ptr(dZ), n0, r, self.ldz, T, B, c.V, c.K,
-                                            c.tau, c.keep_prob, self._out_seed, st), "lcb_mos_bwd_dz")
-                gemm(dZ[:, :ro], self._outbf, 0, 1, out=dXtop[n0:n0 + r], dropout=top_drop and top_drop + (n0 * 2 * c.P,))
-                gemm(dZ[:, :ro], Xbf[n0:n0 + r], 1, 1, out=gW, accumulate=(ci > 0))
-                _lib.check(L.lcb_colsum(_lib.ptr(dZ), 1, r, ro, self.ldz, _lib.ptr(gb), st), "lcb_colsum")
+            first = [True]
+
+            def rows(n0, n1):
+                """mixture backward of rows [n0, n1): recompute z, dz, dX (+ the top layer's mask), += dW, += db"""
+                for m0 in range(n0, n1, R):
+                    r = min(R, n1 - m0)
+                    Z, dZ = ws["Z"][:r], ws["dZ"][:r]
+                    gemm(X16[m0:m0 + r], self._out16, 0, 0, out=Z[:, :ro], bias=self.params.w("out/ball"))   # recompute z
+                    _lib.check(L.lcb_mos_bwd_dz(_lib.ptr(Z), _lib.ptr(dlogits), _lib.ptr(dZ), m0, r, self.ldz, T, B, c.V, c.K,
+                                                c.tau, c.keep_prob, self._out_seed, _lib.stream_ptr()), "lcb_mos_bwd_dz")
+                    gemm(dZ[:, :ro], self._outbf, 0, 1, out=dXtop[m0:m0 + r], dropout=top_drop and top_drop + (m0 * 2 * c.P,))
+                    gemm(dZ[:, :ro], Xbf[m0:m0 + r], 1, 1, out=gW, accumulate=not first[0])
+                    first[0] = False
+                    _lib.check(L.lcb_colsum(_lib.ptr(dZ), 1, r, ro, self.ldz, _lib.ptr(gb), _lib.stream_ptr()), "lcb_colsum")
+
+            enc = self.enc
+            s1, s2 = T // 6, T // 3
+            if (self.top_overlap and self.ostream is not None and enc.overlap_wgrad and s1 >= 16
+                    and L.lcb_lstm_rec_bwd_can_split(c.Hp) and not c.uni):
+                # Bands of frames, outermost first: [0,s1) + [T-s1,T) on this stream (whole chip), then [s1,s2) + [T-s2,T-s1) and the
+                # middle [s2,T-s2) on a side stream, capped to the SMs the BPTT clusters leave idle; the encoder launches the top
+                # layer's BPTT over scan steps [0,s1) as soon as the first band is done, [s1,s2) after the second, [s2,T) after the
+                # third (lcb_lstm_rec_bwd_range: bit-identical to one launch), so two thirds of this layer's backward hide behind it.
+                main = torch.cuda.current_stream()
+                rows(0, s1 * B)
+                rows((T - s1) * B, N)
+                ev1 = torch.cuda.Event(); ev1.record(main)
+                with torch.cuda.stream(self.ostream), grid_cap(enc.idle_sms(B, 1)):
+                    self.ostream.wait_event(ev1)
+                    rows(s1 * B, s2 * B)
+                    rows((T - s2) * B, (T - s1) * B)
+                    ev2 = torch.cuda.Event(); ev2.record(self.ostream)
+                    rows(s2 * B, (T - s2) * B)
+                    ev3 = torch.cuda.Event(); ev3.record(self.ostream)
+                    if bucket_ready is not None:
+                        bucket_ready(["out/Wall", "out/ball"])
+                enc.backward(dXtop, bucket_ready, top_dropped=top_drop is not None, top_ready=[(s1, ev1), (s2, ev2), (T, ev3)])
+                return
+            rows(0, N)
         if bucket_ready is not None:
             bucket_ready(["out/Wall", "out/ball"])
         self.enc.backward(dXtop, bucket_ready, top_dropped=top_drop is not None)

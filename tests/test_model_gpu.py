@@ -299,3 +299,35 @@ def test_edge_lengths_through_the_whole_path(cuda_dev, T):
         if rel > 5e-2:
             bad[k] = rel
     assert not bad, bad
+
+
+@pytest.mark.parametrize("B,T,keep", [(40, 120, 0.9), (64, 100, 1.0)])
+def test_banded_mixture_backward_equals_serial(cuda_dev, B, T, keep):
+    """AcousticModel.top_overlap: the mixture layer's backward runs in three bands of frames, outermost first, the inner two on a
+    side stream, and the top layer's BPTT starts on the outer band as range launches [0,T/6), [T/6,T/3), [T/3,T).  d loss / d z of
+    every layer is bit-identical to the serial order; the parameter gradients agree up to the fp32 summation order of the
+    accumulating weight-gradient GEMMs."""
+    from lstm_ctc_b200.model import AcousticModel
+    cfg = oracle.OracleConfig(input_dim=24, num_layers=2, num_neurons=512, num_projects=512, num_targets=20, use_peepholes=True, num_experts=4)
+    params = oracle.init_params(cfg, seed=31, bias_scale=0.1)
+    x, lens, labels = make_batch(cfg, B=B, T=T, Lmax=10, seed=32)
+    nc = nnet_config(cfg)
+    nc["dropout_rate"] = keep
+    res = []
+    for top in (False, True):
+        m = AcousticModel(nc, cuda_dev, init=False)
+        m.from_tf_dict(params)
+        m.top_overlap = top
+        m.enc.debug_dz = {}
+        loss_sum, _ = m.loss_and_grad(x.float().to(cuda_dev), lens.to(cuda_dev), labels.to(cuda_dev), seq_len_host=lens)
+        torch.cuda.synchronize()
+        res.append((float(loss_sum), m.params.gflat.clone(), {k: v.clone() for k, v in m.enc.debug_dz.items()}))
+    from lstm_ctc_b200 import _lib
+    assert _lib.lib().lcb_device_error(1) == 0
+    (l0, g0, dz0), (l1, g1, dz1) = res
+    assert l0 == l1
+    assert sorted(dz0) == sorted(dz1) == [0, 1]
+    for k in dz0:
+        assert torch.equal(dz0[k], dz1[k])
+    assert (g0 - g1).abs().max().item() <= 1e-5 * g0.abs().max().item()
+    assert g0.abs().max().item() > 0

@@ -45,11 +45,11 @@ def apply(cfg):
     model.enc.bwd_progress = cfg.get("pg", True)
     model.enc.bwd_early_fracs = cfg.get("early", [0.67, 0.85])
     model.enc.flow_fracs = cfg.get("fracs", [0.3, 0.55, 0.8])
+    model.top_overlap = cfg.get("top", True)
 
 
-configs = {"default": {}, "bwd_range_launches": {"pg": False}, "fwd_range_launches": {"flow": False}, "fwd_paired_layout": {"layout": "paired"},
-           "no_host_lens": {"host": False}, "round1_schedule": {"pg": False, "flow": False, "layout": "paired", "host": False},
-           "early_0.6_0.75_0.9": {"early": [0.6, 0.75, 0.9]}}
+configs = {"default": {}, "no_top_overlap": {"top": False}, "fwd_range_launches": {"flow": False},
+           "round1_schedule": {"pg": False, "flow": False, "layout": "paired", "host": False, "top": False}}
 samples = {k: [] for k in configs}
 for rnd in range(7):                      # interleaved rounds: the power-capped clock drifts by more than the effects compared
     for k, cfg in configs.items():
