@@ -39,7 +39,7 @@ def run(B, lens_mode, host_lens=False):
     lens_host = (_lib.ctypes.c_int32 * B)(*[int(v) for v in lens.cpu().tolist()]) if host_lens else None
 
     def fwd():
-        _lib.check(L.lcb_lstm_rec_fwd_range_hl(_lib.ptr(G), _lib.ptr(fold16), _lib.ptr(peep), _lib.ptr(lens), lens_host, _lib.ptr(M),
+        _lib.check(L.lcb_lstm_rec_fwd_range_hl(_lib.ptr(G), _lib.ptr(fold16), _lib.ptr(peep), _lib.ptr(lens), lens_host, None, _lib.ptr(M),
                                                _lib.ptr(gates), _lib.ptr(cst), None, None, T, B, Hp, 2, 5.0, 0, T, _lib.ptr(ws), ws.numel(),
                                                st), "fwd")
 

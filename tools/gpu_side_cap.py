@@ -48,8 +48,9 @@ def apply(cfg):
     model.top_overlap = cfg.get("top", True)
 
 
-configs = {"default": {}, "no_top_overlap": {"top": False}, "fwd_range_launches": {"flow": False},
-           "round1_schedule": {"pg": False, "flow": False, "layout": "paired", "host": False, "top": False}}
+configs = {"default_0.3_0.55_0.8": {}, "0.2_0.45_0.75": {"fracs": [0.2, 0.45, 0.75]}, "0.25_0.5_0.75": {"fracs": [0.25, 0.5, 0.75]},
+           "0.35_0.6_0.85": {"fracs": [0.35, 0.6, 0.85]}, "0.2_0.4_0.6_0.8": {"fracs": [0.2, 0.4, 0.6, 0.8]}, "0.25_0.6": {"fracs": [0.25, 0.6]},
+           "0.15_0.35_0.6_0.8": {"fracs": [0.15, 0.35, 0.6, 0.8]}}
 samples = {k: [] for k in configs}
 for rnd in range(7):                      # interleaved rounds: the power-capped clock drifts by more than the effects compared
     for k, cfg in configs.items():
