@@ -240,7 +240,7 @@ class BLSTMEncoder:
         self.bwd_progress = True
         self.xstream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None   # early rows of dX / dM
         # share of the SMs a recurrence launch leaves idle that the GEMMs beside it may occupy (forward, BPTT): < 1 trades GEMM
-        # time (hidden under the recurrence) for power and L2 headroom of the latency-bound clusters (tools/gpu_side_cap.py)
+        # time (hidden under the recurrence) for power and L2 headroom of the latency-bound clusters (tools/gpu_schedule_ab.py)
         self.side_sm_scale = [1.0, 1.0]
         self.ndir = 1 if cfg.uni else 2          # nnet_type 'lstm': only direction-0 clusters / column halves run (lstm.py)
         self.num_sms = _lib.lib().lcb_device_sm_count() if torch.cuda.is_available() else 0

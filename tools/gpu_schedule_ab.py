@@ -1,4 +1,5 @@
-"""C3 training step time against the share of the idle SMs the side-stream GEMMs may use and the forward launch boundaries
+"""Interleaved A/B of the schedule options on the C3 training step (one box, medians over rounds: the power-capped clock drifts by
+more than some of the effects).  Historical first purpose: step time against the share of the idle SMs the side-stream GEMMs may use
 (what a forward recurrence on 96 instead of 64 SMs would leave to the projection GEMMs beside it)."""
 import sys
 import json
