@@ -398,7 +398,7 @@ def kernel_breakdown(model, x, lens, y, w, frames):
             self._lib = lib
         def __getattr__(self, k):
             f = getattr(self._lib, k)
-            m = {"lcb_lstm_rec_fwd": "lstm_rec_fwd", "lcb_lstm_rec_fwd_range": "lstm_rec_fwd", "lcb_lstm_rec_fwd_range_hl": "lstm_rec_fwd", "lcb_lstm_rec_bwd": "lstm_rec_bwd", "lcb_lstm_rec_bwd_range": "lstm_rec_bwd", "lcb_output_fwd": "output_fwd",
+            m = {"lcb_lstm_rec_fwd": "lstm_rec_fwd", "lcb_lstm_rec_fwd_range": "lstm_rec_fwd", "lcb_lstm_rec_fwd_range_hl": "lstm_rec_fwd", "lcb_lstm_rec_bwd": "lstm_rec_bwd", "lcb_lstm_rec_bwd_range": "lstm_rec_bwd", "lcb_lstm_rec_bwd_range_pg": "lstm_rec_bwd", "lcb_output_fwd": "output_fwd",
                  "lcb_mos_bwd_dz": "mos_bwd_dz", "lcb_optimizer_step": "optimizer"}.get(k)
             return timed(m, f) if m else f
 
