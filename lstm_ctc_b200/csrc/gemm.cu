@@ -29,7 +29,8 @@ static inline int gemm_cta_cap(int max_ctas) { const int n = num_sms(); return (
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;          // 64 bf16 = 128 B = one swizzle row
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;    // epilogue warps: two per TMEM lane quarter, taking alternate column chunks of a tile
+constexpr int GEMM_THREADS = 32 * (2 + GEMM_EPI_WARPS);
 
 // optional inverted dropout fused into the epilogue (DropoutWrapper(output_keep_prob) of nnet/bilstm.py:128,137 on the layer
 // output, and the same mask on its gradient): element (row, col) of C is element base + row*ldc + col of the counter-based
@@ -46,7 +47,7 @@ template <int BN> struct GemmCfg {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;         // 16 KB
     static constexpr int B_BYTES = BN * GEMM_BK * 2;              // 16/32 KB
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int EPI_BYTES = 4 * 2 * 4096;                // per epilogue warp: two 32-row x 128 B staging boxes
+    static constexpr int EPI_BYTES = GEMM_EPI_WARPS * 4096;       // per epilogue warp: one 32-row x 128 B staging box
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;
@@ -88,7 +89,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         tma_prefetch_desc(&tmB);
         if (tma_out) tma_prefetch_desc(&tmC);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], GEMM_EPI_WARPS); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -171,18 +172,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         __syncwarp();
     } else {
-        // ================= epilogue (warps 2..5) =================
+        // ================= epilogue (warps 2..9) =================
         // TMEM -> registers (lane = output row, 32 consecutive columns) -> +bias -> 128B-swizzled smem box of 32 rows x 128 B
         // -> ONE TMA tensor store (or fp32 reduce-add for accumulate / split-K) per box; the TMA unit clips rows >= M and
-        // columns >= N.  Two boxes per warp so the next chunk is staged while the previous store drains.
+        // columns >= N.  Two warps per TMEM lane quarter take alternate column chunks (round 2; measured against four warps with
+        // two boxes each: K = 120 projection 337 -> 310 us, K = 1024 projection with fp32 output 709 -> 694 us -- that one is
+        // bound by the 1.57 GB of pre-activations it writes, 2.3 TB/s of DRAM writes, not by the epilogue: 600 us with 16-bit
+        // output -- the other shapes unchanged, profiles/r02_gemm_shapes.txt).
         const int q = warp & 3;                               // TMEM lane quarter this warp may access
+        const int ehalf = (warp - 2) >> 2;                    // which of the quarter's two warps
         int acc = 0; uint32_t acc_phase = 0;
         bool ok = true;
         if (tma_out) {
             constexpr int CW = (CT == 0) ? 32 : 64;           // columns per box (128 B)
-            const uint32_t stage_base = smem_u32(epi) + (uint32_t)(warp - 2) * 8192u;
+            const uint32_t stage_base = smem_u32(epi) + (uint32_t)(warp - 2) * 4096u;
             const bool reduce = (CT == 0) && (accumulate || splits > 1);
-            int buf = 0;
             for (int work = blockIdx.x; work < nwork && ok; work += gridDim.x) {
                 const int tile = work % ntiles, split = work / ntiles;
                 const int m0 = (tile / tiles_n) * GEMM_BM;
@@ -193,7 +197,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
                 if (!skip) {
 #pragma unroll 1
-                    for (int ch = 0; ch < BN / CW; ++ch) {
+                    for (int ch = ehalf; ch < BN / CW; ch += 2) {
                         const int c0 = n0 + ch * CW;
                         if (c0 >= N) break;                   // warp-uniform
                         uint32_t r[CW];
@@ -230,9 +234,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                                 }
                             }
                         }
-                        if (lane == 0) bulk_wait_group_read_pending<1>();   // the store that last used this box has read it
+                        if (lane == 0) bulk_wait_group_read_pending<0>();   // the store that last used this box has read it
                         __syncwarp();
-                        const uint32_t row_addr = stage_base + (uint32_t)buf * 4096u + (uint32_t)lane * 128u;
+                        const uint32_t row_addr = stage_base + (uint32_t)lane * 128u;
                         const uint32_t sw = (uint32_t)(lane & 7);
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
@@ -257,11 +261,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         fence_proxy_async_smem();             // generic-proxy smem writes -> visible to the TMA (async proxy)
                         __syncwarp();
                         if (lane == 0) {
-                            if (reduce) tma_reduce_add_2d(&tmC, stage_base + (uint32_t)buf * 4096u, c0, m0 + q * 32);
-                            else tma_store_2d(&tmC, stage_base + (uint32_t)buf * 4096u, c0, m0 + q * 32);
+                            if (reduce) tma_reduce_add_2d(&tmC, stage_base, c0, m0 + q * 32);
+                            else tma_store_2d(&tmC, stage_base, c0, m0 + q * 32);
                             bulk_commit_group();
                         }
-                        buf ^= 1;
                     }
                 }
                 tc_fence_before();
@@ -273,6 +276,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             __syncwarp();
         } else {
         // fallback for outputs the TMA cannot address (base or pitch not 16-byte aligned): smem-transposed scalar stores
+        // (only the first warp of each quarter works here: its scratch is 32 x 33 floats of the 4 KB box area of two warps)
         float* st = epi + (warp - 2) * (32 * 33);
         for (int work = blockIdx.x; work < nwork && ok; work += gridDim.x) {
             const int tile = work % ntiles, split = work / ntiles;
@@ -283,7 +287,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ++ch) {
+            for (int ch = 0; ch < (ehalf == 0 ? BN / 32 : 0); ++ch) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(t_addr + ch * 32, r);
                 tmem_ld_wait();
