@@ -598,8 +598,8 @@ def dp_check_and_strong_scaling(model, reducer, w, args, rank, world, device):
     # Full length: a randomly initialised 5-layer stack with forget bias 5 has a gradient norm of ~1e11 at T = 1500: BPTT amplifies
     # any perturbation of d loss / d logits by that much.  What differs between the sharded and the unsharded run is only the ORDER
     # of fp32 additions (the red.global.add of the CTC gammas inside an utterance, the K loops / split-K of the weight-gradient
-    # GEMMs; forward activations are bit-identical per utterance), and that order noise shows at 1e-5 .. 3e-4 of the norm, varying
-    # from run to run and growing with the number of shards (measured: 7e-6 .. 2e-5 at 2 ranks, 1e-4 .. 3e-4 at 4).  The 256-frame cut
+    # GEMMs; forward activations are bit-identical per utterance), and that order noise shows at 1e-5 .. 4e-4 of the norm, varying
+    # from run to run (measured: 7e-6 .. 4e-4 at 2 ranks, 1e-4 .. 3e-4 at 4).  The 256-frame cut
     # of the same batch (gradient norm ~1e7, no such amplification) pins the exchange itself: 4e-6.
     full, cut = compare(w["T"]), compare(min(256, w["T"]))
     res = None
