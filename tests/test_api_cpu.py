@@ -114,3 +114,18 @@ def test_param_store_bucket_order_matches_backward():
         assert lo >= prev - 63 and lo % 64 == 0 and hi > lo
         prev = hi
     assert ps.nodecay_ranges() == [(ps.specs["L%d/bias" % i].offset, ps.specs["L%d/bias" % i].offset + 9) for i in (2, 1, 0)]
+
+
+def test_flow_control_interlock(monkeypatch):
+    """BLSTMEncoder.fwd_flow_control (one recurrence launch that waits in-kernel for GEMMs of another stream) is switched off when
+    the process runs under a tool that serialises kernels."""
+    from lstm_ctc_b200 import blstm
+    monkeypatch.delenv("CUDA_INJECTION64_PATH", raising=False)
+    monkeypatch.delenv("CUDA_LAUNCH_BLOCKING", raising=False)
+    assert blstm._kernels_serialised() is False
+    monkeypatch.setenv("CUDA_LAUNCH_BLOCKING", "1")
+    assert blstm._kernels_serialised() is True
+    monkeypatch.setenv("CUDA_LAUNCH_BLOCKING", "0")
+    assert blstm._kernels_serialised() is False
+    monkeypatch.setenv("CUDA_INJECTION64_PATH", "/opt/nvidia/nsight-compute/target/libcuda-injection.so")
+    assert blstm._kernels_serialised() is True
