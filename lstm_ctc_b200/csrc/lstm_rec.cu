@@ -1157,27 +1157,27 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
         // raw prefetch of the next step's saved activations (loads only, stay in flight behind the current step)
         struct Pre { uint2 gp[2]; float c[2], cp[2], dmo[2]; };
         const long long row_stride = (dir ? 1 : -1) * (long long)B * (long long)ld2;      // elements per time step, in scan order
-        long long idx_j[2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int b = b0 + ub * 8 + 2 * g + j;
-            idx_j[j] = ((long long)(dir ? S0 : T - 1 - S0) * B + (b < B ? b : 0)) * (long long)ld2 + (long long)dir * Hp + unit;
-        }
-        auto load_pre = [&](int s, Pre& r) {              // s: GLOBAL scan step
+        // running pointers of utterance j = 0 at the step to be prefetched next (utterance j = 1 is the next row, + ld2 elements; a
+        // scan step moves them by one frame); predicated loads, no branches: the prefetch used to cost ~90 instructions and two
+        // divergent branches per step, issued in front of the wait for the partial tiles
+        const size_t pidx0 = ((size_t)(dir ? S0 : T - 1 - S0) * B + (size_t)(b0 + ub * 8 + 2 * g)) * ld2 + (size_t)dir * Hp + unit;
+        const uint2* gq = p.gates + pidx0;
+        const float* cq = p.cst + pidx0;
+        const float* dq = p.dM + pidx0;
+        auto load_pre = [&](int s, Pre& r) {              // s: GLOBAL scan step (the pointers already stand on it); advances them
             const int t = dir ? s : (T - 1 - s);
+            const int tp = dir ? (t + 1) : (t - 1);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const bool live = (s < T) && (t < len_j[j]);
-                r.gp[j] = make_uint2(0u, 0u); r.c[j] = 0.f; r.cp[j] = 0.f; r.dmo[j] = 0.f;
-                if (live) {
-                    r.gp[j] = __ldg(p.gates + idx_j[j]);
-                    r.c[j] = __ldg(p.cst + idx_j[j]);
-                    r.dmo[j] = __ldg(p.dM + idx_j[j]);
-                    const int tp = dir ? (t + 1) : (t - 1);
-                    const bool has_prev = dir ? (tp < len_j[j]) : (tp >= 0);
-                    if (has_prev) r.cp[j] = __ldg(p.cst + idx_j[j] + row_stride);
-                }
+                const bool live = (s < T) && (t < len_j[j]);           // (a padding utterance has len 0: never live, never read)
+                const bool has_prev = live && (dir ? (tp < len_j[j]) : (tp >= 0));
+                const size_t o = j ? ld2 : 0;
+                r.gp[j] = ldg_u2_if(gq + o, live);
+                r.c[j] = ldg_f32_if(cq + o, live);
+                r.dmo[j] = ldg_f32_if(dq + o, live);
+                r.cp[j] = ldg_f32_if(cq + o + row_stride, has_prev);
             }
+            gq += row_stride; cq += row_stride; dq += row_stride;
         };
         Pre cur, nxt;
         load_pre(S0, cur);
@@ -1210,8 +1210,6 @@ lstm_rec_bwd3_kernel(const RecBwdParams p, const __grid_constant__ CUtensorMap t
         };
         for (int s = 0; s < S; ++s) {
             REC_PROBE(8);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) idx_j[j] += row_stride;
             load_pre(S0 + s + 1, nxt);
             REC_PROBE(9);
             // ---- phase A: dm_rec = sum of the four partial tiles of the previous step, then dz_t ----

@@ -56,6 +56,17 @@ __device__ __forceinline__ int ld_acquire_gpu_s32(const int* p) {
 __device__ __forceinline__ void st_release_gpu_s32(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// predicated read-only global loads (0 when the predicate is false): one predicated LDG each, no branch, free to be scheduled
+__device__ __forceinline__ float ldg_f32_if(const float* p, bool pred) {
+    float v = 0.f;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}\n" : "+f"(v) : "l"(p), "r"((int)pred));
+    return v;
+}
+__device__ __forceinline__ uint2 ldg_u2_if(const uint2* p, bool pred) {
+    uint2 v = make_uint2(0u, 0u);
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q ld.global.nc.v2.u32 {%0, %1}, [%2];\n\t}\n" : "+r"(v.x), "+r"(v.y) : "l"(p), "r"((int)pred));
+    return v;
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile(
