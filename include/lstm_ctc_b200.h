@@ -59,6 +59,12 @@ size_t lcb_ctc_workspace_bytes(int B, int T, int V, int Lmax);
 int lcb_ctc_loss_grad_f32(const float* logits, const int64_t* labels, int Lmax, const int32_t* seq_len,
                           int B, int T, int V, float* loss, float* grad,
                           void* workspace, size_t workspace_bytes, void* stream);
+/* Same call with the lattice layout stated: -1 chosen by batch size (what lcb_ctc_loss_grad_f32 does: the alpha and beta
+ * sweeps of an utterance as the two CTAs of a cluster when 2 B <= SMs, otherwise as two warp groups of one CTA), 0 one CTA
+ * per utterance, 1 two.  Results agree up to the order of the gradient's atomic adds. */
+int lcb_ctc_loss_grad_f32_layout(const float* logits, const int64_t* labels, int Lmax, const int32_t* seq_len,
+                                 int B, int T, int V, float* loss, float* grad,
+                                 void* workspace, size_t workspace_bytes, int lattice_layout, void* stream);
 /* 0, or LCB_ERR_INVALID_LABEL if the last call on this workspace saw an out-of-range label.
  * Synchronises `stream`. */
 int lcb_ctc_status(const void* workspace, void* stream);

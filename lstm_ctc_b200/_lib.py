@@ -61,6 +61,8 @@ _SIGS = {
     "lcb_ctc_workspace_bytes": (c_size_t, [c_int] * 4),
     "lcb_ctc_loss_grad_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                       c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "lcb_ctc_loss_grad_f32_layout": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+                                             c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "lcb_ctc_status": (c_int, [c_void_p, c_void_p]),
     "lcb_gemm_bf16": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
                               c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),

@@ -322,7 +322,12 @@ template <int SPT> struct CtcLat {
     static size_t smem_bytes(int NW) { return off_rows(NW) + (ROWPF ? (size_t)PF * 2 * NW * 32 * 16 : 0); }
 };
 
-template <int SPT, int MAXT>
+//
+// SPLIT (few utterances: 2 B <= SMs).  The call is then bound by the per-frame chain of one warp, and the alpha and beta warps of an utterance
+// compete for the same four schedulers.  The two sweeps run as the two CTAs of a cluster instead (rank 0: alpha, rank 1: beta), on two SMs:
+// the spilled rows travel through L2 as before (st.cg / ld.cg / cp.async.cg), the two CTA barriers become barrier.cluster (release / acquire
+// at cluster scope orders the spills), and p reaches the beta CTA as three remote shared-memory stores before the second one.
+template <int SPT, int MAXT, bool SPLIT>
 __global__ void __launch_bounds__(MAXT)
 ctc_lattice_kernel(const float* __restrict__ logits, const CtcMeta* __restrict__ meta, const int* __restrict__ lab, int LABP,
                    const float4* __restrict__ frame, int2* __restrict__ spill,
@@ -332,19 +337,22 @@ ctc_lattice_kernel(const float* __restrict__ logits, const CtcMeta* __restrict__
     constexpr int HL = C::HL, PF = C::PF;
     constexpr bool ROWPF = C::ROWPF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int NT = 2 * NW * 32;                                               // threads of the CTA
+    const int NT = (SPLIT ? 1 : 2) * NW * 32;                                 // threads of the CTA
     const int NTG = NW * 32;                                                  // threads per group
     CtcXch* xch = reinterpret_cast<CtcXch*>(smem_raw);                       // [2 groups][NW]  (entry w: written by warp w of the group)
     float* red_m = reinterpret_cast<float*>(xch + 2 * NW);                   // [NW]
     int* red_e = reinterpret_cast<int*>(red_m + NW);                         // [NW]
     float* p_sh = reinterpret_cast<float*>(red_e + NW);                      // [4]: -, e_p (bits), 1/m_p, no-path flag (bits)
 
-    const int b = blockIdx.x;
+    const int b = SPLIT ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const int wg = __shfl_sync(0xffffffffu, tid >> 5, 0);                     // warp of the CTA (provably warp-uniform)
-    const int grp = wg >= NW ? 1 : 0;                                         // 0: alpha sweep, 1: beta sweep
-    const int w = wg - grp * NW;                                              // warp inside the group
-    const int gt = tid - grp * NTG;                                           // thread index inside the group
+    const int grp = SPLIT ? (int)(blockIdx.x & 1) : (wg >= NW ? 1 : 0);       // 0: alpha sweep, 1: beta sweep (SPLIT: the CTA's rank in its pair)
+    const int w = SPLIT ? wg : wg - grp * NW;                                 // warp inside the group
+    const int gt = SPLIT ? tid : tid - grp * NTG;                             // thread index inside the group
+    auto sync_both = [&]() {                                                  // both sweeps of the utterance
+        if constexpr (SPLIT) cluster_sync_all(); else asm volatile("bar.sync 0;" ::: "memory");
+    };
     const CtcMeta mt = meta[b];
     if (mt.skip) { if (tid == 0) loss[b] = 0.f; return; }                     // (the softmax pass zeroed the gradient rows)
     const int Tb = __shfl_sync(0xffffffffu, mt.Tb, 0), L = __shfl_sync(0xffffffffu, mt.L, 0), S = 2 * L + 1;
@@ -549,10 +557,15 @@ ctc_lattice_kernel(const float* __restrict__ logits, const CtcMeta* __restrict__
                         me_norm(tm, te, fm, fe);
                         const bool none = fe < (ME_ZERO >> 1);                       // no valid alignment
                         p_sh[1] = __int_as_float(fe); p_sh[2] = none ? 0.f : 1.0f / fm; p_sh[3] = __int_as_float(none ? 1 : 0);
+                        if constexpr (SPLIT) {                                        // the beta CTA's copy (visible after B2's release / acquire)
+                            const uint32_t ra = mapa_shared(smem_u32(p_sh), 1);
+                            st_cluster_b32(ra + 4, (uint32_t)fe); st_cluster_b32(ra + 8, __float_as_uint(none ? 0.f : 1.0f / fm));
+                            st_cluster_b32(ra + 12, none ? 1u : 0u);
+                        }
                         // loss = -ln p; no valid alignment: +inf and the gradient stays = softmax (TF behaviour)
                         loss[b] = none ? INFINITY : (float)(-(log2((double)fm) + (double)fe) * 0.6931471805599453);
                     }
-                    asm volatile("bar.sync 0;" ::: "memory");                         // B2: p is published
+                    sync_both();                                                      // B2: p is published
                     read_p();
                 }
                 if (!nopath) gamma_row(om, oe);
@@ -565,7 +578,7 @@ ctc_lattice_kernel(const float* __restrict__ logits, const CtcMeta* __restrict__
             frame(0, TT{}, FF{});
             for (t = 1; t < mid; ++t) frame(t, FF{}, FF{});
         }
-        asm volatile("bar.sync 0;" ::: "memory");                              // B1: every spill of phase 1 (both sweeps) is visible
+        sync_both();                                                           // B1: every spill of phase 1 (both sweeps) is visible
         if (mid == 0) { frame(0, TT{}, TT{}); t = 1; }
         for (; t < Tb; ++t) frame(t, FF{}, TT{});
         cp_async_wait<0>();
@@ -639,8 +652,8 @@ ctc_lattice_kernel(const float* __restrict__ logits, const CtcMeta* __restrict__
         using TT = std::true_type; using FF = std::false_type;
         int n = 0;
         for (; n < Tb - mid; ++n) bframe(n, FF{});                            // frames Tb-1 .. mid: spill
-        asm volatile("bar.sync 0;" ::: "memory");                             // B1
-        asm volatile("bar.sync 0;" ::: "memory");                             // B2
+        sync_both();                                                          // B1
+        sync_both();                                                          // B2
         read_p();
         for (; n < Tb; ++n) bframe(n, TT{});                                  // frames mid-1 .. 0: gamma
         cp_async_wait<0>();
@@ -717,14 +730,28 @@ static void dispatch_softmax(const float* logits, float* grad, int B, int T, int
     ctc_softmax_bigrow_kernel<<<grid, 256, 0, st>>>(logits, grad, B, T, V, meta, frame);
 }
 
-template <int SPT, int MAXT>
+template <int SPT, int MAXT, bool SPLIT>
 static cudaError_t launch_lattice(const CtcPlan& p, int B, int T, int V, const float* logits, const CtcMeta* meta, const int* lab,
                                   const float4* frame, int2* spill, float* grad, float* loss, cudaStream_t st)
 {
-    if (cudaFuncSetAttribute(ctc_lattice_kernel<SPT, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess)
+    auto kern = ctc_lattice_kernel<SPT, MAXT, SPLIT>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess)
         return cudaErrorInvalidValue;
-    ctc_lattice_kernel<SPT, MAXT><<<B, 2 * p.NW * 32, p.smem, st>>>(logits, meta, lab, p.LABP, frame, spill, loss, grad, T, V, p.NW);
-    return cudaGetLastError();
+    if constexpr (!SPLIT) {
+        kern<<<B, 2 * p.NW * 32, p.smem, st>>>(logits, meta, lab, p.LABP, frame, spill, loss, grad, T, V, p.NW);
+        return cudaGetLastError();
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * B), 1, 1);
+        cfg.blockDim = dim3((unsigned)(p.NW * 32), 1, 1);
+        cfg.dynamicSmemBytes = p.smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kern, logits, meta, lab, p.LABP, frame, (int2*)spill, loss, grad, T, V, p.NW);
+    }
 }
 
 }  // namespace lcb
@@ -739,10 +766,13 @@ extern "C" size_t lcb_ctc_workspace_bytes(int B, int T, int V, int Lmax)
     return p.total;
 }
 
-extern "C" int lcb_ctc_loss_grad_f32(const float* logits, const int64_t* labels, int Lmax, const int32_t* seq_len,
-                                     int B, int T, int V, float* loss, float* grad, void* workspace,
-                                     size_t workspace_bytes, void* stream)
+// lattice_layout: -1 chosen by batch size (the two sweeps of an utterance on two SMs when 2 B <= SMs, else one CTA per utterance),
+// 0 one CTA per utterance, 1 two.  Same results up to the order of the gradient's atomic adds; 0 / 1 are for tests and A/B timing.
+extern "C" int lcb_ctc_loss_grad_f32_layout(const float* logits, const int64_t* labels, int Lmax, const int32_t* seq_len,
+                                            int B, int T, int V, float* loss, float* grad, void* workspace,
+                                            size_t workspace_bytes, int lattice_layout, void* stream)
 {
+    if (lattice_layout < -1 || lattice_layout > 1) return LCB_ERR_BAD_SHAPE;
     if (!logits || !seq_len || !loss || !grad || !workspace) return LCB_ERR_NULL_POINTER;
     if (B <= 0 || T <= 0 || V < 2 || Lmax < 0) return LCB_ERR_BAD_SHAPE;
     if (Lmax > 0 && !labels) return LCB_ERR_NULL_POINTER;
@@ -778,12 +808,21 @@ extern "C" int lcb_ctc_loss_grad_f32(const float* logits, const int64_t* labels,
         const int nt = 2 * p.NW * 32;
         cudaError_t e = cudaSuccess;
         g_launches += 1;
-#define LCB_CTC_LAUNCH(SPT_, MAXT_) e = launch_lattice<SPT_, MAXT_>(p, nb, T, V, x, meta + b0, lab + (size_t)b0 * p.LABP, frame + (size_t)b0 * T, \
-                                                                     spill + (size_t)b0 * T * NSP, g, loss + b0, s)
-        if (p.SPT == 2) { if (nt <= 256) LCB_CTC_LAUNCH(2, 256); else if (nt <= 512) LCB_CTC_LAUNCH(2, 512); else LCB_CTC_LAUNCH(2, 1024); }
-        else if (p.SPT == 4) LCB_CTC_LAUNCH(4, 1024);
-        else if (p.SPT == 8) LCB_CTC_LAUNCH(8, 1024);
-        else LCB_CTC_LAUNCH(16, 1024);
+#define LCB_CTC_LAUNCH(SPT_, MAXT_, SPLIT_) e = launch_lattice<SPT_, MAXT_, SPLIT_>(p, nb, T, V, x, meta + b0, lab + (size_t)b0 * p.LABP, \
+                                                                     frame + (size_t)b0 * T, spill + (size_t)b0 * T * NSP, g, loss + b0, s)
+        // few utterances: the two sweeps of an utterance on two SMs (see the kernel)
+        const bool split = lattice_layout >= 0 ? lattice_layout != 0 : 2 * nb <= num_sms();
+        if (split) {
+            const int ns = p.NW * 32;
+            if (p.SPT == 2) { if (ns <= 128) LCB_CTC_LAUNCH(2, 128, true); else if (ns <= 256) LCB_CTC_LAUNCH(2, 256, true); else LCB_CTC_LAUNCH(2, 512, true); }
+            else if (p.SPT == 4) LCB_CTC_LAUNCH(4, 512, true);
+            else if (p.SPT == 8) LCB_CTC_LAUNCH(8, 512, true);
+            else LCB_CTC_LAUNCH(16, 512, true);
+        }
+        else if (p.SPT == 2) { if (nt <= 256) LCB_CTC_LAUNCH(2, 256, false); else if (nt <= 512) LCB_CTC_LAUNCH(2, 512, false); else LCB_CTC_LAUNCH(2, 1024, false); }
+        else if (p.SPT == 4) LCB_CTC_LAUNCH(4, 1024, false);
+        else if (p.SPT == 8) LCB_CTC_LAUNCH(8, 1024, false);
+        else LCB_CTC_LAUNCH(16, 1024, false);
 #undef LCB_CTC_LAUNCH
         return e;
     };
@@ -796,6 +835,13 @@ extern "C" int lcb_ctc_loss_grad_f32(const float* logits, const int64_t* labels,
     if (e != cudaSuccess) return LCB_ERR_CUDA;
     e = cudaGetLastError();
     return e == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
+}
+
+extern "C" int lcb_ctc_loss_grad_f32(const float* logits, const int64_t* labels, int Lmax, const int32_t* seq_len,
+                                     int B, int T, int V, float* loss, float* grad, void* workspace,
+                                     size_t workspace_bytes, void* stream)
+{
+    return lcb_ctc_loss_grad_f32_layout(logits, labels, Lmax, seq_len, B, T, V, loss, grad, workspace, workspace_bytes, -1, stream);
 }
 
 // status word written by the last lcb_ctc_loss_grad_f32 on this workspace (device pointer):

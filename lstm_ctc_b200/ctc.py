@@ -20,9 +20,10 @@ def _workspace(nbytes, device):
     return ws
 
 
-def ctc_loss_grad(logits, labels, seq_len, check_labels=True):
+def ctc_loss_grad(logits, labels, seq_len, check_labels=True, lattice_layout=-1):
     """logits [B,T,V] f32 cuda (batch-major), labels [B,Lmax] int64 cuda (-1 padded),
-    seq_len [B] int32 cuda.  Returns (loss[B], grad[B,T,V]) -- one pass, TF semantics."""
+    seq_len [B] int32 cuda.  Returns (loss[B], grad[B,T,V]) -- one pass, TF semantics.
+    lattice_layout: -1 chosen by batch size, 0 / 1 force one / two CTAs per utterance (tests, A/B timing)."""
     L = _lib.lib()
     assert logits.is_cuda and logits.dtype == torch.float32 and logits.dim() == 3
     logits = logits.contiguous()
@@ -36,8 +37,9 @@ def ctc_loss_grad(logits, labels, seq_len, check_labels=True):
     ws = _workspace(nbytes, logits.device)
     loss = torch.empty(B, dtype=torch.float32, device=logits.device)
     grad = torch.empty_like(logits)
-    st = L.lcb_ctc_loss_grad_f32(_lib.ptr(logits), _lib.ptr(labels) if Lmax > 0 else None, Lmax, _lib.ptr(seq_len),
-                                 B, T, V, _lib.ptr(loss), _lib.ptr(grad), _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+    st = L.lcb_ctc_loss_grad_f32_layout(_lib.ptr(logits), _lib.ptr(labels) if Lmax > 0 else None, Lmax, _lib.ptr(seq_len),
+                                        B, T, V, _lib.ptr(loss), _lib.ptr(grad), _lib.ptr(ws), ws.numel(), int(lattice_layout),
+                                        _lib.stream_ptr())
     _lib.check(st, "lcb_ctc_loss_grad_f32")
     if check_labels:
         _lib.check(L.lcb_ctc_status(_lib.ptr(ws), _lib.stream_ptr()), "tf.nn.ctc_loss labels")

@@ -14,12 +14,23 @@ G = os.path.join(os.path.dirname(__file__), "golden")
 RTOL = 1e-4
 
 
+_LAYOUT = [0]
+
+
+@pytest.fixture(autouse=True, params=[0, 1], ids=["one_cta_per_utt", "two_cta_per_utt"])
+def lattice_layout(request):
+    """Every oracle comparison runs on both lattice layouts (lcb_ctc_loss_grad_f32_layout): alpha + beta sweeps as two warp
+    groups of one CTA, and as the two CTAs of a cluster (what the default picks when 2 B <= SMs)."""
+    _LAYOUT[0] = request.param
+    yield request.param
+
+
 def run_gpu(logits, labels, seq_len):
     from lstm_ctc_b200.ctc import ctc_loss_grad
     d = torch.device("cuda:0")
     loss, grad = ctc_loss_grad(torch.tensor(logits, dtype=torch.float32, device=d),
                                torch.tensor(labels, dtype=torch.int64, device=d),
-                               torch.tensor(seq_len, dtype=torch.int32, device=d))
+                               torch.tensor(seq_len, dtype=torch.int32, device=d), lattice_layout=_LAYOUT[0])
     torch.cuda.synchronize()
     return loss.cpu().numpy().astype(np.float64), grad.cpu().numpy().astype(np.float64)
 
@@ -110,7 +121,7 @@ def test_gradient_rows_sum_to_zero_at_full_size(cuda_dev):
     x = (torch.randn(B, T, V, generator=g) * 3).to(d)
     sl = torch.randint(int(0.8 * T), T + 1, (B,), generator=g).to(torch.int32)
     lab = torch.randint(0, V - 1, (B, L), generator=g)
-    loss, grad = ctc_loss_grad(x, lab.to(d), sl.to(d))
+    loss, grad = ctc_loss_grad(x, lab.to(d), sl.to(d), lattice_layout=_LAYOUT[0])
     rows = grad.sum(-1).cpu()
     assert rows.abs().max() < 2e-5
     mask = torch.arange(T).unsqueeze(0) >= sl.unsqueeze(1)
@@ -133,3 +144,20 @@ def test_autograd_wrapper(cuda_dev):
     _, og = oracle.ctc_loss_grad(x.astype(np.float64), lab, sl)
     og *= np.array([1.0, 2.0, 0.5, 1.0])[:, None, None]
     assert np.abs(xt.grad.cpu().numpy() - og).max() < 2e-4
+
+
+def test_default_layout_by_batch_size(cuda_dev):
+    """The plain entry point picks the layout from the batch size; both choices agree with the forced layouts up to the order
+    of the gradient's atomic adds (B = 4: two CTAs per utterance; B = 80 > SMs / 2: one)."""
+    from lstm_ctc_b200.ctc import ctc_loss_grad
+    d = torch.device("cuda:0")
+    for B in (4, 80):
+        rng = np.random.RandomState(B)
+        x, lab, sl = _random_case(rng, B, 90, 72, 30)
+        a = [torch.tensor(x, device=d), torch.tensor(lab, device=d), torch.tensor(sl, dtype=torch.int32, device=d)]
+        l_def, g_def = ctc_loss_grad(*a)
+        for lay in (0, 1):
+            l, g = ctc_loss_grad(*a, lattice_layout=lay)
+            fin = torch.isfinite(l_def)
+            assert torch.equal(torch.isfinite(l), fin)
+            assert torch.allclose(l[fin], l_def[fin], rtol=1e-6, atol=1e-6) and (g - g_def).abs().max() < 2e-6
