@@ -238,6 +238,8 @@ def main():
                     help="forward recurrence as consecutive range launches instead of one launch that waits in-kernel for the "
                          "projection chunks (needed when kernels cannot run concurrently, e.g. under ncu; detected automatically "
                          "from CUDA_INJECTION64_PATH / CUDA_LAUNCH_BLOCKING)")
+    ap.add_argument("--fwd-hproj-frac", type=float, default=None,
+                    help="A/B: share of the forward scan whose output projection runs beside the recurrence (0: all of it after the launch)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -257,6 +259,8 @@ def main():
     model = AcousticModel(cfg, device, seed=1234)
     if args.no_flow_control:
         model.enc.fwd_flow_control = False
+    if args.fwd_hproj_frac is not None:
+        model.enc.fwd_hproj_fracs = [args.fwd_hproj_frac] if args.fwd_hproj_frac > 0 else []
     reducer = lcb_dist.GradientAllReducer(model.params)
     reducer.broadcast_weights()
     x_h, lens_h, y_h = synth_batch(w, 777 + rank)
@@ -332,7 +336,7 @@ def main():
            "config": {"workload": w["desc"], "name": args.workload, "per_gpu_batch": w["B"], "frames_per_step_global": frames_global,
                       "optimizer": "adam", "keep_prob": args.keep_prob, "l2": 1e-5, "clip_norm": 5.0,
                       "l2_cache": "inputs_exceed_l2 (per-step activations >> 126 MB)", "parallelism": "dp%d" % world,
-                      "fwd_flow_control": bool(model.enc.fwd_flow_control), "fwd_rec_sms": int(L.lcb_lstm_rec_grid(w["B"], model.cfg.Hp, 2, 0)),
+                      "fwd_flow_control": bool(model.enc.fwd_flow_control), "fwd_hproj_fracs": list(model.enc.fwd_hproj_fracs), "fwd_rec_sms": int(L.lcb_lstm_rec_grid(w["B"], model.cfg.Hp, 2, 0)),
                       "final_loss": last_loss, "device_error": dev_err},
            "clocks": clocks, "gpu_launches": launches, "e2e": e2e}
     if kt is not None:
@@ -398,7 +402,7 @@ def kernel_breakdown(model, x, lens, y, w, frames):
             self._lib = lib
         def __getattr__(self, k):
             f = getattr(self._lib, k)
-            m = {"lcb_lstm_rec_fwd": "lstm_rec_fwd", "lcb_lstm_rec_fwd_range": "lstm_rec_fwd", "lcb_lstm_rec_fwd_range_hl": "lstm_rec_fwd", "lcb_lstm_rec_bwd": "lstm_rec_bwd", "lcb_lstm_rec_bwd_range": "lstm_rec_bwd", "lcb_lstm_rec_bwd_range_pg": "lstm_rec_bwd", "lcb_output_fwd": "output_fwd",
+            m = {"lcb_lstm_rec_fwd": "lstm_rec_fwd", "lcb_lstm_rec_fwd_range": "lstm_rec_fwd", "lcb_lstm_rec_fwd_range_hl": "lstm_rec_fwd", "lcb_lstm_rec_fwd_range_pg": "lstm_rec_fwd", "lcb_lstm_rec_bwd": "lstm_rec_bwd", "lcb_lstm_rec_bwd_range": "lstm_rec_bwd", "lcb_lstm_rec_bwd_range_pg": "lstm_rec_bwd", "lcb_output_fwd": "output_fwd",
                  "lcb_mos_bwd_dz": "mos_bwd_dz", "lcb_optimizer_step": "optimizer"}.get(k)
             return timed(m, f) if m else f
 

@@ -181,6 +181,18 @@ int lcb_lstm_rec_fwd_range_hl(const float* G, const void* WfoldT, const float* p
                               void* Mout, void* gates, float* cst, float* cfin, float* mfin,
                               int T, int B, int Hp, int num_dirs, float forget_bias, int s_begin, int s_end,
                               void* workspace, size_t workspace_bytes, void* stream);
+/* The same launch publishing its progress (the forward mirror of lcb_lstm_rec_bwd_range_pg): word (cluster, sub-group, CTA) of
+ * `progress` -- lcb_lstm_rec_fwd_progress_words(B, Hp, num_dirs) int32 words, zeroed by the caller, NULL = none -- counts the
+ * leading scan steps whose Mout rows that CTA has written (rows [0, n) of the forward, [T-n, T) of the backward direction's column
+ * half); advanced every 16 steps, set to s_end when the sub-group is done.  lcb_wait_progress(progress, words, n) on another
+ * stream then releases the output projection h = m*W_proj (nnet/bilstm.py:128) of the finished frames -- and the half of the
+ * next layer's input projection that reads them -- beside the running recurrence.  The launch never waits for its readers. */
+int lcb_lstm_rec_fwd_progress_words(int B, int Hp, int num_dirs);
+int lcb_lstm_rec_fwd_range_pg(const float* G, const void* WfoldT, const float* peep, const int32_t* lens, const int32_t* lens_host,
+                              const int32_t* ready_steps,
+                              void* Mout, void* gates, float* cst, float* cfin, float* mfin,
+                              int T, int B, int Hp, int num_dirs, float forget_bias, int s_begin, int s_end,
+                              int32_t* progress, void* workspace, size_t workspace_bytes, void* stream);
 /* BPTT of the above (replaces tf.gradients through the while_loop, nnet/graph.py:190-191).
  *   dM    [T*B, 2Hp] f32   d loss / d m_t arriving from the output projection
  *   Wfold [2*Hp, 4Hp] bf16 W' = W_proj*W_h per direction: rows = units, cols = packed gate columns

@@ -228,6 +228,14 @@ class BLSTMEncoder:
         self.fwd_flow_control = not _kernels_serialised()
         self.flow_fracs = [0.3, 0.55, 0.8]
         self.overlap_hproj = False     # output projection of finished chunks on the side stream (c3: +-0, c2: 15 % slower)
+        # Flow-controlled forward only: the launch publishes its progress (lcb_lstm_rec_fwd_range_pg) and the output projection
+        # h = m W_proj of the scan steps before each of these fractions of T runs on the side stream beside the rest of the
+        # recurrence (lcb_wait_progress); only the last steps' rows stay on the main stream between two layers.  Empty: the whole
+        # projection follows the launch (the schedule before this option; same values bit for bit either way).
+        # (Measured and dropped, profiles/r02_fwd_progress_ab.jsonl: also accumulating the next layer's head projection from two
+        # K halves, the early one beside the recurrence -- the head GEMMs are bound by their fp32 output, K = 512 costs what
+        # K = 1024 does.)
+        self.fwd_hproj_fracs = [0.6, 0.85]
         self.bwd_split_frac = 0.0      # > 0: BPTT as two launches at this fraction (lcb_lstm_rec_bwd_range; tests)
         # increasing fractions > 0.5 of the scan at which BPTT of layers 1.. is cut into consecutive launches; the rows of dX (and of
         # the next layer's dM) whose dG is final in BOTH directions after a launch are computed beside the next one (backward(),
@@ -444,8 +452,10 @@ class BLSTMEncoder:
               "G": a.rows("G", N, 8 * c.Hp, F32),
               "rec_ws": a.flat("rec_ws", max(16, _lib.lib().lcb_lstm_rec_workspace_bytes(B, c.Hp)), torch.uint8),
               "ready": a.flat("ready", max(c.num_layers, 1), torch.int32),
+              "fwd_prog_words": _lib.lib().lcb_lstm_rec_fwd_progress_words(B, c.Hp, self.ndir),
               "cfin": a.flat("cfin", B * 2 * c.Hp, F32).view(B, 2, c.Hp),
               "mfin": a.flat("mfin", B * 2 * c.Hp, F32).view(B, 2, c.Hp)}
+        ws["fwd_prog"] = a.flat("fwd_prog", max(1, nl * ws["fwd_prog_words"]), torch.int32)
         if training:
             ws["M"] = [a.rows("M%d" % i, N, 2 * c.Hp, F16) for i in range(nl)]
             ws["Hout"] = [a.rows("Hout%d" % i, N, 2 * c.P, F16) for i in range(nl)]
@@ -504,6 +514,7 @@ class BLSTMEncoder:
         seq_len = seq_len.to(device=self.device, dtype=torch.int32).contiguous()
         _lib.check(L.lcb_pack_input(_lib.ptr(nnet_input), _lib.ptr(ws["X0"]), B, T, D, c.Dp0, st), "lcb_pack_input")
         ws["ready"].zero_()                         # flow-control counters (one per layer) of this pass
+        ws["fwd_prog"].zero_()                      # progress words of the recurrence launches (per layer)
         ws["cfin"].zero_()                          # utterances of length 0 keep the zero initial state (bilstm.py:140-144)
         ws["mfin"].zero_()
         X = ws["X0"]
@@ -513,6 +524,7 @@ class BLSTMEncoder:
             lens_host = (_lib.ctypes.c_int32 * B)(*[int(v) for v in (seq_len_host.tolist() if hasattr(seq_len_host, "tolist") else seq_len_host)])
         H4n = nd * 4 * c.Hp                         # gate columns that exist: both directions' or direction 0's
         side_cap = self.idle_sms(B, 0)              # SMs the forward recurrence clusters leave free
+        pw = ws["fwd_prog_words"]
         for i in range(c.num_layers):
             if i == 1:
                 self._await_refresh()               # layers 1.. were refreshed on the side stream during layer 0's recurrence
@@ -523,12 +535,13 @@ class BLSTMEncoder:
             W16, bias, G = self._bf[("Wx16", i)], self.params.w("L%d/bias" % i), ws["G"]
             kin = X.shape[1] if (i == 0 or nd == 2) else c.P     # uni: layers 1.. read the forward half of the layer below only
 
-            def rec(s0, s1, ready=None):
-                _lib.check(L.lcb_lstm_rec_fwd_range_hl(_lib.ptr(G), _lib.ptr(self._bf[("fold16", i)]), _lib.ptr(peep), _lib.ptr(seq_len),
+            def rec(s0, s1, ready=None, progress=None):
+                _lib.check(L.lcb_lstm_rec_fwd_range_pg(_lib.ptr(G), _lib.ptr(self._bf[("fold16", i)]), _lib.ptr(peep), _lib.ptr(seq_len),
                                                        lens_host, _lib.ptr(ready), _lib.ptr(ws["M"][i]), _lib.ptr(gates), _lib.ptr(cst),
                                                        _lib.ptr(ws["cfin"]) if last else None, _lib.ptr(ws["mfin"]) if last else None,
-                                                       T, B, c.Hp, nd, c.forget_bias, s0, s1, _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(),
-                                                       _lib.stream_ptr()), "lcb_lstm_rec_fwd_range_hl")
+                                                       T, B, c.Hp, nd, c.forget_bias, s0, s1, _lib.ptr(progress),
+                                                       _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(),
+                                                       _lib.stream_ptr()), "lcb_lstm_rec_fwd_range_pg")
 
             Hout = ws["Hout"][i]
             # h = m * W_proj with DropoutWrapper(output_keep_prob) (bilstm.py:128,137) applied in the GEMM epilogue: element
@@ -592,7 +605,27 @@ class BLSTMEncoder:
                         ev.record(self.pstream)
                         chunk_ready.append(ev)
                 prev = 0
-                if flow:
+                rel = []                            # scan steps at which finished rows are released to the output projection
+                for fr in (self.fwd_hproj_fracs if (flow and pw > 0) else []):
+                    s_ = (int(fr * T) // 16) * 16
+                    if s_ >= 16 and s_ <= T - 16 and (not rel or s_ > rel[-1]):
+                        rel.append(s_)
+                if flow and rel:
+                    # ... and it publishes its progress: the output projection of the scan steps before each release point follows
+                    # on the side stream (behind the chunks, beside the rest of the scan); only the rows of the last steps stay
+                    # between two layers.  (The launch is enqueued BEFORE the waits: a tool that serialises kernels in launch
+                    # order still terminates.)
+                    prog = ws["fwd_prog"][i * pw:(i + 1) * pw]
+                    rec(0, T, ready, prog)
+                    side_hp = torch.cuda.Event()
+                    with torch.cuda.stream(self.pstream), grid_cap(side_cap):
+                        for s0_, s1_ in zip([0] + rel[:-1], rel):
+                            _lib.check(L.lcb_wait_progress(_lib.ptr(prog), pw, s1_, _lib.stream_ptr()), "lcb_wait_progress")
+                            hproj(s0_, s1_)
+                        side_hp.record(self.pstream)
+                    hproj(rel[-1], T)
+                    main.wait_event(side_hp)
+                elif flow:
                     # every chunk is enqueued: ONE launch over the whole scan, its prefetch warps wait for the counter
                     rec(0, T, ready)
                     main.wait_event(chunk_ready[-1])

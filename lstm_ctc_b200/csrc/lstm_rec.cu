@@ -74,6 +74,8 @@ struct RecFwdParams {
                                   // 2c and 2c+1, cluster c >= n_paired holds group n_paired + c alone (fwd_layout())
     int gmax[REC_MAXGRP];         // longest utterance of each 16-utterance group (T when the caller gave no host-side lengths)
     const int* ready;             // nullable: device word = number of leading scan steps whose G rows exist (see the loader warp)
+    int* progress;                // nullable: [clusters * NSG * NC] words; word (cluster, sub-group, CTA) = number of leading scan steps
+                                  //     whose Mout rows this CTA has written for the sub-group's utterances (lcb_lstm_rec_fwd_range_pg)
 };
 
 struct RecBwdParams {
@@ -301,6 +303,7 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
     long long* prof = (blockIdx.x == 0 && lane == 0 && sg == (g_rec_prof_steps >> 16) && ((role == 1 && rw == 0) || (role == 0 && rw == 0))) ? g_rec_prof : nullptr;
     const int prof_steps = g_rec_prof_steps & 0xffff;
     const int nvalid = (B - b0) < BG ? (B - b0) : BG;           // utterances of this group that exist
+    int* const prog = p.progress ? p.progress + (size_t)(cid * NSG + sg) * NC + cta : nullptr;
     if (nvalid <= 0) role = 4;                                  // an empty second sub-group (in every CTA of the cluster alike) idles
 
     bool ok = true;
@@ -363,6 +366,11 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
                 bulk_wait_group_all();
                 bulk_load_multicast(smem_u32(Bsm) + (uint32_t)((s + 1) & 1) * OPB + cta * (uint32_t)SLICE, g, (uint32_t)SLICE,
                                     smem_u32(&mbar_op[(s + 1) & 1]), mask);
+                // Progress for the projection GEMMs that consume finished Mout rows beside this launch (lcb_wait_progress on their
+                // stream): every compute warp stored its Mout rows of step s-1 (and the zero rows before S0) before it arrived on
+                // mbar_slice for step s (release.cta, acquired by the wait above), so a gpu-scope release here covers them.
+                // Every 16th step, behind the multicast: off the chain.
+                if (prog && (s & 15) == 15) st_release_gpu_s32(prog, S0 + s);
             }
         }
         __syncwarp();
@@ -589,7 +597,12 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
             REC_PROBE(14);
         }
         zero_steps(LS - act1_me);                 // ... and behind its last one (forward direction)
+        if (prog) {                               // every row of this sub-group and CTA is written: the launch's last scan step
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + sg), "n"(NCW * 32) : "memory");      // the sub-group's compute warps
+            if (rw == 0 && lane == 0) { __threadfence(); st_release_gpu_s32(prog, p.s_end); }
+        }
     }
+    if (role == 4 && prog && wl == 0 && lane == 0) st_release_gpu_s32(prog, p.s_end);      // an empty sub-group has nothing to write
     tc_fence_before();
     cluster_sync_all();          // nobody leaves while multicast traffic addressed to it may still be in flight
     if (warp == NSG * NCW) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
@@ -1495,6 +1508,30 @@ extern "C" int lcb_lstm_rec_fwd_range_hl(const float* G, const void* WfoldT, con
                                          int T, int B, int Hp, int num_dirs, float forget_bias, int s_begin, int s_end,
                                          void* workspace, size_t workspace_bytes, void* stream)
 {
+    return lcb_lstm_rec_fwd_range_pg(G, WfoldT, peep, lens, lens_host, ready_steps, Mout, gates, cst, cfin, mfin, T, B, Hp, num_dirs,
+                                     forget_bias, s_begin, s_end, nullptr, workspace, workspace_bytes, stream);
+}
+
+// words of the progress array of lcb_lstm_rec_fwd_range_pg for a batch of B utterances
+extern "C" int lcb_lstm_rec_fwd_progress_words(int B, int Hp, int num_dirs)
+{
+    int nc;
+    if (!rec_plan(Hp, nc) || B <= 0 || num_dirs < 1 || num_dirs > 2) return 0;
+    int ncd, npair;
+    fwd_layout(B, nc, num_dirs, ncd, npair);
+    return num_dirs * ncd * (npair > 0 ? 2 : 1) * nc;
+}
+
+// The same launch publishing its progress: word (cluster, sub-group, CTA) of `progress` (zeroed by the caller,
+// lcb_lstm_rec_fwd_progress_words words) counts the leading scan steps whose Mout rows that CTA has written -- advanced every 16 steps
+// and set to s_end when the sub-group is done.  lcb_wait_progress on another stream releases the output-projection GEMMs of the
+// finished frames while the recurrence is still running; the launch itself never waits for it.
+extern "C" int lcb_lstm_rec_fwd_range_pg(const float* G, const void* WfoldT, const float* peep, const int32_t* lens,
+                                         const int32_t* lens_host, const int32_t* ready_steps,
+                                         void* Mout, void* gates, float* cst, float* cfin, float* mfin,
+                                         int T, int B, int Hp, int num_dirs, float forget_bias, int s_begin, int s_end,
+                                         int32_t* progress, void* workspace, size_t workspace_bytes, void* stream)
+{
     if (!G || !WfoldT || !lens || !Mout || !workspace) return LCB_ERR_NULL_POINTER;
     if (T <= 0 || B <= 0 || num_dirs < 1 || num_dirs > 2) return LCB_ERR_BAD_SHAPE;
     if (s_begin < 0 || s_end > T || s_begin >= s_end) return LCB_ERR_BAD_SHAPE;
@@ -1513,6 +1550,7 @@ extern "C" int lcb_lstm_rec_fwd_range_hl(const float* G, const void* WfoldT, con
     fwd_layout(B, nc, num_dirs, ncd, npair);
     p.n_paired = npair;
     p.ready = ready_steps;
+    p.progress = progress;
     for (int g = 0; g < REC_MAXGRP; ++g) {
         int m = T;
         if (lens_host && g * 16 < B) {

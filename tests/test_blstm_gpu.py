@@ -170,11 +170,16 @@ def test_host_lengths_skip_dead_steps(cuda_dev, H, B, T, order):
     outs = []
     # (launch structure, host lengths, flow control): range launches vs ONE launch whose prefetch warps wait for the projection
     # chunks still running beside it (ready_steps)
-    for fracs, host, flow in (([], None, False), ([], lens, False), ([0.3, 0.6], None, False), ([0.3, 0.6], lens.numpy(), False),
-                              ([0.5], lens.tolist(), False), ([0.25, 0.5, 0.8], lens, True), ([0.2], None, True)):
+    # The flow-controlled launch also publishes its progress (lcb_lstm_rec_fwd_range_pg): the output projection of the first
+    # fwd_hproj_fracs of the scan runs beside the rest of it (same GEMM per row: bit-identical).
+    cases = (([], None, False, [0.7]), ([], lens, False, [0.7]), ([0.3, 0.6], None, False, [0.7]), ([0.3, 0.6], lens.numpy(), False, [0.7]),
+             ([0.5], lens.tolist(), False, [0.7]), ([0.25, 0.5, 0.8], lens, True, [0.7]), ([0.2], None, True, [0.7]),
+             ([0.25, 0.5, 0.8], lens, True, [0.3, 0.55, 0.8]), ([0.3], None, True, [0.5]), ([0.25, 0.5], lens, True, []))
+    for fracs, host, flow, hfr in cases:
         enc = BLSTMEncoder(ModelConfig(nnet_config(cfg)), dev)
         enc.from_tf_dict(params)
         enc.fwd_flow_control = flow
+        enc.fwd_hproj_fracs = hfr
         enc.flow_fracs = fracs
         enc.head_fracs = fracs
         enc.head_fracs_tight = fracs

@@ -47,13 +47,22 @@ def apply(cfg):
     model.enc.bwd_early_fracs = cfg.get("early", [0.67, 0.85])
     model.enc.flow_fracs = cfg.get("fracs", [0.3, 0.55, 0.8])
     model.top_overlap = cfg.get("top", True)
+    model.enc.fwd_hproj_fracs = cfg.get("hfracs", [0.6, 0.85])
 
 
-configs = {"default_0.3_0.55_0.8": {}, "0.2_0.45_0.75": {"fracs": [0.2, 0.45, 0.75]}, "0.25_0.5_0.75": {"fracs": [0.25, 0.5, 0.75]},
-           "0.35_0.6_0.85": {"fracs": [0.35, 0.6, 0.85]}, "0.2_0.4_0.6_0.8": {"fracs": [0.2, 0.4, 0.6, 0.8]}, "0.25_0.6": {"fracs": [0.25, 0.6]},
-           "0.15_0.35_0.6_0.8": {"fracs": [0.15, 0.35, 0.6, 0.8]}}
+# (earlier visits compared the chunk fractions: profiles/r02_flow_fracs_ab.jsonl)
+configs = {"default_hproj_0.6_0.85": {}, "hproj_0.7": {"hfracs": [0.7]}, "hproj_after_launch": {"hfracs": []}, "hproj_0.6": {"hfracs": [0.6]}, "hproj_0.8": {"hfracs": [0.8]},
+           "hproj_0.5_0.75_0.9": {"hfracs": [0.5, 0.75, 0.9]},
+           "hproj_0.7_chunks_0.25_0.5_0.75": {"fracs": [0.25, 0.5, 0.75]}}
+ROUNDS = 7
+for a in sys.argv[1:]:
+    if a.startswith("--rounds="):
+        ROUNDS = int(a.split("=")[1])
+names = [a for a in sys.argv[1:] if not a.startswith("--")]
+if names:
+    configs = {k: v for k, v in configs.items() if k in names}
 samples = {k: [] for k in configs}
-for rnd in range(7):                      # interleaved rounds: the power-capped clock drifts by more than the effects compared
+for rnd in range(ROUNDS):                      # interleaved rounds: the power-capped clock drifts by more than the effects compared
     for k, cfg in configs.items():
         apply(cfg)
         samples[k].append(timed(6))
