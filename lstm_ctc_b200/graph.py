@@ -116,6 +116,12 @@ class _Graph:
         self._staged = None            # (batch, device tensors, copy-done event) of the NEXT step, or the OutOfRangeError to raise
         self._copy_stream = None
         self._staged_epoch = 0
+        # early read-back of a training step's scalars: [CTC loss sum, token count, label-smoothing term] leave the device right
+        # behind the CTC kernels (own stream, pinned buffer), so Session.run returns the step's loss without draining the backward
+        # pass and the update that are still queued -- the next step's launches follow them without a gap
+        self._early = None             # (pinned host tensor, copy-done event) of the running step
+        self._d2h_stream = None
+        self._scal_host = None
 
     # host -> device staging ------------------------------------------------------
     def _stage(self):
@@ -166,10 +172,13 @@ class _Graph:
         size = int((batch["nnet_target"] != -1).sum())                # graph.py:105-106
         out = {"size": size, "sequence_length": seq_len_host.numpy(), "summary": None,
                "raw_target": batch["nnet_target"].numpy()}
+        self._early = None
         if "train" in wanted:
             tc = self.train_cfg
             self.reducer.begin_step()
-            loss_sum, _ = m.loss_and_grad(x, lens, y, bucket_ready=self.reducer.bucket_ready, seq_len_host=seq_len_host)
+            early = self._read_back_early if ("eval" not in wanted and dev.type == "cuda") else None
+            self._early_size = size
+            loss_sum, _ = m.loss_and_grad(x, lens, y, bucket_ready=self.reducer.bucket_ready, seq_len_host=seq_len_host, on_loss=early)
             self.reducer.finish()
             m.optimizer_step(tc["optimizer"], tc["learn_rate"], tc["clip_norm"], tc["l2_decay_weight"])
             out["train"] = None
@@ -180,7 +189,13 @@ class _Graph:
             loss_sum = loss.sum()
         reg = m.reg_loss if "train" in wanted else m.label_smoothing(logits)
         ev = self._greedy_edit_distance(logits, batch) if "eval" in wanted else 0.0
-        if self.reducer.world > 1:
+        if self._early is not None:
+            host, copied = self._early
+            copied.synchronize()                                      # the read-back of the step's result; backward + update still run
+            out["eval_loss"], regv = float(host[0]), float(host[2])
+            if self.reducer.world > 1:
+                out["size"] = int(round(float(host[1])))
+        elif self.reducer.world > 1:
             # every reported scalar is a sum over the GLOBAL batch (graph.py:105-106,116,120-136,150): CTC loss, token count,
             # label-smoothing term and edit distance travel in one all-reduce
             self._scal[0] = loss_sum.double()
@@ -200,6 +215,31 @@ class _Graph:
         if "eval" in wanted:
             out["eval"] = ev
         return out
+
+    def _read_back_early(self, loss_sum, reg):
+        """on_loss hook of AcousticModel.loss_and_grad: runs between the CTC kernels and the backward pass.  Packs the step's
+        scalars, sums them over the ranks (graph.py:105-106,116 are sums over the global batch; every rank issues this
+        all-reduce at the same point, before its first gradient bucket) and copies them to pinned host memory on a side stream."""
+        main = torch.cuda.current_stream()
+        if self._d2h_stream is None:
+            self._d2h_stream = torch.cuda.Stream(device=self.model.device)
+            self._scal_host = torch.zeros(4, dtype=torch.float64).pin_memory()
+            self._scal_ring = [torch.zeros(4, dtype=torch.float64, device=self.model.device) for _ in range(2)]
+            self._early_n = 0
+        self._early_n += 1
+        sc = self._scal_ring[self._early_n & 1]      # two staging buffers in turn: the main stream never waits for the copy stream
+        sc[0] = loss_sum.double()
+        sc[1] = float(self._early_size)
+        sc[2] = reg.double().sum() if reg is not None else 0.0
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(self._d2h_stream):
+            self._d2h_stream.wait_event(ready)
+            self.reducer.all_reduce_scalars(sc)
+            self._scal_host.copy_(sc, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(self._d2h_stream)
+        self._early = (self._scal_host, copied)
 
     def _greedy_edit_distance(self, logits, batch):
         """ctc_greedy_decoder(merge_repeated=True) + edit_distance(normalize=False), summed (graph.py:138-150)."""

@@ -279,15 +279,20 @@ class AcousticModel:
         """tf.nn.ctc_loss(..., ignore_longer_outputs_than_inputs=True) + its gradient (graph.py:109-114)."""
         return ctc_loss_grad(logits, labels, seq_len, check_labels=check_labels)
 
-    def loss_and_grad(self, nnet_input, seq_len, labels, bucket_ready=None, check_labels=True, seq_len_host=None):
+    def loss_and_grad(self, nnet_input, seq_len, labels, bucket_ready=None, check_labels=True, seq_len_host=None, on_loss=None):
         """Forward + CTC + backward for one minibatch.  Returns (sum of per-utt CTC losses as a device
-        scalar, per-utt losses).  Gradients are left in params.gflat (un-clipped, no L2 yet)."""
+        scalar, per-utt losses).  Gradients are left in params.gflat (un-clipped, no L2 yet).
+        on_loss(loss_sum, reg_loss): called once the loss kernels are enqueued and BEFORE the backward pass is, so a caller can
+        start reading the step's loss back while the rest of the step still runs (graph.py: Session.run)."""
         self.params.gflat.zero_()
         logits = self.forward_logits(nnet_input, seq_len, training=True, seq_len_host=seq_len_host)
         loss, dlogits = self.ctc(logits, labels, seq_len, check_labels)
         self.reg_loss = self.label_smoothing(logits, dlogits)
+        loss_sum = loss.sum()
+        if on_loss is not None:
+            on_loss(loss_sum, self.reg_loss)
         self.backward(dlogits, bucket_ready)
-        return loss.sum(), loss
+        return loss_sum, loss
 
     def label_smoothing(self, logits, dlogits=None):
         """reg_loss of create_logits_blstm (bilstm.py:254-269), added to the training loss by graph.py:120-133.
