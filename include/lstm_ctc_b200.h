@@ -61,7 +61,8 @@ int lcb_ctc_loss_grad_f32(const float* logits, const int64_t* labels, int Lmax, 
                           void* workspace, size_t workspace_bytes, void* stream);
 /* Same call with the lattice layout stated: -1 chosen by batch size (what lcb_ctc_loss_grad_f32 does: the alpha and beta
  * sweeps of an utterance as the two CTAs of a cluster when 2 B <= SMs, otherwise as two warp groups of one CTA), 0 one CTA
- * per utterance, 1 two.  Results agree up to the order of the gradient's atomic adds. */
+ * per utterance, 1 two.  Results agree up to the order of the gradient's atomic adds.  (More than 1023 labels per utterance --
+ * 8 or 16 lattice states per thread -- always run as two CTAs.) */
 int lcb_ctc_loss_grad_f32_layout(const float* logits, const int64_t* labels, int Lmax, const int32_t* seq_len,
                                  int B, int T, int V, float* loss, float* grad,
                                  void* workspace, size_t workspace_bytes, int lattice_layout, void* stream);
@@ -143,6 +144,9 @@ int lcb_debug_rec_profile(long long* buf, int steps);
 /* debug: forward cluster layout (0 = automatic: as many clusters as stay resident, the surplus 16-utterance groups paired into
  * the first clusters; 1 = two groups in every cluster, the round-1 layout).  Results are identical, only the timing differs. */
 int lcb_debug_fwd_layout(int mode);
+/* debug / measurements: smallest number of CTC lattice states per thread the plan may choose (2 | 4 | 8 | 16; default 2).
+ * Changes lcb_ctc_workspace_bytes as well. */
+int lcb_debug_ctc_min_spt(int spt);
 /* workspace (required): device scratch of lcb_lstm_rec_workspace_bytes(B, Hp) bytes (16-byte aligned, caller-owned, one per
  * concurrently running launch): the per-step exchange of m_t goes  shared memory -> bulk store -> this L2-resident
  * scratch -> ONE multicast bulk load into all CTAs of the cluster.

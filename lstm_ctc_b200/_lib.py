@@ -72,6 +72,7 @@ _SIGS = {
     "lcb_lstm_rec_max_clusters": (c_int, [c_int, c_int]),
     "lcb_debug_rec_profile": (c_int, [c_void_p, c_int]),
     "lcb_debug_fwd_layout": (c_int, [c_int]),
+    "lcb_debug_ctc_min_spt": (c_int, [c_int]),
     "lcb_lstm_rec_workspace_bytes": (c_size_t, [c_int, c_int]),
     "lcb_lstm_rec_grid": (c_int, [c_int, c_int, c_int, c_int]),
     "lcb_lstm_rec_fwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),

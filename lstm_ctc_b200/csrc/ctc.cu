@@ -668,12 +668,13 @@ struct CtcPlan {
     size_t smem;
 };
 
+static int g_ctc_min_spt = 2;          // debug (lcb_debug_ctc_min_spt): smallest states-per-thread the plan may choose
 static bool ctc_make_plan(int B, int T, int V, int Lmax, CtcPlan& p) {
     const int S = 2 * Lmax + 1;
     // fewest states per thread that fit one CTA (two sweeps x NW warps, <= 1024 threads): the frame loop of a warp is
     // issue-bound in its per-thread instruction count, and skewed warps cost no barrier
     p.SPT = 0;
-    for (int spt = 2; spt <= 16; spt *= 2)
+    for (int spt = g_ctc_min_spt; spt <= 16; spt *= 2)
         if (S <= 512 * spt) { p.SPT = spt; break; }
     if (p.SPT == 0) return false;
     p.NW = (S + 32 * p.SPT - 1) / (32 * p.SPT);
@@ -811,7 +812,10 @@ extern "C" int lcb_ctc_loss_grad_f32_layout(const float* logits, const int64_t* 
 #define LCB_CTC_LAUNCH(SPT_, MAXT_, SPLIT_) e = launch_lattice<SPT_, MAXT_, SPLIT_>(p, nb, T, V, x, meta + b0, lab + (size_t)b0 * p.LABP, \
                                                                      frame + (size_t)b0 * T, spill + (size_t)b0 * T * NSP, g, loss + b0, s)
         // few utterances: the two sweeps of an utterance on two SMs (see the kernel)
-        const bool split = lattice_layout >= 0 ? lattice_layout != 0 : 2 * nb <= num_sms();
+        // (8 and 16 states per thread -- more than 1023 labels -- always run split: one sweep per CTA is <= 512 threads and may
+        // use 128 registers; compiled for 1024 threads = 64 registers those instantiations spill and were observed to fault with
+        // five or more warps per sweep, tools/gpu_ctc_spt_repro.py)
+        const bool split = p.SPT >= 8 || (lattice_layout >= 0 ? lattice_layout != 0 : 2 * nb <= num_sms());
         if (split) {
             const int ns = p.NW * 32;
             if (p.SPT == 2) { if (ns <= 128) LCB_CTC_LAUNCH(2, 128, true); else if (ns <= 256) LCB_CTC_LAUNCH(2, 256, true); else LCB_CTC_LAUNCH(2, 512, true); }
@@ -820,9 +824,7 @@ extern "C" int lcb_ctc_loss_grad_f32_layout(const float* logits, const int64_t* 
             else LCB_CTC_LAUNCH(16, 512, true);
         }
         else if (p.SPT == 2) { if (nt <= 256) LCB_CTC_LAUNCH(2, 256, false); else if (nt <= 512) LCB_CTC_LAUNCH(2, 512, false); else LCB_CTC_LAUNCH(2, 1024, false); }
-        else if (p.SPT == 4) LCB_CTC_LAUNCH(4, 1024, false);
-        else if (p.SPT == 8) LCB_CTC_LAUNCH(8, 1024, false);
-        else LCB_CTC_LAUNCH(16, 1024, false);
+        else LCB_CTC_LAUNCH(4, 1024, false);
 #undef LCB_CTC_LAUNCH
         return e;
     };
@@ -842,6 +844,15 @@ extern "C" int lcb_ctc_loss_grad_f32(const float* logits, const int64_t* labels,
                                      size_t workspace_bytes, void* stream)
 {
     return lcb_ctc_loss_grad_f32_layout(logits, labels, Lmax, seq_len, B, T, V, loss, grad, workspace, workspace_bytes, -1, stream);
+}
+
+// debug / measurements: smallest number of lattice states per thread the plan may choose (2, 4, 8, 16; default 2).  Affects
+// lcb_ctc_workspace_bytes as well: set it before sizing the workspace.
+extern "C" int lcb_debug_ctc_min_spt(int spt)
+{
+    if (spt != 2 && spt != 4 && spt != 8 && spt != 16) return LCB_ERR_BAD_SHAPE;
+    lcb::g_ctc_min_spt = spt;
+    return LCB_OK;
 }
 
 // status word written by the last lcb_ctc_loss_grad_f32 on this workspace (device pointer):

@@ -161,3 +161,18 @@ def test_default_layout_by_batch_size(cuda_dev):
             fin = torch.isfinite(l_def)
             assert torch.equal(torch.isfinite(l), fin)
             assert torch.allclose(l[fin], l_def[fin], rtol=1e-6, atol=1e-6) and (g - g_def).abs().max() < 2e-6
+
+
+@pytest.mark.parametrize("B,T,V,Lmax,nchk", [(2, 2300, 30, 1100, 2), (80, 2300, 30, 1100, 2), (2, 4300, 30, 2100, 1)])
+def test_very_long_label_sequences(cuda_dev, B, T, V, Lmax, nchk):
+    """More than 1023 labels per utterance: 8 / 16 lattice states per thread (always the two-CTA layout, whatever the batch size or
+    the requested layout).  Full-length labels so that the coarse mappings are really the ones running."""
+    rng = np.random.RandomState(T + B)
+    x = (rng.randn(B, T, V) * 3).astype(np.float32)
+    sl = np.full(B, T); sl[-1] = T - 3
+    lab = rng.randint(0, V - 1, size=(B, Lmax)).astype(np.int64)
+    loss, grad = run_gpu(x, lab, sl)
+    idx = list(range(B))[:nchk - 1] + [B - 1]
+    oloss, ograd = oracle.ctc_loss_grad(x[idx].astype(np.float64), lab[idx], sl[idx])
+    assert_close(loss[idx], grad[idx], oloss, ograd, (B, T, V, Lmax))
+    assert np.isfinite(loss).all() and np.abs(grad.sum(-1)).max() < 5e-5
