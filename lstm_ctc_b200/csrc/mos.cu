@@ -24,7 +24,12 @@
 
 namespace lcb {
 
-constexpr int OUT_BM = 128, OUT_BN = 256, OUT_BK = 64, OUT_STAGES = 3, OUT_THREADS = 192;
+// OUT_EPQ epilogue warps per TMEM lane quarter: the epilogue (tanh, mask, mixture sum: ~70 dependent instructions per column) is
+// latency-bound with one warp per scheduler, and the tensor pipe finishes a 256-column pass ~6x faster than four warps consume it.
+// Warps of a quarter share its 32 rows and take the 32-column chunks of a pass in turn -- possible when the K experts of a target
+// never straddle a chunk (32 % K == 0, or the affine layer); otherwise only the first warp of each quarter works, as before.
+constexpr int OUT_EPQ = 4;
+constexpr int OUT_BM = 128, OUT_BN = 256, OUT_BK = 64, OUT_STAGES = 3, OUT_THREADS = 64 + 128 * OUT_EPQ;
 constexpr int OUT_A_BYTES = OUT_BM * OUT_BK * 2, OUT_B_BYTES = OUT_BN * OUT_BK * 2;
 constexpr int OUT_STAGE_BYTES = OUT_A_BYTES + OUT_B_BYTES;
 
@@ -67,7 +72,7 @@ out_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmWp);
         for (int s = 0; s < OUT_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4 * OUT_EPQ); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -132,11 +137,15 @@ out_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         __syncwarp();
     } else {
         // ================= epilogue: softmax over experts, tanh mixture, batch-major store =================
-        const int q = warp & 3;
+        const int q = warp & 3;                                   // TMEM lane quarter this warp may read (= warp % 4)
+        const int eh = (warp - 2) >> 2;                           // which of the quarter's OUT_EPQ warps
         const int rloc = q * 32 + lane;
         float* pir = pi_s + (size_t)rloc * p.pis;
         int acc = 0; uint32_t acc_phase = 0; bool ok = true;
         const int K = p.K, V = p.V, KV = p.KV;
+        const bool share = OUT_EPQ > 1 && (K == 0 || (32 % K) == 0);   // chunks of 32 columns hold whole targets: warps take turns
+        const bool idle = !share && eh > 0;
+        const int c_first = share ? eh * 32 : 0, c_step = share ? OUT_EPQ * 32 : 32;
         for (int tile = blockIdx.x; tile < tiles_m && ok; tile += gridDim.x) {
             const int n = tile * OUT_BM + rloc;
             const bool rowok = n < p.N;
@@ -148,7 +157,13 @@ out_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                 if (!mbar_wait(&tfull_bar[acc], acc_phase)) { ok = false; break; }
                 tc_fence_after();
                 const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * OUT_BN;
-                if (prior) {
+                if (prior && OUT_EPQ > 1 && share)                 // the quarter's warps are done reading the previous tile's pi
+                    asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * OUT_EPQ) : "memory");
+                if (idle) {
+                    // (K does not divide 32: the first warp of the quarter carries the running mixture state through all columns)
+                } else if (prior && eh > 0) {
+                    // the quarter's first warp forms pi
+                } else if (prior) {
                     // pass A: max; pass B: exp, sum -> smem; then normalise
                     float mx = -INFINITY;
                     for (int c0 = 0; c0 < K; c0 += 32) {
@@ -175,10 +190,11 @@ out_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                         pir[k] = rng_keepq(p.seed_pi, (uint64_t)n * K + k, p.thr) ? pir[k] * inv * p.inv_keep : 0.f;
                 } else {
                     const int c_base = (ps - (K > 0 ? 1 : 0)) * OUT_BN;
-                    for (int c0 = 0; c0 < OUT_BN && c_base + c0 < KV; c0 += 32) {
+                    for (int c0 = c_first; c0 < OUT_BN && c_base + c0 < KV; c0 += c_step) {
                         uint32_t r[32];
                         tmem_ld_32x32b_x32(t_addr + c0, r);
                         tmem_ld_wait();
+                        if (share && K > 0) { kk = 0; accv = 0.f; vv = (c_base + c0) / K; }      // a chunk starts at a target boundary
                         if (K > 0) {
                             // phase 1 (independent per column -> instruction-level parallelism): th[j] = dropout mask * tanh(z + b).
                             // One 64-bit hash decides four consecutive elements of the [N, K*V] mask stream (moe.py:61); the
@@ -226,6 +242,8 @@ out_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                         }
                     }
                 }
+                if (prior && OUT_EPQ > 1 && share)                 // pi of this tile is in shared memory for the whole quarter
+                    asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * OUT_EPQ) : "memory");
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);

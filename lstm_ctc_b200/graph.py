@@ -228,13 +228,16 @@ class _Graph:
             self._early_n = 0
         self._early_n += 1
         sc = self._scal_ring[self._early_n & 1]      # two staging buffers in turn: the main stream never waits for the copy stream
-        sc[0] = loss_sum.double()
-        sc[1] = float(self._early_size)
-        sc[2] = reg.double().sum() if reg is not None else 0.0
         ready = torch.cuda.Event()
         ready.record(main)
-        with torch.cuda.stream(self._d2h_stream):
+        with torch.cuda.stream(self._d2h_stream):                     # (the packing kernels too: nothing is added to the main stream)
             self._d2h_stream.wait_event(ready)
+            sc[0] = loss_sum.double()
+            sc[1] = float(self._early_size)
+            sc[2] = reg.double().sum() if reg is not None else 0.0
+            loss_sum.record_stream(self._d2h_stream)
+            if reg is not None:
+                reg.record_stream(self._d2h_stream)
             self.reducer.all_reduce_scalars(sc)
             self._scal_host.copy_(sc, non_blocking=True)
             copied = torch.cuda.Event()
