@@ -190,9 +190,11 @@ int lcb_lstm_rec_fwd_range_hl(const float* G, const void* WfoldT, const float* p
  * leading scan steps whose Mout rows that CTA has written (rows [0, n) of the forward, [T-n, T) of the backward direction's column
  * half); advanced every 16 steps, set to s_end when the sub-group is done.  lcb_wait_progress(progress, words, n) on another
  * stream then releases the output projection h = m*W_proj (nnet/bilstm.py:128) of the finished frames -- and the half of the
- * next layer's input projection that reads them -- beside the running recurrence.  The launch never waits for its readers. */
+ * next layer's input projection that reads them -- beside the running recurrence.  The launch never waits for its readers.
+ * g_dtype (dtype codes of lcb_gemm16): 0 = G is fp32, 2 = G is fp16 -- lcb_gemm16 then writes half the bytes and this kernel
+ * reloads half of them; the forget bias and the recurrent product are added in fp32 either way. */
 int lcb_lstm_rec_fwd_progress_words(int B, int Hp, int num_dirs);
-int lcb_lstm_rec_fwd_range_pg(const float* G, const void* WfoldT, const float* peep, const int32_t* lens, const int32_t* lens_host,
+int lcb_lstm_rec_fwd_range_pg(const void* G, int g_dtype, const void* WfoldT, const float* peep, const int32_t* lens, const int32_t* lens_host,
                               const int32_t* ready_steps,
                               void* Mout, void* gates, float* cst, float* cfin, float* mfin,
                               int T, int B, int Hp, int num_dirs, float forget_bias, int s_begin, int s_end,

@@ -236,6 +236,10 @@ class BLSTMEncoder:
         # K halves, the early one beside the recurrence -- the head GEMMs are bound by their fp32 output, K = 512 costs what
         # K = 1024 does.)
         self.fwd_hproj_fracs = [0.6, 0.85]
+        # The hoisted pre-activations G = x W_x + b as fp16 instead of fp32: the projections write, and the recurrence reloads, half
+        # the bytes (7.9 -> 3.9 GB per C3 step); the forget bias and the recurrent product are added in fp32 in the accumulator
+        # either way.  Costs one fp16 rounding (2^-11 relative) of every pre-activation's input part.
+        self.g_half = False
         self.bwd_split_frac = 0.0      # > 0: BPTT as two launches at this fraction (lcb_lstm_rec_bwd_range; tests)
         # increasing fractions > 0.5 of the scan at which BPTT of layers 1.. is cut into consecutive launches; the rows of dX (and of
         # the next layer's dM) whose dG is final in BOTH directions after a launch are computed beside the next one (backward(),
@@ -443,13 +447,13 @@ class BLSTMEncoder:
     def _workspace(self, T, B, training):
         """Views of the arena for a (T, B) minibatch.  Inference keeps ONE m buffer and two ping-pong layer outputs; training
         keeps every layer's m / gates / c for BPTT."""
-        key = (T, B, training, self._arena.generation)
+        key = (T, B, training, self._arena.generation, self.g_half)
         if self._ws_key == key:
             return self._ws_views
         c, a = self.cfg, self._arena
         N, nl = T * B, c.num_layers
         ws = {"X0": a.rows("X0", N, c.Dp0, F16),
-              "G": a.rows("G", N, 8 * c.Hp, F32),
+              "G": a.rows("G16" if self.g_half else "G", N, 8 * c.Hp, F16 if self.g_half else F32),
               "rec_ws": a.flat("rec_ws", max(16, _lib.lib().lcb_lstm_rec_workspace_bytes(B, c.Hp)), torch.uint8),
               "ready": a.flat("ready", max(c.num_layers, 1), torch.int32),
               "fwd_prog_words": _lib.lib().lcb_lstm_rec_fwd_progress_words(B, c.Hp, self.ndir),
@@ -478,7 +482,7 @@ class BLSTMEncoder:
             ho = [a.rows("Hout%d" % k, N, 2 * c.P, F16) for k in range(min(2, nl))]
             ws["M"] = [m1] * nl
             ws["Hout"] = [ho[i % len(ho)] for i in range(nl)]
-        key = (T, B, training, a.generation)          # (allocation above may have bumped the generation)
+        key = (T, B, training, a.generation, self.g_half)          # (allocation above may have bumped the generation)
         self._ws_key, self._ws_views = key, ws
         return ws
 
@@ -536,7 +540,8 @@ class BLSTMEncoder:
             kin = X.shape[1] if (i == 0 or nd == 2) else c.P     # uni: layers 1.. read the forward half of the layer below only
 
             def rec(s0, s1, ready=None, progress=None):
-                _lib.check(L.lcb_lstm_rec_fwd_range_pg(_lib.ptr(G), _lib.ptr(self._bf[("fold16", i)]), _lib.ptr(peep), _lib.ptr(seq_len),
+                _lib.check(L.lcb_lstm_rec_fwd_range_pg(_lib.ptr(G), 2 if G.dtype == F16 else 0, _lib.ptr(self._bf[("fold16", i)]), _lib.ptr(peep),
+                                                       _lib.ptr(seq_len),
                                                        lens_host, _lib.ptr(ready), _lib.ptr(ws["M"][i]), _lib.ptr(gates), _lib.ptr(cst),
                                                        _lib.ptr(ws["cfin"]) if last else None, _lib.ptr(ws["mfin"]) if last else None,
                                                        T, B, c.Hp, nd, c.forget_bias, s0, s1, _lib.ptr(progress),

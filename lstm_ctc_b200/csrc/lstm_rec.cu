@@ -166,7 +166,9 @@ template <int BG, int NSG = 1> struct RecFwd2Cfg {
     static size_t smem_bytes(int KB) { return 1024 + NSG * sg_bytes(KB) + 64; }
 };
 
-template <int BG, int NSG>
+// GH: the hoisted pre-activations G arrive as fp16 (half the store + reload of the projections' output; the forget bias and the
+// recurrent product are still added in fp32 in the accumulator) instead of fp32.
+template <int BG, int NSG, bool GH = false>
 __global__ void __launch_bounds__(RecFwd2Cfg<BG, NSG>::THREADS, 1)
 lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap tmG)
 {
@@ -346,7 +348,7 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
                 ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
                 if (!ok) break;
             }
-            if (lane == 0) mbar_arrive_expect_tx(&mbar_g[stage], (uint32_t)(BG * 512));     // the whole box counts (rows past B are zero-filled)
+            if (lane == 0) mbar_arrive_expect_tx(&mbar_g[stage], (uint32_t)(BG * (GH ? 256 : 512)));     // the whole box counts (rows past B are zero-filled)
             if (lane == 0) tma_load_3d(Gsm + (size_t)stage * BG * REC_GCOLS, &tmG, &mbar_g[stage], dir * 4 * Hp + (int)cta * 128, b0, t);
         }
     } else if (role == 3) {
@@ -474,7 +476,8 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
         // accumulator := hoisted x-part of step s2's pre-activations (G tile, forget bias folded in; padding utterances 0),
         // then release the G stage and tell the issuers that they may accumulate onto it
         // shared-space addresses (32-bit, explicit ld/st.shared: the generic-address forms cost an address-space check per access)
-        const uint32_t g_addr = smem_u32(Gsm) + (uint32_t)(((ub * 8 + 2 * g) * REC_GCOLS + q * 32 + up) * 4);     // row of utterance j = 0
+        constexpr int GE = GH ? 2 : 4;                            // bytes per staged G element (a stage keeps its fp32-sized slot either way)
+        const uint32_t g_addr = smem_u32(Gsm) + (uint32_t)(((ub * 8 + 2 * g) * REC_GCOLS + q * 32 + up) * GE);     // row of utterance j = 0
         const uint32_t ms_addr = smem_u32(Msm) + (uint32_t)((q * NUB + ub) * 128 + (2 * g) * 16 + up * 2);        // staged m_t, utterance j = 0
         auto load_acc = [&](int s2) {
             const int stage = s2 % SG;
@@ -483,11 +486,18 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
             uint32_t a0[4], a1[4];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const uint32_t gr = ga + (uint32_t)(j * REC_GCOLS * 4);
-                a0[j] = pad_j[j] ? 0u : lds_b32(gr);
-                a0[2 + j] = pad_j[j] ? 0u : lds_b32(gr + 32);
-                a1[j] = pad_j[j] ? 0u : __float_as_uint(__uint_as_float(lds_b32(gr + 64)) + fbias);
-                a1[2 + j] = pad_j[j] ? 0u : lds_b32(gr + 96);
+                const uint32_t gr = ga + (uint32_t)(j * REC_GCOLS * GE);
+                if constexpr (GH) {
+                    a0[j] = pad_j[j] ? 0u : __float_as_uint(lds_f16(gr));
+                    a0[2 + j] = pad_j[j] ? 0u : __float_as_uint(lds_f16(gr + 16));
+                    a1[j] = pad_j[j] ? 0u : __float_as_uint(lds_f16(gr + 32) + fbias);
+                    a1[2 + j] = pad_j[j] ? 0u : __float_as_uint(lds_f16(gr + 48));
+                } else {
+                    a0[j] = pad_j[j] ? 0u : lds_b32(gr);
+                    a0[2 + j] = pad_j[j] ? 0u : lds_b32(gr + 32);
+                    a1[j] = pad_j[j] ? 0u : __float_as_uint(__uint_as_float(lds_b32(gr + 64)) + fbias);
+                    a1[2 + j] = pad_j[j] ? 0u : lds_b32(gr + 96);
+                }
             }
             tmem_st_16x256b_x1(t_addr, a0);
             tmem_st_16x256b_x1(t_addr + (16u << 16), a1);
@@ -1508,7 +1518,7 @@ extern "C" int lcb_lstm_rec_fwd_range_hl(const float* G, const void* WfoldT, con
                                          int T, int B, int Hp, int num_dirs, float forget_bias, int s_begin, int s_end,
                                          void* workspace, size_t workspace_bytes, void* stream)
 {
-    return lcb_lstm_rec_fwd_range_pg(G, WfoldT, peep, lens, lens_host, ready_steps, Mout, gates, cst, cfin, mfin, T, B, Hp, num_dirs,
+    return lcb_lstm_rec_fwd_range_pg(G, 0, WfoldT, peep, lens, lens_host, ready_steps, Mout, gates, cst, cfin, mfin, T, B, Hp, num_dirs,
                                      forget_bias, s_begin, s_end, nullptr, workspace, workspace_bytes, stream);
 }
 
@@ -1526,12 +1536,14 @@ extern "C" int lcb_lstm_rec_fwd_progress_words(int B, int Hp, int num_dirs)
 // lcb_lstm_rec_fwd_progress_words words) counts the leading scan steps whose Mout rows that CTA has written -- advanced every 16 steps
 // and set to s_end when the sub-group is done.  lcb_wait_progress on another stream releases the output-projection GEMMs of the
 // finished frames while the recurrence is still running; the launch itself never waits for it.
-extern "C" int lcb_lstm_rec_fwd_range_pg(const float* G, const void* WfoldT, const float* peep, const int32_t* lens,
+extern "C" int lcb_lstm_rec_fwd_range_pg(const void* G, int g_dtype, const void* WfoldT, const float* peep, const int32_t* lens,
                                          const int32_t* lens_host, const int32_t* ready_steps,
                                          void* Mout, void* gates, float* cst, float* cfin, float* mfin,
                                          int T, int B, int Hp, int num_dirs, float forget_bias, int s_begin, int s_end,
                                          int32_t* progress, void* workspace, size_t workspace_bytes, void* stream)
 {
+    if (g_dtype != 0 && g_dtype != 2) return LCB_ERR_UNSUPPORTED;          // 0: fp32, 2: fp16 (dtype codes of lcb_gemm16)
+    const bool gh = g_dtype == 2;
     if (!G || !WfoldT || !lens || !Mout || !workspace) return LCB_ERR_NULL_POINTER;
     if (T <= 0 || B <= 0 || num_dirs < 1 || num_dirs > 2) return LCB_ERR_BAD_SHAPE;
     if (s_begin < 0 || s_end > T || s_begin >= s_end) return LCB_ERR_BAD_SHAPE;
@@ -1542,7 +1554,7 @@ extern "C" int lcb_lstm_rec_fwd_range_pg(const float* G, const void* WfoldT, con
     if (((uintptr_t)G & 15) || ((uintptr_t)WfoldT & 15) || ((uintptr_t)workspace & 15)) return LCB_ERR_MISALIGNED;
     if (workspace_bytes < lcb_lstm_rec_workspace_bytes(B, Hp)) return LCB_ERR_WORKSPACE_TOO_SMALL;
     RecFwdParams p;
-    p.G = G; p.Wt = (const __half*)WfoldT; p.peep = peep; p.lens = lens; p.Mout = (__half*)Mout;
+    p.G = (const float*)G; p.Wt = (const __half*)WfoldT; p.peep = peep; p.lens = lens; p.Mout = (__half*)Mout;
     p.gates = (uint2*)gates; p.cst = cst; p.cfin = cfin; p.mfin = mfin;
     p.T = T; p.B = B; p.Hp = Hp; p.NC = nc; p.ndir = num_dirs; p.forget_bias = forget_bias; p.s_begin = s_begin; p.s_end = s_end;
     p.xch = (unsigned char*)workspace;
@@ -1563,12 +1575,15 @@ extern "C" int lcb_lstm_rec_fwd_range_pg(const float* G, const void* WfoldT, con
     cudaStream_t st = (cudaStream_t)stream;
     // G as a 3-D tensor [T][B][8Hp] fp32, box = 128 packed gate columns x 16 utterances of one frame (dense, no swizzle)
     CUtensorMap tm;
-    if (!make_tmap_3d(&tm, true, G, (uint64_t)8 * Hp, (uint64_t)B, (uint64_t)T, (uint64_t)8 * Hp * 4, (uint64_t)B * 8 * Hp * 4,
+    const uint64_t ge = gh ? 2 : 4;          // (a 16-bit tensor map moves fp16 as it moves bf16)
+    if (!make_tmap_3d(&tm, !gh, G, (uint64_t)8 * Hp, (uint64_t)B, (uint64_t)T, (uint64_t)8 * Hp * ge, (uint64_t)B * 8 * Hp * ge,
                       128, 16u, 1, false)) return LCB_ERR_CUDA;
     if (npair == 0)
-        return launch_cluster(lstm_rec_fwd2_kernel<16, 1>, ncl * nc, RecFwd2Cfg<16>::THREADS, RecFwd2Cfg<16>::smem_bytes(Hp / 64), nc, st, p, tm);
+        return gh ? launch_cluster(lstm_rec_fwd2_kernel<16, 1, true>, ncl * nc, RecFwd2Cfg<16>::THREADS, RecFwd2Cfg<16>::smem_bytes(Hp / 64), nc, st, p, tm)
+                  : launch_cluster(lstm_rec_fwd2_kernel<16, 1, false>, ncl * nc, RecFwd2Cfg<16>::THREADS, RecFwd2Cfg<16>::smem_bytes(Hp / 64), nc, st, p, tm);
     // too many 16-utterance groups for one wave of clusters: two of them in some (or all) clusters, stepping independently
-    return launch_cluster(lstm_rec_fwd2_kernel<16, 2>, ncl * nc, RecFwd2Cfg<16, 2>::THREADS, RecFwd2Cfg<16, 2>::smem_bytes(Hp / 64), nc, st, p, tm);
+    return gh ? launch_cluster(lstm_rec_fwd2_kernel<16, 2, true>, ncl * nc, RecFwd2Cfg<16, 2>::THREADS, RecFwd2Cfg<16, 2>::smem_bytes(Hp / 64), nc, st, p, tm)
+              : launch_cluster(lstm_rec_fwd2_kernel<16, 2, false>, ncl * nc, RecFwd2Cfg<16, 2>::THREADS, RecFwd2Cfg<16, 2>::smem_bytes(Hp / 64), nc, st, p, tm);
 }
 
 extern "C" int lcb_lstm_rec_bwd(const float* dM, const void* gates, const float* cst, const void* Wfold, const float* peep,

@@ -215,6 +215,11 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_group_pending() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 // explicit shared-space accesses through 32-bit addresses (no generic-address arithmetic)
 __device__ __forceinline__ void sts_b16(uint32_t addr, uint16_t v) { asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
+__device__ __forceinline__ float lds_f16(uint32_t addr) {                 // one fp16 from shared memory, widened
+    uint16_t h; asm volatile("ld.shared.b16 %0, [%1];" : "=h"(h) : "r"(addr) : "memory");
+    float f; asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(h));
+    return f;
+}
 __device__ __forceinline__ uint32_t lds_b32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
