@@ -336,7 +336,7 @@ def main():
            "config": {"workload": w["desc"], "name": args.workload, "per_gpu_batch": w["B"], "frames_per_step_global": frames_global,
                       "optimizer": "adam", "keep_prob": args.keep_prob, "l2": 1e-5, "clip_norm": 5.0,
                       "l2_cache": "inputs_exceed_l2 (per-step activations >> 126 MB)", "parallelism": "dp%d" % world,
-                      "fwd_flow_control": bool(model.enc.fwd_flow_control), "fwd_hproj_fracs": list(model.enc.fwd_hproj_fracs), "fwd_rec_sms": int(L.lcb_lstm_rec_grid(w["B"], model.cfg.Hp, 2, 0)),
+                      "fwd_flow_control": bool(model.enc.fwd_flow_control), "fwd_hproj_fracs": list(model.enc.fwd_hproj_fracs), "preactivation_dtype": "f16" if model.enc.g_half else "f32", "fwd_rec_sms": int(L.lcb_lstm_rec_grid(w["B"], model.cfg.Hp, 2, 0)),
                       "final_loss": last_loss, "device_error": dev_err},
            "clocks": clocks, "gpu_launches": launches, "e2e": e2e}
     if kt is not None:

@@ -238,8 +238,11 @@ class BLSTMEncoder:
         self.fwd_hproj_fracs = [0.6, 0.85]
         # The hoisted pre-activations G = x W_x + b as fp16 instead of fp32: the projections write, and the recurrence reloads, half
         # the bytes (7.9 -> 3.9 GB per C3 step); the forget bias and the recurrent product are added in fp32 in the accumulator
-        # either way.  Costs one fp16 rounding (2^-11 relative) of every pre-activation's input part.
-        self.g_half = False
+        # either way.  Costs one fp16 rounding (2^-11 relative) of every pre-activation's input part: against the exact oracle the
+        # config-shape errors do not move (logits 1.5e-2 -> 1.6e-2 of scale, gradients 4.3e-2 -> 4.2e-2 in the default-init regime,
+        # 6.5e-4 -> 7.7e-4 / 7.3e-3 -> 7.4e-3 in the stable one; profiles/r02_parity_config_shapes_g32.json vs _shapes.json), the
+        # C3 step gains 0.7 ms (profiles/r02_g_fp16_ab.jsonl).  False: fp32 G (round-1 / early round-2 behaviour).
+        self.g_half = True
         self.bwd_split_frac = 0.0      # > 0: BPTT as two launches at this fraction (lcb_lstm_rec_bwd_range; tests)
         # increasing fractions > 0.5 of the scan at which BPTT of layers 1.. is cut into consecutive launches; the rows of dX (and of
         # the next layer's dM) whose dG is final in BOTH directions after a launch are computed beside the next one (backward(),

@@ -2,7 +2,8 @@
 (/root/reference/nnet/bilstm.py:104-273, moe.py:29-72), evaluated in fp64 on the CPU, but with every tensor rounded to 16 bits
 at exactly the points where the CUDA path stores or feeds a 16-bit operand:
 
-  forward   features, layer outputs h, the recurrent operand m_t, W_x, W_proj, the output-layer weights: fp16;
+  forward   features, layer outputs h, the recurrent operand m_t, W_x, W_proj, the output-layer weights, the hoisted pre-activations
+            x W_x + b (G_HALF): fp16;
             the folded recurrent weight W' = W_proj * W_h: formed in full precision, then fp16 (the device folds it once per update
             and multiplies m_{t-1} by it, instead of h_{t-1} = m_{t-1} W_proj by W_h);
             accumulation, biases, gate pre-activations, gates, cell state: full precision (fp32 on the device)
@@ -43,6 +44,9 @@ def gq_bf16(x):
     return _Round.apply(x, None, torch.bfloat16)
 
 
+G_HALF = True        # mirror of BLSTMEncoder.g_half (the device default): x W_x + b is rounded to fp16 once before the recurrence adds to it
+
+
 def _twin_dynamic_rnn(X16, seq_len, cellp, forget_bias, zs=None):
     """One direction of one layer in the device's formulation.  X16 [B,T,Din] already rounded.  Returns m16 [B,T,H] (fp16-rounded
     o*tanh(c), 0 past seq_len) -- the projection h = m W_proj is a bulk product afterwards, as on the device."""
@@ -52,6 +56,8 @@ def _twin_dynamic_rnn(X16, seq_len, cellp, forget_bias, zs=None):
     Wx16 = q16(kernel[:din])
     fold16 = q16(proj @ kernel[din:])                        # W' [H, 4H]
     G = X16.reshape(B * T, din) @ Wx16 + bias                # hoisted projection, all frames
+    if G_HALF:
+        G = q16(G)                                           # the device stores the hoisted pre-activations as fp16 (BLSTMEncoder.g_half)
     G = G.reshape(B, T, 4 * H)
     c = X16.new_zeros(B, H)
     m = X16.new_zeros(B, H)

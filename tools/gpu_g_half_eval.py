@@ -1,6 +1,6 @@
-"""Parity of the fp16-G option (BLSTMEncoder.g_half): the whole-path config-shape tests, the recurrence tests and the model tests
-with the option forced on; the report of observed errors goes to gpurun_out/r02_parity_config_shapes_g16.json (compare with
-profiles/r02_parity_config_shapes.json, the fp32-G figures)."""
+"""Parity with fp32 pre-activations (BLSTMEncoder.g_half = False, the behaviour before the fp16-G default): the whole-path config-shape
+tests, the recurrence tests and the model tests with the option forced off (twin.G_HALF off as well); the report of observed errors
+goes to gpurun_out/r02_parity_config_shapes_g32.json (compare with profiles/r02_parity_config_shapes.json, the default)."""
 import sys
 
 import pytest
@@ -13,14 +13,17 @@ _init = blstm.BLSTMEncoder.__init__
 
 def init(self, *a, **k):
     _init(self, *a, **k)
-    self.g_half = True
+    self.g_half = False
 
 
 blstm.BLSTMEncoder.__init__ = init
+from oracle import twin  # noqa: E402
+
+twin.G_HALF = False
 rc = pytest.main(["-q", "-m", "gpu", "tests/test_config_shapes_gpu.py", "tests/test_blstm_gpu.py", "tests/test_model_gpu.py",
                   "tests/test_full_size_gpu.py"] + sys.argv[1:])
 import os  # noqa: E402
 
 if os.path.exists("gpurun_out/r02_parity_config_shapes.json"):
-    os.replace("gpurun_out/r02_parity_config_shapes.json", "gpurun_out/r02_parity_config_shapes_g16.json")
+    os.replace("gpurun_out/r02_parity_config_shapes.json", "gpurun_out/r02_parity_config_shapes_g32.json")
 sys.exit(rc)
