@@ -97,6 +97,13 @@ int lcb_gemm16_dropout(int M, int N, int K, const void* A, int lda, int a_layout
                        const void* B, int ldb, int b_layout, int b_dtype,
                        void* C, int ldc, int c_dtype, const float* bias, int accumulate,
                        float keep_prob, unsigned long long seed, unsigned long long mask_base, int max_ctas, void* stream);
+/* Same, writing the fp16 result a second time as bf16 into C_bf16 (same shape and pitch; NULL = lcb_gemm16_dropout; c_dtype must be 2):
+ * the layer output h = dropout(m*W_proj) feeds the next layer's forward GEMM as fp16 and its weight-gradient GEMM as bf16
+ * (tcgen05 kind::f16 cannot mix the two), and the second store from the staged tile replaces a conversion pass over [N, 2P]. */
+int lcb_gemm16_twin(int M, int N, int K, const void* A, int lda, int a_layout, int a_dtype,
+                    const void* B, int ldb, int b_layout, int b_dtype,
+                    void* C, int ldc, int c_dtype, void* C_bf16, const float* bias, int accumulate,
+                    float keep_prob, unsigned long long seed, unsigned long long mask_base, int max_ctas, void* stream);
 /* number of SMs of the current device (what max_ctas = 0 means; grids of every kernel are sized from it). */
 int lcb_device_sm_count(void);
 /* bf16 x bf16 shorthand of the above (max_ctas = 0). */
@@ -192,11 +199,13 @@ int lcb_lstm_rec_fwd_range_hl(const float* G, const void* WfoldT, const float* p
  * stream then releases the output projection h = m*W_proj (nnet/bilstm.py:128) of the finished frames -- and the half of the
  * next layer's input projection that reads them -- beside the running recurrence.  The launch never waits for its readers.
  * g_dtype (dtype codes of lcb_gemm16): 0 = G is fp32, 2 = G is fp16 -- lcb_gemm16 then writes half the bytes and this kernel
- * reloads half of them; the forget bias and the recurrent product are added in fp32 either way. */
+ * reloads half of them; the forget bias and the recurrent product are added in fp32 either way.
+ * Mout_bf16 (NULL = none): [T*B, 2Hp] bf16 twin of Mout, written beside it -- the weight-gradient GEMMs take bf16 operands
+ * (tcgen05 kind::f16 cannot mix fp16 x bf16), and a conversion pass over Mout costs a read and a launch per layer. */
 int lcb_lstm_rec_fwd_progress_words(int B, int Hp, int num_dirs);
 int lcb_lstm_rec_fwd_range_pg(const void* G, int g_dtype, const void* WfoldT, const float* peep, const int32_t* lens, const int32_t* lens_host,
                               const int32_t* ready_steps,
-                              void* Mout, void* gates, float* cst, float* cfin, float* mfin,
+                              void* Mout, void* Mout_bf16, void* gates, float* cst, float* cfin, float* mfin,
                               int T, int B, int Hp, int num_dirs, float forget_bias, int s_begin, int s_end,
                               int32_t* progress, void* workspace, size_t workspace_bytes, void* stream);
 /* BPTT of the above (replaces tf.gradients through the while_loop, nnet/graph.py:190-191).

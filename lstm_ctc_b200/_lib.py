@@ -79,7 +79,7 @@ _SIGS = {
     "lcb_lstm_rec_fwd_range": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "lcb_store_i32": (c_int, [c_void_p, c_int, c_void_p]),
     "lcb_lstm_rec_fwd_range_hl": (c_int, [c_void_p] * 11 + [c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_size_t, c_void_p]),
-    "lcb_lstm_rec_fwd_range_pg": (c_int, [c_void_p, c_int] + [c_void_p] * 10 + [c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p,
+    "lcb_lstm_rec_fwd_range_pg": (c_int, [c_void_p, c_int] + [c_void_p] * 11 + [c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p,
                                           c_void_p, c_size_t, c_void_p]),
     "lcb_lstm_rec_fwd_progress_words": (c_int, [c_int, c_int, c_int]),
     "lcb_lstm_rec_bwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
@@ -95,6 +95,8 @@ _SIGS = {
                            c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "lcb_gemm16_dropout": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                    c_void_p, c_int, c_int, c_void_p, c_int, c_float, ctypes.c_ulonglong, ctypes.c_ulonglong, c_int, c_void_p]),
+    "lcb_gemm16_twin": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                                c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_float, ctypes.c_ulonglong, ctypes.c_ulonglong, c_int, c_void_p]),
     "lcb_gemm16_simt_check": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                       c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "lcb_split_f32_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

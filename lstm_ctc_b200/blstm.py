@@ -138,7 +138,12 @@ def _cast16(src, dtype, dst=None):
     return dst
 
 
+_SKIP_BF16_CONV = [False]      # timing experiment only (tools/gpu_schedule_ab.py): leaves stale bf16 copies -> wrong gradients
+
+
 def _to_bf16(src, dst):
+    if _SKIP_BF16_CONV[0]:
+        return dst
     """fp16 activation -> bf16 scratch copy (same shape, both contiguous) for the wgrad GEMMs."""
     assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
     _lib.check(_lib.lib().lcb_f16_to_bf16(_lib.ptr(src), _lib.ptr(dst), src.numel(), _lib.stream_ptr()), "lcb_f16_to_bf16")
@@ -466,6 +471,10 @@ class BLSTMEncoder:
         if training:
             ws["M"] = [a.rows("M%d" % i, N, 2 * c.Hp, F16) for i in range(nl)]
             ws["Hout"] = [a.rows("Hout%d" % i, N, 2 * c.P, F16) for i in range(nl)]
+            # bf16 twins of the layer outputs, written by the output-projection GEMM's second store (lcb_gemm16_twin): the next
+            # layer's / the output layer's weight-gradient operand.  None where the layer output is modified after the GEMM
+            # (layer-0 residual, the uni-directional stack's residual add): backward() converts those.
+            ws["Hbf"] = [None if (c.uni_residual(i) or (i == 0 and c.residual0)) else a.rows("Hbf%d" % i, N, 2 * c.P, BF16) for i in range(nl)]
             ws["gates"] = [a.rows("gates%d" % i, N, 2 * c.Hp, torch.int64) for i in range(nl)]   # 4 x fp16
             ws["cst"] = [a.rows("cst%d" % i, N, 2 * c.Hp, F32) for i in range(nl)]
             ws["dM"] = a.rows("dM", N, 2 * c.Hp, F32)
@@ -476,7 +485,9 @@ class BLSTMEncoder:
             ws["dX"] = [a.rows("dX%d" % k, N, 2 * c.P, BF16) for k in range(3)]
             ws["dfold"] = [a.rows("dfold%d" % k, 4 * c.Hp, c.Hp, F32) for k in range(2)]
             ws["Xbf"] = [a.flat("Xbf%d" % k, N * max(c.Dp0, 2 * c.P), BF16) for k in range(2)]   # bf16 copies for wgrad
-            ws["Mbf"] = [a.rows("Mbf%d" % k, N, 2 * c.Hp, BF16) for k in range(2)]
+            # bf16 twins of every layer's m, written by the recurrence kernel beside the fp16 rows (wgrad operand; was: two rotating
+            # scratch copies made by a conversion pass in backward())
+            ws["Mbf"] = [a.rows("Mbf%d" % k, N, 2 * c.Hp, BF16) for k in range(nl)]
             ws["bwd_carry"] = a.flat("bwd_carry", B * 2 * c.Hp * 2, F32)
             ws["bwd_prog_words"] = _lib.lib().lcb_lstm_rec_bwd_progress_words(B, c.Hp, self.ndir)
             ws["bwd_prog"] = a.flat("bwd_prog", max(1, nl * ws["bwd_prog_words"]), torch.int32)
@@ -545,13 +556,15 @@ class BLSTMEncoder:
             def rec(s0, s1, ready=None, progress=None):
                 _lib.check(L.lcb_lstm_rec_fwd_range_pg(_lib.ptr(G), 2 if G.dtype == F16 else 0, _lib.ptr(self._bf[("fold16", i)]), _lib.ptr(peep),
                                                        _lib.ptr(seq_len),
-                                                       lens_host, _lib.ptr(ready), _lib.ptr(ws["M"][i]), _lib.ptr(gates), _lib.ptr(cst),
+                                                       lens_host, _lib.ptr(ready), _lib.ptr(ws["M"][i]),
+                                                       _lib.ptr(ws["Mbf"][i]) if training else None, _lib.ptr(gates), _lib.ptr(cst),
                                                        _lib.ptr(ws["cfin"]) if last else None, _lib.ptr(ws["mfin"]) if last else None,
                                                        T, B, c.Hp, nd, c.forget_bias, s0, s1, _lib.ptr(progress),
                                                        _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(),
                                                        _lib.stream_ptr()), "lcb_lstm_rec_fwd_range_pg")
 
             Hout = ws["Hout"][i]
+            Hbf = ws["Hbf"][i] if training else None
             # h = m * W_proj with DropoutWrapper(output_keep_prob) (bilstm.py:128,137) applied in the GEMM epilogue: element
             # [n, d*P + p] of Hout uses element n*2P + d*P + p of the layer's mask stream
             drop = (c.keep_prob, self.dropout_seed(i)) if (training and c.keep_prob < 1.0) else None
@@ -562,7 +575,8 @@ class BLSTMEncoder:
                 for d, (r0, r1) in enumerate(((s0 * B, s1 * B), ((T - s1) * B, (T - s0) * B))[:nd]):
                     gemm(ws["M"][i][r0:r1, d * c.Hp:(d + 1) * c.Hp], self._bf[("WpT16", i)][d], 0, 0,
                          out=Hout[r0:r1, d * c.P:(d + 1) * c.P],
-                         dropout=(drop + (r0 * 2 * c.P + d * c.P,)) if drop else None)
+                         dropout=(drop + (r0 * 2 * c.P + d * c.P,)) if drop else None,
+                         out_bf16=Hbf[r0:r1, d * c.P:(d + 1) * c.P] if Hbf is not None else None)
 
             # scan-step boundaries of the recurrence launches / projection chunks (training, side stream available, long enough
             # sequences)
@@ -744,8 +758,11 @@ class BLSTMEncoder:
                     side.wait_event(after)
                 # bf16 copies of the fp16 forward activations (tcgen05 kind::f16 cannot mix f16 x bf16 operands); layer 0's are
                 # made while its BPTT still runs
-                X = _to_bf16(X16, ws["Xbf"][k][:X16.numel()].view(X16.shape))
-                M = _to_bf16(ws["M"][i], ws["Mbf"][k])
+                if i > 0 and ws["Hbf"][i - 1] is not None:
+                    X = ws["Hbf"][i - 1]             # written beside the fp16 rows by the layer below's output projection
+                else:
+                    X = _to_bf16(X16, ws["Xbf"][k][:X16.numel()].view(X16.shape))
+                M = ws["Mbf"][i]                 # written by the forward recurrence beside the fp16 rows
                 if split:
                     # dW_p^T = dH^T * M needs nothing from layer 0's BPTT: both directions run beside it (capped grid)
                     with grid_cap(max(8, bwd_cap - 4)):

@@ -40,6 +40,7 @@ struct GemmDropout {
     float inv_keep;
     unsigned long long seed;
     unsigned long long base;
+    void* twin;                // fp16 outputs only, nullable: the same matrix (same pitch) written a second time as bf16 (lcb_gemm16_twin)
 };
 
 template <int BN> struct GemmCfg {
@@ -56,7 +57,7 @@ template <int BN> struct GemmCfg {
 template <int BN, bool A_MN, bool B_MN, int CT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmC, int tma_out,
+                         const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, int tma_out,
                          void* __restrict__ Cptr, int ldc, const float* __restrict__ bias, int accumulate,
                          int M, int N, int K, uint32_t idesc, int splits, const GemmDropout drop)
 {
@@ -265,6 +266,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             else tma_store_2d(&tmC, stage_base, c0, m0 + q * 32);
                             bulk_commit_group();
                         }
+                        if constexpr (CT == 2) {
+                            if (drop.twin != nullptr) {       // the bf16 twin of the box: same registers, same staging box, second store
+                                if (lane == 0) bulk_wait_group_read_pending<0>();     // the fp16 store has read the box
+                                __syncwarp();
+#pragma unroll
+                                for (int c = 0; c < 8; ++c)
+                                    sts_v4(row_addr + (((uint32_t)c ^ sw) << 4),
+                                           pack_bf16x2(__uint_as_float(r[8 * c]), __uint_as_float(r[8 * c + 1])),
+                                           pack_bf16x2(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3])),
+                                           pack_bf16x2(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5])),
+                                           pack_bf16x2(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7])));
+                                fence_proxy_async_smem();
+                                __syncwarp();
+                                if (lane == 0) { tma_store_2d(&tmC2, stage_base, c0, m0 + q * 32); bulk_commit_group(); }
+                            }
+                        }
                     }
                 }
                 tc_fence_before();
@@ -372,6 +389,11 @@ static int launch_gemm(int M, int N, int K, const CUtensorMap& ta, const CUtenso
     memset(&tc, 0, sizeof(tc));
     if (drop.thr16 < 65536u && (!tma_out || ((drop.base | (unsigned long long)ldc) & 3ull))) return LCB_ERR_MISALIGNED;
     if (tma_out && !make_tmap_2d_out(&tc, CT, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, CT == 0 ? 32 : 64)) return LCB_ERR_CUDA;
+    CUtensorMap tc2 = tc;
+    if (drop.twin != nullptr) {
+        if (CT != 2 || !tma_out || ((uintptr_t)drop.twin & 15)) return LCB_ERR_UNSUPPORTED;
+        if (!make_tmap_2d_out(&tc2, 1, drop.twin, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 64)) return LCB_ERR_CUDA;
+    }
     const int tiles0 = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
     const int nkb0 = (K + GEMM_BK - 1) / GEMM_BK;
     // split-K for reductions whose output tiles do not fill the persistent grid evenly (wgrad: K = frames): work item =
@@ -402,7 +424,7 @@ static int launch_gemm(int M, int N, int K, const CUtensorMap& ta, const CUtenso
     const int tiles = tiles0 * splits;
     int nsm = ctas;
     int grid = tiles < nsm ? tiles : nsm;
-    g_launches += 1; kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tma_out, C, ldc, bias, accumulate, M, N, K, idesc, splits, drop);
+    g_launches += 1; kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tc2, tma_out, C, ldc, bias, accumulate, M, N, K, idesc, splits, drop);
     return cudaGetLastError() == cudaSuccess ? LCB_OK : LCB_ERR_CUDA;
 }
 
@@ -454,11 +476,21 @@ extern "C" int lcb_gemm16_dropout(int M, int N, int K, const void* A, int lda, i
                                   void* C, int ldc, int c_dtype, const float* bias, int accumulate,
                                   float keep_prob, unsigned long long seed, unsigned long long mask_base, int max_ctas, void* stream)
 {
+    return lcb_gemm16_twin(M, N, K, A, lda, a_layout, a_dtype, B, ldb, b_layout, b_dtype, C, ldc, c_dtype, nullptr, bias, accumulate,
+                           keep_prob, seed, mask_base, max_ctas, stream);
+}
+
+extern "C" int lcb_gemm16_twin(int M, int N, int K, const void* A, int lda, int a_layout, int a_dtype,
+                               const void* B, int ldb, int b_layout, int b_dtype,
+                               void* C, int ldc, int c_dtype, void* C_bf16, const float* bias, int accumulate,
+                               float keep_prob, unsigned long long seed, unsigned long long mask_base, int max_ctas, void* stream)
+{
     if (!(keep_prob > 0.f) || keep_prob > 1.f) return LCB_ERR_BAD_SHAPE;
     if (keep_prob < 1.f && accumulate) return LCB_ERR_UNSUPPORTED;
+    if (C_bf16 != nullptr && c_dtype != 2) return LCB_ERR_UNSUPPORTED;
     GemmDropout drop;
     drop.thr16 = keep_prob < 1.f ? keep_threshold16(keep_prob) : 65536u;
-    drop.inv_keep = 1.f / keep_prob; drop.seed = seed; drop.base = mask_base;
+    drop.inv_keep = 1.f / keep_prob; drop.seed = seed; drop.base = mask_base; drop.twin = C_bf16;
     int rc = gemm_check_args(M, N, K, A, lda, a_layout, a_dtype, B, ldb, b_layout, b_dtype, C, ldc, c_dtype, accumulate);
     if (rc != LCB_OK) return rc;
     if ((lda & 7) || (ldb & 7) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) return LCB_ERR_MISALIGNED;

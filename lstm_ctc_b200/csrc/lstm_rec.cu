@@ -60,6 +60,7 @@ struct RecFwdParams {
     const float* peep;            // [2][3][Hp]  (w_f, w_i, w_o) or nullptr
     const int* lens;              // [B]
     __half* Mout;                 // [T*B][2Hp]   m_t, fp16 (0 where t >= len)
+    __nv_bfloat16* Mbf;           // nullable: the same rows as bf16, the operand of the weight-gradient GEMMs (which cannot mix fp16 x bf16)
     uint2* gates;                 // [T*B][2Hp]   saved (i, tanh j, f, o) as 4 x fp16   (nullptr: inference)
     float* cst;                   // [T*B][2Hp]   saved cell state c_t                   (nullptr: inference)
     float* cfin;                  // [B][2][Hp] final cell state   (nullable)
@@ -469,6 +470,8 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
         const size_t idx0 = ((size_t)(dir ? (T - 1 - LS0) : LS0) * B + bj0) * ld2 + (size_t)dir * Hp + unit;
         const bool save = p.gates != nullptr;
         __half* mo_p = p.Mout + idx0;
+        const bool twin = p.Mbf != nullptr;
+        __nv_bfloat16* mb_p = (twin ? p.Mbf : reinterpret_cast<__nv_bfloat16*>(p.Mout)) + idx0;        // (never dereferenced unless twin)
         uint2* ga_p = (save ? p.gates : reinterpret_cast<uint2*>(p.Mout)) + idx0;        // (never dereferenced unless save)
         float* cs_p = (save ? p.cst : reinterpret_cast<float*>(p.Mout)) + idx0;
         // frame at which an utterance's final state is emitted: its last live step in this direction's own order (-1: never)
@@ -518,7 +521,11 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
             for (int i = 0; i < n; ++i) {
                 if (!pad_j[0]) *mo_p = __float2half_rn(0.f);
                 if (!pad_j[1]) mo_p[ld2] = __float2half_rn(0.f);
-                mo_p += tstep;
+                if (twin) {
+                    if (!pad_j[0]) *mb_p = __float2bfloat16_rn(0.f);
+                    if (!pad_j[1]) mb_p[ld2] = __float2bfloat16_rn(0.f);
+                }
+                mo_p += tstep; mb_p += tstep;
             }
             ga_p += (long long)n * tstep; cs_p += (long long)n * tstep;
         };
@@ -581,6 +588,7 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
             // ---- off the critical path: outputs and saved activations (running pointers: one add per array and step) ----
             if (!pad_j[0]) {
                 *mo_p = __low2half(mh);
+                if (twin) *mb_p = __float2bfloat16_rn(mo[0]);
                 if (save) {
                     const __half2 g01 = __floats2half2_rn(ig[0], jt[0]), g23 = __floats2half2_rn(fg[0], og[0]);
                     *ga_p = make_uint2(*reinterpret_cast<const uint32_t*>(&g01), *reinterpret_cast<const uint32_t*>(&g23));
@@ -593,6 +601,7 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
             }
             if (!pad_j[1]) {
                 mo_p[ld2] = __high2half(mh);
+                if (twin) mb_p[ld2] = __float2bfloat16_rn(mo[1]);
                 if (save) {
                     const __half2 g01 = __floats2half2_rn(ig[1], jt[1]), g23 = __floats2half2_rn(fg[1], og[1]);
                     ga_p[ld2] = make_uint2(*reinterpret_cast<const uint32_t*>(&g01), *reinterpret_cast<const uint32_t*>(&g23));
@@ -603,7 +612,7 @@ lstm_rec_fwd2_kernel(const RecFwdParams p, const __grid_constant__ CUtensorMap t
                     p.mfin[((size_t)(bj0 + 1) * 2 + dir) * Hp + unit] = mo[1];
                 }
             }
-            mo_p += tstep; ga_p += tstep; cs_p += tstep;
+            mo_p += tstep; mb_p += tstep; ga_p += tstep; cs_p += tstep;
             REC_PROBE(14);
         }
         zero_steps(LS - act1_me);                 // ... and behind its last one (forward direction)
@@ -1518,7 +1527,7 @@ extern "C" int lcb_lstm_rec_fwd_range_hl(const float* G, const void* WfoldT, con
                                          int T, int B, int Hp, int num_dirs, float forget_bias, int s_begin, int s_end,
                                          void* workspace, size_t workspace_bytes, void* stream)
 {
-    return lcb_lstm_rec_fwd_range_pg(G, 0, WfoldT, peep, lens, lens_host, ready_steps, Mout, gates, cst, cfin, mfin, T, B, Hp, num_dirs,
+    return lcb_lstm_rec_fwd_range_pg(G, 0, WfoldT, peep, lens, lens_host, ready_steps, Mout, nullptr, gates, cst, cfin, mfin, T, B, Hp, num_dirs,
                                      forget_bias, s_begin, s_end, nullptr, workspace, workspace_bytes, stream);
 }
 
@@ -1538,7 +1547,7 @@ extern "C" int lcb_lstm_rec_fwd_progress_words(int B, int Hp, int num_dirs)
 // finished frames while the recurrence is still running; the launch itself never waits for it.
 extern "C" int lcb_lstm_rec_fwd_range_pg(const void* G, int g_dtype, const void* WfoldT, const float* peep, const int32_t* lens,
                                          const int32_t* lens_host, const int32_t* ready_steps,
-                                         void* Mout, void* gates, float* cst, float* cfin, float* mfin,
+                                         void* Mout, void* Mout_bf16, void* gates, float* cst, float* cfin, float* mfin,
                                          int T, int B, int Hp, int num_dirs, float forget_bias, int s_begin, int s_end,
                                          int32_t* progress, void* workspace, size_t workspace_bytes, void* stream)
 {
@@ -1556,6 +1565,7 @@ extern "C" int lcb_lstm_rec_fwd_range_pg(const void* G, int g_dtype, const void*
     RecFwdParams p;
     p.G = (const float*)G; p.Wt = (const __half*)WfoldT; p.peep = peep; p.lens = lens; p.Mout = (__half*)Mout;
     p.gates = (uint2*)gates; p.cst = cst; p.cfin = cfin; p.mfin = mfin;
+    p.Mbf = (__nv_bfloat16*)Mout_bf16;
     p.T = T; p.B = B; p.Hp = Hp; p.NC = nc; p.ndir = num_dirs; p.forget_bias = forget_bias; p.s_begin = s_begin; p.s_end = s_end;
     p.xch = (unsigned char*)workspace;
     int ncd, npair;

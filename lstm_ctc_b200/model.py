@@ -188,7 +188,12 @@ class AcousticModel:
         keep = c.keep_prob if training else 1.0
         self._out_seed = self.enc.dropout_seed(255)
         self._xbf_done = None
-        if training and self.enc.wstream is not None:
+        self._top_bf = None
+        if training:
+            hbf = self.enc._workspace(T, B, True)["Hbf"][-1]
+            if hbf is not None:                    # the top layer's output projection already wrote the bf16 twin (lcb_gemm16_twin)
+                self._top_bf = hbf
+        if training and self._top_bf is None and self.enc.wstream is not None:
             # bf16 copy of the encoder output for the output layer's weight gradient: made on the side stream beside the output
             # layer and the CTC sweep (both leave most of the chip idle) instead of at the head of backward()
             main = torch.cuda.current_stream()
@@ -212,7 +217,9 @@ class AcousticModel:
         N = T * B
         ws = self._out_ws(T, B)
         st = _lib.stream_ptr()
-        if getattr(self, "_xbf_done", None) is not None:
+        if getattr(self, "_top_bf", None) is not None:
+            Xbf = self._top_bf
+        elif getattr(self, "_xbf_done", None) is not None:
             torch.cuda.current_stream().wait_event(self._xbf_done)
             self._xbf_done = None
             Xbf = ws["Xbf"]

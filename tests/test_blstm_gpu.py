@@ -288,3 +288,39 @@ def test_early_rows_schedule_equals_serial(cuda_dev, B, T, fracs, keep, layers):
             assert torch.equal(a, b)
         assert (g0 - g1).abs().max().item() <= 1e-5 * g0.abs().max().item()
     assert g0.abs().max().item() > 0
+
+
+def test_bf16_twins_of_the_saved_activations(cuda_dev):
+    """The wgrad operands: the recurrence kernel writes m_t as fp16 AND bf16 (Mout_bf16 of lcb_lstm_rec_fwd_range_pg), the output
+    projection writes h as fp16 AND bf16 (lcb_gemm16_twin).  Each twin is the bf16 rounding of the same fp32 value the fp16 row was
+    rounded from: they agree to the coarser format's half ulp, zero rows (frames past sequence_length) are zero in both, and the
+    gradients backward() forms from them match the ones from converted copies of the fp16 rows."""
+    from lstm_ctc_b200 import blstm
+    from lstm_ctc_b200.blstm import BLSTMEncoder, ModelConfig
+    cfg, params, x, lens = make_case(512, 512, 24, 2, 40, 48, True, seed=31)
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(9)
+    B, T = 40, 48
+    dX = torch.randn(T * B, 2 * 512, generator=g).to(dev).bfloat16()
+    enc = BLSTMEncoder(ModelConfig(nnet_config(cfg)), dev)
+    enc.from_tf_dict(params)
+    enc.forward(x.float().to(dev), lens.to(dev), training=True)
+    ws = enc._workspace(T, B, True)
+    valid = (torch.arange(T).unsqueeze(1) < lens.unsqueeze(0)).reshape(T * B).to(dev)
+    for i in range(2):
+        for f16, bf in ((ws["M"][i], ws["Mbf"][i]), (ws["Hout"][i], ws["Hbf"][i])):
+            a, b = f16.float(), bf.float()
+            assert (b[~valid] == 0).all() and (a[~valid] == 0).all()
+            assert ((a - b).abs() <= 2.0 ** -8 * a.abs() + 1e-7).all()
+    enc.params.gflat.zero_()
+    enc.backward(dX.clone())
+    g_twin = enc.params.gflat.clone()
+    # the same backward from converted copies of the fp16 rows (what backward() did before the twins existed)
+    for i in range(2):
+        ws["Mbf"][i].copy_(ws["M"][i])
+        ws["Hbf"][i].copy_(ws["Hout"][i])
+    enc.params.gflat.zero_()
+    enc.backward(dX.clone())
+    g_conv = enc.params.gflat.clone()
+    torch.cuda.synchronize()
+    assert (g_twin - g_conv).norm().item() <= 2e-3 * g_conv.norm().item()

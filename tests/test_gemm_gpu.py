@@ -137,3 +137,31 @@ def test_fused_dropout_equals_separate_pass(cuda_dev, odt):
     assert (got - want).abs().max().item() <= tol * max(1.0, want.abs().max().item())
     assert torch.equal(got == 0, want == 0)
     assert full[:, :off].abs().max().item() == 0 and full[:, off + N:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("keep", [1.0, 0.8])
+@pytest.mark.parametrize("M,N,K", [(1000, 512, 512), (333, 200, 136), (4096, 64, 64)])
+def test_twin_store_writes_the_same_tile_as_bf16(cuda_dev, M, N, K, keep):
+    """lcb_gemm16_twin: the fp16 result and its bf16 twin come from the same fp32 accumulator values (bias and dropout applied) --
+    each equals the round-to-nearest cast of the fp32 result of the identical launch with fp32 output; a column slice of a wider
+    matrix (how the two directions' output projections write their halves) leaves the other columns untouched."""
+    from lstm_ctc_b200.gemm import gemm
+    torch.manual_seed(M + K)
+    A = (torch.randn(M, K, device=cuda_dev) * 0.5).half()
+    W = (torch.randn(N, K, device=cuda_dev) * 0.1).half()
+    bias = torch.randn(N, device=cuda_dev)
+    ld = 2 * ((N + 7) // 8 * 8) + 8
+    C16 = torch.full((M, ld), 7.0, device=cuda_dev, dtype=torch.float16)
+    Cbf = torch.full((M, ld), 7.0, device=cuda_dev, dtype=torch.bfloat16)
+    C32 = torch.zeros((M, ld), device=cuda_dev)
+    drop = (keep, 1234, 8) if keep < 1.0 else None
+    gemm(A, W, 0, 0, out=C16[:, 8:8 + N], bias=bias, dropout=drop, out_bf16=Cbf[:, 8:8 + N])
+    gemm(A, W, 0, 0, out=C32[:, 8:8 + N], bias=bias, dropout=drop)
+    torch.cuda.synchronize()
+    assert torch.equal(C16[:, 8:8 + N], C32[:, 8:8 + N].half())
+    assert torch.equal(Cbf[:, 8:8 + N], C32[:, 8:8 + N].bfloat16())
+    for C in (C16, Cbf):
+        assert (C[:, :8] == 7.0).all() and (C[:, 8 + N:] == 7.0).all()
+    if keep < 1.0:
+        z = (C32[:, 8:8 + N] == 0).float().mean().item()
+        assert abs(z - (1 - keep)) < 0.02
