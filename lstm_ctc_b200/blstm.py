@@ -248,6 +248,9 @@ class BLSTMEncoder:
         # 6.5e-4 -> 7.7e-4 / 7.3e-3 -> 7.4e-3 in the stable one; profiles/r02_parity_config_shapes_g32.json vs _shapes.json), the
         # C3 step gains 0.7 ms (profiles/r02_g_fp16_ab.jsonl).  False: fp32 G (round-1 / early round-2 behaviour).
         self.g_half = True
+        # bf16 twins of the saved activations (wgrad operands) written by their producers -- the recurrence kernel (Mout_bf16) and the
+        # output-projection GEMM (lcb_gemm16_twin) -- instead of conversion passes over the fp16 rows in backward()
+        self.bf16_twins = True
         self.bwd_split_frac = 0.0      # > 0: BPTT as two launches at this fraction (lcb_lstm_rec_bwd_range; tests)
         # increasing fractions > 0.5 of the scan at which BPTT of layers 1.. is cut into consecutive launches; the rows of dX (and of
         # the next layer's dM) whose dG is final in BOTH directions after a launch are computed beside the next one (backward(),
@@ -557,14 +560,14 @@ class BLSTMEncoder:
                 _lib.check(L.lcb_lstm_rec_fwd_range_pg(_lib.ptr(G), 2 if G.dtype == F16 else 0, _lib.ptr(self._bf[("fold16", i)]), _lib.ptr(peep),
                                                        _lib.ptr(seq_len),
                                                        lens_host, _lib.ptr(ready), _lib.ptr(ws["M"][i]),
-                                                       _lib.ptr(ws["Mbf"][i]) if training else None, _lib.ptr(gates), _lib.ptr(cst),
+                                                       _lib.ptr(ws["Mbf"][i]) if (training and self.bf16_twins) else None, _lib.ptr(gates), _lib.ptr(cst),
                                                        _lib.ptr(ws["cfin"]) if last else None, _lib.ptr(ws["mfin"]) if last else None,
                                                        T, B, c.Hp, nd, c.forget_bias, s0, s1, _lib.ptr(progress),
                                                        _lib.ptr(ws["rec_ws"]), ws["rec_ws"].numel(),
                                                        _lib.stream_ptr()), "lcb_lstm_rec_fwd_range_pg")
 
             Hout = ws["Hout"][i]
-            Hbf = ws["Hbf"][i] if training else None
+            Hbf = ws["Hbf"][i] if (training and self.bf16_twins) else None
             # h = m * W_proj with DropoutWrapper(output_keep_prob) (bilstm.py:128,137) applied in the GEMM epilogue: element
             # [n, d*P + p] of Hout uses element n*2P + d*P + p of the layer's mask stream
             drop = (c.keep_prob, self.dropout_seed(i)) if (training and c.keep_prob < 1.0) else None
@@ -758,11 +761,12 @@ class BLSTMEncoder:
                     side.wait_event(after)
                 # bf16 copies of the fp16 forward activations (tcgen05 kind::f16 cannot mix f16 x bf16 operands); layer 0's are
                 # made while its BPTT still runs
-                if i > 0 and ws["Hbf"][i - 1] is not None:
+                if self.bf16_twins and i > 0 and ws["Hbf"][i - 1] is not None:
                     X = ws["Hbf"][i - 1]             # written beside the fp16 rows by the layer below's output projection
                 else:
                     X = _to_bf16(X16, ws["Xbf"][k][:X16.numel()].view(X16.shape))
-                M = ws["Mbf"][i]                 # written by the forward recurrence beside the fp16 rows
+                # m: written by the forward recurrence beside the fp16 rows, or converted here
+                M = ws["Mbf"][i] if self.bf16_twins else _to_bf16(ws["M"][i], ws["Mbf"][i])
                 if split:
                     # dW_p^T = dH^T * M needs nothing from layer 0's BPTT: both directions run beside it (capped grid)
                     with grid_cap(max(8, bwd_cap - 4)):

@@ -191,7 +191,7 @@ class AcousticModel:
         self._top_bf = None
         if training:
             hbf = self.enc._workspace(T, B, True)["Hbf"][-1]
-            if hbf is not None:                    # the top layer's output projection already wrote the bf16 twin (lcb_gemm16_twin)
+            if hbf is not None and self.enc.bf16_twins:                    # the top layer's output projection already wrote the bf16 twin (lcb_gemm16_twin)
                 self._top_bf = hbf
         if training and self._top_bf is None and self.enc.wstream is not None:
             # bf16 copy of the encoder output for the output layer's weight gradient: made on the side stream beside the output

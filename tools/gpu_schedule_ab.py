@@ -49,6 +49,7 @@ def apply(cfg):
     model.top_overlap = cfg.get("top", True)
     model.enc.fwd_hproj_fracs = cfg.get("hfracs", [0.6, 0.85])
     model.enc.g_half = cfg.get("g_half", True)
+    model.enc.bf16_twins = cfg.get("twins", True)
     import lstm_ctc_b200.blstm as _b
     _b._SKIP_BF16_CONV[0] = cfg.get("skip_bf16_conv", False)
 
@@ -57,7 +58,7 @@ def apply(cfg):
 configs = {"default_hproj_0.6_0.85": {}, "hproj_0.7": {"hfracs": [0.7]}, "hproj_after_launch": {"hfracs": []}, "hproj_0.6": {"hfracs": [0.6]}, "hproj_0.8": {"hfracs": [0.8]},
            "hproj_0.5_0.75_0.9": {"hfracs": [0.5, 0.75, 0.9]},
            "hproj_0.7_chunks_0.25_0.5_0.75": {"fracs": [0.25, 0.5, 0.75]},
-           "g_fp32": {"g_half": False}, "timing_only_no_bf16_conversions": {"skip_bf16_conv": True}, "g_fp16_head0.25": {"fracs": [0.25, 0.5, 0.78]},
+           "g_fp32": {"g_half": False}, "bf16_conversion_passes": {"twins": False}, "timing_only_no_bf16_conversions": {"skip_bf16_conv": True}, "g_fp16_head0.25": {"fracs": [0.25, 0.5, 0.78]},
            # BPTT release points of the early-rows schedule (one launch publishing its progress)
            "early_0.67_0.85_0.95": {"early": [0.67, 0.85, 0.95]}, "early_0.6_0.8_0.9_0.96": {"early": [0.6, 0.8, 0.9, 0.96]},
            "early_0.7_0.9": {"early": [0.7, 0.9]}, "early_0.67_0.85_0.93_0.98": {"early": [0.67, 0.85, 0.93, 0.98]}}
