@@ -138,12 +138,7 @@ def _cast16(src, dtype, dst=None):
     return dst
 
 
-_SKIP_BF16_CONV = [False]      # timing experiment only (tools/gpu_schedule_ab.py): leaves stale bf16 copies -> wrong gradients
-
-
 def _to_bf16(src, dst):
-    if _SKIP_BF16_CONV[0]:
-        return dst
     """fp16 activation -> bf16 scratch copy (same shape, both contiguous) for the wgrad GEMMs."""
     assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
     _lib.check(_lib.lib().lcb_f16_to_bf16(_lib.ptr(src), _lib.ptr(dst), src.numel(), _lib.stream_ptr()), "lcb_f16_to_bf16")

@@ -50,8 +50,11 @@ def apply(cfg):
     model.enc.fwd_hproj_fracs = cfg.get("hfracs", [0.6, 0.85])
     model.enc.g_half = cfg.get("g_half", True)
     model.enc.bf16_twins = cfg.get("twins", True)
+    # timing-only experiment: no conversion pass at all (stale bf16 copies -> WRONG gradients; the time is what is measured)
     import lstm_ctc_b200.blstm as _b
-    _b._SKIP_BF16_CONV[0] = cfg.get("skip_bf16_conv", False)
+    if not hasattr(_b, "_to_bf16_real"):
+        _b._to_bf16_real = _b._to_bf16
+    _b._to_bf16 = (lambda src, dst: dst) if cfg.get("skip_bf16_conv", False) else _b._to_bf16_real
 
 
 # (earlier visits compared the chunk fractions: profiles/r02_flow_fracs_ab.jsonl)
